@@ -1,0 +1,177 @@
+/*
+ * mgcfd_b200.h -- C-ABI of the B200-native MG-CFD hot path (libmgcfd_b200.so).
+ *
+ * Drop-in boundary = the reference's op_par_loop call sites in euler3d.cpp.
+ * OP2's code generator turns every op_par_loop into one host stub per kernel; this header
+ * exports one entry point per such call site, plus the set/map/dat declaration, constant
+ * declaration, fetch and teardown calls the driver makes around them.  Each declaration
+ * cites the reference interface it replaces.  Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns MGCFD_OK (0) or a negative error code; mgcfd_last_error() gives the
+ *     message.  No exceptions cross the ABI.  (Reference: print + op_exit() + return 1,
+ *     euler3d.cpp:480-484, 544-548.)
+ *   - host arrays are borrowed for the duration of the call only; the context owns all
+ *     device storage (OP2 likewise owns dat storage after op_decl_*).
+ *   - node/edge/boundary arrays are passed and fetched in FILE order; the planner's
+ *     renumbering, blocking and partitioning are invisible to the caller.
+ *   - loops are enqueued on the context's CUDA stream and are stream-ordered; only calls that
+ *     return a value to the host (get_min_dt, calc_rms, count_bad_vals, fetch, sync) block.
+ *   - there is no CPU fallback: without a CUDA device mgcfd_create() fails.
+ */
+#ifndef MGCFD_B200_H
+#define MGCFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGCFD_NVAR 5   /* const.h:41 */
+#define MGCFD_NDIM 3   /* const.h:29 */
+#define MGCFD_RK   3   /* const.h:31 */
+
+enum {
+    MGCFD_OK = 0,
+    MGCFD_ERR_ARG = -1,        /* bad argument / call order */
+    MGCFD_ERR_CUDA = -2,       /* CUDA runtime error (message has the details) */
+    MGCFD_ERR_NODEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
+    MGCFD_ERR_MIN_DT = -4,     /* min_dt < 0 (euler3d.cpp:480-484) */
+    MGCFD_ERR_BAD_VALS = -5,   /* NaN/Inf in variables (euler3d.cpp:544-548) */
+    MGCFD_ERR_PLAN = -6        /* planner limit exceeded */
+};
+
+/* flux-edge implementations (north_star: colouring scheme vs atomics, choice by measurement) */
+enum {
+    MGCFD_FLUX_ATOMIC = 0,     /* thread per edge, register accumulators, warp-aggregated fp64 RED */
+    MGCFD_FLUX_COLOUR = 1,     /* OP2-style hierarchical colouring: edge blocks staged in shared memory,
+                                  thread-colour-ordered shared accumulation, block-colour-ordered launches */
+    MGCFD_FLUX_OWNER = 2,      /* owner-compute node chunks: cut edges recomputed, per-edge fluxes staged in
+                                  shared memory, gathered per owned node, plain coalesced stores (default) */
+    MGCFD_FLUX_NVARIANTS = 3
+};
+
+typedef struct mgcfd_ctx mgcfd_ctx;
+
+/* op_decl_const set, euler3d.cpp:232-238 (values computed at :47, :157-189) */
+typedef struct {
+    double smoothing_coefficient;
+    double ff_variable[MGCFD_NVAR];
+    double ff_flux_contribution_momentum_x[MGCFD_NDIM];
+    double ff_flux_contribution_momentum_y[MGCFD_NDIM];
+    double ff_flux_contribution_momentum_z[MGCFD_NDIM];
+    double ff_flux_contribution_density_energy[MGCFD_NDIM];
+    int mesh_name;
+    int pad_;
+} mgcfd_consts;
+
+/* One multigrid level = the sets, maps and dats euler3d.cpp:248-312 declares from one level
+ * file; field names are the HDF5 dataset names with "-->" spelled "_to_". */
+typedef struct {
+    int n_nodes;                       /* op_decl_set_hdf5_infer_size(.., "node_coordinates")   :251 */
+    int n_edges;                       /* op_decl_set_hdf5_infer_size(.., "edge-->node")        :258 */
+    int n_bnd_nodes;                   /* op_decl_set_hdf5_infer_size(.., "bnd_node-->node")    :265 */
+    int n_owned_nodes;                 /* == n_nodes on one GPU; on a partition: nodes [0,n_owned) are owned,
+                                          the rest are import halo (OP2 keeps this inside op_set) */
+    const double *node_coordinates;    /* [n_nodes*3]   op_decl_dat_hdf5 :311 */
+    const int    *edge_to_node;        /* [n_edges*2]   op_decl_map_hdf5 :273, base_array_index-based */
+    const double *edge_weights;        /* [n_edges*3]   op_decl_dat_hdf5 :304 */
+    const int    *bnd_node_to_node;    /* [n_bnd_nodes] op_decl_map_hdf5 :274, base_array_index-based */
+    const int    *bnd_node_to_group;   /* [n_bnd_nodes] op_decl_dat_hdf5 :276 */
+    const double *bnd_node_weights;    /* [n_bnd_nodes*3] op_decl_dat_hdf5 :306 */
+    const int    *node_to_mg_node;     /* [n_nodes] map into level+1 (op_decl_map_hdf5 :283), NULL on the coarsest */
+} mgcfd_level_host;
+
+typedef struct {
+    int flux_variant;      /* MGCFD_FLUX_*; default MGCFD_FLUX_OWNER */
+    int renumber;          /* 1 (default): Hilbert-curve locality renumbering of nodes; 0: keep file order */
+    int owner_chunk_nodes; /* owner variant: max owned nodes per chunk (default 256) */
+    int colour_block_edges;/* colour variant: edges per block (default 256) */
+    int exact_arith;       /* 1: reference operation order, IEEE div/sqrt, no FMA contraction in the flux kernels */
+    int reserved[11];
+} mgcfd_options;
+
+/* ---- lifetime (op_init / op_exit, euler3d.cpp:126, :824) ---- */
+void mgcfd_default_options(mgcfd_options *opt);
+int  mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options *opt);
+void mgcfd_destroy(mgcfd_ctx *ctx);
+const char *mgcfd_last_error(const mgcfd_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+const char *mgcfd_version(void);
+
+/* ---- declarations ---- */
+/* far-field constants exactly as euler3d.cpp:47,157-189 evaluates them */
+void mgcfd_compute_farfield_consts(mgcfd_consts *out);
+int  mgcfd_decl_consts(mgcfd_ctx *ctx, const mgcfd_consts *c);                        /* op_decl_const x7 :232-238 */
+int  mgcfd_decl_level(mgcfd_ctx *ctx, int level, const mgcfd_level_host *lv, int base_array_index); /* :248-312 */
+/* op_partition/op_renumber/op_decl_dat_temp_char point (:340-409): renumber, build the edge plans
+ * (chunks / blocks / colours), allocate the temp dats variables, old_variables, residuals, volumes,
+ * step_factors, fluxes, up_scratch zero-initialised */
+int  mgcfd_plan(mgcfd_ctx *ctx);
+
+/* ---- initialisation loops, euler3d.cpp:413-441 (run once; see DESIGN.md "init on host") ---- */
+int mgcfd_loop_initialize_variables(mgcfd_ctx *ctx, int level);     /* :414 initialize_variables_kernel */
+int mgcfd_loop_zero_fluxes(mgcfd_ctx *ctx, int level);              /* :416 zero_5d_array_kernel(p_fluxes) */
+int mgcfd_loop_zero_volumes(mgcfd_ctx *ctx, int level);             /* :424 zero_1d_array_kernel(p_volumes) */
+int mgcfd_loop_calculate_cell_volumes(mgcfd_ctx *ctx, int level);   /* :426-431 */
+int mgcfd_loop_dampen_ewt_edges(mgcfd_ctx *ctx, int level);         /* :437 dampen_ewt(p_edge_weights) */
+int mgcfd_loop_dampen_ewt_bnd(mgcfd_ctx *ctx, int level);           /* :439 dampen_ewt(p_bnd_node_weights) */
+
+/* ---- the 14 live op_par_loop call sites of the cycle loop, euler3d.cpp:467-631 ---- */
+int mgcfd_loop_copy_double(mgcfd_ctx *ctx, int level);                          /* :467-469 */
+int mgcfd_loop_calculate_dt(mgcfd_ctx *ctx, int level);                         /* :472-475 */
+int mgcfd_loop_get_min_dt(mgcfd_ctx *ctx, int level, double *min_dt);           /* :477-479 op_arg_gbl OP_MIN (in/out) */
+int mgcfd_loop_compute_step_factor(mgcfd_ctx *ctx, int level, const double *min_dt); /* :485-489 op_arg_gbl OP_READ */
+int mgcfd_loop_compute_flux_edge(mgcfd_ctx *ctx, int level);                    /* :498-503 */
+int mgcfd_loop_compute_bnd_node_flux(mgcfd_ctx *ctx, int level);                /* :505-509 */
+int mgcfd_loop_time_step(mgcfd_ctx *ctx, int level, const int *rkCycle);        /* :511-516 op_arg_gbl OP_READ */
+int mgcfd_loop_unstructured_stream(mgcfd_ctx *ctx, int level);                  /* :518-525 (-b) into p_dummy_fluxes */
+int mgcfd_loop_residual(mgcfd_ctx *ctx, int level);                             /* :528-531 */
+int mgcfd_loop_calc_rms(mgcfd_ctx *ctx, int level, double *rms);                /* :534-536 op_arg_gbl OP_INC */
+int mgcfd_loop_count_bad_vals(mgcfd_ctx *ctx, int level, int *count);           /* :540-542 op_arg_gbl OP_INC */
+int mgcfd_loop_up_pre(mgcfd_ctx *ctx, int level_above);                         /* :581-583 set = nodes[level_above-1] */
+int mgcfd_loop_up(mgcfd_ctx *ctx, int level_above);                             /* :585-588 */
+int mgcfd_loop_up_post(mgcfd_ctx *ctx, int level_above);                        /* :590-592 */
+int mgcfd_loop_down(mgcfd_ctx *ctx, int level);                                 /* :626-631 prolong level+1 -> level */
+
+/* ---- whole V-cycles on the device: the schedule of euler3d.cpp:458-641 with the per-visit host
+ * checks (:480, :544) deferred to one flag read per call.  Results equal the loop-by-loop path. ---- */
+int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles);
+
+/* ---- op_fetch_data / test hooks ---- */
+/* dat names: "variables" "old_variables" "residuals" "fluxes" "dummy_fluxes" (dim 5), "volumes"
+ * "step_factors" (dim 1), "node_coordinates" (dim 3) -> double, n_nodes*dim, file node order;
+ * "edge_weights" (double, n_edges*3, file edge order), "bnd_node_weights" (double, n_bnd*3),
+ * "up_scratch" (int, n_nodes).  op_fetch_data_hdf5_file: euler3d.cpp:564,740-770 */
+int mgcfd_fetch_dat(mgcfd_ctx *ctx, int level, const char *name, void *host_out);
+int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_in);   /* tests / restart */
+int mgcfd_sync(mgcfd_ctx *ctx);                                                        /* cudaStreamSynchronize */
+
+/* ---- -v validation path, euler3d.cpp:662-716 (identify_differences + count_non_zeros on device) ---- */
+int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master_variables, int *n_differences);
+
+/* ---- plan introspection (bit-exactness tests of renumbering / colouring / chunking) ---- */
+/* what: "node_perm" (int[n_nodes]: internal index of file node i), "edge_order" (int[n_edges]: file edge at
+ * sorted position i), "edge_block_colour" / "edge_thread_colour" (int[n_edges], colour variant, file edge
+ * order), "n_block_colours" (int[1]), "owner_chunk_start" (int[n_chunks+1]), ...  Returns the number of
+ * elements written, or a negative error; out may be NULL to query the count. */
+long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out, long long capacity);
+
+/* ---- measurement hooks ---- */
+/* per-call-site device timers (CUDA events on the context's stream), off by default */
+int  mgcfd_timers_enable(mgcfd_ctx *ctx, int on);
+int  mgcfd_timers_reset(mgcfd_ctx *ctx);
+/* accumulated milliseconds / launch count / element count of a call site ("compute_flux_edge", ...) */
+int  mgcfd_timers_get(mgcfd_ctx *ctx, const char *loop_name, int level, double *ms, long long *calls,
+                      long long *elements);
+long long mgcfd_kernel_launches(const mgcfd_ctx *ctx);      /* kernels launched by this library so far */
+int  mgcfd_set_flux_variant(mgcfd_ctx *ctx, int variant);   /* switch implementation (plans built lazily) */
+void *mgcfd_stream(mgcfd_ctx *ctx);                         /* cudaStream_t the loops are enqueued on */
+void *mgcfd_device_ptr(mgcfd_ctx *ctx, int level, const char *name); /* raw device pointer of a dat (internal order) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGCFD_B200_H */

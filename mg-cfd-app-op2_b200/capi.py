@@ -1,0 +1,327 @@
+"""ctypes binding of include/mgcfd_b200.h (libmgcfd_b200.so) and a driver restating euler3d.cpp.
+
+This is the Python face of the C-ABI for tests and bench.py; the native host driver is
+host/euler3d_b200.cpp.  There is no fallback: if the CUDA library is missing or no device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmgcfd_b200.so")
+
+NVAR, NDIM, RK = 5, 3, 3
+FLUX_ATOMIC, FLUX_COLOUR, FLUX_OWNER = 0, 1, 2
+FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWNER}
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NODEVICE", -4: "ERR_MIN_DT",
+             -5: "ERR_BAD_VALS", -6: "ERR_PLAN"}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class MgcfdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Consts(C.Structure):
+    _fields_ = [("smoothing_coefficient", C.c_double), ("ff_variable", C.c_double * 5),
+                ("ff_flux_contribution_momentum_x", C.c_double * 3),
+                ("ff_flux_contribution_momentum_y", C.c_double * 3),
+                ("ff_flux_contribution_momentum_z", C.c_double * 3),
+                ("ff_flux_contribution_density_energy", C.c_double * 3),
+                ("mesh_name", C.c_int), ("pad_", C.c_int)]
+
+
+class LevelHost(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("n_edges", C.c_int), ("n_bnd_nodes", C.c_int), ("n_owned_nodes", C.c_int),
+                ("node_coordinates", _dp), ("edge_to_node", _ip), ("edge_weights", _dp),
+                ("bnd_node_to_node", _ip), ("bnd_node_to_group", _ip), ("bnd_node_weights", _dp),
+                ("node_to_mg_node", _ip)]
+
+
+class Options(C.Structure):
+    _fields_ = [("flux_variant", C.c_int), ("renumber", C.c_int), ("owner_chunk_nodes", C.c_int),
+                ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("reserved", C.c_int * 11)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmgcfd_b200.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MgcfdError(-3, f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mgcfd_last_error.restype = C.c_char_p
+    lib.mgcfd_last_error.argtypes = [C.c_void_p]
+    lib.mgcfd_version.restype = C.c_char_p
+    lib.mgcfd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Options)]
+    lib.mgcfd_destroy.argtypes = [C.c_void_p]
+    lib.mgcfd_plan_query.restype = C.c_longlong
+    lib.mgcfd_plan_query.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _ip, C.c_longlong]
+    lib.mgcfd_kernel_launches.restype = C.c_longlong
+    lib.mgcfd_kernel_launches.argtypes = [C.c_void_p]
+    lib.mgcfd_stream.restype = C.c_void_p
+    lib.mgcfd_stream.argtypes = [C.c_void_p]
+    lib.mgcfd_device_ptr.restype = C.c_void_p
+    lib.mgcfd_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    _lib = lib
+    return lib
+
+
+# every symbol include/mgcfd_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "mgcfd_default_options", "mgcfd_create", "mgcfd_destroy", "mgcfd_last_error", "mgcfd_version",
+    "mgcfd_compute_farfield_consts", "mgcfd_decl_consts", "mgcfd_decl_level", "mgcfd_plan",
+    "mgcfd_loop_initialize_variables", "mgcfd_loop_zero_fluxes", "mgcfd_loop_zero_volumes",
+    "mgcfd_loop_calculate_cell_volumes", "mgcfd_loop_dampen_ewt_edges", "mgcfd_loop_dampen_ewt_bnd",
+    "mgcfd_loop_copy_double", "mgcfd_loop_calculate_dt", "mgcfd_loop_get_min_dt",
+    "mgcfd_loop_compute_step_factor", "mgcfd_loop_compute_flux_edge", "mgcfd_loop_compute_bnd_node_flux",
+    "mgcfd_loop_time_step", "mgcfd_loop_unstructured_stream", "mgcfd_loop_residual", "mgcfd_loop_calc_rms",
+    "mgcfd_loop_count_bad_vals", "mgcfd_loop_up_pre", "mgcfd_loop_up", "mgcfd_loop_up_post", "mgcfd_loop_down",
+    "mgcfd_run_cycles", "mgcfd_fetch_dat", "mgcfd_set_dat", "mgcfd_sync", "mgcfd_validate_level",
+    "mgcfd_plan_query", "mgcfd_timers_enable", "mgcfd_timers_reset", "mgcfd_timers_get",
+    "mgcfd_kernel_launches", "mgcfd_set_flux_variant", "mgcfd_stream", "mgcfd_device_ptr",
+]
+
+_DAT_DIMS = {"variables": 5, "old_variables": 5, "residuals": 5, "fluxes": 5, "dummy_fluxes": 5,
+             "volumes": 1, "step_factors": 1, "node_coordinates": 3}
+
+
+def farfield_consts(mesh_name=0):
+    lib = load_library()
+    c = Consts()
+    lib.mgcfd_compute_farfield_consts(C.byref(c))
+    c.mesh_name = mesh_name
+    return c
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class MGCFD:
+    """One context = one GPU's share of the mesh.  Methods are the op_par_loop call sites of euler3d.cpp."""
+
+    def __init__(self, levels, base_array_index=1, device=0, flux_variant="owner", renumber=True,
+                 exact_arith=False, owner_chunk_nodes=256, colour_block_edges=256, consts=None,
+                 n_owned=None, init=True):
+        """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"])."""
+        self.lib = load_library()
+        self.n_levels = len(levels)
+        opt = Options()
+        self.lib.mgcfd_default_options(C.byref(opt))
+        opt.flux_variant = FLUX_VARIANTS[flux_variant] if isinstance(flux_variant, str) else int(flux_variant)
+        opt.renumber = int(bool(renumber))
+        opt.exact_arith = int(bool(exact_arith))
+        opt.owner_chunk_nodes = int(owner_chunk_nodes)
+        opt.colour_block_edges = int(colour_block_edges)
+        self.ctx = C.c_void_p()
+        rc = self.lib.mgcfd_create(C.byref(self.ctx), int(device), self.n_levels, C.byref(opt))
+        if rc != 0:
+            raise MgcfdError(rc, self.lib.mgcfd_last_error(None).decode())
+        self.consts = consts if consts is not None else farfield_consts()
+        self._ck(self.lib.mgcfd_decl_consts(self.ctx, C.byref(self.consts)))
+        self.sizes = []
+        for l, lev in enumerate(levels):
+            coords = _as(lev["node_coordinates"], np.float64)
+            e2n = _as(lev["edge-->node"], np.int32)
+            ewt = _as(lev["edge_weights"], np.float64)
+            b2n = _as(lev["bnd_node-->node"], np.int32)
+            bgr = _as(lev["bnd_node-->group"], np.int32)
+            bwt = _as(lev["bnd_node_weights"], np.float64)
+            mg = _as(lev["node-->mg_node"], np.int32) if "node-->mg_node" in lev else None
+            h = LevelHost()
+            h.n_nodes, h.n_edges, h.n_bnd_nodes = coords.shape[0], e2n.shape[0], b2n.shape[0]
+            h.n_owned_nodes = h.n_nodes if n_owned is None else int(n_owned[l])
+            h.node_coordinates = coords.ctypes.data_as(_dp)
+            h.edge_to_node = e2n.ctypes.data_as(_ip)
+            h.edge_weights = ewt.ctypes.data_as(_dp)
+            h.bnd_node_to_node = b2n.ctypes.data_as(_ip)
+            h.bnd_node_to_group = bgr.ctypes.data_as(_ip)
+            h.bnd_node_weights = bwt.ctypes.data_as(_dp)
+            h.node_to_mg_node = mg.ctypes.data_as(_ip) if mg is not None else _ip()
+            self._ck(self.lib.mgcfd_decl_level(self.ctx, l, C.byref(h), int(base_array_index)))
+            self.sizes.append((h.n_nodes, h.n_edges, h.n_bnd_nodes))
+        self._ck(self.lib.mgcfd_plan(self.ctx))
+        if init:
+            self.init_loops()
+
+    # ---- plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise MgcfdError(rc, self.lib.mgcfd_last_error(self.ctx).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.mgcfd_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- euler3d.cpp:413-441
+    def init_loops(self):
+        L = self.lib
+        for l in range(self.n_levels):
+            self._ck(L.mgcfd_loop_initialize_variables(self.ctx, l))
+            self._ck(L.mgcfd_loop_zero_fluxes(self.ctx, l))
+            self._ck(L.mgcfd_loop_zero_volumes(self.ctx, l))
+            self._ck(L.mgcfd_loop_calculate_cell_volumes(self.ctx, l))
+        for l in range(self.n_levels):
+            self._ck(L.mgcfd_loop_dampen_ewt_edges(self.ctx, l))
+            self._ck(L.mgcfd_loop_dampen_ewt_bnd(self.ctx, l))
+
+    # ---- call sites of the cycle loop
+    def copy_double(self, l): self._ck(self.lib.mgcfd_loop_copy_double(self.ctx, l))
+    def calculate_dt(self, l): self._ck(self.lib.mgcfd_loop_calculate_dt(self.ctx, l))
+
+    def get_min_dt(self, l, start=np.finfo(np.float64).max):
+        m = C.c_double(start)
+        self._ck(self.lib.mgcfd_loop_get_min_dt(self.ctx, l, C.byref(m)))
+        return m.value
+
+    def compute_step_factor(self, l, min_dt):
+        m = C.c_double(min_dt)
+        self._ck(self.lib.mgcfd_loop_compute_step_factor(self.ctx, l, C.byref(m)))
+
+    def compute_flux_edge(self, l): self._ck(self.lib.mgcfd_loop_compute_flux_edge(self.ctx, l))
+    def compute_bnd_node_flux(self, l): self._ck(self.lib.mgcfd_loop_compute_bnd_node_flux(self.ctx, l))
+
+    def time_step(self, l, rk):
+        r = C.c_int(rk)
+        self._ck(self.lib.mgcfd_loop_time_step(self.ctx, l, C.byref(r)))
+
+    def unstructured_stream(self, l): self._ck(self.lib.mgcfd_loop_unstructured_stream(self.ctx, l))
+    def residual(self, l): self._ck(self.lib.mgcfd_loop_residual(self.ctx, l))
+
+    def calc_rms(self, l, start=0.0):
+        r = C.c_double(start)
+        self._ck(self.lib.mgcfd_loop_calc_rms(self.ctx, l, C.byref(r)))
+        return r.value
+
+    def count_bad_vals(self, l, start=0):
+        c = C.c_int(start)
+        self._ck(self.lib.mgcfd_loop_count_bad_vals(self.ctx, l, C.byref(c)))
+        return c.value
+
+    def up_pre(self, la): self._ck(self.lib.mgcfd_loop_up_pre(self.ctx, la))
+    def up(self, la): self._ck(self.lib.mgcfd_loop_up(self.ctx, la))
+    def up_post(self, la): self._ck(self.lib.mgcfd_loop_up_post(self.ctx, la))
+    def down(self, l): self._ck(self.lib.mgcfd_loop_down(self.ctx, l))
+
+    def run_cycles(self, n):
+        """Device-driven V-cycles (host checks deferred to one flag read)."""
+        self._ck(self.lib.mgcfd_run_cycles(self.ctx, int(n)))
+
+    def run_cycles_loopwise(self, n_cycles):
+        """euler3d.cpp:458-641 call site by call site, host checks included.  Returns (rms, min_dt)."""
+        nl = self.n_levels
+        level, mg_dir, i = 0, 0, 0
+        rms, min_dt = 0.0, np.finfo(np.float64).max
+        while i < n_cycles:
+            self.copy_double(level)
+            self.calculate_dt(level)
+            min_dt = self.get_min_dt(level)
+            if min_dt < 0.0:
+                raise MgcfdError(-4, f"Fatal error during 'step factor' calculation, min_dt = {min_dt:.5e}")
+            self.compute_step_factor(level, min_dt)
+            for rk in range(RK):
+                self.compute_flux_edge(level)
+                self.compute_bnd_node_flux(level)
+                self.time_step(level, rk)
+            self.residual(level)
+            if level == 0:
+                rms = np.sqrt(self.calc_rms(level) / self.sizes[level][0])
+                if self.count_bad_vals(level) > 0:
+                    raise MgcfdError(-5, "Bad variable values detected, aborting")
+            if nl <= 1:
+                i += 1
+            elif mg_dir == 0:
+                level += 1
+                self.up_pre(level)
+                self.up(level)
+                self.up_post(level)
+                if level == nl - 1:
+                    mg_dir = 1
+            else:
+                level -= 1
+                self.down(level)
+                if level == 0:
+                    mg_dir = 0
+                    i += 1
+        return rms, min_dt
+
+    # ---- data access (file order)
+    def fetch(self, l, name):
+        n, e, b = self.sizes[l]
+        if name == "edge_weights":
+            out = np.empty((e, 3))
+        elif name == "bnd_node_weights":
+            out = np.empty((b, 3))
+        elif name == "up_scratch":
+            out = np.empty(n, dtype=np.int32)
+        else:
+            d = _DAT_DIMS[name]
+            out = np.empty((n, d) if d > 1 else n)
+        self._ck(self.lib.mgcfd_fetch_dat(self.ctx, l, name.encode(), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set(self, l, name, arr):
+        dt = np.int32 if name == "up_scratch" else np.float64
+        a = _as(arr, dt)
+        self._ck(self.lib.mgcfd_set_dat(self.ctx, l, name.encode(), a.ctypes.data_as(C.c_void_p)))
+
+    def sync(self): self._ck(self.lib.mgcfd_sync(self.ctx))
+
+    def validate(self, l, master):
+        m = _as(master, np.float64)
+        c = C.c_int(0)
+        self._ck(self.lib.mgcfd_validate_level(self.ctx, l, m.ctypes.data_as(_dp), C.byref(c)))
+        return c.value
+
+    def plan_query(self, l, what):
+        n = self.lib.mgcfd_plan_query(self.ctx, l, what.encode(), None, 0)
+        if n < 0:
+            raise MgcfdError(int(n), f"plan_query({what})")
+        out = np.empty(n, dtype=np.int32)
+        self.lib.mgcfd_plan_query(self.ctx, l, what.encode(), out.ctypes.data_as(_ip), n)
+        return out
+
+    def set_flux_variant(self, v):
+        self._ck(self.lib.mgcfd_set_flux_variant(self.ctx, FLUX_VARIANTS[v] if isinstance(v, str) else int(v)))
+
+    # ---- measurement
+    def timers_enable(self, on=True): self._ck(self.lib.mgcfd_timers_enable(self.ctx, int(on)))
+    def timers_reset(self): self._ck(self.lib.mgcfd_timers_reset(self.ctx))
+
+    def timer(self, loop, level=-1):
+        ms, calls, el = C.c_double(0), C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.lib.mgcfd_timers_get(self.ctx, loop.encode(), level, C.byref(ms), C.byref(calls), C.byref(el)))
+        return ms.value, calls.value, el.value
+
+    def kernel_launches(self):
+        return int(self.lib.mgcfd_kernel_launches(self.ctx))
+
+    def stream(self):
+        return self.lib.mgcfd_stream(self.ctx)

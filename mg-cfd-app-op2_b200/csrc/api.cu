@@ -1,0 +1,1100 @@
+// api.cu -- the C-ABI of libmgcfd_b200: context, declarations, planning, the op_par_loop call
+// sites of euler3d.cpp, fetch, timers.  See include/mgcfd_b200.h for the contract.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "internal.h"
+
+using namespace mgcfd;
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return MGCFD_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                               \
+    do {                                                                                                 \
+        if (!(cond)) {                                                                                   \
+            ctx->err = (msg);                                                                            \
+            return MGCFD_ERR_ARG;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define CHECK_LEVEL(l) REQUIRE(ctx && (l) >= 0 && (l) < ctx->n_levels, "level out of range")
+#define CHECK_PLANNED() REQUIRE(ctx->planned, "mgcfd_plan() has not been called")
+
+static int check_launch(mgcfd_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return MGCFD_ERR_CUDA;
+    }
+    return MGCFD_OK;
+}
+
+template <typename T>
+static int dev_alloc(mgcfd_ctx *ctx, T **p, size_t count, bool zero = true)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)p, count * sizeof(T)));
+    if (zero) CK(cudaMemsetAsync(*p, 0, count * sizeof(T), ctx->stream));
+    return MGCFD_OK;
+}
+
+template <typename T>
+static int dev_upload(mgcfd_ctx *ctx, T **p, const std::vector<T> &h)
+{
+    int rc = dev_alloc(ctx, p, h.size(), false);
+    if (rc) return rc;
+    if (!h.empty()) {
+        CK(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // h may be a temporary
+    }
+    return MGCFD_OK;
+}
+
+static DevConsts dev_consts(const mgcfd_ctx *ctx)
+{
+    DevConsts c;
+    c.smoothing = ctx->consts.smoothing_coefficient;
+    for (int i = 0; i < 5; i++) c.ff_variable[i] = ctx->consts.ff_variable[i];
+    for (int d = 0; d < 3; d++) {
+        c.ff_fc[0][d] = 0.0;
+        c.ff_fc[1][d] = ctx->consts.ff_flux_contribution_momentum_x[d];
+        c.ff_fc[2][d] = ctx->consts.ff_flux_contribution_momentum_y[d];
+        c.ff_fc[3][d] = ctx->consts.ff_flux_contribution_momentum_z[d];
+        c.ff_fc[4][d] = ctx->consts.ff_flux_contribution_density_energy[d];
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// timers
+// ------------------------------------------------------------------------------------------
+struct LoopScope {
+    mgcfd_ctx *ctx;
+    LoopTimer *t = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    long long elems;
+    static cudaEvent_t get_event(mgcfd_ctx *ctx)
+    {
+        if (!ctx->event_pool.empty()) {
+            cudaEvent_t e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
+    {
+        if (!ctx->timers_on) return;
+        t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
+        e0 = get_event(ctx);
+        e1 = get_event(ctx);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~LoopScope()
+    {
+        if (!t) return;
+        cudaEventRecord(e1, ctx->stream);
+        t->pending.push_back({e0, e1});
+        t->pending_elems.push_back(elems);
+    }
+};
+
+static void timers_collect(mgcfd_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->timers) {
+        LoopTimer &t = kv.second;
+        for (size_t i = 0; i < t.pending.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t.pending[i].first, t.pending[i].second);
+            t.ms += ms;
+            t.calls++;
+            t.elements += t.pending_elems[i];
+            ctx->event_pool.push_back(t.pending[i].first);
+            ctx->event_pool.push_back(t.pending[i].second);
+        }
+        t.pending.clear();
+        t.pending_elems.clear();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *mgcfd_version(void) { return "mgcfd_b200 0.1 (sm_100a)"; }
+
+void mgcfd_default_options(mgcfd_options *opt)
+{
+    memset(opt, 0, sizeof(*opt));
+    opt->flux_variant = MGCFD_FLUX_OWNER;
+    opt->renumber = 1;
+    opt->owner_chunk_nodes = 256;
+    opt->colour_block_edges = 256;
+    opt->exact_arith = 0;
+}
+
+const char *mgcfd_last_error(const mgcfd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options *opt)
+{
+    if (!out || n_levels < 1 || n_levels > 64) {
+        g_create_error = "mgcfd_create: bad arguments";
+        return MGCFD_ERR_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                         "); libmgcfd_b200 has no CPU fallback";
+        return MGCFD_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "mgcfd_create: device index out of range";
+        return MGCFD_ERR_ARG;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return MGCFD_ERR_CUDA;
+    }
+    mgcfd_ctx *ctx = new mgcfd_ctx();
+    ctx->device = device;
+    ctx->n_levels = n_levels;
+    if (opt) ctx->opt = *opt; else mgcfd_default_options(&ctx->opt);
+    if (ctx->opt.owner_chunk_nodes <= 0) ctx->opt.owner_chunk_nodes = 256;
+    if (ctx->opt.colour_block_edges <= 0) ctx->opt.colour_block_edges = 256;
+    if (ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
+    ctx->H.resize(n_levels);
+    ctx->D.resize(n_levels);
+    auto fail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return MGCFD_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaMalloc((void **)&ctx->d_min_dt, sizeof(double) * n_levels)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_rms, sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_flags, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMemset(ctx->d_flags, 0, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaMallocHost((void **)&ctx->h_pinned, sizeof(double) * 8)) != cudaSuccess) return fail("cudaMallocHost", e);
+    std::string ce = flux_configure();
+    if (!ce.empty()) {
+        g_create_error = ce;
+        delete ctx;
+        return MGCFD_ERR_CUDA;
+    }
+    *out = ctx;
+    return MGCFD_OK;
+}
+
+static void free_level(LevelDev &d)
+{
+    void *ptrs[] = {d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
+                    d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.atomic.nodes, d.atomic.w,
+                    d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
+                    d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    d = LevelDev();
+}
+
+void mgcfd_destroy(mgcfd_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &d : ctx->D) free_level(d);
+    for (auto &kv : ctx->timers)
+        for (auto &p : kv.second.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
+    if (ctx->d_rms) cudaFree(ctx->d_rms);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------
+// declarations
+// ------------------------------------------------------------------------------------------
+void mgcfd_compute_farfield_consts(mgcfd_consts *c)
+{
+    // euler3d.cpp:47 and :157-189, with the flux contributions of inlined_funcs.h:70-96
+    const double gamma = 1.4, pi = 3.1415926535897931, ff_mach = 1.2, deg_aoa = 0.0;
+    memset(c, 0, sizeof(*c));
+    c->smoothing_coefficient = double(0.2f);
+    const double aoa = double(pi / 180.0) * double(deg_aoa);
+    c->ff_variable[0] = 1.4;
+    double ff_p = 1.0;
+    double ff_c = sqrt(gamma * ff_p / c->ff_variable[0]);
+    double ff_speed = ff_mach * ff_c;
+    double v[3] = {ff_speed * cos(aoa), ff_speed * sin(aoa), 0.0};
+    for (int d = 0; d < 3; d++) c->ff_variable[1 + d] = c->ff_variable[0] * v[d];
+    c->ff_variable[4] = c->ff_variable[0] * (0.5 * (ff_speed * ff_speed)) + (ff_p / (gamma - 1.0));
+    const double *m = &c->ff_variable[1];
+    double *fx = c->ff_flux_contribution_momentum_x, *fy = c->ff_flux_contribution_momentum_y,
+           *fz = c->ff_flux_contribution_momentum_z, *fe = c->ff_flux_contribution_density_energy;
+    fx[0] = v[0] * m[0] + ff_p; fx[1] = v[0] * m[1];        fx[2] = v[0] * m[2];
+    fy[0] = fx[1];              fy[1] = v[1] * m[1] + ff_p; fy[2] = v[1] * m[2];
+    fz[0] = fx[2];              fz[1] = fy[2];              fz[2] = v[2] * m[2] + ff_p;
+    double ep = c->ff_variable[4] + ff_p;
+    fe[0] = v[0] * ep; fe[1] = v[1] * ep; fe[2] = v[2] * ep;
+}
+
+int mgcfd_decl_consts(mgcfd_ctx *ctx, const mgcfd_consts *c)
+{
+    REQUIRE(ctx && c, "null argument");
+    ctx->consts = *c;
+    ctx->have_consts = true;
+    for (auto &d : ctx->D) d.atomic.valid = d.colour.valid = d.owner.valid = false;   // g depends on smoothing
+    return MGCFD_OK;
+}
+
+int mgcfd_decl_level(mgcfd_ctx *ctx, int level, const mgcfd_level_host *lv, int base)
+{
+    CHECK_LEVEL(level);
+    REQUIRE(lv, "null level");
+    REQUIRE(!ctx->planned, "levels must be declared before mgcfd_plan()");
+    REQUIRE(lv->n_nodes >= 0 && lv->n_edges >= 0 && lv->n_bnd_nodes >= 0, "negative set size");
+    REQUIRE(lv->n_owned_nodes >= 0 && lv->n_owned_nodes <= lv->n_nodes, "n_owned_nodes out of range");
+    LevelHost &L = ctx->H[level];
+    L = LevelHost();
+    L.n_nodes = lv->n_nodes; L.n_edges = lv->n_edges; L.n_bnd = lv->n_bnd_nodes; L.n_owned = lv->n_owned_nodes;
+    const size_t n = L.n_nodes, E = L.n_edges, B = L.n_bnd;
+    L.coords.assign(lv->node_coordinates, lv->node_coordinates + n * 3);
+    L.ewt.assign(lv->edge_weights, lv->edge_weights + E * 3);
+    L.bwt.assign(lv->bnd_node_weights, lv->bnd_node_weights + B * 3);
+    L.e2n.resize(E * 2);
+    for (size_t i = 0; i < E * 2; i++) {
+        int v = lv->edge_to_node[i] - base;
+        REQUIRE(v >= 0 && v < L.n_nodes, "edge-->node entry out of range (check base_array_index)");
+        L.e2n[i] = v;
+    }
+    for (size_t e = 0; e < E; e++) REQUIRE(L.e2n[2 * e] != L.e2n[2 * e + 1], "self edge in edge-->node");
+    L.b2n.resize(B);
+    L.bgroup.assign(lv->bnd_node_to_group, lv->bnd_node_to_group + B);
+    for (size_t i = 0; i < B; i++) {
+        int v = lv->bnd_node_to_node[i] - base;
+        REQUIRE(v >= 0 && v < L.n_nodes, "bnd_node-->node entry out of range");
+        L.b2n[i] = v;
+    }
+    if (lv->node_to_mg_node) {
+        REQUIRE(level + 1 < ctx->n_levels, "node-->mg_node given on the coarsest level");
+        L.mg.resize(n);
+        for (size_t i = 0; i < n; i++) L.mg[i] = lv->node_to_mg_node[i] - base;   // range-checked in mgcfd_plan
+    }
+    return MGCFD_OK;
+}
+
+// boundary entries grouped by unique internal node, ascending file order inside a node
+static int upload_bnd(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    std::vector<int> idx;
+    for (int i = 0; i < L.n_bnd; i++)
+        if (L.new_of_old[L.b2n[i]] < L.n_owned) idx.push_back(i);
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return L.new_of_old[L.b2n[x]] < L.new_of_old[L.b2n[y]]; });
+    std::vector<int> bu_node, bu_ptr, group(idx.size());
+    std::vector<double> wt(idx.size() * 3);
+    for (size_t k = 0; k < idx.size(); k++) {
+        int i = idx[k], node = L.new_of_old[L.b2n[i]];
+        if (bu_node.empty() || bu_node.back() != node) { bu_node.push_back(node); bu_ptr.push_back((int)k); }
+        group[k] = L.bgroup[i];
+        for (int d = 0; d < 3; d++) wt[k * 3 + d] = L.bwt[(size_t)i * 3 + d];
+    }
+    bu_ptr.push_back((int)idx.size());
+    D.n_bnd_unique = (int)bu_node.size();
+    int rc;
+    if ((rc = dev_upload(ctx, &D.bu_node, bu_node))) return rc;
+    if ((rc = dev_upload(ctx, &D.bu_ptr, bu_ptr))) return rc;
+    if ((rc = dev_upload(ctx, &D.b_group, group))) return rc;
+    if ((rc = dev_upload(ctx, &D.b_wt, wt))) return rc;
+    return MGCFD_OK;
+}
+
+static int upload_node_dat(mgcfd_ctx *ctx, int level, double *dst, const double *src_file_order, int dim)
+{
+    LevelHost &L = ctx->H[level];
+    std::vector<double> tmp((size_t)L.n_nodes * dim);
+    for (int i = 0; i < L.n_nodes; i++)
+        for (int d = 0; d < dim; d++) tmp[(size_t)L.new_of_old[i] * dim + d] = src_file_order[(size_t)i * dim + d];
+    CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MGCFD_OK;
+}
+
+int mgcfd_plan(mgcfd_ctx *ctx)
+{
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(ctx->have_consts, "mgcfd_decl_consts() must precede mgcfd_plan()");
+    CK(cudaSetDevice(ctx->device));
+    for (int l = 0; l < ctx->n_levels; l++) {
+        LevelHost &L = ctx->H[l];
+        if (l + 1 < ctx->n_levels) REQUIRE((int)L.mg.size() == L.n_nodes, "node-->mg_node missing on a non-coarsest level");
+        plan_renumber(L, ctx->opt.renumber != 0);
+    }
+    for (int l = 0; l < ctx->n_levels; l++) {
+        LevelHost &L = ctx->H[l];
+        LevelDev &D = ctx->D[l];
+        const size_t n = L.n_nodes;
+        int rc;
+        if ((rc = dev_alloc(ctx, &D.var, n * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &D.old, n * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &D.res, n * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &D.flux, n * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &D.vol, n))) return rc;
+        if ((rc = dev_alloc(ctx, &D.cbrt_vol, n))) return rc;
+        if ((rc = dev_alloc(ctx, &D.sf, n))) return rc;
+        if ((rc = dev_alloc(ctx, &D.coords, n * 3))) return rc;
+        if ((rc = dev_alloc(ctx, &D.up_count, n))) return rc;
+        D.flux_is_zero = true;
+        if ((rc = upload_node_dat(ctx, l, D.coords, L.coords.data(), 3))) return rc;
+        if ((rc = upload_bnd(ctx, l))) return rc;
+        if (l + 1 < ctx->n_levels) {
+            LevelHost &Cs = ctx->H[l + 1];
+            std::vector<int> mg(n);
+            for (size_t i = 0; i < n; i++) {
+                int p = L.mg[L.old_of_new[i]];
+                REQUIRE(p >= 0 && p < Cs.n_nodes, "node-->mg_node entry out of range");
+                mg[i] = Cs.new_of_old[p];
+            }
+            if ((rc = dev_upload(ctx, &D.mg, mg))) return rc;
+            // restrict gather lists on the coarse level: children in ascending fine FILE order
+            std::vector<int> cptr(Cs.n_nodes + 1, 0), cidx;
+            for (int f = 0; f < L.n_nodes; f++)
+                if (L.new_of_old[f] < L.n_owned) cptr[Cs.new_of_old[L.mg[f]] + 1]++;
+            for (int p = 0; p < Cs.n_nodes; p++) cptr[p + 1] += cptr[p];
+            cidx.resize(cptr[Cs.n_nodes]);
+            std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+            for (int f = 0; f < L.n_nodes; f++)
+                if (L.new_of_old[f] < L.n_owned) cidx[fill[Cs.new_of_old[L.mg[f]]]++] = L.new_of_old[f];
+            LevelDev &DC = ctx->D[l + 1];
+            if ((rc = dev_upload(ctx, &DC.child_ptr, cptr))) return rc;
+            if ((rc = dev_upload(ctx, &DC.child_idx, cidx))) return rc;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->planned = true;
+    return MGCFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// flux plans (built lazily per variant; weights re-packed when the host weights changed)
+// ------------------------------------------------------------------------------------------
+static inline void pack_weight(const mgcfd_ctx *ctx, const LevelHost &L, int e, double out[4])
+{
+    const double *w = &L.ewt[(size_t)e * 3];
+    double ewt = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);                 // flux.h:48-50
+    out[0] = w[0]; out[1] = w[1]; out[2] = w[2];
+    out[3] = -ewt * ctx->consts.smoothing_coefficient * 0.5;                    // flux.h:139 prefix
+}
+
+static int ensure_atomic(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    if (D.atomic.valid) return MGCFD_OK;
+    if (!L.have_sorted) plan_sort_edges(L);
+    std::vector<int2> nodes(L.n_edges);
+    std::vector<double4> w(L.n_edges);
+    for (int i = 0; i < L.n_edges; i++) {
+        int e = L.sorted.order[i];
+        nodes[i] = make_int2(L.new_of_old[L.e2n[2 * (size_t)e]], L.new_of_old[L.e2n[2 * (size_t)e + 1]]);
+        double p[4];
+        pack_weight(ctx, L, e, p);
+        w[i] = make_double4(p[0], p[1], p[2], p[3]);
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &D.atomic.nodes, nodes))) return rc;
+    if ((rc = dev_upload(ctx, &D.atomic.w, w))) return rc;
+    D.atomic.valid = true;
+    return MGCFD_OK;
+}
+
+static int ensure_colour(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    if (D.colour.valid) return MGCFD_OK;
+    if (!L.have_colour) plan_colour(L, ctx->opt.colour_block_edges);
+    ColourPlanHost &C = L.colour;
+    for (int k = 0; k < C.n_blocks; k++)
+        if (C.block_ncol[k] > 63 || C.block_colour[k] > 62) {
+            ctx->err = "colour plan needs more than 63 colours";
+            return MGCFD_ERR_PLAN;
+        }
+    if (flux_colour_smem_bytes(C.max_nodes, true) > 227 * 1024 || flux_colour_smem_bytes(C.max_nodes, false) > 227 * 1024) {
+        ctx->err = "colour plan block does not fit in shared memory";
+        return MGCFD_ERR_PLAN;
+    }
+    std::vector<int> edge0(C.n_blocks + 1, 0), ncol(C.n_blocks);
+    for (int s = 0; s < C.n_blocks; s++) {
+        int k = C.exec_block[s];
+        int lo = k * C.block_edges, hi = std::min(L.n_edges, lo + C.block_edges);
+        edge0[s + 1] = edge0[s] + (hi - lo);
+        ncol[s] = C.block_ncol[k];
+    }
+    std::vector<double4> w(L.n_edges);
+    for (int i = 0; i < L.n_edges; i++) {
+        double p[4];
+        pack_weight(ctx, L, C.exec_edge[i], p);
+        w[i] = make_double4(p[0], p[1], p[2], p[3]);
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &D.colour.blk_edge0, edge0))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.blk_node0, C.node_off))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.blk_ncol, ncol))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.node_gid, C.node_gid))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.lab, C.lab))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.ecol, C.ecol))) return rc;
+    if ((rc = dev_upload(ctx, &D.colour.w, w))) return rc;
+    D.colour.valid = true;
+    return MGCFD_OK;
+}
+
+static int ensure_owner(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    if (D.owner.valid) return MGCFD_OK;
+    if (!L.have_owner) {
+        int nb = ctx->opt.owner_chunk_nodes;
+        // caps sized so that the fast build keeps >= 2 CTAs per SM (DESIGN.md "owner chunk sizing")
+        int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
+        std::string err;
+        if (!plan_owner(L, nb, max_loc, max_edges, err)) {
+            ctx->err = err;
+            return MGCFD_ERR_PLAN;
+        }
+    }
+    OwnerPlanHost &O = L.owner;
+    if (flux_owner_smem_bytes(O.max_loc, O.max_edges, ctx->opt.exact_arith != 0) > 227 * 1024) {
+        ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
+        return MGCFD_ERR_PLAN;
+    }
+    std::vector<OwnerChunkDesc> desc(O.n_chunks);
+    std::vector<unsigned char> blob((size_t)O.blob_off[O.n_chunks], 0);
+    for (int k = 0; k < O.n_chunks; k++) {
+        OwnerChunkDesc &d = desc[k];
+        d.node0 = O.node0[k];
+        d.n_own = O.node0[k + 1] - O.node0[k];
+        d.n_halo = O.halo_off[k + 1] - O.halo_off[k];
+        d.halo_off = O.halo_off[k];
+        d.n_edges = O.n_edges[k];
+        d.e_pad = (d.n_edges + 3) & ~3;
+        d.n_inc = O.n_inc[k];
+        d.pad_ = 0;
+        d.blob_off = O.blob_off[k];
+        unsigned char *base = blob.data() + d.blob_off;
+        double *w0 = reinterpret_cast<double *>(base), *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *g = w2 + d.e_pad;
+        uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);
+        uint16_t *rowptr = reinterpret_cast<uint16_t *>(lab + d.e_pad);
+        uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
+        for (int i = 0; i < d.n_edges; i++) {
+            double p[4];
+            pack_weight(ctx, L, O.edge_file[O.edge_off[k] + i], p);
+            w0[i] = p[0]; w1[i] = p[1]; w2[i] = p[2]; g[i] = p[3];
+            lab[i] = O.lab[O.edge_off[k] + i];
+        }
+        memcpy(rowptr, &O.rowptr[O.rowptr_off[k]], sizeof(uint16_t) * (d.n_own + 1));
+        memcpy(csr, &O.csr[O.csr_off[k]], sizeof(uint16_t) * d.n_inc);
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &D.owner.desc, desc))) return rc;
+    if ((rc = dev_upload(ctx, &D.owner.halo_gid, O.halo_gid))) return rc;
+    if ((rc = dev_upload(ctx, &D.owner.blob, blob))) return rc;
+    D.owner.blob_bytes = (long long)blob.size();
+    D.owner.valid = true;
+    return MGCFD_OK;
+}
+
+static int ensure_flux_plan(mgcfd_ctx *ctx, int level)
+{
+    switch (ctx->opt.flux_variant) {
+    case MGCFD_FLUX_ATOMIC: return ensure_atomic(ctx, level);
+    case MGCFD_FLUX_COLOUR: return ensure_colour(ctx, level);
+    case MGCFD_FLUX_OWNER: return ensure_owner(ctx, level);
+    }
+    ctx->err = "unknown flux variant";
+    return MGCFD_ERR_ARG;
+}
+
+int mgcfd_set_flux_variant(mgcfd_ctx *ctx, int variant)
+{
+    REQUIRE(ctx && variant >= 0 && variant < MGCFD_FLUX_NVARIANTS, "unknown flux variant");
+    ctx->opt.flux_variant = variant;
+    return MGCFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// initialisation loops (euler3d.cpp:413-441)
+// ------------------------------------------------------------------------------------------
+int mgcfd_loop_initialize_variables(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LoopScope t(ctx, "initialize_variables", level, ctx->H[level].n_nodes);
+    ctx->launches += k_init_vars(ctx->stream, ctx->H[level].n_nodes, ctx->D[level].var, dev_consts(ctx));
+    return check_launch(ctx, "initialize_variables_kernel");
+}
+
+int mgcfd_loop_zero_fluxes(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    ctx->launches += k_fill(ctx->stream, (long long)ctx->H[level].n_nodes * 5, ctx->D[level].flux, 0.0);
+    ctx->D[level].flux_is_zero = true;
+    return check_launch(ctx, "zero_5d_array_kernel");
+}
+
+static int upload_volumes(mgcfd_ctx *ctx, int level, const std::vector<double> &vol_file_order)
+{
+    LevelHost &L = ctx->H[level];
+    std::vector<double> cb(vol_file_order.size());
+    for (size_t i = 0; i < cb.size(); i++) cb[i] = cbrt(vol_file_order[i]);   // time_stepping_kernels.h:31 evaluates cbrt(volume)
+    int rc;
+    if ((rc = upload_node_dat(ctx, level, ctx->D[level].vol, vol_file_order.data(), 1))) return rc;
+    if ((rc = upload_node_dat(ctx, level, ctx->D[level].cbrt_vol, cb.data(), 1))) return rc;
+    (void)L;
+    return MGCFD_OK;
+}
+
+int mgcfd_loop_zero_volumes(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    std::vector<double> vol(ctx->H[level].n_nodes, 0.0);
+    return upload_volumes(ctx, level, vol);
+}
+
+int mgcfd_loop_calculate_cell_volumes(mgcfd_ctx *ctx, int level)
+{
+    // misc.h:40-76.  Run once, on the host, in file order: the volumes (an OP_INC reduction over edges) and the
+    // rewritten edge weights are then bit-identical to OP2-seq.  The volumes on the device are read back first
+    // so that the OP_INC semantics (vol += ...) hold for whatever they contained.
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LevelHost &L = ctx->H[level];
+    std::vector<double> vol(L.n_nodes);
+    int rc = mgcfd_fetch_dat(ctx, level, "volumes", vol.data());
+    if (rc) return rc;
+    for (int e = 0; e < L.n_edges; e++) {
+        int a = L.e2n[2 * (size_t)e], b = L.e2n[2 * (size_t)e + 1];
+        const double *c1 = &L.coords[(size_t)a * 3], *c2 = &L.coords[(size_t)b * 3];
+        double *w = &L.ewt[(size_t)e * 3];
+        double d[3], dist = 0.0, area = 0.0;
+        for (int i = 0; i < 3; i++) { d[i] = c2[i] - c1[i]; dist += d[i] * d[i]; }
+        dist = sqrt(dist);
+        for (int i = 0; i < 3; i++) area += w[i] * w[i];
+        area = sqrt(area);
+        double tet = (1.0 / 3.0) * 0.5 * dist * area;
+        vol[a] += tet;
+        vol[b] += tet;
+        for (int i = 0; i < 3; i++) w[i] = (d[i] / dist) * area;
+        for (int i = 0; i < 3; i++) w[i] /= dist;
+    }
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = false;
+    return upload_volumes(ctx, level, vol);
+}
+
+int mgcfd_loop_dampen_ewt_edges(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    for (double &w : ctx->H[level].ewt) w *= 1e-7;                               // misc.h:78-84
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = false;
+    return MGCFD_OK;
+}
+
+int mgcfd_loop_dampen_ewt_bnd(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    for (double &w : ctx->H[level].bwt) w *= 1e-7;
+    return upload_bnd(ctx, level);
+}
+
+// ------------------------------------------------------------------------------------------
+// cycle loops
+// ------------------------------------------------------------------------------------------
+int mgcfd_loop_copy_double(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LoopScope t(ctx, "copy_double", level, ctx->H[level].n_owned);
+    ctx->launches += k_copy(ctx->stream, ctx->H[level].n_owned, ctx->D[level].var, ctx->D[level].old);
+    return check_launch(ctx, "copy_double_kernel");
+}
+
+int mgcfd_loop_calculate_dt(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LoopScope t(ctx, "calculate_dt", level, ctx->H[level].n_owned);
+    ctx->launches += k_calculate_dt(ctx->stream, ctx->H[level].n_owned, ctx->D[level].var, ctx->D[level].cbrt_vol,
+                                    ctx->D[level].sf);
+    return check_launch(ctx, "calculate_dt_kernel");
+}
+
+int mgcfd_loop_get_min_dt(mgcfd_ctx *ctx, int level, double *min_dt)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(min_dt, "null min_dt");
+    {
+        LoopScope t(ctx, "get_min_dt", level, ctx->H[level].n_owned);
+        ctx->h_pinned[0] = *min_dt;
+        CK(cudaMemcpyAsync(&ctx->d_min_dt[level], &ctx->h_pinned[0], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->launches += k_min_dt(ctx->stream, ctx->H[level].n_owned, ctx->D[level].sf, &ctx->d_min_dt[level], ctx->d_flags);
+        CK(cudaMemcpyAsync(&ctx->h_pinned[1], &ctx->d_min_dt[level], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *min_dt = ctx->h_pinned[1];
+    return check_launch(ctx, "get_min_dt_kernel");
+}
+
+int mgcfd_loop_compute_step_factor(mgcfd_ctx *ctx, int level, const double *min_dt)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(min_dt, "null min_dt");
+    LoopScope t(ctx, "compute_step_factor", level, ctx->H[level].n_owned);
+    ctx->h_pinned[2] = *min_dt;
+    CK(cudaMemcpyAsync(&ctx->d_min_dt[level], &ctx->h_pinned[2], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // h_pinned[2] is reused by the next call
+    ctx->launches += k_step_factor(ctx->stream, ctx->H[level].n_owned, ctx->D[level].vol, &ctx->d_min_dt[level], ctx->D[level].sf);
+    return check_launch(ctx, "compute_step_factor_kernel");
+}
+
+static int run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel)
+{
+    int rc = ensure_flux_plan(ctx, level);
+    if (rc) return rc;
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    FluxArgs a;
+    a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
+    a.var = D.var;
+    a.stream_kernel = stream_kernel;
+    if (stream_kernel) {
+        if (!D.dummy_flux) {
+            if ((rc = dev_alloc(ctx, &D.dummy_flux, (size_t)L.n_nodes * 5))) return rc;
+        }
+        a.flux = D.dummy_flux;
+        a.overwrite = false;
+    } else {
+        a.flux = D.flux;
+        a.overwrite = D.flux_is_zero;
+    }
+    const bool exact = ctx->opt.exact_arith != 0;
+    LoopScope t(ctx, stream_kernel ? "unstructured_stream" : "compute_flux_edge", level, L.n_edges);
+    switch (ctx->opt.flux_variant) {
+    case MGCFD_FLUX_ATOMIC: ctx->launches += flux_atomic(ctx->stream, a, D.atomic, exact); break;
+    case MGCFD_FLUX_COLOUR: ctx->launches += flux_colour(ctx->stream, a, D.colour, L.colour, exact); break;
+    case MGCFD_FLUX_OWNER: ctx->launches += flux_owner(ctx->stream, a, D.owner, L.owner, exact); break;
+    }
+    if (!stream_kernel) D.flux_is_zero = false;
+    return check_launch(ctx, "compute_flux_edge_kernel");
+}
+
+int mgcfd_loop_compute_flux_edge(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    return run_flux(ctx, level, false);
+}
+
+int mgcfd_loop_unstructured_stream(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    return run_flux(ctx, level, true);
+}
+
+int mgcfd_loop_compute_bnd_node_flux(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LevelDev &D = ctx->D[level];
+    LoopScope t(ctx, "compute_bnd_node_flux", level, ctx->H[level].n_bnd);
+    ctx->launches += k_bnd_flux(ctx->stream, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux,
+                                dev_consts(ctx), ctx->opt.exact_arith != 0);
+    D.flux_is_zero = false;
+    return check_launch(ctx, "compute_bnd_node_flux_kernel");
+}
+
+int mgcfd_loop_time_step(mgcfd_ctx *ctx, int level, const int *rk)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(rk && *rk >= 0 && *rk < MGCFD_RK, "rkCycle out of range");
+    LevelDev &D = ctx->D[level];
+    LoopScope t(ctx, "time_step", level, ctx->H[level].n_owned);
+    ctx->launches += k_time_step(ctx->stream, ctx->H[level].n_owned, *rk, D.sf, D.flux, D.old, D.var);
+    D.flux_is_zero = true;
+    return check_launch(ctx, "time_step_kernel");
+}
+
+int mgcfd_loop_residual(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    LevelDev &D = ctx->D[level];
+    LoopScope t(ctx, "residual", level, ctx->H[level].n_owned);
+    ctx->launches += k_residual(ctx->stream, ctx->H[level].n_owned, D.old, D.var, D.res);
+    return check_launch(ctx, "residual_kernel");
+}
+
+int mgcfd_loop_calc_rms(mgcfd_ctx *ctx, int level, double *rms)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(rms, "null rms");
+    {
+        LoopScope t(ctx, "calc_rms", level, ctx->H[level].n_owned);
+        ctx->h_pinned[3] = *rms;
+        CK(cudaMemcpyAsync(ctx->d_rms, &ctx->h_pinned[3], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->launches += k_rms(ctx->stream, ctx->H[level].n_owned, ctx->D[level].res, ctx->d_rms);
+        CK(cudaMemcpyAsync(&ctx->h_pinned[4], ctx->d_rms, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *rms = ctx->h_pinned[4];
+    return check_launch(ctx, "calc_rms_kernel");
+}
+
+int mgcfd_loop_count_bad_vals(mgcfd_ctx *ctx, int level, int *count)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(count, "null count");
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[5]);
+    {
+        LoopScope t(ctx, "count_bad_vals", level, ctx->H[level].n_owned);
+        hp[0] = *count;
+        CK(cudaMemcpyAsync(&ctx->d_flags[0], &hp[0], sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->launches += k_bad_vals(ctx->stream, ctx->H[level].n_owned, ctx->D[level].var, &ctx->d_flags[0]);
+        CK(cudaMemcpyAsync(&hp[1], &ctx->d_flags[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *count = hp[1];
+    return check_launch(ctx, "count_bad_vals");
+}
+
+int mgcfd_loop_up_pre(mgcfd_ctx *ctx, int la)
+{
+    CHECK_LEVEL(la); CHECK_PLANNED();
+    REQUIRE(la >= 1, "up_pre needs a finer level below");
+    LoopScope t(ctx, "up_pre", la, ctx->H[la - 1].n_owned);
+    ctx->launches += k_up_pre(ctx->stream, ctx->H[la - 1].n_owned, ctx->D[la - 1].mg, ctx->D[la].var, ctx->D[la].up_count);
+    return check_launch(ctx, "up_pre_kernel");
+}
+
+int mgcfd_loop_up(mgcfd_ctx *ctx, int la)
+{
+    CHECK_LEVEL(la); CHECK_PLANNED();
+    REQUIRE(la >= 1, "up needs a finer level below");
+    LoopScope t(ctx, "up", la, ctx->H[la - 1].n_owned);
+    ctx->launches += k_up(ctx->stream, ctx->H[la].n_nodes, ctx->D[la].child_ptr, ctx->D[la].child_idx, ctx->D[la - 1].var,
+                          ctx->D[la].var, ctx->D[la].up_count);
+    return check_launch(ctx, "up_kernel");
+}
+
+int mgcfd_loop_up_post(mgcfd_ctx *ctx, int la)
+{
+    CHECK_LEVEL(la); CHECK_PLANNED();
+    REQUIRE(la >= 1, "up_post needs a finer level below");
+    LoopScope t(ctx, "up_post", la, ctx->H[la].n_owned);
+    ctx->launches += k_up_post(ctx->stream, ctx->H[la].n_owned, ctx->D[la].var, ctx->D[la].up_count);
+    return check_launch(ctx, "up_post_kernel");
+}
+
+int mgcfd_loop_down(mgcfd_ctx *ctx, int level)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(level + 1 < ctx->n_levels, "down needs a coarser level above");
+    LevelDev &D = ctx->D[level], &A = ctx->D[level + 1];
+    LoopScope t(ctx, "down", level, ctx->H[level].n_owned);
+    ctx->launches += k_down(ctx->stream, ctx->H[level].n_owned, D.mg, D.var, D.res, D.coords, A.res, A.coords);
+    return check_launch(ctx, "down_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
+// whole cycles without host round trips (euler3d.cpp:458-641)
+// ------------------------------------------------------------------------------------------
+int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
+{
+    REQUIRE(ctx, "null ctx");
+    CHECK_PLANNED();
+    REQUIRE(n_cycles >= 0, "negative cycle count");
+    const int nl = ctx->n_levels;
+    for (int l = 0; l < nl; l++) {
+        int rc = ensure_flux_plan(ctx, l);
+        if (rc) return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    const bool exact = ctx->opt.exact_arith != 0;
+    const DevConsts dc = dev_consts(ctx);
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, s));
+    int level = 0, dir = 0, i = 0;
+    while (i < n_cycles) {
+        LevelHost &L = ctx->H[level];
+        LevelDev &D = ctx->D[level];
+        const int no = L.n_owned;
+        { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
+        { LoopScope t(ctx, "calculate_dt", level, no); ctx->launches += k_calculate_dt(s, no, D.var, D.cbrt_vol, D.sf); }
+        {
+            LoopScope t(ctx, "get_min_dt", level, no);
+            ctx->launches += k_fill(s, 1, &ctx->d_min_dt[level], DBL_MAX);
+            ctx->launches += k_min_dt(s, no, D.sf, &ctx->d_min_dt[level], ctx->d_flags);
+        }
+        { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor(s, no, D.vol, &ctx->d_min_dt[level], D.sf); }
+        for (int rk = 0; rk < MGCFD_RK; rk++) {
+            int rc = run_flux(ctx, level, false);
+            if (rc) return rc;
+            {
+                LoopScope t(ctx, "compute_bnd_node_flux", level, L.n_bnd);
+                ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+            }
+            { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
+            D.flux_is_zero = true;
+        }
+        { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
+        if (level == 0) {
+            { LoopScope t(ctx, "calc_rms", level, no); ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0); ctx->launches += k_rms(s, no, D.res, ctx->d_rms); }
+            { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+        }
+        if (nl <= 1) {
+            i++;
+        } else if (dir == 0) {
+            level++;
+            LevelDev &A = ctx->D[level], &F = ctx->D[level - 1];
+            const int nf = ctx->H[level - 1].n_owned;
+            { LoopScope t(ctx, "up_pre", level, nf); ctx->launches += k_up_pre(s, nf, F.mg, A.var, A.up_count); }
+            { LoopScope t(ctx, "up", level, nf); ctx->launches += k_up(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count); }
+            { LoopScope t(ctx, "up_post", level, ctx->H[level].n_owned); ctx->launches += k_up_post(s, ctx->H[level].n_owned, A.var, A.up_count); }
+            if (level == nl - 1) dir = 1;
+        } else {
+            level--;
+            LevelDev &F = ctx->D[level], &A = ctx->D[level + 1];
+            { LoopScope t(ctx, "down", level, ctx->H[level].n_owned); ctx->launches += k_down(s, ctx->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords); }
+            if (level == 0) { dir = 0; i++; }
+        }
+    }
+    int rc = check_launch(ctx, "mgcfd_run_cycles");
+    if (rc) return rc;
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
+    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
+    if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
+    return MGCFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fetch / set / validate / introspection
+// ------------------------------------------------------------------------------------------
+struct DatRef { double *ptr; int dim; };
+static bool find_node_dat(mgcfd_ctx *ctx, int level, const char *name, DatRef &r)
+{
+    LevelDev &D = ctx->D[level];
+    std::string s(name);
+    if (s == "variables") r = {D.var, 5};
+    else if (s == "old_variables") r = {D.old, 5};
+    else if (s == "residuals") r = {D.res, 5};
+    else if (s == "fluxes") r = {D.flux, 5};
+    else if (s == "dummy_fluxes") r = {D.dummy_flux, 5};
+    else if (s == "volumes") r = {D.vol, 1};
+    else if (s == "step_factors") r = {D.sf, 1};
+    else if (s == "node_coordinates") r = {D.coords, 3};
+    else return false;
+    return true;
+}
+
+int mgcfd_sync(mgcfd_ctx *ctx)
+{
+    REQUIRE(ctx, "null ctx");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MGCFD_OK;
+}
+
+int mgcfd_fetch_dat(mgcfd_ctx *ctx, int level, const char *name, void *host_out)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(name && host_out, "null argument");
+    LevelHost &L = ctx->H[level];
+    std::string s(name);
+    if (s == "edge_weights") { memcpy(host_out, L.ewt.data(), L.ewt.size() * sizeof(double)); return MGCFD_OK; }
+    if (s == "bnd_node_weights") { memcpy(host_out, L.bwt.data(), L.bwt.size() * sizeof(double)); return MGCFD_OK; }
+    if (s == "up_scratch") {
+        std::vector<int> tmp(L.n_nodes);
+        CK(cudaMemcpyAsync(tmp.data(), ctx->D[level].up_count, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int *out = static_cast<int *>(host_out);
+        for (int i = 0; i < L.n_nodes; i++) out[i] = tmp[L.new_of_old[i]];
+        return MGCFD_OK;
+    }
+    DatRef r;
+    REQUIRE(find_node_dat(ctx, level, name, r), std::string("unknown dat '") + name + "'");
+    REQUIRE(r.ptr, std::string("dat '") + name + "' has not been allocated");
+    std::vector<double> tmp((size_t)L.n_nodes * r.dim);
+    CK(cudaMemcpyAsync(tmp.data(), r.ptr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double *out = static_cast<double *>(host_out);
+    for (int i = 0; i < L.n_nodes; i++)
+        for (int d = 0; d < r.dim; d++) out[(size_t)i * r.dim + d] = tmp[(size_t)L.new_of_old[i] * r.dim + d];
+    return MGCFD_OK;
+}
+
+int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_in)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(name && host_in, "null argument");
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    std::string s(name);
+    if (s == "edge_weights") {
+        memcpy(L.ewt.data(), host_in, L.ewt.size() * sizeof(double));
+        D.atomic.valid = D.colour.valid = D.owner.valid = false;
+        return MGCFD_OK;
+    }
+    if (s == "bnd_node_weights") {
+        memcpy(L.bwt.data(), host_in, L.bwt.size() * sizeof(double));
+        return upload_bnd(ctx, level);
+    }
+    if (s == "up_scratch") {
+        std::vector<int> tmp(L.n_nodes);
+        const int *in = static_cast<const int *>(host_in);
+        for (int i = 0; i < L.n_nodes; i++) tmp[L.new_of_old[i]] = in[i];
+        CK(cudaMemcpyAsync(D.up_count, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MGCFD_OK;
+    }
+    if (s == "volumes") {
+        const double *in = static_cast<const double *>(host_in);
+        return upload_volumes(ctx, level, std::vector<double>(in, in + L.n_nodes));
+    }
+    if (s == "dummy_fluxes" && !D.dummy_flux) {
+        int rc = dev_alloc(ctx, &D.dummy_flux, (size_t)L.n_nodes * 5);
+        if (rc) return rc;
+    }
+    DatRef r;
+    REQUIRE(find_node_dat(ctx, level, name, r), std::string("unknown dat '") + name + "'");
+    if (s == "fluxes") D.flux_is_zero = false;
+    return upload_node_dat(ctx, level, r.ptr, static_cast<const double *>(host_in), r.dim);
+}
+
+int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master, int *n_diff)
+{
+    CHECK_LEVEL(level); CHECK_PLANNED();
+    REQUIRE(master && n_diff, "null argument");
+    LevelHost &L = ctx->H[level];
+    double *d_master = nullptr;
+    int rc = dev_alloc(ctx, &d_master, (size_t)L.n_nodes * 5, false);
+    if (rc) return rc;
+    if ((rc = upload_node_dat(ctx, level, d_master, master, 5))) { cudaFree(d_master); return rc; }
+    CK(cudaMemsetAsync(&ctx->d_flags[2], 0, sizeof(int), ctx->stream));
+    ctx->launches += k_validate(ctx->stream, L.n_owned, ctx->D[level].var, d_master, &ctx->d_flags[2]);
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[7]);
+    CK(cudaMemcpyAsync(hp, &ctx->d_flags[2], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_master);
+    *n_diff = hp[0];
+    return check_launch(ctx, "identify_differences");
+}
+
+static long long emit(const std::vector<int> &v, int *out, long long cap)
+{
+    if (out) {
+        if (cap < (long long)v.size()) return MGCFD_ERR_ARG;
+        std::copy(v.begin(), v.end(), out);
+    }
+    return (long long)v.size();
+}
+
+long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out, long long cap)
+{
+    if (!ctx || level < 0 || level >= ctx->n_levels || !what || !ctx->planned) return MGCFD_ERR_ARG;
+    LevelHost &L = ctx->H[level];
+    std::string s(what);
+    if (s == "node_perm") return emit(L.new_of_old, out, cap);
+    if (s == "edge_order") {
+        if (!L.have_sorted) plan_sort_edges(L);
+        return emit(L.sorted.order, out, cap);
+    }
+    if (s == "edge_thread_colour" || s == "edge_block_colour" || s == "n_block_colours" || s == "colour_exec_edge") {
+        if (!L.have_colour) plan_colour(L, ctx->opt.colour_block_edges);
+        ColourPlanHost &C = L.colour;
+        if (s == "n_block_colours") return emit(std::vector<int>{C.n_block_colours}, out, cap);
+        if (s == "colour_exec_edge") return emit(C.exec_edge, out, cap);
+        std::vector<int> v(L.n_edges);
+        for (int i = 0; i < L.n_edges; i++)
+            v[L.sorted.order[i]] = (s == "edge_thread_colour") ? C.thread_colour[i] : C.block_colour[i / C.block_edges];
+        return emit(v, out, cap);
+    }
+    if (s.rfind("owner_", 0) == 0) {
+        if (!L.have_owner && ensure_owner(ctx, level)) return MGCFD_ERR_PLAN;
+        OwnerPlanHost &O = L.owner;
+        if (s == "owner_chunk_start") return emit(O.node0, out, cap);
+        if (s == "owner_halo_off") return emit(O.halo_off, out, cap);
+        if (s == "owner_halo_gid") return emit(O.halo_gid, out, cap);
+        if (s == "owner_edge_off") return emit(O.edge_off, out, cap);
+        if (s == "owner_edge_file") return emit(O.edge_file, out, cap);
+        if (s == "owner_stats") return emit(std::vector<int>{O.n_chunks, O.max_loc, O.max_edges, O.max_own, O.max_inc,
+                                                             (int)std::min<long long>(O.total_edges, 0x7fffffff)}, out, cap);
+    }
+    return MGCFD_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------
+// measurement hooks
+// ------------------------------------------------------------------------------------------
+int mgcfd_timers_enable(mgcfd_ctx *ctx, int on)
+{
+    REQUIRE(ctx, "null ctx");
+    if (!on && ctx->timers_on) timers_collect(ctx);
+    ctx->timers_on = on != 0;
+    return MGCFD_OK;
+}
+
+int mgcfd_timers_reset(mgcfd_ctx *ctx)
+{
+    REQUIRE(ctx, "null ctx");
+    timers_collect(ctx);
+    for (auto &kv : ctx->timers) { kv.second.ms = 0.0; kv.second.calls = 0; kv.second.elements = 0; }
+    return MGCFD_OK;
+}
+
+int mgcfd_timers_get(mgcfd_ctx *ctx, const char *loop_name, int level, double *ms, long long *calls, long long *elements)
+{
+    REQUIRE(ctx && loop_name, "null argument");
+    timers_collect(ctx);
+    double m = 0.0;
+    long long c = 0, el = 0;
+    for (auto &kv : ctx->timers) {
+        size_t h = kv.first.rfind('#');
+        if (kv.first.substr(0, h) != loop_name) continue;
+        if (level >= 0 && std::stoi(kv.first.substr(h + 1)) != level) continue;
+        m += kv.second.ms; c += kv.second.calls; el += kv.second.elements;
+    }
+    if (ms) *ms = m;
+    if (calls) *calls = c;
+    if (elements) *elements = el;
+    return MGCFD_OK;
+}
+
+long long mgcfd_kernel_launches(const mgcfd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *mgcfd_stream(mgcfd_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+void *mgcfd_device_ptr(mgcfd_ctx *ctx, int level, const char *name)
+{
+    if (!ctx || level < 0 || level >= ctx->n_levels || !name || !ctx->planned) return nullptr;
+    DatRef r;
+    if (!find_node_dat(ctx, level, name, r)) return nullptr;
+    return r.ptr;
+}
+
+}  // extern "C"

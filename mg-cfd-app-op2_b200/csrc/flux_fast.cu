@@ -1,0 +1,22 @@
+// flux_fast.cu -- fast-math build of the flux kernels (default nvcc contraction).
+#include "flux_kernels.cuh"
+
+namespace mgcfd {
+int fast_flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p) { return fast::launch_atomic(s, a, p); }
+int fast_flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h)
+{
+    return fast::launch_colour(s, a, p, h);
+}
+int fast_flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h)
+{
+    return fast::launch_owner(s, a, p, h);
+}
+int fast_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
+                  const double *b_wt, const double *var, double *flux, const DevConsts &c)
+{
+    return fast::launch_bnd(s, n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c);
+}
+std::string fast_configure() { return fast::configure(); }
+size_t fast_owner_smem(int max_loc, int max_edges) { return fast::owner_smem(max_loc, max_edges, false); }
+size_t fast_colour_smem(int max_nodes) { return fast::colour_smem(max_nodes, false); }
+}  // namespace mgcfd

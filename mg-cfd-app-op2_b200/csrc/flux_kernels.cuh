@@ -1,0 +1,508 @@
+// flux_kernels.cuh -- the three compute_flux_edge_kernel implementations, the boundary flux and
+// (as a body switch) unstructured_stream_kernel.  Included by two translation units:
+//   kernels.cu    with MGCFD_EXACT defined, compiled -fmad=false: reference operation order
+//                 (flux.h:41-208), IEEE div/sqrt, no contraction -> per-edge increments are
+//                 bit-identical to the CPU reference;
+//   flux_fast.cu  default flags: per-node derived quantities (p, |v|+c, 1/rho) computed once
+//                 per staged node, one antisymmetric 5-vector per edge, FMA contraction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "internal.h"
+
+namespace mgcfd {
+
+#ifdef MGCFD_EXACT
+#define FLUX_NS exact
+#else
+#define FLUX_NS fast
+#endif
+
+namespace FLUX_NS {
+
+constexpr double GAMMA = 1.4;   // const.h:27
+
+// ------------------------------------------------------------------------------------------
+// per-node state
+// ------------------------------------------------------------------------------------------
+#ifdef MGCFD_EXACT
+constexpr int NF = 5;           // staged fields per node: the conserved variables only
+struct Side {                   // everything flux.h:52-91 / :101-136 derives for one end
+    double rho, m[3], E, v[3], q2, speed, p, c;
+};
+__device__ __forceinline__ Side derive(const double u[5])
+{
+    Side s;
+    s.rho = u[0]; s.m[0] = u[1]; s.m[1] = u[2]; s.m[2] = u[3]; s.E = u[4];
+    s.v[0] = s.m[0] / s.rho; s.v[1] = s.m[1] / s.rho; s.v[2] = s.m[2] / s.rho;     // inlined_funcs.h:120-125
+    s.q2 = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];                     // :98-101
+    s.speed = sqrt(s.q2);
+    s.p = (GAMMA - 1.0) * (s.E - 0.5 * s.rho * s.q2);                               // :103-106
+    s.c = sqrt(GAMMA * s.p / s.rho);                                                // :126-129
+    return s;
+}
+// fc[i][d]: flux contribution of momentum component i (0..2) / energy (3) in direction d; inlined_funcs.h:70-96
+__device__ __forceinline__ void contributions(const Side &s, double fc[4][3])
+{
+    fc[0][0] = s.v[0] * s.m[0] + s.p; fc[0][1] = s.v[0] * s.m[1];       fc[0][2] = s.v[0] * s.m[2];
+    fc[1][0] = fc[0][1];              fc[1][1] = s.v[1] * s.m[1] + s.p; fc[1][2] = s.v[1] * s.m[2];
+    fc[2][0] = fc[0][2];              fc[2][1] = fc[1][2];              fc[2][2] = s.v[2] * s.m[2] + s.p;
+    double ep = s.E + s.p;
+    fc[3][0] = s.v[0] * ep; fc[3][1] = s.v[1] * ep; fc[3][2] = s.v[2] * ep;
+}
+// both increments in the reference's association order, flux.h:139-207.  g = ((-|w|)*smoothing)*0.5 (host)
+__device__ __forceinline__ void edge_flux(const double ua[5], const double ub[5], double w0, double w1, double w2,
+                                          double g, double fa[5], double fb[5])
+{
+    Side B = derive(ub), A = derive(ua);
+    double fcA[4][3], fcB[4][3];
+    contributions(B, fcB);
+    contributions(A, fcA);
+    double factor_a = g * (A.speed + B.speed + A.c + B.c);
+    double factor_b = g * (B.speed + A.speed + B.c + A.c);
+    double fx = -0.5 * w0, fy = -0.5 * w1, fz = -0.5 * w2;
+    fa[0] = factor_a * (A.rho - B.rho) + fx * (A.m[0] + B.m[0]) + fy * (A.m[1] + B.m[1]) + fz * (A.m[2] + B.m[2]);
+    fa[4] = factor_a * (A.E - B.E) + fx * (fcA[3][0] + fcB[3][0]) + fy * (fcA[3][1] + fcB[3][1]) + fz * (fcA[3][2] + fcB[3][2]);
+    fb[0] = factor_b * (B.rho - A.rho) - fx * (A.m[0] + B.m[0]) - fy * (A.m[1] + B.m[1]) - fz * (A.m[2] + B.m[2]);
+    fb[4] = factor_b * (B.E - A.E) - fx * (fcA[3][0] + fcB[3][0]) - fy * (fcA[3][1] + fcB[3][1]) - fz * (fcA[3][2] + fcB[3][2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        fa[1 + i] = factor_a * (A.m[i] - B.m[i]) + fx * (fcA[i][0] + fcB[i][0]) + fy * (fcA[i][1] + fcB[i][1]) + fz * (fcA[i][2] + fcB[i][2]);
+        fb[1 + i] = factor_b * (B.m[i] - A.m[i]) - fx * (fcA[i][0] + fcB[i][0]) - fy * (fcA[i][1] + fcB[i][1]) - fz * (fcA[i][2] + fcB[i][2]);
+    }
+}
+constexpr int NFLUX = 10;       // per-edge values kept for the gather: fa[5], fb[5]
+#else
+constexpr int NF = 8;           // staged fields per node: rho, mx, my, mz, E, p, s = |v|+c, 1/rho
+__device__ __forceinline__ void derive(const double u[5], double r[8])
+{
+    double rinv = 1.0 / u[0];
+    double vx = u[1] * rinv, vy = u[2] * rinv, vz = u[3] * rinv;
+    double q2 = vx * vx + vy * vy + vz * vz;
+    double p = (GAMMA - 1.0) * (u[4] - 0.5 * u[0] * q2);
+    r[0] = u[0]; r[1] = u[1]; r[2] = u[2]; r[3] = u[3]; r[4] = u[4];
+    r[5] = p;
+    r[6] = sqrt(q2) + sqrt(GAMMA * p * rinv);
+    r[7] = rinv;
+}
+// one antisymmetric increment F: flux_a += F, flux_b -= F.  Same mathematics as flux.h:139-207 with
+// sum_d w_d*fc_i[d] rewritten as v_i*(w.m) + p*w_i and fc_E[d] as v_d*(E+p).
+__device__ __forceinline__ void edge_flux(const double a[8], const double b[8], double w0, double w1, double w2,
+                                          double g, double F[5])
+{
+    double factor = g * (a[6] + b[6]);
+    double wma = w0 * a[1] + w1 * a[2] + w2 * a[3];
+    double wmb = w0 * b[1] + w1 * b[2] + w2 * b[3];
+    double wva = wma * a[7], wvb = wmb * b[7];       // w . v
+    double psum = a[5] + b[5];
+    F[0] = factor * (a[0] - b[0]) - 0.5 * (wma + wmb);
+    F[1] = factor * (a[1] - b[1]) - 0.5 * (wva * a[1] + wvb * b[1] + w0 * psum);
+    F[2] = factor * (a[2] - b[2]) - 0.5 * (wva * a[2] + wvb * b[2] + w1 * psum);
+    F[3] = factor * (a[3] - b[3]) - 0.5 * (wva * a[3] + wvb * b[3] + w2 * psum);
+    F[4] = factor * (a[4] - b[4]) - 0.5 * (wva * (a[4] + a[5]) + wvb * (b[4] + b[5]));
+}
+constexpr int NFLUX = 5;
+#endif
+
+// unstructured_stream.h:7-57 on raw variables
+__device__ __forceinline__ void stream_flux(const double ua[5], const double ub[5], double w0, double w1, double w2,
+                                            double fa[5], double fb[5])
+{
+    fa[0] = ub[0] + w0; fa[1] = ub[1] + w2; fa[2] = ub[2]; fa[3] = ub[3]; fa[4] = ub[4] + w1;
+    fb[0] = ua[0]; fb[1] = ua[1]; fb[2] = ua[2]; fb[3] = ua[3]; fb[4] = ua[4];
+}
+
+__device__ __forceinline__ void load5(const double *__restrict__ p, double u[5])
+{
+#pragma unroll
+    for (int v = 0; v < 5; v++) u[v] = __ldg(p + v);
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 0: thread per edge, fp64 RED with warp aggregation on the sorted (lower) endpoint
+// ------------------------------------------------------------------------------------------
+template <bool STREAM>
+__global__ void __launch_bounds__(256)
+flux_atomic_kernel(int E, int n_owned, const int2 *__restrict__ nodes, const double4 *__restrict__ wts,
+                   const double *__restrict__ var, double *__restrict__ flux)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int lo = -1 - lane, hi = -1;
+    double flo[5] = {0, 0, 0, 0, 0}, fhi[5] = {0, 0, 0, 0, 0};
+    if (e < E) {
+        int2 ab = nodes[e];
+        double4 w = wts[e];
+        double ua[5], ub[5], fa[5], fb[5];
+        load5(var + (size_t)ab.x * 5, ua);
+        load5(var + (size_t)ab.y * 5, ub);
+        if (STREAM) {
+            stream_flux(ua, ub, w.x, w.y, w.z, fa, fb);
+        } else {
+#ifdef MGCFD_EXACT
+            edge_flux(ua, ub, w.x, w.y, w.z, w.w, fa, fb);
+#else
+            double ra[8], rb[8];
+            derive(ua, ra);
+            derive(ub, rb);
+            edge_flux(ra, rb, w.x, w.y, w.z, w.w, fa);
+#pragma unroll
+            for (int v = 0; v < 5; v++) fb[v] = -fa[v];
+#endif
+        }
+        bool a_low = ab.x <= ab.y;
+        lo = a_low ? ab.x : ab.y;
+        hi = a_low ? ab.y : ab.x;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            flo[v] = a_low ? fa[v] : fb[v];
+            fhi[v] = a_low ? fb[v] : fa[v];
+        }
+    }
+    // segmented inclusive scan over runs of equal `lo` (runs are contiguous: edges are sorted by lo)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int key = __shfl_up_sync(0xffffffffu, lo, d);
+        bool take = lane >= d && key == lo;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double t = __shfl_up_sync(0xffffffffu, flo[v], d);
+            if (take) flo[v] += t;
+        }
+    }
+    int next = __shfl_down_sync(0xffffffffu, lo, 1);
+    bool tail = lane == 31 || next != lo;
+    if (e < E) {
+        if (tail && lo < n_owned) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) atomicAdd(flux + (size_t)lo * 5 + v, flo[v]);
+        }
+        if (hi < n_owned) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) atomicAdd(flux + (size_t)hi * 5 + v, fhi[v]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 1: OP2-style hierarchical colouring.  One launch per block colour; a CTA stages the
+// block's nodes in shared memory, computes one edge per thread, accumulates into shared memory
+// thread colour by thread colour, then adds the block's sums to HBM without atomics.
+// shared: rec[NF][max_nodes] | acc[5][max_nodes]
+// ------------------------------------------------------------------------------------------
+template <bool STREAM>
+__global__ void __launch_bounds__(256)
+flux_colour_kernel(int slot0, int max_nodes, int n_owned, const int *__restrict__ blk_edge0,
+                   const int *__restrict__ blk_node0, const int *__restrict__ blk_ncol,
+                   const int *__restrict__ node_gid, const uint32_t *__restrict__ lab,
+                   const unsigned char *__restrict__ ecol, const double4 *__restrict__ wts,
+                   const double *__restrict__ var, double *__restrict__ flux)
+{
+    extern __shared__ double sm[];
+    constexpr int NREC = STREAM ? 5 : NF;
+    double *rec = sm;
+    double *acc = sm + (size_t)NREC * max_nodes;
+    const int s = slot0 + blockIdx.x, tid = threadIdx.x;
+    const int e0 = blk_edge0[s], ne = blk_edge0[s + 1] - e0;
+    const int n0 = blk_node0[s], nn = blk_node0[s + 1] - n0;
+
+    for (int i = tid; i < nn; i += blockDim.x) {
+        double u[5];
+        load5(var + (size_t)node_gid[n0 + i] * 5, u);
+#ifdef MGCFD_EXACT
+#pragma unroll
+        for (int f = 0; f < 5; f++) rec[f * max_nodes + i] = u[f];
+#else
+        if (STREAM) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) rec[f * max_nodes + i] = u[f];
+        } else {
+            double r[8];
+            derive(u, r);
+#pragma unroll
+            for (int f = 0; f < 8; f++) rec[f * max_nodes + i] = r[f];
+        }
+#endif
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v * max_nodes + i] = 0.0;
+    }
+    __syncthreads();
+
+    double fa[5], fb[5];
+    int la = 0, lb = 0, col = -1;
+    if (tid < ne) {
+        uint32_t l = lab[e0 + tid];
+        la = l & 0xffff;
+        lb = l >> 16;
+        col = ecol[e0 + tid];
+        double4 w = wts[e0 + tid];
+        double a[NREC], b[NREC];
+#pragma unroll
+        for (int f = 0; f < NREC; f++) { a[f] = rec[f * max_nodes + la]; b[f] = rec[f * max_nodes + lb]; }
+        if (STREAM) {
+            stream_flux(a, b, w.x, w.y, w.z, fa, fb);
+        } else {
+#ifdef MGCFD_EXACT
+            edge_flux(a, b, w.x, w.y, w.z, w.w, fa, fb);
+#else
+            edge_flux(a, b, w.x, w.y, w.z, w.w, fa);
+#pragma unroll
+            for (int v = 0; v < 5; v++) fb[v] = -fa[v];
+#endif
+        }
+    }
+    const int ncol = blk_ncol[s];
+    for (int c = 0; c < ncol; c++) {
+        if (col == c) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) {
+                acc[v * max_nodes + la] += fa[v];
+                acc[v * max_nodes + lb] += fb[v];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < nn; i += blockDim.x) {
+        int gid = node_gid[n0 + i];
+        if (gid < n_owned) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) flux[(size_t)gid * 5 + v] += acc[v * max_nodes + i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 2: owner-compute chunks.  A CTA owns a run of consecutive nodes; it stages owned + halo
+// node states in shared memory, computes every edge touching an owned node (cut edges are
+// recomputed by the neighbouring chunk), parks the per-edge fluxes in shared memory, then each
+// owned node sums its incident edges in ascending file order and stores the result: no atomics,
+// no colours, deterministic, and in the exact build bit-identical to OP2-seq.
+// shared: rec[NREC][max_loc] | F[NFLUX][max_edges]
+// ------------------------------------------------------------------------------------------
+template <bool STREAM, bool OVERWRITE>
+__global__ void __launch_bounds__(256)
+flux_owner_kernel(int max_loc, int max_edges, const OwnerChunkDesc *__restrict__ descs,
+                  const int *__restrict__ halo_gid, const unsigned char *__restrict__ blob,
+                  const double *__restrict__ var, double *__restrict__ flux)
+{
+    extern __shared__ double sm[];
+    constexpr int NREC = STREAM ? 5 : NF;
+    constexpr int NFL = STREAM ? 10 : NFLUX;
+    double *rec = sm;
+    double *F = sm + (size_t)NREC * max_loc;
+    const OwnerChunkDesc d = descs[blockIdx.x];
+    const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
+
+    for (int i = tid; i < nloc; i += blockDim.x) {
+        int gid = i < d.n_own ? d.node0 + i : halo_gid[d.halo_off + i - d.n_own];
+        double u[5];
+        load5(var + (size_t)gid * 5, u);
+#ifdef MGCFD_EXACT
+#pragma unroll
+        for (int f = 0; f < 5; f++) rec[f * max_loc + i] = u[f];
+#else
+        if (STREAM) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) rec[f * max_loc + i] = u[f];
+        } else {
+            double r[8];
+            derive(u, r);
+#pragma unroll
+            for (int f = 0; f < 8; f++) rec[f * max_loc + i] = r[f];
+        }
+#endif
+    }
+    __syncthreads();
+
+    const unsigned char *base = blob + d.blob_off;
+    const double *w0 = reinterpret_cast<const double *>(base);
+    const double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
+    const uint32_t *lab = reinterpret_cast<const uint32_t *>(gg + d.e_pad);
+    const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + d.e_pad);
+    const uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
+
+    for (int e = tid; e < d.n_edges; e += blockDim.x) {
+        uint32_t l = __ldg(lab + e);
+        int la = l & 0xffff, lb = l >> 16;
+        double x = __ldg(w0 + e), y = __ldg(w1 + e), z = __ldg(w2 + e), g = __ldg(gg + e);
+        double a[NREC], b[NREC];
+#pragma unroll
+        for (int f = 0; f < NREC; f++) { a[f] = rec[f * max_loc + la]; b[f] = rec[f * max_loc + lb]; }
+        if (STREAM) {
+            double fa[5], fb[5];
+            stream_flux(a, b, x, y, z, fa, fb);
+#pragma unroll
+            for (int v = 0; v < 5; v++) { F[v * max_edges + e] = fa[v]; F[(5 + v) * max_edges + e] = fb[v]; }
+        } else {
+#ifdef MGCFD_EXACT
+            double fa[5], fb[5];
+            edge_flux(a, b, x, y, z, g, fa, fb);
+#pragma unroll
+            for (int v = 0; v < 5; v++) { F[v * max_edges + e] = fa[v]; F[(5 + v) * max_edges + e] = fb[v]; }
+#else
+            double fa[5];
+            edge_flux(a, b, x, y, z, g, fa);
+#pragma unroll
+            for (int v = 0; v < 5; v++) F[v * max_edges + e] = fa[v];
+#endif
+        }
+    }
+    __syncthreads();
+
+    for (int n = tid; n < d.n_own; n += blockDim.x) {
+        double acc[5];
+        double *out = flux + (size_t)(d.node0 + n) * 5;
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] = OVERWRITE ? 0.0 : out[v];
+        int j0 = rowptr[n], j1 = rowptr[n + 1];
+        for (int j = j0; j < j1; j++) {
+            uint16_t c = csr[j];
+            int e = c & 0x7fff;
+            bool is_b = c & 0x8000;
+            if (NFL == 10) {
+                int off = is_b ? 5 : 0;
+#pragma unroll
+                for (int v = 0; v < 5; v++) acc[v] += F[(off + v) * max_edges + e];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 5; v++) {
+                    double f = F[v * max_edges + e];
+                    acc[v] += is_b ? -f : f;
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 5; v++) out[v] = acc[v];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// compute_bnd_node_flux_kernel, flux.h:14-39 (+ flux_boundary.elem_func, flux_wall.elem_func).
+// One thread per UNIQUE boundary-touched node; its boundary entries are applied in ascending
+// file order, so several entries on one node need no atomics and the sum order is OP2-seq's.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bnd_flux_kernel(int n_unique, const int *__restrict__ bu_node, const int *__restrict__ bu_ptr,
+                const int *__restrict__ b_group, const double *__restrict__ b_wt,
+                const double *__restrict__ var, double *__restrict__ flux, DevConsts c)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_unique) return;
+    int node = bu_node[t];
+    double u[5];
+    load5(var + (size_t)node * 5, u);
+    double *out = flux + (size_t)node * 5;
+    double fl[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) fl[k] = out[k];
+    double rho = u[0], m[3] = {u[1], u[2], u[3]}, E = u[4];
+    double v[3] = {m[0] / rho, m[1] / rho, m[2] / rho};
+    double q2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double p = (GAMMA - 1.0) * (E - 0.5 * rho * q2);
+    double fc[4][3];
+    fc[0][0] = v[0] * m[0] + p; fc[0][1] = v[0] * m[1];     fc[0][2] = v[0] * m[2];
+    fc[1][0] = fc[0][1];        fc[1][1] = v[1] * m[1] + p; fc[1][2] = v[1] * m[2];
+    fc[2][0] = fc[0][2];        fc[2][1] = fc[1][2];        fc[2][2] = v[2] * m[2] + p;
+    double ep = E + p;
+    fc[3][0] = v[0] * ep; fc[3][1] = v[1] * ep; fc[3][2] = v[2] * ep;
+    for (int i = bu_ptr[t]; i < bu_ptr[t + 1]; i++) {
+        int g = b_group[i];
+        double w[3] = {b_wt[(size_t)i * 3], b_wt[(size_t)i * 3 + 1], b_wt[(size_t)i * 3 + 2]};
+        if (g <= 2) {
+            // pressure-only wall (flux_boundary.elem_func:50-54); "+= 0" only matters for -0.0
+            fl[0] += 0.0;
+            fl[1] += w[0] * p;
+            fl[2] += w[1] * p;
+            fl[3] += w[2] * p;
+            fl[4] += 0.0;
+        } else if (g == 3 || (g >= 4 && g <= 7)) {
+            // far field (flux_wall.elem_func:49-76)
+            double fx = 0.5 * w[0], fy = 0.5 * w[1], fz = 0.5 * w[2];
+            fl[0] += fx * (c.ff_variable[1] + m[0]) + fy * (c.ff_variable[2] + m[1]) + fz * (c.ff_variable[3] + m[2]);
+            fl[4] += fx * (c.ff_fc[4][0] + fc[3][0]) + fy * (c.ff_fc[4][1] + fc[3][1]) + fz * (c.ff_fc[4][2] + fc[3][2]);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                fl[1 + k] += fx * (c.ff_fc[1 + k][0] + fc[k][0]) + fy * (c.ff_fc[1 + k][1] + fc[k][1]) + fz * (c.ff_fc[1 + k][2] + fc[k][2]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[k] = fl[k];
+}
+
+inline int launch_bnd(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
+                      const double *b_wt, const double *var, double *flux, const DevConsts &c)
+{
+    if (n_unique == 0) return 0;
+    bnd_flux_kernel<<<(n_unique + 127) / 128, 128, 0, s>>>(n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+inline size_t colour_smem(int max_nodes, bool stream) { return (size_t)((stream ? 5 : NF) + 5) * max_nodes * sizeof(double); }
+inline size_t owner_smem(int max_loc, int max_edges, bool stream)
+{
+    return ((size_t)(stream ? 5 : NF) * max_loc + (size_t)(stream ? 10 : NFLUX) * max_edges) * sizeof(double);
+}
+
+inline int launch_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p)
+{
+    if (a.n_edges == 0) return 0;
+    int grid = (a.n_edges + 255) / 256;
+    if (a.stream_kernel)
+        flux_atomic_kernel<true><<<grid, 256, 0, s>>>(a.n_edges, a.n_owned, p.nodes, p.w, a.var, a.flux);
+    else
+        flux_atomic_kernel<false><<<grid, 256, 0, s>>>(a.n_edges, a.n_owned, p.nodes, p.w, a.var, a.flux);
+    return 1;
+}
+
+inline int launch_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h)
+{
+    int launches = 0;
+    size_t smem = colour_smem(h.max_nodes, a.stream_kernel);
+    for (int c = 0; c < h.n_block_colours; c++) {
+        int slot0 = h.colour_start[c], nb = h.colour_start[c + 1] - slot0;
+        if (nb == 0) continue;
+        if (a.stream_kernel)
+            flux_colour_kernel<true><<<nb, h.block_edges, smem, s>>>(slot0, h.max_nodes, a.n_owned, p.blk_edge0, p.blk_node0,
+                                                                    p.blk_ncol, p.node_gid, p.lab, p.ecol, p.w, a.var, a.flux);
+        else
+            flux_colour_kernel<false><<<nb, h.block_edges, smem, s>>>(slot0, h.max_nodes, a.n_owned, p.blk_edge0, p.blk_node0,
+                                                                     p.blk_ncol, p.node_gid, p.lab, p.ecol, p.w, a.var, a.flux);
+        launches++;
+    }
+    return launches;
+}
+
+inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h)
+{
+    if (h.n_chunks == 0) return 0;
+    size_t smem = owner_smem(h.max_loc, h.max_edges, a.stream_kernel);
+    if (a.stream_kernel)
+        flux_owner_kernel<true, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+    else if (a.overwrite)
+        flux_owner_kernel<false, true><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+    else
+        flux_owner_kernel<false, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+    return 1;
+}
+
+inline std::string configure()
+{
+    const int max_smem = 227 * 1024;
+    cudaError_t e;
+#define OPT_IN(k)                                                                                  \
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);            \
+    if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(" #k "): ") + cudaGetErrorString(e);
+    OPT_IN((flux_colour_kernel<true>));
+    OPT_IN((flux_colour_kernel<false>));
+    OPT_IN((flux_owner_kernel<true, false>));
+    OPT_IN((flux_owner_kernel<false, true>));
+    OPT_IN((flux_owner_kernel<false, false>));
+#undef OPT_IN
+    return "";
+}
+
+}  // namespace FLUX_NS
+}  // namespace mgcfd

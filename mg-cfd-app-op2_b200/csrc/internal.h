@@ -1,0 +1,210 @@
+// internal.h -- shared declarations of libmgcfd_b200 (not part of the public C-ABI).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "mgcfd_b200.h"
+
+namespace mgcfd {
+
+constexpr int NVAR = MGCFD_NVAR;
+constexpr int NDIM = MGCFD_NDIM;
+
+// ------------------------------------------------------------------ host-side plans
+// Sorted edge list shared by the atomic and colour variants: edges ordered by
+// (min(internal a, internal b), max(..), file index).
+struct SortedEdges {
+    std::vector<int> order;      // order[i] = file edge at sorted position i
+};
+
+// OP2-style two-level colouring over blocks of consecutive sorted edges (SURVEY.md 8c "index-set oracle")
+struct ColourPlanHost {
+    int block_edges = 0;
+    int n_blocks = 0, n_block_colours = 0;
+    std::vector<int> thread_colour;   // [E] by sorted position
+    std::vector<int> block_colour;    // [n_blocks] by block (sorted-position order)
+    std::vector<int> block_ncol;      // [n_blocks] number of thread colours in the block
+    // execution layout: blocks grouped by block colour
+    std::vector<int> exec_block;      // [n_blocks] block id at execution slot
+    std::vector<int> colour_start;    // [n_block_colours+1] into exec_block
+    std::vector<int> node_off;        // [n_blocks+1] into node_gid (by execution slot)
+    std::vector<int> node_gid;        // internal node ids of each block, ascending
+    std::vector<uint32_t> lab;        // [E] by execution position: local a | local b << 16
+    std::vector<int> exec_edge;       // [E] file edge at execution position
+    std::vector<unsigned char> ecol;  // [E] thread colour at execution position
+    int max_nodes = 0;
+};
+
+// Owner-compute chunks of consecutive internal nodes
+struct OwnerPlanHost {
+    int n_chunks = 0;
+    std::vector<int> node0;           // [n_chunks+1] first owned internal node of each chunk
+    std::vector<int> halo_off;        // [n_chunks+1] into halo_gid
+    std::vector<int> halo_gid;        // internal ids of halo nodes per chunk, ascending
+    std::vector<int> n_edges;         // [n_chunks]
+    std::vector<int> n_inc;           // [n_chunks] owned incidences (CSR length)
+    std::vector<long long> blob_off;  // [n_chunks] byte offset of the chunk's edge blob (16B aligned)
+    std::vector<int> edge_file;       // file edge ids per chunk, concatenated in blob order
+    std::vector<int> edge_off;        // [n_chunks+1] into edge_file
+    std::vector<uint32_t> lab;        // per edge_file entry: local a | local b << 16
+    std::vector<uint16_t> rowptr;     // per chunk (n_own+1), concatenated
+    std::vector<int> rowptr_off;      // [n_chunks+1]
+    std::vector<uint16_t> csr;        // per chunk n_inc entries: local edge | (is_b << 15)
+    std::vector<int> csr_off;         // [n_chunks+1]
+    int max_loc = 0, max_edges = 0, max_own = 0, max_inc = 0;
+    long long total_edges = 0;
+};
+
+struct LevelHost {
+    int n_nodes = 0, n_edges = 0, n_bnd = 0, n_owned = 0;
+    std::vector<double> coords, ewt, bwt;     // file order
+    std::vector<int> e2n, b2n, bgroup, mg;    // 0-based, file order (mg empty on the coarsest)
+    std::vector<int> new_of_old, old_of_new;  // node renumbering
+    SortedEdges sorted;
+    ColourPlanHost colour;
+    OwnerPlanHost owner;
+    bool have_sorted = false, have_colour = false, have_owner = false;
+};
+
+// planner entry points (plan.cpp)
+void plan_renumber(LevelHost &L, bool renumber);
+void plan_sort_edges(LevelHost &L);
+void plan_colour(LevelHost &L, int block_edges);
+// returns false if a chunk cannot satisfy the local-index limits
+bool plan_owner(LevelHost &L, int max_own, int max_loc, int max_edges, std::string &err);
+
+// ------------------------------------------------------------------ device-side level
+struct DevConsts {
+    double smoothing;
+    double ff_variable[NVAR];
+    double ff_fc[NVAR][NDIM];   // rows 1..3 momentum x,y,z; row 4 density-energy; row 0 unused
+};
+
+struct AtomicPlanDev {
+    int2 *nodes = nullptr;      // [E] internal (a, b)
+    double4 *w = nullptr;       // [E] (wx, wy, wz, g) with g = -|w|*smoothing*0.5
+    bool valid = false;
+};
+
+struct ColourPlanDev {
+    int *blk_edge0 = nullptr;   // [n_blocks+1] by execution slot
+    int *blk_node0 = nullptr;   // [n_blocks+1]
+    int *blk_ncol = nullptr;    // [n_blocks]
+    int *node_gid = nullptr;
+    uint32_t *lab = nullptr;
+    unsigned char *ecol = nullptr;
+    double4 *w = nullptr;       // [E] by execution position
+    bool valid = false;
+};
+
+struct OwnerChunkDesc {         // one per chunk, read by the kernel
+    int node0, n_own, n_halo, halo_off;
+    int n_edges, e_pad, n_inc, pad_;
+    long long blob_off;
+};
+
+struct OwnerPlanDev {
+    OwnerChunkDesc *desc = nullptr;
+    int *halo_gid = nullptr;
+    unsigned char *blob = nullptr;   // per chunk: w0[e_pad] w1 w2 g (double) | lab[e_pad] (u32) | rowptr | csr (u16)
+    long long blob_bytes = 0;
+    bool valid = false;
+};
+
+struct LevelDev {
+    double *var = nullptr, *old = nullptr, *res = nullptr, *flux = nullptr, *dummy_flux = nullptr;
+    double *vol = nullptr, *sf = nullptr, *coords = nullptr;
+    int *up_count = nullptr;       // p_up_scratch payload
+    int *mg = nullptr;             // internal fine node -> internal coarse node (level+1)
+    int *child_ptr = nullptr;      // restrict gather CSR over this level's nodes: children on level-1
+    int *child_idx = nullptr;
+    // boundary entries grouped by unique node (ascending file order within a node)
+    int n_bnd_unique = 0;
+    int *bu_node = nullptr, *bu_ptr = nullptr, *b_group = nullptr;
+    double *b_wt = nullptr;
+    double *cbrt_vol = nullptr;    // cbrt(volume) per node, evaluated once on the host (volumes are static after init)
+    AtomicPlanDev atomic;
+    ColourPlanDev colour;
+    OwnerPlanDev owner;
+    bool flux_is_zero = false;     // tracked so that the owner variant may overwrite instead of accumulate
+};
+
+struct LoopTimer {
+    double ms = 0.0;
+    long long calls = 0, elements = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<long long> pending_elems;
+};
+
+}  // namespace mgcfd
+
+struct mgcfd_ctx {
+    int device = 0, n_levels = 0;
+    mgcfd_options opt{};
+    mgcfd_consts consts{};
+    bool have_consts = false, planned = false;
+    std::vector<mgcfd::LevelHost> H;
+    std::vector<mgcfd::LevelDev> D;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // device scalars
+    double *d_min_dt = nullptr;      // [n_levels] scratch for reductions
+    double *d_rms = nullptr;
+    int *d_flags = nullptr;          // [0]=bad value count, [1]=min_dt<0 flag, [2]=validate count
+    double *h_pinned = nullptr;      // pinned host scratch (8 doubles)
+    long long launches = 0;
+    bool timers_on = false;
+    std::map<std::string, mgcfd::LoopTimer> timers;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace mgcfd {
+
+// kernels.cu / flux_*.cu launchers.  All enqueue on `s` and return the number of kernels launched.
+int k_copy(cudaStream_t s, int n, const double *var, double *old);
+int k_calculate_dt(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *sf);
+int k_min_dt(cudaStream_t s, int n, const double *sf, double *d_min, int *d_flags);  // d_min must hold the start value
+int k_step_factor(cudaStream_t s, int n, const double *vol, const double *d_min, double *sf);
+int k_time_step(cudaStream_t s, int n, int rk, const double *sf, double *flux, const double *old, double *var);
+int k_residual(cudaStream_t s, int n, const double *old, const double *var, double *res);
+int k_rms(cudaStream_t s, int n, const double *res, double *d_rms);
+int k_bad_vals(cudaStream_t s, int n, const double *var, int *d_count);
+int k_up_pre(cudaStream_t s, int n_fine, const int *mg, double *var_above, int *count_above);
+int k_up(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
+         double *var_above, int *count_above);
+int k_up_post(cudaStream_t s, int n_coarse, double *var, const int *count);
+int k_down(cudaStream_t s, int n_fine, const int *mg, double *var, const double *res, const double *coords,
+           const double *res_above, const double *coords_above);
+int k_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
+               const double *b_wt, const double *var, double *flux, const DevConsts &c, bool exact);
+int k_validate(cudaStream_t s, int n, const double *test, const double *master, int *d_count);
+int k_fill(cudaStream_t s, long long n, double *a, double v);
+int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c);
+
+struct FluxArgs {
+    int n_edges = 0, n_owned = 0, n_nodes = 0;
+    const double *var = nullptr;
+    double *flux = nullptr;
+    bool stream_kernel = false;     // unstructured_stream_kernel body instead of the flux body
+    bool overwrite = false;         // owner variant: flux known to be zero -> plain store, no read
+};
+int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
+int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);
+int flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact);
+// one-time kernel attribute setup (dynamic shared memory opt-in); returns "" or an error text
+std::string flux_configure();
+// the fast-math translation unit (flux_fast.cu)
+int fast_flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p);
+int fast_flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h);
+int fast_flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h);
+int fast_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
+                  const double *b_wt, const double *var, double *flux, const DevConsts &c);
+std::string fast_configure();
+size_t flux_owner_smem_bytes(int max_loc, int max_edges, bool exact);
+size_t flux_colour_smem_bytes(int max_nodes, bool exact);
+
+}  // namespace mgcfd

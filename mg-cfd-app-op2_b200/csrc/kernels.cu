@@ -1,0 +1,396 @@
+// kernels.cu -- node-set kernels of the MG-CFD cycle and the reference-order ("exact") build of the
+// flux kernels.  This translation unit is compiled with -fmad=false and keeps the reference's
+// operation order, so every kernel here is bit-identical to the CPU reference element by element
+// (double division and sqrt are IEEE-rounded on the device).  They are all bandwidth-bound
+// streaming kernels; contraction would not make them faster.
+#define MGCFD_EXACT 1
+#include "flux_kernels.cuh"
+
+namespace mgcfd {
+
+size_t fast_owner_smem(int max_loc, int max_edges);
+size_t fast_colour_smem(int max_nodes);
+
+namespace {
+
+constexpr int TPB = 256;
+inline int blocks_for(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+// order-preserving map double -> uint64 so that atomicMin implements OP_MIN on doubles
+__device__ __forceinline__ unsigned long long enc_min(double d)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_min(unsigned long long u)
+{
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+// copy_double_kernel.h:6-13 over the flattened [n*5] array
+__global__ void copy_kernel(long long n, const double *__restrict__ src, double *__restrict__ dst)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void fill_kernel(long long n, double *__restrict__ a, double v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// misc.h:10-16
+__global__ void init_vars_kernel(int n, double *__restrict__ var, DevConsts c)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) var[(size_t)i * 5 + v] = c.ff_variable[v];
+    }
+}
+
+// time_stepping_kernels.h:13-32; cbrt(volume) is precomputed on the host (volumes never change after init)
+__global__ void calculate_dt_kernel(int n, const double *__restrict__ var, const double *__restrict__ cbrt_vol,
+                                    double *__restrict__ dt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *u = var + (size_t)i * 5;
+    double rho = u[0];
+    double vx = u[1] / rho, vy = u[2] / rho, vz = u[3] / rho;
+    double q2 = vx * vx + vy * vy + vz * vz;
+    double p = (1.4 - 1.0) * (u[4] - 0.5 * rho * q2);
+    double c = sqrt(1.4 * p / rho);
+    dt[i] = 0.5 * (cbrt_vol[i] / (sqrt(q2) + c));
+}
+
+// time_stepping_kernels.h:34-41: OP_MIN reduction; NaN never wins the comparison `dt < min_dt`
+__global__ void min_dt_kernel(int n, const double *__restrict__ dt, unsigned long long *__restrict__ d_min)
+{
+    __shared__ unsigned long long smin[TPB / 32];
+    unsigned long long m = ~0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double d = dt[i];
+        if (d == d) {
+            unsigned long long k = enc_min(d);
+            if (k < m) m = k;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        if (t < m) m = t;
+    }
+    if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TPB / 32; w++)
+            if (smin[w] < m) m = smin[w];
+        atomicMin(d_min, m);
+    }
+}
+
+// decode the reduced minimum in place and raise the deferred "min_dt < 0" flag (euler3d.cpp:480)
+__global__ void finish_min_kernel(unsigned long long *d_min, int *d_flags)
+{
+    double m = dec_min(*d_min);
+    *reinterpret_cast<double *>(d_min) = m;
+    if (m < 0.0f) d_flags[1] = 1;
+}
+
+__global__ void encode_min_kernel(unsigned long long *d_min)
+{
+    *d_min = enc_min(*reinterpret_cast<double *>(d_min));
+}
+
+// time_stepping_kernels.h:43-64 (only line :63 has an effect)
+__global__ void step_factor_kernel(int n, const double *__restrict__ vol, const double *__restrict__ d_min,
+                                   double *__restrict__ sf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sf[i] = (*d_min) / vol[i];
+}
+
+// time_stepping_kernels.h:66-86
+__global__ void time_step_kernel(int n, int rk, const double *__restrict__ sf, double *__restrict__ flux,
+                                 const double *__restrict__ old, double *__restrict__ var)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * 5) return;
+    double factor = sf[i / 5] / (double)(MGCFD_RK + 1 - rk);
+    var[i] = old[i] + factor * flux[i];
+    flux[i] = 0.0;
+}
+
+// validation.h:27-35
+__global__ void residual_kernel(long long n5, const double *__restrict__ old, const double *__restrict__ var,
+                                double *__restrict__ res)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n5) res[i] = var[i] - old[i];
+}
+
+// validation.h:37-44 (OP_INC into a global; summation order is not the sequential one)
+__global__ void rms_kernel(long long n5, const double *__restrict__ res, double *__restrict__ d_rms)
+{
+    __shared__ double ssum[TPB / 32];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n5; i += (long long)gridDim.x * blockDim.x)
+        s += res[i] * res[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TPB / 32; w++) s += ssum[w];
+        atomicAdd(d_rms, s);
+    }
+}
+
+// validation.h:102-115
+__global__ void bad_vals_kernel(long long n5, const double *__restrict__ var, int *__restrict__ d_count)
+{
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n5; i += (long long)gridDim.x * blockDim.x) {
+        double v = var[i];
+        if (isnan(v) || isinf(v)) c++;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(d_count, c);
+}
+
+// validation.h:46-100: identify_differences + count_non_zeros fused
+__global__ void validate_kernel(long long n5, const double *__restrict__ test, const double *__restrict__ master,
+                                int *__restrict__ d_count)
+{
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n5; i += (long long)gridDim.x * blockDim.x) {
+        double tol = master[i] * 10.0e-8;
+        if (tol < 0.0) tol *= -1.0;
+        if (tol < 3.0e-19) tol = 3.0e-19;
+        double d = test[i] - master[i];
+        if (d < 0.0) d *= -1.0;
+        if (d > tol) c++;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(d_count, c);
+}
+
+// mg.h:29-39 through node-->mg_node: only coarse nodes with a child are zeroed (all writers store 0)
+__global__ void up_pre_kernel(int n_fine, const int *__restrict__ mg, double *__restrict__ var_above,
+                              int *__restrict__ count_above)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_fine) return;
+    int p = mg[i];
+#pragma unroll
+    for (int v = 0; v < 5; v++) var_above[(size_t)p * 5 + v] = 0.0;
+    count_above[p] = 0;
+}
+
+// mg.h:41-52 as a gather: one thread per coarse node adds its children in ascending FILE order,
+// which is the order OP2-seq applies the increments in
+__global__ void up_gather_kernel(int n_coarse, const int *__restrict__ child_ptr, const int *__restrict__ child_idx,
+                                 const double *__restrict__ var, double *__restrict__ var_above,
+                                 int *__restrict__ count_above)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_coarse) return;
+    int j0 = child_ptr[p], j1 = child_ptr[p + 1];
+    if (j0 == j1) return;
+    double acc[5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) acc[v] = var_above[(size_t)p * 5 + v];
+    for (int j = j0; j < j1; j++) {
+        const double *u = var + (size_t)child_idx[j] * 5;
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] += u[v];
+    }
+#pragma unroll
+    for (int v = 0; v < 5; v++) var_above[(size_t)p * 5 + v] = acc[v];
+    count_above[p] += j1 - j0;
+}
+
+// mg.h:54-64
+__global__ void up_post_kernel(int n_coarse, double *__restrict__ var, const int *__restrict__ count)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_coarse) return;
+    int k = count[p];
+    double avg = k == 0 ? 1.0 : 1.0 / (double)k;
+#pragma unroll
+    for (int v = 0; v < 5; v++) var[(size_t)p * 5 + v] *= avg;
+}
+
+// mg.h:66-88
+__global__ void down_kernel(int n_fine, const int *__restrict__ mg, double *__restrict__ var,
+                            const double *__restrict__ res, const double *__restrict__ xyz,
+                            const double *__restrict__ res_above, const double *__restrict__ xyz_above)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_fine) return;
+    int p = mg[i];
+    double dx = fabs(xyz[(size_t)i * 3] - xyz_above[(size_t)p * 3]);
+    double dy = fabs(xyz[(size_t)i * 3 + 1] - xyz_above[(size_t)p * 3 + 1]);
+    double dz = fabs(xyz[(size_t)i * 3 + 2] - xyz_above[(size_t)p * 3 + 2]);
+    double dm = sqrt(dx * dx + dy * dy + dz * dz);
+    double *u = var + (size_t)i * 5;
+    const double *r = res + (size_t)i * 5, *ra = res_above + (size_t)p * 5;
+    u[0] -= dm * (ra[0] - r[0]);
+    u[1] -= dx * (ra[1] - r[1]);
+    u[2] -= dy * (ra[2] - r[2]);
+    u[3] -= dz * (ra[3] - r[3]);
+    u[4] -= dm * (ra[4] - r[4]);
+}
+
+}  // namespace
+
+int k_copy(cudaStream_t s, int n, const double *var, double *old)
+{
+    if (n == 0) return 0;
+    long long n5 = (long long)n * 5;
+    copy_kernel<<<blocks_for(n5), TPB, 0, s>>>(n5, var, old);
+    return 1;
+}
+int k_fill(cudaStream_t s, long long n, double *a, double v)
+{
+    if (n == 0) return 0;
+    fill_kernel<<<blocks_for(n), TPB, 0, s>>>(n, a, v);
+    return 1;
+}
+int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c)
+{
+    if (n == 0) return 0;
+    init_vars_kernel<<<blocks_for(n), TPB, 0, s>>>(n, var, c);
+    return 1;
+}
+int k_calculate_dt(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *sf)
+{
+    if (n == 0) return 0;
+    calculate_dt_kernel<<<blocks_for(n), TPB, 0, s>>>(n, var, cbrt_vol, sf);
+    return 1;
+}
+int k_min_dt(cudaStream_t s, int n, const double *sf, double *d_min, int *d_flags)
+{
+    // d_min holds the start value as a double; encode, reduce, decode in place
+    unsigned long long *u = reinterpret_cast<unsigned long long *>(d_min);
+    encode_min_kernel<<<1, 1, 0, s>>>(u);
+    int launches = 2;
+    if (n > 0) {
+        int grid = blocks_for(n);
+        if (grid > 148 * 8) grid = 148 * 8;
+        min_dt_kernel<<<grid, TPB, 0, s>>>(n, sf, u);
+        launches++;
+    }
+    finish_min_kernel<<<1, 1, 0, s>>>(u, d_flags);
+    return launches;
+}
+int k_step_factor(cudaStream_t s, int n, const double *vol, const double *d_min, double *sf)
+{
+    if (n == 0) return 0;
+    step_factor_kernel<<<blocks_for(n), TPB, 0, s>>>(n, vol, d_min, sf);
+    return 1;
+}
+int k_time_step(cudaStream_t s, int n, int rk, const double *sf, double *flux, const double *old, double *var)
+{
+    if (n == 0) return 0;
+    time_step_kernel<<<blocks_for((long long)n * 5), TPB, 0, s>>>(n, rk, sf, flux, old, var);
+    return 1;
+}
+int k_residual(cudaStream_t s, int n, const double *old, const double *var, double *res)
+{
+    if (n == 0) return 0;
+    long long n5 = (long long)n * 5;
+    residual_kernel<<<blocks_for(n5), TPB, 0, s>>>(n5, old, var, res);
+    return 1;
+}
+static int reduce_grid(long long n)
+{
+    int grid = blocks_for(n);
+    return grid > 148 * 8 ? 148 * 8 : grid;
+}
+int k_rms(cudaStream_t s, int n, const double *res, double *d_rms)
+{
+    if (n == 0) return 0;
+    long long n5 = (long long)n * 5;
+    rms_kernel<<<reduce_grid(n5), TPB, 0, s>>>(n5, res, d_rms);
+    return 1;
+}
+int k_bad_vals(cudaStream_t s, int n, const double *var, int *d_count)
+{
+    if (n == 0) return 0;
+    long long n5 = (long long)n * 5;
+    bad_vals_kernel<<<reduce_grid(n5), TPB, 0, s>>>(n5, var, d_count);
+    return 1;
+}
+int k_validate(cudaStream_t s, int n, const double *test, const double *master, int *d_count)
+{
+    if (n == 0) return 0;
+    long long n5 = (long long)n * 5;
+    validate_kernel<<<reduce_grid(n5), TPB, 0, s>>>(n5, test, master, d_count);
+    return 1;
+}
+int k_up_pre(cudaStream_t s, int n_fine, const int *mg, double *var_above, int *count_above)
+{
+    if (n_fine == 0) return 0;
+    up_pre_kernel<<<blocks_for(n_fine), TPB, 0, s>>>(n_fine, mg, var_above, count_above);
+    return 1;
+}
+int k_up(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
+         double *var_above, int *count_above)
+{
+    if (n_coarse == 0) return 0;
+    up_gather_kernel<<<blocks_for(n_coarse), TPB, 0, s>>>(n_coarse, child_ptr, child_idx, var, var_above, count_above);
+    return 1;
+}
+int k_up_post(cudaStream_t s, int n_coarse, double *var, const int *count)
+{
+    if (n_coarse == 0) return 0;
+    up_post_kernel<<<blocks_for(n_coarse), TPB, 0, s>>>(n_coarse, var, count);
+    return 1;
+}
+int k_down(cudaStream_t s, int n_fine, const int *mg, double *var, const double *res, const double *coords,
+           const double *res_above, const double *coords_above)
+{
+    if (n_fine == 0) return 0;
+    down_kernel<<<blocks_for(n_fine), TPB, 0, s>>>(n_fine, mg, var, res, coords, res_above, coords_above);
+    return 1;
+}
+
+// ---- flux dispatch: exact build lives here, fast build in flux_fast.cu
+int k_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
+               const double *b_wt, const double *var, double *flux, const DevConsts &c, bool exact_mode)
+{
+    return exact_mode ? exact::launch_bnd(s, n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c)
+                      : fast_bnd_flux(s, n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c);
+}
+int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact_mode)
+{
+    return exact_mode ? exact::launch_atomic(s, a, p) : fast_flux_atomic(s, a, p);
+}
+int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact_mode)
+{
+    return exact_mode ? exact::launch_colour(s, a, p, h) : fast_flux_colour(s, a, p, h);
+}
+int flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact_mode)
+{
+    return exact_mode ? exact::launch_owner(s, a, p, h) : fast_flux_owner(s, a, p, h);
+}
+std::string flux_configure()
+{
+    std::string e = exact::configure();
+    if (!e.empty()) return e;
+    return fast_configure();
+}
+size_t flux_owner_smem_bytes(int max_loc, int max_edges, bool exact_mode)
+{
+    size_t stream = exact::owner_smem(max_loc, max_edges, true);
+    size_t body = exact_mode ? exact::owner_smem(max_loc, max_edges, false) : fast_owner_smem(max_loc, max_edges);
+    return stream > body ? stream : body;
+}
+size_t flux_colour_smem_bytes(int max_nodes, bool exact_mode)
+{
+    return exact_mode ? exact::colour_smem(max_nodes, false) : fast_colour_smem(max_nodes);
+}
+
+}  // namespace mgcfd

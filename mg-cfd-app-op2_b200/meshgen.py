@@ -1,0 +1,209 @@
+"""Deterministic synthetic multigrid meshes in the reference's level-file layout.
+
+The reference reads one HDF5 file per multigrid level (euler3d.cpp:248-312) holding the
+datasets named below; its real decks (README.md:97-103) are not available offline, so the
+BASELINE.json configs are realised as seeded synthetic meshes with the same dataset names,
+shapes, dtypes and 1-based maps:
+
+    node_coordinates   float64 [N,3]
+    edge-->node        int32   [E,2]   (base_array_index-based, default 1: euler3d.cpp:92)
+    edge_weights       float64 [E,3]
+    bnd_node-->node    int32   [B,1]
+    bnd_node-->group   int32   [B,1]
+    bnd_node_weights   float64 [B,3]
+    node-->mg_node     int32   [N,1]   map into the next coarser level (absent on the coarsest)
+
+Each level is a perturbed structured grid relabelled as an unstructured mesh: axis edges
+plus seeded diagonal edges, all six faces as boundary nodes (groups chosen so that every
+branch of compute_bnd_node_flux_kernel, flux.h:29-37, runs), and a seeded random file
+order for nodes and edges so that the planner's renumbering has real work to do.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DATASETS = (
+    "node_coordinates", "edge-->node", "edge_weights", "bnd_node-->node",
+    "bnd_node-->group", "bnd_node_weights", "node-->mg_node",
+)
+
+# name -> (mesh_name for input.dat, [(nx, ny, nz, total_edges or None)], base seed)
+CONFIGS = {
+    # BASELINE.json configs[0], [1]: Onera-M6-shaped, 300K nodes / 930K edges, 4 levels
+    "m6": ("m6wing", [(100, 60, 50, 930_000), (75, 55, 40, 643_000), (60, 50, 37, 488_000),
+                      (54, 50, 30, 377_117)], 1),
+    # BASELINE.json configs[2]: Rotor37-1M-shaped
+    "rotor37_1m": ("rotor37", [(100, 100, 100, 3_200_000), (80, 80, 80, 1_638_400),
+                               (63, 63, 63, 800_150), (50, 50, 50, 400_000)], 100),
+    # BASELINE.json configs[3]: Rotor37-8M-shaped
+    "rotor37_8m": ("rotor37", [(200, 200, 200, 25_600_000), (160, 160, 160, 13_107_200),
+                               (126, 126, 126, 6_401_203), (100, 100, 100, 3_200_000)], 100),
+    # BASELINE.json configs[4]: one eighth of the 600x500x500 single-level deck (a 75x500x500 slab),
+    # the per-GPU share of the 8-way partition; axis edges only
+    "rotor37_150m_slab": ("rotor37", [(75, 500, 500, None)], 100),
+    # small decks for CPU tests and goldens
+    "tiny": ("m6wing", [(9, 7, 6, 1_000), (7, 6, 5, 560), (5, 4, 4, 200)], 7),
+    "small": ("m6wing", [(24, 18, 14, 18_000), (18, 14, 11, 8_600), (13, 11, 8, 3_500),
+                         (10, 8, 6, 1_400)], 11),
+    "medium": ("rotor37", [(48, 40, 36, 215_000), (36, 30, 27, 92_000), (27, 23, 20, 40_000)], 21),
+}
+
+# face -> boundary group: far-field in/out on x, walls on y and z-min,
+# a no-op group (>7) on z-max
+FACE_GROUPS = {"xmin": 3, "xmax": 5, "ymin": 0, "ymax": 1, "zmin": 2, "zmax": 9}
+
+
+def _axis_edges(nx, ny, nz):
+    idx = np.arange(nx * ny * nz, dtype=np.int64).reshape(nx, ny, nz)
+    parts = [
+        (idx[:-1, :, :].ravel(), idx[1:, :, :].ravel()),
+        (idx[:, :-1, :].ravel(), idx[:, 1:, :].ravel()),
+        (idx[:, :, :-1].ravel(), idx[:, :, 1:].ravel()),
+    ]
+    a = np.concatenate([p[0] for p in parts])
+    b = np.concatenate([p[1] for p in parts])
+    axis = np.concatenate([np.full(p[0].size, k, dtype=np.int8) for k, p in enumerate(parts)])
+    return a, b, axis
+
+
+_DIAG_DIRS = np.array([(1, 1, 0), (1, 0, 1), (0, 1, 1), (1, -1, 0), (1, 0, -1), (0, 1, -1)], dtype=np.int64)
+
+
+def _diagonal_edges(nx, ny, nz, count, rng):
+    """`count` distinct face-diagonal edges, drawn without replacement from all valid ones."""
+    if count <= 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    n = nx * ny * nz
+    i, j, k = np.unravel_index(np.arange(n, dtype=np.int64), (nx, ny, nz))
+    cand_a, cand_b = [], []
+    for d in _DIAG_DIRS:
+        i2, j2, k2 = i + d[0], j + d[1], k + d[2]
+        ok = (i2 >= 0) & (i2 < nx) & (j2 >= 0) & (j2 < ny) & (k2 >= 0) & (k2 < nz)
+        cand_a.append(np.nonzero(ok)[0])
+        cand_b.append((i2[ok] * ny + j2[ok]) * nz + k2[ok])
+    cand_a = np.concatenate(cand_a)
+    cand_b = np.concatenate(cand_b)
+    if count > cand_a.size:
+        raise ValueError(f"asked for {count} diagonal edges, only {cand_a.size} exist")
+    pick = rng.choice(cand_a.size, size=count, replace=False)
+    pick.sort()
+    return cand_a[pick], cand_b[pick]
+
+
+def make_level(nx, ny, nz, total_edges, seed, coarse_dims=None, base=1, shuffle=True, extent=None):
+    """One level as a dict of the reference's datasets (maps `base`-based, default 1)."""
+    rng = np.random.default_rng(seed)
+    n = nx * ny * nz
+    ext = extent if extent is not None else (1.0, 0.6, 0.5)
+    h = np.array([ext[0] / max(nx - 1, 1), ext[1] / max(ny - 1, 1), ext[2] / max(nz - 1, 1)])
+    hm = float(h.mean())
+
+    # --- nodes: perturbed grid
+    i, j, k = np.unravel_index(np.arange(n, dtype=np.int64), (nx, ny, nz))
+    coords = np.stack([i * h[0], j * h[1], k * h[2]], axis=1)
+    coords += rng.uniform(-0.2, 0.2, size=(n, 3)) * h
+
+    # --- edges: all axis edges + seeded diagonals, random orientation
+    ea, eb, axis = _axis_edges(nx, ny, nz)
+    n_axis = ea.size
+    n_diag = 0 if total_edges is None else total_edges - n_axis
+    if n_diag < 0:
+        raise ValueError(f"total_edges={total_edges} is below the {n_axis} axis edges")
+    da, db = _diagonal_edges(nx, ny, nz, n_diag, rng)
+    ea = np.concatenate([ea, da])
+    eb = np.concatenate([eb, db])
+    ne = ea.size
+    flip = rng.random(ne) < 0.5
+    ea, eb = np.where(flip, eb, ea), np.where(flip, ea, eb)
+    # face-normal-like weights of magnitude ~h^2 (direction is re-aimed at init: misc.h:65-75)
+    mag = hm * hm * rng.uniform(0.9, 1.1, size=ne)
+    mag[n_axis:] *= 0.35
+    w = np.zeros((ne, 3))
+    ax_full = np.concatenate([axis.astype(np.int64), rng.integers(0, 3, size=n_diag)])
+    w[np.arange(ne), ax_full] = mag
+
+    # --- boundary nodes: six faces (edge/corner nodes appear once per face they lie on)
+    faces = [
+        ("xmin", i == 0, (-1, 0, 0), h[1] * h[2]), ("xmax", i == nx - 1, (1, 0, 0), h[1] * h[2]),
+        ("ymin", j == 0, (0, -1, 0), h[0] * h[2]), ("ymax", j == ny - 1, (0, 1, 0), h[0] * h[2]),
+        ("zmin", k == 0, (0, 0, -1), h[0] * h[1]), ("zmax", k == nz - 1, (0, 0, 1), h[0] * h[1]),
+    ]
+    bn, bg, bw = [], [], []
+    for name, mask, normal, area in faces:
+        ids = np.nonzero(mask)[0]
+        bn.append(ids)
+        bg.append(np.full(ids.size, FACE_GROUPS[name], dtype=np.int32))
+        bw.append(np.outer(area * rng.uniform(0.9, 1.1, size=ids.size), np.array(normal, dtype=float)))
+    bn = np.concatenate(bn)
+    bg = np.concatenate(bg)
+    bw = np.concatenate(bw)
+
+    # --- multigrid map: nearest coarse grid index per axis, then a seeded 2 % of the coarse
+    #     nodes hand their children to the +x neighbour so that childless coarse nodes exist
+    mg = None
+    if coarse_dims is not None:
+        cx, cy, cz = coarse_dims
+        ci = np.rint(i * ((cx - 1) / max(nx - 1, 1))).astype(np.int64)
+        cj = np.rint(j * ((cy - 1) / max(ny - 1, 1))).astype(np.int64)
+        ck = np.rint(k * ((cz - 1) / max(nz - 1, 1))).astype(np.int64)
+        hole = rng.random(cx * cy * cz) < 0.02
+        hole.reshape(cx, cy, cz)[cx - 1, :, :] = False
+        mg = (ci * cy + cj) * cz + ck
+        mg = np.where(hole[mg], mg + cy * cz, mg)
+
+    # --- relabel: seeded random file order of nodes, edges and boundary entries
+    if shuffle:
+        perm = rng.permutation(n)            # new label of old node
+        inv = np.empty(n, dtype=np.int64)
+        inv[perm] = np.arange(n)
+        coords = coords[inv]
+        ea, eb = perm[ea], perm[eb]
+        eorder = rng.permutation(ne)
+        ea, eb, w = ea[eorder], eb[eorder], w[eorder]
+        bn = perm[bn]
+        border = rng.permutation(bn.size)
+        bn, bg, bw = bn[border], bg[border], bw[border]
+        if mg is not None:
+            mg = mg[inv]                     # still indexes the coarse grid's *grid* labels
+    else:
+        perm = np.arange(n)
+
+    level = {
+        "node_coordinates": np.ascontiguousarray(coords, dtype=np.float64),
+        "edge-->node": np.ascontiguousarray(np.stack([ea, eb], axis=1) + base, dtype=np.int32),
+        "edge_weights": np.ascontiguousarray(w, dtype=np.float64),
+        "bnd_node-->node": np.ascontiguousarray(bn[:, None] + base, dtype=np.int32),
+        "bnd_node-->group": np.ascontiguousarray(bg[:, None], dtype=np.int32),
+        "bnd_node_weights": np.ascontiguousarray(bw, dtype=np.float64),
+    }
+    return level, perm, mg
+
+
+def make_multigrid(config, base=1, shuffle=True):
+    """All levels of a named config.  Returns {"mesh_name", "base_array_index", "levels": [dict]}."""
+    if isinstance(config, str):
+        mesh_name, dims, seed0 = CONFIGS[config]
+    else:
+        mesh_name, dims, seed0 = config
+    levels, perms, mgs = [], [], []
+    for l, (nx, ny, nz, ne) in enumerate(dims):
+        coarse = dims[l + 1][:3] if l + 1 < len(dims) else None
+        lev, perm, mg = make_level(nx, ny, nz, ne, seed0 + l, coarse_dims=coarse, base=base, shuffle=shuffle)
+        levels.append(lev)
+        perms.append(perm)
+        mgs.append(mg)
+    # the fine level's mg map must point at the coarse level's *file* labels
+    for l in range(len(dims) - 1):
+        levels[l]["node-->mg_node"] = np.ascontiguousarray(
+            perms[l + 1][mgs[l]][:, None] + base, dtype=np.int32)
+    return {"mesh_name": mesh_name, "base_array_index": base, "levels": levels,
+            "dims": [tuple(d[:3]) for d in dims]}
+
+
+def zero_based(level, base=1):
+    """The 0-based maps the C-ABI and the oracle take (OP2 subtracts OP_MAPS_BASE_INDEX at load)."""
+    out = dict(level)
+    for key in ("edge-->node", "bnd_node-->node", "node-->mg_node"):
+        if key in out:
+            out[key] = np.ascontiguousarray(out[key] - base, dtype=np.int32)
+    return out

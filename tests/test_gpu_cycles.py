@@ -1,0 +1,115 @@
+"""GPU parity of whole multigrid runs (euler3d.cpp:458-641) against the golden solutions of the
+reference's own arithmetic, plus the reference's -v criterion (validation.h:46-100, Q13)."""
+import numpy as np
+import pytest
+
+from conftest import mesh0
+
+pytestmark = pytest.mark.gpu
+STATE_TOL = 1e-10      # BASELINE.json north_star: per-variable flow state within 1e-10 relative
+
+
+def normwise(a, b):
+    return np.abs(a - b).max(axis=0) / np.maximum(np.abs(b).max(axis=0), 1e-300)
+
+
+def check_levels(gpu, ref_vars, ff, exact=False):
+    for l, ref in enumerate(ref_vars):
+        got = gpu.fetch(l, "variables")
+        if exact:
+            assert np.array_equal(got, ref), (l, np.abs(got - ref).max())
+            continue
+        assert (normwise(got, ref) <= STATE_TOL).all(), (l, normwise(got, ref))
+        # the same error measured against the increment from the far-field start state
+        # (otherwise the test is blind to five digits)
+        inc = np.abs(ref - ff[None, :]).max(axis=0)
+        assert (np.abs(got - ref).max(axis=0) <= 1e-6 * inc + 1e-15).all(), (l, np.abs(got - ref).max(axis=0) / inc)
+        assert gpu.validate(l, ref) == 0                     # reference -v: no value outside 1e-7 relative
+        assert gpu.validate(l, ref) <= ref.shape[0] // 5000  # ... and its pass criterion (euler3d.cpp:700)
+
+
+@pytest.mark.parametrize("variant", ["owner", "colour", "atomic"])
+@pytest.mark.parametrize("name,cycles", [("tiny", 3), ("small", 10)])
+def test_cycles_golden(pkg, meshgen, golden, variant, name, cycles):
+    g = golden(f"{name}_cycles{cycles}.npz")
+    mesh = meshgen.make_multigrid(name)
+    with pkg.MGCFD(mesh["levels"], flux_variant=variant) as gpu:
+        gpu.run_cycles(cycles)
+        ff = np.array(list(gpu.consts.ff_variable))
+        check_levels(gpu, [g[f"var_L{l}"] for l in range(len(mesh["levels"]))], ff)
+        for l in range(len(mesh["levels"])):
+            assert np.array_equal(gpu.fetch(l, "volumes"), g[f"vol_L{l}"])
+
+
+@pytest.mark.parametrize("name,cycles", [("tiny", 3), ("small", 10)])
+def test_cycles_exact_mode_bit_identical(pkg, meshgen, golden, name, cycles):
+    """exact_arith + owner variant: reference operation order, per-node sums in file order, cbrt(vol) from the
+    host -> the whole multigrid run reproduces the reference bit for bit."""
+    g = golden(f"{name}_cycles{cycles}.npz")
+    mesh = meshgen.make_multigrid(name)
+    with pkg.MGCFD(mesh["levels"], flux_variant="owner", exact_arith=True) as gpu:
+        gpu.run_cycles(cycles)
+        check_levels(gpu, [g[f"var_L{l}"] for l in range(len(mesh["levels"]))], None, exact=True)
+
+
+def test_loopwise_equals_device_driven(pkg, meshgen):
+    mesh = meshgen.make_multigrid("small")
+    with pkg.MGCFD(mesh["levels"]) as a, pkg.MGCFD(mesh["levels"]) as b:
+        a.run_cycles(3)
+        rms, min_dt = b.run_cycles_loopwise(3)
+        assert rms > 0 and min_dt > 0
+        for l in range(len(mesh["levels"])):
+            assert np.array_equal(a.fetch(l, "variables"), b.fetch(l, "variables"))
+
+
+def test_renumbering_is_invisible(pkg, meshgen):
+    mesh = meshgen.make_multigrid("small")
+    with pkg.MGCFD(mesh["levels"], renumber=True, exact_arith=True) as a, \
+            pkg.MGCFD(mesh["levels"], renumber=False, exact_arith=True) as b:
+        a.run_cycles(2)
+        b.run_cycles(2)
+        for l in range(len(mesh["levels"])):
+            assert np.array_equal(a.fetch(l, "variables"), b.fetch(l, "variables"))
+
+
+def test_single_level_and_zero_based_maps(pkg, meshgen, oracle_port):
+    mesh = meshgen.make_multigrid(("m6wing", [(11, 9, 7, 2200)], 5), base=0)
+    lev0 = [meshgen.zero_based(l, base=0) for l in mesh["levels"]]
+    run = oracle_port.make_state(lev0)
+    run.init()
+    assert run.run(4)[0] == 0
+    with pkg.MGCFD(mesh["levels"], base_array_index=0) as gpu:
+        gpu.run_cycles(4)
+        assert (normwise(gpu.fetch(0, "variables"), run.levels[0]["var"]) <= STATE_TOL).all()
+
+
+def test_errors_are_reported_not_thrown(pkg, meshgen):
+    mesh = meshgen.make_multigrid("tiny")
+    with pkg.MGCFD(mesh["levels"]) as gpu:
+        bad = gpu.fetch(0, "variables")
+        bad[0, 0] = np.nan
+        gpu.set(0, "variables", bad)
+        with pytest.raises(pkg.MgcfdError) as ei:
+            gpu.run_cycles(1)
+        assert ei.value.code == -5                      # MGCFD_ERR_BAD_VALS, euler3d.cpp:544-548
+    with pkg.MGCFD(mesh["levels"]) as gpu:
+        with pytest.raises(pkg.MgcfdError):
+            gpu.fetch(7, "variables")
+        with pytest.raises(pkg.MgcfdError):
+            gpu.time_step(0, 5)
+    with pytest.raises(pkg.MgcfdError):
+        pkg.MGCFD(mesh["levels"], base_array_index=2)  # maps out of range for the wrong base index
+
+
+@pytest.mark.parametrize("variant", ["owner", "colour", "atomic"])
+def test_m6_full_size(pkg, meshgen, oracle_port, variant):
+    """BASELINE.json configs[0]/[1]: the M6-shaped 4-level deck at full size, 2 cycles against the live oracle."""
+    mesh = meshgen.make_multigrid("m6")
+    lev0 = [meshgen.zero_based(l) for l in mesh["levels"]]
+    run = oracle_port.make_state(lev0)
+    run.init()
+    assert run.run(2)[0] == 0
+    with pkg.MGCFD(mesh["levels"], flux_variant=variant) as gpu:
+        gpu.run_cycles(2)
+        ff = np.array(list(gpu.consts.ff_variable))
+        check_levels(gpu, [a["var"] for a in run.levels], ff)
