@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- MG-CFD hot path on B200: flux-edge edges/s through full multigrid cycles.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mesh m6] [--variant owner]
+
+One "step" is one multigrid V-cycle (euler3d.cpp:458-641) over the synthetic deck.  At N=1 the deck is
+BASELINE.json configs[1] (Onera-M6-shaped, 4 levels).  Prints ONE JSON line (rank 0).
+
+  value        flux-edge edge updates per second of whole-cycle time, deck resident in HBM, CUDA-event timed
+  e2e          same metric through the C-ABI with HOST buffers: per step the flow state of every level is
+               uploaded, one cycle runs, the state is fetched back (copies inside the timed region)
+  roofline     compute_flux_edge_kernel alone: algorithmic bytes (32*E + 120*N per call) over
+               the CUDA-event time of the flux launches inside the timed region, against the measured HBM peak
+  cpu_baseline the reference's own elemental kernels (oracle/_ref, OpenMP block-coloured, all host threads)
+               on a bounded sample of the same deck
+
+`--impl reference` times that CPU implementation as the whole job instead (the reference has no GPU code in
+its tree; its OP2 build cannot be produced offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+RK = 3
+
+
+def visits_per_cycle(n_levels):
+    """level visits of one V-cycle: L0..L(n-1) upward then L(n-2)..L1 downward (euler3d.cpp:573-640)"""
+    return list(range(n_levels)) + list(range(n_levels - 2, 0, -1)) if n_levels > 1 else [0]
+
+
+def flux_edges_per_cycle(sizes):
+    return RK * sum(sizes[l][1] for l in visits_per_cycle(len(sizes)))
+
+
+def flux_bytes_per_cycle(sizes):
+    """algorithmic bytes of the flux-edge loops of one cycle: 32*E + 120*N per invocation"""
+    return RK * sum(32 * sizes[l][1] + 120 * sizes[l][0] for l in visits_per_cycle(len(sizes)))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reorder_for_cpu(levels0, perms, edge_orders):
+    """Apply the GPU planner's locality ordering to a 0-based deck so that the CPU baseline is not
+    handicapped by the shuffled file order."""
+    out = []
+    for l, lev in enumerate(levels0):
+        new_of_old, eo = perms[l].astype(np.int64), edge_orders[l].astype(np.int64)
+        old_of_new = np.empty_like(new_of_old)
+        old_of_new[new_of_old] = np.arange(new_of_old.size)
+        d = {
+            "node_coordinates": lev["node_coordinates"][old_of_new],
+            "edge-->node": new_of_old[lev["edge-->node"][eo]].astype(np.int32),
+            "edge_weights": lev["edge_weights"][eo],
+            "bnd_node-->node": new_of_old[lev["bnd_node-->node"]].astype(np.int32),
+            "bnd_node-->group": lev["bnd_node-->group"],
+            "bnd_node_weights": lev["bnd_node_weights"],
+        }
+        if "node-->mg_node" in lev:
+            d["node-->mg_node"] = perms[l + 1].astype(np.int64)[lev["node-->mg_node"][old_of_new]].astype(np.int32)
+        out.append(d)
+    return out
+
+
+def hilbert_orders(levels0):
+    """node permutation + edge order per level without a GPU: same rule as the planner, via its numpy restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import plan_oracle
+    perms, orders = [], []
+    for lev in levels0:
+        p = plan_oracle.hilbert_renumber(lev["node_coordinates"])
+        perms.append(p)
+        orders.append(plan_oracle.sort_edges(lev["edge-->node"], p))
+    return perms, orders
+
+
+def cpu_run(levels0_ordered, n_cycles, warmup, threads):
+    """oracle/_ref (the reference's own headers) if present, else the port; OpenMP block-coloured."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    flags = open("/proc/cpuinfo").read()
+    fast_ok = " avx2" in flags and " fma" in flags
+    for kind, label in (("ref_fast", "reference"), ("ref", "reference"), ("port_fast", "port"), ("port", "port")):
+        if kind.endswith("_fast") and not fast_ok:
+            continue
+        if orc.available(kind):
+            break
+    o = orc.Oracle(kind)
+    used = o.set_threads(threads)
+    run = o.make_state(levels0_ordered)
+    run.init()
+    if warmup:
+        run.run(warmup)
+    rc, st = run.run(n_cycles)
+    if rc != 0:
+        raise RuntimeError(f"CPU baseline failed rc={rc}")
+    return {"edges_per_s": st.flux_edges / st.wall_total, "cycles_per_s": n_cycles / st.wall_total,
+            "flux_kernel_edges_per_s": st.flux_edges / st.wall_flux_edge, "wall_s": st.wall_total,
+            "kind": label, "lib": kind, "cores": used}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mesh", default="m6")
+    ap.add_argument("--variant", default="owner", choices=["owner", "colour", "atomic"])
+    ap.add_argument("--exact", action="store_true")
+    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--cpu-cycles", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    pkg = ge.load_package()
+    mesh = pkg.meshgen.make_multigrid(args.mesh)
+    levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
+    sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
+    workload = (f"{args.mesh}: {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
+                f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
+    config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
+              "arith": "exact" if args.exact else "fast",
+              "l2": "no flush between steps: the V-cycle working set (~%d MB) exceeds the 126 MB L2"
+                    % (sum(300 * s[0] + 32 * s[1] for s in sizes) // 2**20)}
+    nthreads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        perms, orders = hilbert_orders(levels0)
+        ordered = reorder_for_cpu(levels0, perms, orders)
+        r = cpu_run(ordered, args.steps, args.warmup, nthreads)
+        sample = f"{args.steps} full V-cycles of the same deck (locality-renumbered), OpenMP block-coloured, {r['lib']}"
+        line = {"impl": "reference", "metric": "mg_cycle_flux_edges_per_s", "value": r["edges_per_s"], "unit": "edges/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["wall_s"] / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "mg_cycles_per_s": r["cycles_per_s"],
+                "cpu_baseline": {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+                "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,
+                    flux_variant=args.variant, exact_arith=args.exact, owner_chunk_nodes=args.chunk)
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up (also builds the flux plans)
+    gpu.run_cycles(args.warmup)
+    # timed region: K cycles, flux-edge launches individually event-timed on the same stream
+    gpu.timers_enable(2)
+    gpu.timers_reset()
+    launches0 = gpu.kernel_launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    gpu.run_cycles(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    launches = gpu.kernel_launches() - launches0
+    flux_ms, flux_calls, flux_elems = gpu.timer("compute_flux_edge")
+    gpu.timers_enable(0)
+
+    edges_step = flux_edges_per_cycle(sizes)
+    value = world * edges_step * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    flux_bytes = flux_bytes_per_cycle(sizes) * args.steps
+    achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"compute_flux_edge_kernel[{args.variant}]", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch_L0": 32 * sizes[0][1] + 120 * sizes[0][0],
+                "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
+                "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms,
+                "note": "deck levels are L2-resident sized (L0 flux loop touches ~66 MB); see config.l2"}
+
+    # end-to-end through the C-ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host_vars = [gpu.fetch(l, "variables") for l in range(len(sizes))]
+        n_e2e = max(3, min(args.steps, 10))
+        for it in range(2 + n_e2e):
+            if it == 2:
+                barrier()
+                t0 = time.perf_counter()
+            for l in range(len(sizes)):
+                gpu.set(l, "variables", host_vars[l])
+            gpu.run_cycles(1)
+            host_vars = [gpu.fetch(l, "variables") for l in range(len(sizes))]
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        nbytes = sum(s[0] * 40 for s in sizes)
+        e2e = {"value": world * edges_step * n_e2e / dt, "unit": "edges/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "what": "per step: mgcfd_set_dat(variables) for every level from host arrays, mgcfd_run_cycles(1), "
+                       "mgcfd_fetch_dat(variables) for every level"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        perms = [gpu.plan_query(l, "node_perm") for l in range(len(sizes))]
+        orders = [gpu.plan_query(l, "edge_order") for l in range(len(sizes))]
+        r = cpu_run(reorder_for_cpu(levels0, perms, orders), args.cpu_cycles, 1, nthreads)
+        cpu = {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{args.cpu_cycles} full V-cycles (+1 warm-up) of the same deck with the GPU run's node/edge ordering, "
+                         f"{r['lib']}, OpenMP block-coloured; flux kernel alone {r['flux_kernel_edges_per_s']:.3e} edges/s",
+               "mg_cycles_per_s": r["cycles_per_s"]}
+    gpu.close()
+    if rank == 0:
+        line = {"metric": "mg_cycle_flux_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "mg_cycles_per_s": world * args.steps / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

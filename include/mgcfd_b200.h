@@ -160,7 +160,8 @@ int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master_variabl
 long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out, long long capacity);
 
 /* ---- measurement hooks ---- */
-/* per-call-site device timers (CUDA events on the context's stream), off by default */
+/* per-call-site device timers (CUDA events on the context's stream): 0 off (default), 1 every call site,
+ * 2 compute_flux_edge launches only */
 int  mgcfd_timers_enable(mgcfd_ctx *ctx, int on);
 int  mgcfd_timers_reset(mgcfd_ctx *ctx);
 /* accumulated milliseconds / launch count / element count of a call site ("compute_flux_edge", ...) */

@@ -273,8 +273,13 @@ class MGCFD:
         return rms, min_dt
 
     # ---- data access (file order)
+    def _level(self, l):
+        if not 0 <= l < self.n_levels:
+            raise MgcfdError(-1, "level out of range")
+        return self.sizes[l]
+
     def fetch(self, l, name):
-        n, e, b = self.sizes[l]
+        n, e, b = self._level(l)
         if name == "edge_weights":
             out = np.empty((e, 3))
         elif name == "bnd_node_weights":
@@ -282,12 +287,15 @@ class MGCFD:
         elif name == "up_scratch":
             out = np.empty(n, dtype=np.int32)
         else:
+            if name not in _DAT_DIMS:
+                raise MgcfdError(-1, f"unknown dat '{name}'")
             d = _DAT_DIMS[name]
             out = np.empty((n, d) if d > 1 else n)
         self._ck(self.lib.mgcfd_fetch_dat(self.ctx, l, name.encode(), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def set(self, l, name, arr):
+        self._level(l)
         dt = np.int32 if name == "up_scratch" else np.float64
         a = _as(arr, dt)
         self._ck(self.lib.mgcfd_set_dat(self.ctx, l, name.encode(), a.ctypes.data_as(C.c_void_p)))

@@ -31,7 +31,14 @@ static std::string g_create_error;
     } while (0)
 
 #define CHECK_LEVEL(l) REQUIRE(ctx && (l) >= 0 && (l) < ctx->n_levels, "level out of range")
-#define CHECK_PLANNED() REQUIRE(ctx->planned, "mgcfd_plan() has not been called")
+#define CHECK_PLANNED()                                                                                  \
+    do {                                                                                                 \
+        REQUIRE(ctx->planned, "mgcfd_plan() has not been called");                                       \
+        if (ctx->device < 0) {                                                                           \
+            ctx->err = "planning-only context (device -1): compute entry points need a CUDA device";     \
+            return MGCFD_ERR_NODEVICE;                                                                   \
+        }                                                                                                \
+    } while (0)
 
 static int check_launch(mgcfd_ctx *ctx, const char *what)
 {
@@ -102,6 +109,7 @@ struct LoopScope {
     LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
     {
         if (!ctx->timers_on) return;
+        if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0) return;   // flux-edge launches only
         t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
         e0 = get_event(ctx);
         e1 = get_event(ctx);
@@ -161,6 +169,19 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
         return MGCFD_ERR_ARG;
     }
     *out = nullptr;
+    if (device == -1) {
+        // planning-only context: host planner + plan_query, no device, no compute (index-set tests on CPU boxes)
+        mgcfd_ctx *ctx = new mgcfd_ctx();
+        ctx->device = -1;
+        ctx->n_levels = n_levels;
+        if (opt) ctx->opt = *opt; else mgcfd_default_options(&ctx->opt);
+        if (ctx->opt.owner_chunk_nodes <= 0) ctx->opt.owner_chunk_nodes = 256;
+        if (ctx->opt.colour_block_edges <= 0 || ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
+        ctx->H.resize(n_levels);
+        ctx->D.resize(n_levels);
+        *out = ctx;
+        return MGCFD_OK;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -220,6 +241,7 @@ static void free_level(LevelDev &d)
 void mgcfd_destroy(mgcfd_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &d : ctx->D) free_level(d);
@@ -348,12 +370,13 @@ int mgcfd_plan(mgcfd_ctx *ctx)
 {
     REQUIRE(ctx, "null ctx");
     REQUIRE(ctx->have_consts, "mgcfd_decl_consts() must precede mgcfd_plan()");
-    CK(cudaSetDevice(ctx->device));
     for (int l = 0; l < ctx->n_levels; l++) {
         LevelHost &L = ctx->H[l];
         if (l + 1 < ctx->n_levels) REQUIRE((int)L.mg.size() == L.n_nodes, "node-->mg_node missing on a non-coarsest level");
         plan_renumber(L, ctx->opt.renumber != 0);
     }
+    if (ctx->device < 0) { ctx->planned = true; return MGCFD_OK; }
+    CK(cudaSetDevice(ctx->device));
     for (int l = 0; l < ctx->n_levels; l++) {
         LevelHost &L = ctx->H[l];
         LevelDev &D = ctx->D[l];
@@ -473,21 +496,28 @@ static int ensure_colour(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
+static int build_owner_host(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    if (L.have_owner) return MGCFD_OK;
+    int nb = ctx->opt.owner_chunk_nodes;
+    // caps on local nodes and edges bound the shared-memory footprint (DESIGN.md "owner chunk sizing")
+    int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
+    std::string err;
+    if (!plan_owner(L, nb, max_loc, max_edges, err)) {
+        ctx->err = err;
+        return MGCFD_ERR_PLAN;
+    }
+    return MGCFD_OK;
+}
+
 static int ensure_owner(mgcfd_ctx *ctx, int level)
 {
     LevelHost &L = ctx->H[level];
     LevelDev &D = ctx->D[level];
     if (D.owner.valid) return MGCFD_OK;
-    if (!L.have_owner) {
-        int nb = ctx->opt.owner_chunk_nodes;
-        // caps sized so that the fast build keeps >= 2 CTAs per SM (DESIGN.md "owner chunk sizing")
-        int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
-        std::string err;
-        if (!plan_owner(L, nb, max_loc, max_edges, err)) {
-            ctx->err = err;
-            return MGCFD_ERR_PLAN;
-        }
-    }
+    int rc0 = build_owner_host(ctx, level);
+    if (rc0) return rc0;
     OwnerPlanHost &O = L.owner;
     if (flux_owner_smem_bytes(O.max_loc, O.max_edges, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
@@ -1036,7 +1066,7 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
         return emit(v, out, cap);
     }
     if (s.rfind("owner_", 0) == 0) {
-        if (!L.have_owner && ensure_owner(ctx, level)) return MGCFD_ERR_PLAN;
+        if (build_owner_host(ctx, level)) return MGCFD_ERR_PLAN;
         OwnerPlanHost &O = L.owner;
         if (s == "owner_chunk_start") return emit(O.node0, out, cap);
         if (s == "owner_halo_off") return emit(O.halo_off, out, cap);
@@ -1056,7 +1086,7 @@ int mgcfd_timers_enable(mgcfd_ctx *ctx, int on)
 {
     REQUIRE(ctx, "null ctx");
     if (!on && ctx->timers_on) timers_collect(ctx);
-    ctx->timers_on = on != 0;
+    ctx->timers_on = on;
     return MGCFD_OK;
 }
 

@@ -157,7 +157,7 @@ struct mgcfd_ctx {
     int *d_flags = nullptr;          // [0]=bad value count, [1]=min_dt<0 flag, [2]=validate count
     double *h_pinned = nullptr;      // pinned host scratch (8 doubles)
     long long launches = 0;
-    bool timers_on = false;
+    int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only
     std::map<std::string, mgcfd::LoopTimer> timers;
     std::vector<cudaEvent_t> event_pool;
 };

@@ -53,6 +53,17 @@ def test_no_cpu_fallback(pkg):
     assert ei.value.code == -3
 
 
+def test_planning_only_context_refuses_compute(pkg):
+    mesh = pkg.meshgen.make_multigrid("tiny")
+    with pkg.MGCFD(mesh["levels"], device=-1, init=False) as ctx:
+        assert ctx.plan_query(0, "node_perm").size == mesh["levels"][0]["node_coordinates"].shape[0]
+        for call in (lambda: ctx.compute_flux_edge(0), lambda: ctx.run_cycles(1), lambda: ctx.fetch(0, "variables"),
+                     lambda: ctx.time_step(0, 0), lambda: ctx.init_loops()):
+            with pytest.raises(pkg.MgcfdError) as ei:
+                call()
+            assert ei.value.code == -3
+
+
 def test_product_never_imports_oracle():
     pkg_dir = os.path.join(ROOT, "mg-cfd-app-op2_b200")
     for dirpath, _, files in os.walk(pkg_dir):
