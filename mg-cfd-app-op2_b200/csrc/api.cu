@@ -519,7 +519,7 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     int rc0 = build_owner_host(ctx, level);
     if (rc0) return rc0;
     OwnerPlanHost &O = L.owner;
-    if (flux_owner_smem_bytes(O.max_loc, O.max_edges, ctx->opt.exact_arith != 0) > 227 * 1024) {
+    if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
         return MGCFD_ERR_PLAN;
     }
@@ -534,8 +534,8 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         d.n_edges = O.n_edges[k];
         d.e_pad = (d.n_edges + 3) & ~3;
         d.n_inc = O.n_inc[k];
-        d.pad_ = 0;
         d.blob_off = O.blob_off[k];
+        d.blob_bytes = (int)(O.blob_off[k + 1] - O.blob_off[k]);
         unsigned char *base = blob.data() + d.blob_off;
         double *w0 = reinterpret_cast<double *>(base), *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *g = w2 + d.e_pad;
         uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);

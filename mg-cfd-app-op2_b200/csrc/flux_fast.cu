@@ -17,6 +17,6 @@ int fast_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *b
     return fast::launch_bnd(s, n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c);
 }
 std::string fast_configure() { return fast::configure(); }
-size_t fast_owner_smem(int max_loc, int max_edges) { return fast::owner_smem(max_loc, max_edges, false); }
+size_t fast_owner_smem(int max_loc, int max_edges, int max_blob) { return fast::owner_smem(max_loc, max_edges, max_blob, false); }
 size_t fast_colour_smem(int max_nodes) { return fast::colour_smem(max_nodes, false); }
 }  // namespace mgcfd

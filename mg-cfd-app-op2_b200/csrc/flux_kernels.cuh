@@ -272,79 +272,132 @@ flux_colour_kernel(int slot0, int max_nodes, int n_owned, const int *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// variant 2: owner-compute chunks.  A CTA owns a run of consecutive nodes; it stages owned + halo
-// node states in shared memory, computes every edge touching an owned node (cut edges are
-// recomputed by the neighbouring chunk), parks the per-edge fluxes in shared memory, then each
-// owned node sums its incident edges in ascending file order and stores the result: no atomics,
-// no colours, deterministic, and in the exact build bit-identical to OP2-seq.
-// shared: rec[NREC][max_loc] | F[NFLUX][max_edges]
+// variant 2: owner-compute chunks.  A CTA owns a run of consecutive nodes.
+//   1. one thread arms an mbarrier and issues ONE bulk async copy (cp.async.bulk, the TMA 1-D path)
+//      of the chunk's contiguous blob -- edge weights, block-local endpoints, incidence CSR -- into
+//      shared memory; meanwhile all threads stage owned + halo node states (SoA, derived quantities
+//      once per node);
+//   2. one thread per edge (cut edges are recomputed by the neighbouring chunk) turns its weights
+//      in place into the edge's flux vector;
+//   3. one thread per owned node sums its incident edges in ascending file order and stores the
+//      result: no atomics, no colours, deterministic, and in the exact build bit-identical to OP2-seq.
+// shared: mbarrier | blob (w0 w1 w2 g [e_pad] doubles, lab [e_pad] u32, rowptr, csr u16) |
+//         extra flux planes [NFL-4][max_edges] | rec[NREC][max_loc]
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+template <bool STREAM>
+__device__ __forceinline__ void stage_node(const double *__restrict__ var, int gid, double *rec, int stride, int i)
+{
+    double u[5];
+    load5(var + (size_t)gid * 5, u);
+#ifdef MGCFD_EXACT
+#pragma unroll
+    for (int f = 0; f < 5; f++) rec[f * stride + i] = u[f];
+#else
+    if (STREAM) {
+#pragma unroll
+        for (int f = 0; f < 5; f++) rec[f * stride + i] = u[f];
+    } else {
+        double r[8];
+        derive(u, r);
+#pragma unroll
+        for (int f = 0; f < 8; f++) rec[f * stride + i] = r[f];
+    }
+#endif
+}
+
 template <bool STREAM, bool OVERWRITE>
 __global__ void __launch_bounds__(256)
-flux_owner_kernel(int max_loc, int max_edges, const OwnerChunkDesc *__restrict__ descs,
+flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
                   const int *__restrict__ halo_gid, const unsigned char *__restrict__ blob,
                   const double *__restrict__ var, double *__restrict__ flux)
 {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int NREC = STREAM ? 5 : NF;
     constexpr int NFL = STREAM ? 10 : NFLUX;
-    double *rec = sm;
-    double *F = sm + (size_t)NREC * max_loc;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+    unsigned char *sblob = smraw + 16;
+    double *Fx = reinterpret_cast<double *>(sblob + max_blob);          // flux planes 4..NFL-1
+    double *rec = Fx + (size_t)(NFL - 4) * max_edges;
     const OwnerChunkDesc d = descs[blockIdx.x];
     const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
 
-    for (int i = tid; i < nloc; i += blockDim.x) {
-        int gid = i < d.n_own ? d.node0 + i : halo_gid[d.halo_off + i - d.n_own];
-        double u[5];
-        load5(var + (size_t)gid * 5, u);
-#ifdef MGCFD_EXACT
-#pragma unroll
-        for (int f = 0; f < 5; f++) rec[f * max_loc + i] = u[f];
-#else
-        if (STREAM) {
-#pragma unroll
-            for (int f = 0; f < 5; f++) rec[f * max_loc + i] = u[f];
-        } else {
-            double r[8];
-            derive(u, r);
-#pragma unroll
-            for (int f = 0; f < 8; f++) rec[f * max_loc + i] = r[f];
-        }
-#endif
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)d.blob_bytes);
+        bulk_g2s(sblob, blob + d.blob_off, (uint32_t)d.blob_bytes, bar);
     }
-    __syncthreads();
+    // node states: two nodes per thread in flight
+    for (int base = 0; base < nloc; base += 2 * blockDim.x) {
+        int i0 = base + tid, i1 = i0 + blockDim.x;
+        int g0 = -1, g1 = -1;
+        if (i0 < nloc) g0 = i0 < d.n_own ? d.node0 + i0 : __ldg(halo_gid + d.halo_off + i0 - d.n_own);
+        if (i1 < nloc) g1 = i1 < d.n_own ? d.node0 + i1 : __ldg(halo_gid + d.halo_off + i1 - d.n_own);
+        if (g0 >= 0) stage_node<STREAM>(var, g0, rec, max_loc, i0);
+        if (g1 >= 0) stage_node<STREAM>(var, g1, rec, max_loc, i1);
+    }
+    __syncthreads();          // node states staged; mbarrier initialisation visible to all threads
+    mbar_wait(bar, 0);        // blob landed
 
-    const unsigned char *base = blob + d.blob_off;
-    const double *w0 = reinterpret_cast<const double *>(base);
-    const double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
+    double *w0 = reinterpret_cast<double *>(sblob);
+    double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
     const uint32_t *lab = reinterpret_cast<const uint32_t *>(gg + d.e_pad);
     const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + d.e_pad);
     const uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
 
     for (int e = tid; e < d.n_edges; e += blockDim.x) {
-        uint32_t l = __ldg(lab + e);
+        uint32_t l = lab[e];
         int la = l & 0xffff, lb = l >> 16;
-        double x = __ldg(w0 + e), y = __ldg(w1 + e), z = __ldg(w2 + e), g = __ldg(gg + e);
+        double x = w0[e], y = w1[e], z = w2[e], g = gg[e];
         double a[NREC], b[NREC];
 #pragma unroll
         for (int f = 0; f < NREC; f++) { a[f] = rec[f * max_loc + la]; b[f] = rec[f * max_loc + lb]; }
+        double fa[5], fb[5];
         if (STREAM) {
-            double fa[5], fb[5];
             stream_flux(a, b, x, y, z, fa, fb);
-#pragma unroll
-            for (int v = 0; v < 5; v++) { F[v * max_edges + e] = fa[v]; F[(5 + v) * max_edges + e] = fb[v]; }
         } else {
 #ifdef MGCFD_EXACT
-            double fa[5], fb[5];
             edge_flux(a, b, x, y, z, g, fa, fb);
-#pragma unroll
-            for (int v = 0; v < 5; v++) { F[v * max_edges + e] = fa[v]; F[(5 + v) * max_edges + e] = fb[v]; }
 #else
-            double fa[5];
             edge_flux(a, b, x, y, z, g, fa);
-#pragma unroll
-            for (int v = 0; v < 5; v++) F[v * max_edges + e] = fa[v];
 #endif
+        }
+        // the edge's weights are dead now: its flux vector takes their place (slot e is private to this thread)
+        w0[e] = fa[0]; w1[e] = fa[1]; w2[e] = fa[2]; gg[e] = fa[3];
+        Fx[e] = fa[4];
+        if (NFL == 10) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) Fx[(1 + v) * max_edges + e] = fb[v];
         }
     }
     __syncthreads();
@@ -360,15 +413,19 @@ flux_owner_kernel(int max_loc, int max_edges, const OwnerChunkDesc *__restrict__
             int e = c & 0x7fff;
             bool is_b = c & 0x8000;
             if (NFL == 10) {
-                int off = is_b ? 5 : 0;
+                if (is_b) {
 #pragma unroll
-                for (int v = 0; v < 5; v++) acc[v] += F[(off + v) * max_edges + e];
-            } else {
-#pragma unroll
-                for (int v = 0; v < 5; v++) {
-                    double f = F[v * max_edges + e];
-                    acc[v] += is_b ? -f : f;
+                    for (int v = 0; v < 5; v++) acc[v] += Fx[(1 + v) * max_edges + e];
+                } else {
+                    acc[0] += w0[e]; acc[1] += w1[e]; acc[2] += w2[e]; acc[3] += gg[e]; acc[4] += Fx[e];
                 }
+            } else {
+                double f0 = w0[e], f1 = w1[e], f2 = w2[e], f3 = gg[e], f4 = Fx[e];
+                acc[0] += is_b ? -f0 : f0;
+                acc[1] += is_b ? -f1 : f1;
+                acc[2] += is_b ? -f2 : f2;
+                acc[3] += is_b ? -f3 : f3;
+                acc[4] += is_b ? -f4 : f4;
             }
         }
 #pragma unroll
@@ -441,9 +498,10 @@ inline int launch_bnd(cudaStream_t s, int n_unique, const int *bu_node, const in
 // launchers
 // ------------------------------------------------------------------------------------------
 inline size_t colour_smem(int max_nodes, bool stream) { return (size_t)((stream ? 5 : NF) + 5) * max_nodes * sizeof(double); }
-inline size_t owner_smem(int max_loc, int max_edges, bool stream)
+inline size_t owner_smem(int max_loc, int max_edges, int max_blob, bool stream)
 {
-    return ((size_t)(stream ? 5 : NF) * max_loc + (size_t)(stream ? 10 : NFLUX) * max_edges) * sizeof(double);
+    return 16 + (size_t)max_blob +
+           ((size_t)(stream ? 5 : NF) * max_loc + (size_t)((stream ? 10 : NFLUX) - 4) * max_edges) * sizeof(double);
 }
 
 inline int launch_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p)
@@ -478,13 +536,13 @@ inline int launch_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev 
 inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h)
 {
     if (h.n_chunks == 0) return 0;
-    size_t smem = owner_smem(h.max_loc, h.max_edges, a.stream_kernel);
+    size_t smem = owner_smem(h.max_loc, h.max_edges, h.max_blob, a.stream_kernel);
     if (a.stream_kernel)
-        flux_owner_kernel<true, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<true, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
     else if (a.overwrite)
-        flux_owner_kernel<false, true><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<false, true><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
     else
-        flux_owner_kernel<false, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<false, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
     return 1;
 }
 

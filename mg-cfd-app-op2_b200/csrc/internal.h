@@ -55,7 +55,7 @@ struct OwnerPlanHost {
     std::vector<int> rowptr_off;      // [n_chunks+1]
     std::vector<uint16_t> csr;        // per chunk n_inc entries: local edge | (is_b << 15)
     std::vector<int> csr_off;         // [n_chunks+1]
-    int max_loc = 0, max_edges = 0, max_own = 0, max_inc = 0;
+    int max_loc = 0, max_edges = 0, max_own = 0, max_inc = 0, max_blob = 0;
     long long total_edges = 0;
 };
 
@@ -103,7 +103,7 @@ struct ColourPlanDev {
 
 struct OwnerChunkDesc {         // one per chunk, read by the kernel
     int node0, n_own, n_halo, halo_off;
-    int n_edges, e_pad, n_inc, pad_;
+    int n_edges, e_pad, n_inc, blob_bytes;
     long long blob_off;
 };
 
@@ -204,7 +204,7 @@ int fast_flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, co
 int fast_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
                   const double *b_wt, const double *var, double *flux, const DevConsts &c);
 std::string fast_configure();
-size_t flux_owner_smem_bytes(int max_loc, int max_edges, bool exact);
+size_t flux_owner_smem_bytes(int max_loc, int max_edges, int max_blob, bool exact);
 size_t flux_colour_smem_bytes(int max_nodes, bool exact);
 
 }  // namespace mgcfd

@@ -8,7 +8,7 @@
 
 namespace mgcfd {
 
-size_t fast_owner_smem(int max_loc, int max_edges);
+size_t fast_owner_smem(int max_loc, int max_edges, int max_blob);
 size_t fast_colour_smem(int max_nodes);
 
 namespace {
@@ -382,10 +382,10 @@ std::string flux_configure()
     if (!e.empty()) return e;
     return fast_configure();
 }
-size_t flux_owner_smem_bytes(int max_loc, int max_edges, bool exact_mode)
+size_t flux_owner_smem_bytes(int max_loc, int max_edges, int max_blob, bool exact_mode)
 {
-    size_t stream = exact::owner_smem(max_loc, max_edges, true);
-    size_t body = exact_mode ? exact::owner_smem(max_loc, max_edges, false) : fast_owner_smem(max_loc, max_edges);
+    size_t stream = exact::owner_smem(max_loc, max_edges, max_blob, true);
+    size_t body = exact_mode ? exact::owner_smem(max_loc, max_edges, max_blob, false) : fast_owner_smem(max_loc, max_edges, max_blob);
     return stream > body ? stream : body;
 }
 size_t flux_colour_smem_bytes(int max_nodes, bool exact_mode)

@@ -316,6 +316,7 @@ bool plan_owner(LevelHost &L, int max_own, int max_loc, int max_edges, std::stri
         bytes += (((long long)(n_own + 1) * 2 + 15) & ~15ll);
         bytes += (((long long)ninc * 2 + 15) & ~15ll);
         blob += bytes;
+        O.max_blob = std::max(O.max_blob, (int)bytes);
         O.max_loc = std::max(O.max_loc, nloc);
         O.max_edges = std::max(O.max_edges, e_pad);
         O.max_own = std::max(O.max_own, n_own);
