@@ -51,7 +51,10 @@ enum {
                                   thread-colour-ordered shared accumulation, block-colour-ordered launches */
     MGCFD_FLUX_OWNER = 2,      /* owner-compute node chunks: cut edges recomputed, per-edge fluxes staged in
                                   shared memory, gathered per owned node, plain coalesced stores (default) */
-    MGCFD_FLUX_NVARIANTS = 3
+    MGCFD_FLUX_GATHER = 3,     /* node gather over the same owner chunks: one thread per owned node evaluates its
+                                  incident edges from its own side (interior edges twice), rows in sliced-ELL
+                                  layout streamed coalesced, neighbour states gathered from shared memory */
+    MGCFD_FLUX_NVARIANTS = 4
 };
 
 typedef struct mgcfd_ctx mgcfd_ctx;
@@ -148,6 +151,10 @@ int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles);
 int mgcfd_fetch_dat(mgcfd_ctx *ctx, int level, const char *name, void *host_out);
 int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_in);   /* tests / restart */
 int mgcfd_sync(mgcfd_ctx *ctx);                                                        /* cudaStreamSynchronize */
+/* page-locked host buffers: fetch/set move them with one DMA (pageable buffers bounce through an internal
+ * pinned buffer).  OP2 has no counterpart; euler3d.cpp never touches dat storage directly. */
+int  mgcfd_host_alloc(void **out, size_t bytes);
+void mgcfd_host_free(void *p);
 
 /* ---- -v validation path, euler3d.cpp:662-716 (identify_differences + count_non_zeros on device) ---- */
 int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master_variables, int *n_differences);

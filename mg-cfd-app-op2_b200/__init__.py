@@ -6,4 +6,4 @@ level-file layout), host/ (native euler3d driver).  Nothing here imports oracle/
 """
 from . import meshgen  # noqa: F401
 from . import capi  # noqa: F401
-from .capi import MGCFD, MgcfdError, load_library, farfield_consts  # noqa: F401
+from .capi import MGCFD, MgcfdError, PinnedArray, load_library, farfield_consts  # noqa: F401

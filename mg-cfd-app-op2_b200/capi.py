@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmgcfd_b200.so")
 
 NVAR, NDIM, RK = 5, 3, 3
-FLUX_ATOMIC, FLUX_COLOUR, FLUX_OWNER = 0, 1, 2
-FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWNER}
+FLUX_ATOMIC, FLUX_COLOUR, FLUX_OWNER, FLUX_GATHER = 0, 1, 2, 3
+FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWNER, "gather": FLUX_GATHER}
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NODEVICE", -4: "ERR_MIN_DT",
              -5: "ERR_BAD_VALS", -6: "ERR_PLAN"}
@@ -76,6 +76,8 @@ def load_library():
     lib.mgcfd_stream.argtypes = [C.c_void_p]
     lib.mgcfd_device_ptr.restype = C.c_void_p
     lib.mgcfd_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.mgcfd_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.mgcfd_host_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -93,6 +95,7 @@ ABI_SYMBOLS = [
     "mgcfd_run_cycles", "mgcfd_fetch_dat", "mgcfd_set_dat", "mgcfd_sync", "mgcfd_validate_level",
     "mgcfd_plan_query", "mgcfd_timers_enable", "mgcfd_timers_reset", "mgcfd_timers_get",
     "mgcfd_kernel_launches", "mgcfd_set_flux_variant", "mgcfd_stream", "mgcfd_device_ptr",
+    "mgcfd_host_alloc", "mgcfd_host_free",
 ]
 
 _DAT_DIMS = {"variables": 5, "old_variables": 5, "residuals": 5, "fluxes": 5, "dummy_fluxes": 5,
@@ -109,6 +112,25 @@ def farfield_consts(mesh_name=0):
 
 def _as(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PinnedArray:
+    """float64 numpy view of a page-locked host buffer (mgcfd_host_alloc); fetch/set DMA it directly."""
+
+    def __init__(self, shape):
+        lib = load_library()
+        self.ptr = C.c_void_p()
+        n = int(np.prod(shape))
+        rc = lib.mgcfd_host_alloc(C.byref(self.ptr), n * 8)
+        if rc != 0:
+            raise MgcfdError(rc, lib.mgcfd_last_error(None).decode())
+        self.array = np.ctypeslib.as_array((C.c_double * n).from_address(self.ptr.value)).reshape(shape)
+
+    def free(self):
+        if self.ptr and self.ptr.value:
+            self.array = None
+            load_library().mgcfd_host_free(self.ptr)
+            self.ptr = C.c_void_p()
 
 
 class MGCFD:
@@ -277,6 +299,13 @@ class MGCFD:
         if not 0 <= l < self.n_levels:
             raise MgcfdError(-1, "level out of range")
         return self.sizes[l]
+
+    def fetch_into(self, l, name, out):
+        """fetch into a caller-provided C-contiguous float64 array (e.g. a PinnedArray.array)"""
+        self._level(l)
+        assert out.flags["C_CONTIGUOUS"] and out.dtype == np.float64
+        self._ck(self.lib.mgcfd_fetch_dat(self.ctx, l, name.encode(), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def fetch(self, l, name):
         n, e, b = self._level(l)

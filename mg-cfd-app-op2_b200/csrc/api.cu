@@ -176,6 +176,7 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
         ctx->n_levels = n_levels;
         if (opt) ctx->opt = *opt; else mgcfd_default_options(&ctx->opt);
         if (ctx->opt.owner_chunk_nodes <= 0) ctx->opt.owner_chunk_nodes = 256;
+        ctx->opt.owner_chunk_nodes = std::max(2, ctx->opt.owner_chunk_nodes & ~1);
         if (ctx->opt.colour_block_edges <= 0 || ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
         ctx->H.resize(n_levels);
         ctx->D.resize(n_levels);
@@ -202,6 +203,7 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     ctx->n_levels = n_levels;
     if (opt) ctx->opt = *opt; else mgcfd_default_options(&ctx->opt);
     if (ctx->opt.owner_chunk_nodes <= 0) ctx->opt.owner_chunk_nodes = 256;
+    ctx->opt.owner_chunk_nodes = std::max(2, ctx->opt.owner_chunk_nodes & ~1);   // chunks own an even number of nodes
     if (ctx->opt.colour_block_edges <= 0) ctx->opt.colour_block_edges = 256;
     if (ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
     ctx->H.resize(n_levels);
@@ -230,9 +232,10 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
 static void free_level(LevelDev &d)
 {
     void *ptrs[] = {d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
-                    d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.atomic.nodes, d.atomic.w,
+                    d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.perm, d.atomic.nodes, d.atomic.w,
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
-                    d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob};
+                    d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.gather.desc, d.gather.halo_gid,
+                    d.gather.row_node, d.gather.row_deg, d.gather.ent, d.gather.w0, d.gather.w1, d.gather.w2, d.gather.g};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     d = LevelDev();
@@ -252,6 +255,8 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     if (ctx->d_rms) cudaFree(ctx->d_rms);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -288,7 +293,7 @@ int mgcfd_decl_consts(mgcfd_ctx *ctx, const mgcfd_consts *c)
     REQUIRE(ctx && c, "null argument");
     ctx->consts = *c;
     ctx->have_consts = true;
-    for (auto &d : ctx->D) d.atomic.valid = d.colour.valid = d.owner.valid = false;   // g depends on smoothing
+    for (auto &d : ctx->D) d.atomic.valid = d.colour.valid = d.owner.valid = d.gather.valid = false;   // g depends on smoothing
     return MGCFD_OK;
 }
 
@@ -355,15 +360,63 @@ static int upload_bnd(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
+// ---- host <-> device transfers of node dats in FILE order -------------------------------------------
+// The copy itself is one DMA between (pinned) host memory and a device staging buffer; the permutation
+// between file order and internal order runs on the device.  Caller buffers that are already pinned
+// (mgcfd_host_alloc / cudaHostRegister) are used directly, pageable ones go through a pinned bounce buffer.
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int ensure_staging(mgcfd_ctx *ctx, size_t bytes, bool need_pinned)
+{
+    if (ctx->d_stage_bytes < bytes) {
+        if (ctx->d_stage) cudaFree(ctx->d_stage);
+        ctx->d_stage = nullptr; ctx->d_stage_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stage, bytes));
+        ctx->d_stage_bytes = bytes;
+    }
+    if (need_pinned && ctx->h_stage_bytes < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+        CK(cudaMallocHost(&ctx->h_stage, bytes));
+        ctx->h_stage_bytes = bytes;
+    }
+    return MGCFD_OK;
+}
+
 static int upload_node_dat(mgcfd_ctx *ctx, int level, double *dst, const double *src_file_order, int dim)
 {
     LevelHost &L = ctx->H[level];
-    std::vector<double> tmp((size_t)L.n_nodes * dim);
-    for (int i = 0; i < L.n_nodes; i++)
-        for (int d = 0; d < dim; d++) tmp[(size_t)L.new_of_old[i] * dim + d] = src_file_order[(size_t)i * dim + d];
-    CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t bytes = (size_t)L.n_nodes * dim * sizeof(double);
+    if (bytes == 0) return MGCFD_OK;
+    const bool pinned = is_pinned(src_file_order);
+    int rc = ensure_staging(ctx, bytes, !pinned);
+    if (rc) return rc;
+    const void *src = src_file_order;
+    if (!pinned) { memcpy(ctx->h_stage, src_file_order, bytes); src = ctx->h_stage; }
+    CK(cudaMemcpyAsync(ctx->d_stage, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += k_permute_rows(ctx->stream, L.n_nodes, dim, static_cast<const double *>(ctx->d_stage), ctx->D[level].perm, dst, true);
     CK(cudaStreamSynchronize(ctx->stream));
-    return MGCFD_OK;
+    return check_launch(ctx, "permute_rows");
+}
+
+static int download_node_dat(mgcfd_ctx *ctx, int level, const double *src, double *dst_file_order, int dim)
+{
+    LevelHost &L = ctx->H[level];
+    const size_t bytes = (size_t)L.n_nodes * dim * sizeof(double);
+    if (bytes == 0) return MGCFD_OK;
+    const bool pinned = is_pinned(dst_file_order);
+    int rc = ensure_staging(ctx, bytes, !pinned);
+    if (rc) return rc;
+    ctx->launches += k_permute_rows(ctx->stream, L.n_nodes, dim, src, ctx->D[level].perm, static_cast<double *>(ctx->d_stage), false);
+    CK(cudaMemcpyAsync(pinned ? (void *)dst_file_order : ctx->h_stage, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!pinned) memcpy(dst_file_order, ctx->h_stage, bytes);
+    return check_launch(ctx, "permute_rows");
 }
 
 int mgcfd_plan(mgcfd_ctx *ctx)
@@ -392,6 +445,7 @@ int mgcfd_plan(mgcfd_ctx *ctx)
         if ((rc = dev_alloc(ctx, &D.coords, n * 3))) return rc;
         if ((rc = dev_alloc(ctx, &D.up_count, n))) return rc;
         D.flux_is_zero = true;
+        if ((rc = dev_upload(ctx, &D.perm, L.new_of_old))) return rc;
         if ((rc = upload_node_dat(ctx, l, D.coords, L.coords.data(), 3))) return rc;
         if ((rc = upload_bnd(ctx, l))) return rc;
         if (l + 1 < ctx->n_levels) {
@@ -519,6 +573,10 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     int rc0 = build_owner_host(ctx, level);
     if (rc0) return rc0;
     OwnerPlanHost &O = L.owner;
+    if (O.max_own > 256 || O.max_loc > 768) {
+        ctx->err = "owner variant needs owner_chunk_nodes <= 256";
+        return MGCFD_ERR_PLAN;
+    }
     if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
         return MGCFD_ERR_PLAN;
@@ -559,9 +617,89 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
+// sliced-ELL re-layout of the owner chunks for the node-gather variant
+static int ensure_gather(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    if (D.gather.valid) return MGCFD_OK;
+    int rc0 = build_owner_host(ctx, level);
+    if (rc0) return rc0;
+    OwnerPlanHost &O = L.owner;
+    if (O.max_own > 256) { ctx->err = "gather variant needs owner_chunk_nodes <= 256"; return MGCFD_ERR_PLAN; }
+    if (flux_gather_smem_bytes(O.max_loc, ctx->opt.exact_arith != 0) > 227 * 1024) {
+        ctx->err = "gather chunk does not fit in shared memory";
+        return MGCFD_ERR_PLAN;
+    }
+    const bool exact = ctx->opt.exact_arith != 0;
+    std::vector<GatherChunkDesc> desc(O.n_chunks);
+    std::vector<uint16_t> row_node((size_t)O.n_chunks * 256, 0xffff), row_deg((size_t)O.n_chunks * 256, 0);
+    std::vector<uint32_t> ent;
+    std::vector<double> w0, w1, w2, g;
+    std::vector<int> order;
+    for (int k = 0; k < O.n_chunks; k++) {
+        GatherChunkDesc &d = desc[k];
+        d.node0 = O.node0[k];
+        d.n_own = O.node0[k + 1] - O.node0[k];
+        d.n_halo = O.halo_off[k + 1] - O.halo_off[k];
+        d.halo_off = O.halo_off[k];
+        d.ent_off = (long long)ent.size();
+        const uint16_t *rowptr = &O.rowptr[O.rowptr_off[k]];
+        const uint16_t *csr = O.csr.data() + O.csr_off[k];
+        order.resize(d.n_own);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            return (rowptr[x + 1] - rowptr[x]) > (rowptr[y + 1] - rowptr[y]);
+        });
+        for (int s = 0; s < 8; s++) {
+            int lo = s * 32, hi = std::min(d.n_own, lo + 32), len = 0;
+            for (int t = lo; t < hi; t++) len = std::max(len, rowptr[order[t] + 1] - rowptr[order[t]]);
+            d.slice_len[s] = (unsigned short)len;
+            size_t base = ent.size();
+            ent.resize(base + (size_t)len * 32, 0);
+            w0.resize(ent.size(), 0.0); w1.resize(ent.size(), 0.0); w2.resize(ent.size(), 0.0); g.resize(ent.size(), 0.0);
+            for (int t = lo; t < hi; t++) {
+                int node = order[t], deg = rowptr[node + 1] - rowptr[node];
+                row_node[(size_t)k * 256 + t] = (uint16_t)node;
+                row_deg[(size_t)k * 256 + t] = (uint16_t)deg;
+                for (int j = 0; j < len; j++) {
+                    size_t idx = base + (size_t)j * 32 + (t - lo);
+                    if (j >= deg) { ent[idx] = (uint32_t)node; continue; }   // padding: neighbour = self, zero weights
+                    uint16_t c = csr[rowptr[node] + j];
+                    int e = c & 0x7fff;
+                    bool is_b = (c & 0x8000) != 0;
+                    uint32_t lab = O.lab[O.edge_off[k] + e];
+                    uint32_t nb = is_b ? (lab & 0xffff) : (lab >> 16);
+                    double p[4];
+                    pack_weight(ctx, L, O.edge_file[O.edge_off[k] + e], p);
+                    // fast build: weights pre-signed so that this node is the edge's end "a" (flipping an edge
+                    // negates its weight vector and leaves |w| unchanged); exact build keeps the file orientation
+                    double sgn = (!exact && is_b) ? -1.0 : 1.0;
+                    ent[idx] = nb | (is_b ? 0x10000u : 0u);
+                    w0[idx] = sgn * p[0]; w1[idx] = sgn * p[1]; w2[idx] = sgn * p[2]; g[idx] = p[3];
+                }
+            }
+        }
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &D.gather.desc, desc))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.halo_gid, O.halo_gid))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.row_node, row_node))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.row_deg, row_deg))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.ent, ent))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.w0, w0))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.w1, w1))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.w2, w2))) return rc;
+    if ((rc = dev_upload(ctx, &D.gather.g, g))) return rc;
+    D.gather.n_ent = (long long)ent.size();
+    D.gather.valid = true;
+    return MGCFD_OK;
+}
+
 static int ensure_flux_plan(mgcfd_ctx *ctx, int level)
 {
     switch (ctx->opt.flux_variant) {
+    case MGCFD_FLUX_GATHER: return ensure_gather(ctx, level);
     case MGCFD_FLUX_ATOMIC: return ensure_atomic(ctx, level);
     case MGCFD_FLUX_COLOUR: return ensure_colour(ctx, level);
     case MGCFD_FLUX_OWNER: return ensure_owner(ctx, level);
@@ -640,7 +778,7 @@ int mgcfd_loop_calculate_cell_volumes(mgcfd_ctx *ctx, int level)
         for (int i = 0; i < 3; i++) w[i] = (d[i] / dist) * area;
         for (int i = 0; i < 3; i++) w[i] /= dist;
     }
-    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = false;
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = false;
     return upload_volumes(ctx, level, vol);
 }
 
@@ -648,7 +786,7 @@ int mgcfd_loop_dampen_ewt_edges(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();
     for (double &w : ctx->H[level].ewt) w *= 1e-7;                               // misc.h:78-84
-    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = false;
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = false;
     return MGCFD_OK;
 }
 
@@ -733,6 +871,7 @@ static int run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel)
     case MGCFD_FLUX_ATOMIC: ctx->launches += flux_atomic(ctx->stream, a, D.atomic, exact); break;
     case MGCFD_FLUX_COLOUR: ctx->launches += flux_colour(ctx->stream, a, D.colour, L.colour, exact); break;
     case MGCFD_FLUX_OWNER: ctx->launches += flux_owner(ctx->stream, a, D.owner, L.owner, exact); break;
+    case MGCFD_FLUX_GATHER: ctx->launches += flux_gather(ctx->stream, a, D.gather, L.owner.n_chunks, L.owner.max_loc, exact); break;
     }
     if (!stream_kernel) D.flux_is_zero = false;
     return check_launch(ctx, "compute_flux_edge_kernel");
@@ -970,13 +1109,7 @@ int mgcfd_fetch_dat(mgcfd_ctx *ctx, int level, const char *name, void *host_out)
     DatRef r;
     REQUIRE(find_node_dat(ctx, level, name, r), std::string("unknown dat '") + name + "'");
     REQUIRE(r.ptr, std::string("dat '") + name + "' has not been allocated");
-    std::vector<double> tmp((size_t)L.n_nodes * r.dim);
-    CK(cudaMemcpyAsync(tmp.data(), r.ptr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    double *out = static_cast<double *>(host_out);
-    for (int i = 0; i < L.n_nodes; i++)
-        for (int d = 0; d < r.dim; d++) out[(size_t)i * r.dim + d] = tmp[(size_t)L.new_of_old[i] * r.dim + d];
-    return MGCFD_OK;
+    return download_node_dat(ctx, level, r.ptr, static_cast<double *>(host_out), r.dim);
 }
 
 int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_in)
@@ -988,7 +1121,7 @@ int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_
     std::string s(name);
     if (s == "edge_weights") {
         memcpy(L.ewt.data(), host_in, L.ewt.size() * sizeof(double));
-        D.atomic.valid = D.colour.valid = D.owner.valid = false;
+        D.atomic.valid = D.colour.valid = D.owner.valid = D.gather.valid = false;
         return MGCFD_OK;
     }
     if (s == "bnd_node_weights") {
@@ -1114,6 +1247,20 @@ int mgcfd_timers_get(mgcfd_ctx *ctx, const char *loop_name, int level, double *m
     if (calls) *calls = c;
     if (elements) *elements = el;
     return MGCFD_OK;
+}
+
+int mgcfd_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return MGCFD_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return MGCFD_ERR_CUDA; }
+    return MGCFD_OK;
+}
+
+void mgcfd_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 long long mgcfd_kernel_launches(const mgcfd_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -16,6 +16,11 @@ int fast_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *b
 {
     return fast::launch_bnd(s, n_unique, bu_node, bu_ptr, b_group, b_wt, var, flux, c);
 }
+int fast_flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc)
+{
+    return fast::launch_gather(s, a, p, n_chunks, max_loc);
+}
+size_t fast_gather_smem(int max_loc) { return fast::gather_smem(max_loc, false); }
 std::string fast_configure() { return fast::configure(); }
 size_t fast_owner_smem(int max_loc, int max_edges, int max_blob) { return fast::owner_smem(max_loc, max_edges, max_blob, false); }
 size_t fast_colour_smem(int max_nodes) { return fast::colour_smem(max_nodes, false); }

@@ -282,7 +282,7 @@ flux_colour_kernel(int slot0, int max_nodes, int n_owned, const int *__restrict_
 //   3. one thread per owned node sums its incident edges in ascending file order and stores the
 //      result: no atomics, no colours, deterministic, and in the exact build bit-identical to OP2-seq.
 // shared: mbarrier | blob (w0 w1 w2 g [e_pad] doubles, lab [e_pad] u32, rowptr, csr u16) |
-//         extra flux planes [NFL-4][max_edges] | rec[NREC][max_loc]
+//         extra flux planes [NFL-4][max_edges] | raw[max_loc][5] (AoS state tile) | der[3][max_loc] (fast build)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -315,25 +315,54 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
         : "memory");
 }
 
-template <bool STREAM>
-__device__ __forceinline__ void stage_node(const double *__restrict__ var, int gid, double *rec, int stride, int i)
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
-    double u[5];
-    load5(var + (size_t)gid * 5, u);
-#ifdef MGCFD_EXACT
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// state of local node i for the edge body: conserved variables from the AoS tile, derived quantities from 3 planes
+template <int NREC>
+__device__ __forceinline__ void load_state(const double *raw, const double *der, int stride, int i, double r[NREC])
+{
 #pragma unroll
-    for (int f = 0; f < 5; f++) rec[f * stride + i] = u[f];
-#else
-    if (STREAM) {
-#pragma unroll
-        for (int f = 0; f < 5; f++) rec[f * stride + i] = u[f];
-    } else {
-        double r[8];
-        derive(u, r);
-#pragma unroll
-        for (int f = 0; f < 8; f++) rec[f * stride + i] = r[f];
+    for (int v = 0; v < 5; v++) r[v] = raw[i * 5 + v];
+    if (NREC == 8) {
+        r[5] = der[i]; r[6] = der[stride + i]; r[7] = der[2 * stride + i];
     }
-#endif
+}
+
+// Stage the conserved variables of a chunk's local nodes into the AoS tile `raw`:
+//   owned nodes: one bulk async copy (they are a contiguous run starting on an even node index, hence 16-byte
+//                aligned; a trailing odd node's last 8 bytes are copied by hand), completion on `bar`;
+//   halo nodes:  8-byte cp.async requests, four per thread in flight at a time.
+// Call with all threads; returns after this thread's cp.async requests have completed.  The caller must
+// __syncthreads() and mbar_wait(bar, 0) before reading the tile.
+__device__ __forceinline__ uint32_t owned_bulk_bytes(int n_own) { return ((uint32_t)n_own * 40u) & ~15u; }
+__device__ __forceinline__ void stage_tile(double *raw, uint64_t *bar, int node0, int n_own,
+                                           int n_halo, const int *__restrict__ hg, const double *__restrict__ var,
+                                           int tid, int nthreads)
+{
+    const uint32_t own_bytes = (uint32_t)n_own * 40u, bulk_bytes = own_bytes & ~15u;
+    if (tid == 0 && bulk_bytes) bulk_g2s(raw, var + (size_t)node0 * 5, bulk_bytes, bar);   // expect_tx armed by the caller
+    if (tid == 32 && bulk_bytes != own_bytes) raw[n_own * 5 - 1] = __ldg(var + (size_t)(node0 + n_own) * 5 - 1);
+    const int nh5 = n_halo * 5;
+    double *hraw = raw + (size_t)n_own * 5;
+    for (int base = 0; base < nh5; base += 4 * nthreads) {
+        int gid[4], f[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            f[k] = base + k * nthreads + tid;
+            gid[k] = f[k] < nh5 ? __ldg(hg + f[k] / 5) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (gid[k] >= 0) cp_async8(hraw + f[k], var + (size_t)gid[k] * 5 + (f[k] % 5));
+    }
+    cp_async_wait_all();
 }
 
 template <bool STREAM, bool OVERWRITE>
@@ -348,26 +377,34 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
     unsigned char *sblob = smraw + 16;
     double *Fx = reinterpret_cast<double *>(sblob + max_blob);          // flux planes 4..NFL-1
-    double *rec = Fx + (size_t)(NFL - 4) * max_edges;
+    double *raw = Fx + (size_t)(NFL - 4) * max_edges;                   // conserved variables, AoS [max_loc][5]
+    double *der = raw + (size_t)max_loc * 5;                            // p, |v|+c, 1/rho planes (fast build only)
     const OwnerChunkDesc d = descs[blockIdx.x];
     const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
 
+    // 1. bulk async copies (TMA 1-D) of the chunk's blob and of the owned nodes' conserved variables; 2. halo nodes
+    //    by 8-byte async copies straight into the tile
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)d.blob_bytes);
+        mbar_expect_tx(bar, (uint32_t)d.blob_bytes + owned_bulk_bytes(d.n_own));
         bulk_g2s(sblob, blob + d.blob_off, (uint32_t)d.blob_bytes, bar);
     }
-    // node states: two nodes per thread in flight
-    for (int base = 0; base < nloc; base += 2 * blockDim.x) {
-        int i0 = base + tid, i1 = i0 + blockDim.x;
-        int g0 = -1, g1 = -1;
-        if (i0 < nloc) g0 = i0 < d.n_own ? d.node0 + i0 : __ldg(halo_gid + d.halo_off + i0 - d.n_own);
-        if (i1 < nloc) g1 = i1 < d.n_own ? d.node0 + i1 : __ldg(halo_gid + d.halo_off + i1 - d.n_own);
-        if (g0 >= 0) stage_node<STREAM>(var, g0, rec, max_loc, i0);
-        if (g1 >= 0) stage_node<STREAM>(var, g1, rec, max_loc, i1);
+    stage_tile(raw, bar, d.node0, d.n_own, d.n_halo, halo_gid + d.halo_off, var, tid, blockDim.x);
+    __syncthreads();          // halo tile complete; mbarrier initialisation visible to all threads
+    mbar_wait(bar, 0);        // blob and owned tile landed
+#ifndef MGCFD_EXACT
+    // 3. derived quantities once per staged node
+    if (!STREAM) {
+        for (int i = tid; i < nloc; i += blockDim.x) {
+            double u[5], r[8];
+#pragma unroll
+            for (int v = 0; v < 5; v++) u[v] = raw[i * 5 + v];
+            derive(u, r);
+            der[i] = r[5]; der[max_loc + i] = r[6]; der[2 * max_loc + i] = r[7];
+        }
+        __syncthreads();
     }
-    __syncthreads();          // node states staged; mbarrier initialisation visible to all threads
-    mbar_wait(bar, 0);        // blob landed
+#endif
 
     double *w0 = reinterpret_cast<double *>(sblob);
     double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
@@ -375,13 +412,14 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + d.e_pad);
     const uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
 
+    // 4. one thread per edge: the edge's weights are replaced in place by its flux vector
     for (int e = tid; e < d.n_edges; e += blockDim.x) {
         uint32_t l = lab[e];
         int la = l & 0xffff, lb = l >> 16;
         double x = w0[e], y = w1[e], z = w2[e], g = gg[e];
         double a[NREC], b[NREC];
-#pragma unroll
-        for (int f = 0; f < NREC; f++) { a[f] = rec[f * max_loc + la]; b[f] = rec[f * max_loc + lb]; }
+        load_state<NREC>(raw, der, max_loc, la, a);
+        load_state<NREC>(raw, der, max_loc, lb, b);
         double fa[5], fb[5];
         if (STREAM) {
             stream_flux(a, b, x, y, z, fa, fb);
@@ -392,8 +430,7 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
             edge_flux(a, b, x, y, z, g, fa);
 #endif
         }
-        // the edge's weights are dead now: its flux vector takes their place (slot e is private to this thread)
-        w0[e] = fa[0]; w1[e] = fa[1]; w2[e] = fa[2]; gg[e] = fa[3];
+        w0[e] = fa[0]; w1[e] = fa[1]; w2[e] = fa[2]; gg[e] = fa[3];      // slot e is private to this thread
         Fx[e] = fa[4];
         if (NFL == 10) {
 #pragma unroll
@@ -402,11 +439,15 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     }
     __syncthreads();
 
-    for (int n = tid; n < d.n_own; n += blockDim.x) {
-        double acc[5];
-        double *out = flux + (size_t)(d.node0 + n) * 5;
+    // 5. one thread per owned node (chunks never own more than blockDim nodes) sums its incident edges in ascending
+    //    file order; the sums go to HBM through shared memory so that the store is one contiguous, coalesced run
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int n = tid;
+    if (n < d.n_own) {
+        if (!OVERWRITE) {
 #pragma unroll
-        for (int v = 0; v < 5; v++) acc[v] = OVERWRITE ? 0.0 : out[v];
+            for (int v = 0; v < 5; v++) acc[v] = flux[(size_t)(d.node0 + n) * 5 + v];
+        }
         int j0 = rowptr[n], j1 = rowptr[n + 1];
         for (int j = j0; j < j1; j++) {
             uint16_t c = csr[j];
@@ -429,8 +470,115 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
             }
         }
 #pragma unroll
-        for (int v = 0; v < 5; v++) out[v] = acc[v];
+        for (int v = 0; v < 5; v++) raw[n * 5 + v] = acc[v];      // the state tile is dead: reuse it for the output
     }
+    __syncthreads();
+    double *out = flux + (size_t)d.node0 * 5;
+    for (int f = tid; f < d.n_own * 5; f += blockDim.x) out[f] = raw[f];
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 3: node gather ("pull").  Same owner chunks, but one thread per owned node walks the node's
+// incident edges and evaluates each edge from its own side only (every interior edge is evaluated
+// twice, once per endpoint).  Rows are stored sliced-ELL: the chunk's nodes are sorted by degree,
+// each warp-slice is padded to its longest row and stored column-major, so neighbour ids and the
+// (pre-signed) weights stream from HBM fully coalesced; only the neighbour's state is gathered, from
+// shared memory.  No per-edge staging, no scatter, sums in ascending file order.
+// shared: mbarrier | raw[max_loc][5] (AoS state tile, reused for the output) | der[3][max_loc] (fast build)
+// ------------------------------------------------------------------------------------------
+template <bool STREAM, bool OVERWRITE>
+__global__ void __launch_bounds__(256, 3)
+flux_gather_kernel(int max_loc, const GatherChunkDesc *__restrict__ descs, const int *__restrict__ halo_gid,
+                   const uint16_t *__restrict__ row_node, const uint16_t *__restrict__ row_deg,
+                   const uint32_t *__restrict__ ent, const double *__restrict__ pw0, const double *__restrict__ pw1,
+                   const double *__restrict__ pw2, const double *__restrict__ pg, const double *__restrict__ var,
+                   double *__restrict__ flux)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int NREC = STREAM ? 5 : NF;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+    double *raw = reinterpret_cast<double *>(smraw + 16);               // conserved variables, AoS [max_loc][5]
+    double *der = raw + (size_t)max_loc * 5;                            // p, |v|+c, 1/rho planes (fast build only)
+    const GatherChunkDesc d = descs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, slice = tid >> 5;
+    const int nloc = d.n_own + d.n_halo;
+
+    // 1. state tile: owned run by one bulk async copy, halo nodes by 8-byte async copies
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, owned_bulk_bytes(d.n_own));
+    }
+    stage_tile(raw, bar, d.node0, d.n_own, d.n_halo, halo_gid + d.halo_off, var, tid, blockDim.x);
+    __syncthreads();
+    mbar_wait(bar, 0);
+#ifndef MGCFD_EXACT
+    // 2. derived quantities once per staged node
+    if (!STREAM) {
+        for (int i = tid; i < nloc; i += blockDim.x) {
+            double u[5], r[8];
+#pragma unroll
+            for (int v = 0; v < 5; v++) u[v] = raw[i * 5 + v];
+            derive(u, r);
+            der[i] = r[5]; der[max_loc + i] = r[6]; der[2 * max_loc + i] = r[7];
+        }
+        __syncthreads();
+    }
+#endif
+
+    // 3. one thread per owned node (degree-sorted order), rows in sliced-ELL layout
+    const int me = row_node[(size_t)blockIdx.x * 256 + tid];          // local owned index or 0xffff
+    const int deg = row_deg[(size_t)blockIdx.x * 256 + tid];
+    int len = 0;
+    long long base = d.ent_off;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        int L = d.slice_len[s];
+        if (s < slice) base += (long long)L * 32;
+        if (s == slice) len = L;
+    }
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (me != 0xffff) {
+        if (!OVERWRITE) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] = flux[(size_t)(d.node0 + me) * 5 + v];
+        }
+    }
+    const int self = me != 0xffff ? me : 0;
+    double a[NREC];
+    load_state<NREC>(raw, der, max_loc, self, a);
+    for (int j = 0; j < len; j++) {
+        long long idx = base + (long long)j * 32 + lane;
+        uint32_t en = __ldg(ent + idx);
+        double x = __ldg(pw0 + idx), y = __ldg(pw1 + idx), z = __ldg(pw2 + idx), g = __ldg(pg + idx);
+        int nb = en & 0xffff;
+        double b[NREC];
+        load_state<NREC>(raw, der, max_loc, nb, b);
+        double fa[5], fb[5];
+        if (STREAM) {
+            // the row stores the edge as seen from this node; bit 16 says whether this node is the edge's end b
+            if (en & 0x10000u) { stream_flux(b, a, x, y, z, fb, fa); } else { stream_flux(a, b, x, y, z, fa, fb); }
+        } else {
+#ifdef MGCFD_EXACT
+            // reference orientation: weights are stored unsigned here, evaluate (a_edge, b_edge) and take my side
+            if (en & 0x10000u) { edge_flux(b, a, x, y, z, g, fb, fa); } else { edge_flux(a, b, x, y, z, g, fa, fb); }
+#else
+            edge_flux(a, b, x, y, z, g, fa);      // weights pre-signed: this node is always "a"
+#endif
+        }
+        if (j < deg) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] += fa[v];
+        }
+    }
+    // 4. coalesced store through shared memory (the state tile is dead after the barrier)
+    __syncthreads();
+    if (me != 0xffff) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) raw[me * 5 + v] = acc[v];
+    }
+    __syncthreads();
+    double *out = flux + (size_t)d.node0 * 5;
+    for (int f = tid; f < d.n_own * 5; f += blockDim.x) out[f] = raw[f];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -533,6 +681,23 @@ inline int launch_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev 
     return launches;
 }
 
+inline size_t gather_smem(int max_loc, bool stream) { return 16 + (size_t)(stream ? 5 : NF) * max_loc * sizeof(double); }
+
+inline int launch_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc)
+{
+    if (n_chunks == 0) return 0;
+    size_t smem = gather_smem(max_loc, a.stream_kernel);
+#define GATHER_ARGS max_loc, p.desc, p.halo_gid, p.row_node, p.row_deg, p.ent, p.w0, p.w1, p.w2, p.g, a.var, a.flux
+    if (a.stream_kernel)
+        flux_gather_kernel<true, false><<<n_chunks, 256, smem, s>>>(GATHER_ARGS);
+    else if (a.overwrite)
+        flux_gather_kernel<false, true><<<n_chunks, 256, smem, s>>>(GATHER_ARGS);
+    else
+        flux_gather_kernel<false, false><<<n_chunks, 256, smem, s>>>(GATHER_ARGS);
+#undef GATHER_ARGS
+    return 1;
+}
+
 inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h)
 {
     if (h.n_chunks == 0) return 0;
@@ -558,6 +723,9 @@ inline std::string configure()
     OPT_IN((flux_owner_kernel<true, false>));
     OPT_IN((flux_owner_kernel<false, true>));
     OPT_IN((flux_owner_kernel<false, false>));
+    OPT_IN((flux_gather_kernel<true, false>));
+    OPT_IN((flux_gather_kernel<false, true>));
+    OPT_IN((flux_gather_kernel<false, false>));
 #undef OPT_IN
     return "";
 }

@@ -115,6 +115,22 @@ struct OwnerPlanDev {
     bool valid = false;
 };
 
+struct GatherChunkDesc {
+    int node0, n_own, n_halo, halo_off;
+    long long ent_off;              // first entry of the chunk in the sliced-ELL planes (multiple of 32)
+    unsigned short slice_len[8];    // padded row length of each 32-row slice
+};
+
+struct GatherPlanDev {
+    GatherChunkDesc *desc = nullptr;
+    int *halo_gid = nullptr;
+    uint16_t *row_node = nullptr, *row_deg = nullptr;   // [n_chunks*256] thread slot -> local owned node / its degree
+    uint32_t *ent = nullptr;                             // neighbour local id | (this node is edge end b) << 16
+    double *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *g = nullptr;
+    long long n_ent = 0;
+    bool valid = false;
+};
+
 struct LevelDev {
     double *var = nullptr, *old = nullptr, *res = nullptr, *flux = nullptr, *dummy_flux = nullptr;
     double *vol = nullptr, *sf = nullptr, *coords = nullptr;
@@ -126,10 +142,12 @@ struct LevelDev {
     int n_bnd_unique = 0;
     int *bu_node = nullptr, *bu_ptr = nullptr, *b_group = nullptr;
     double *b_wt = nullptr;
+    int *perm = nullptr;           // new_of_old: internal index of file node i
     double *cbrt_vol = nullptr;    // cbrt(volume) per node, evaluated once on the host (volumes are static after init)
     AtomicPlanDev atomic;
     ColourPlanDev colour;
     OwnerPlanDev owner;
+    GatherPlanDev gather;
     bool flux_is_zero = false;     // tracked so that the owner variant may overwrite instead of accumulate
 };
 
@@ -156,6 +174,8 @@ struct mgcfd_ctx {
     double *d_rms = nullptr;
     int *d_flags = nullptr;          // [0]=bad value count, [1]=min_dt<0 flag, [2]=validate count
     double *h_pinned = nullptr;      // pinned host scratch (8 doubles)
+    void *d_stage = nullptr, *h_stage = nullptr;   // device / pinned-host staging for file-order transfers
+    size_t d_stage_bytes = 0, h_stage_bytes = 0;
     long long launches = 0;
     int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only
     std::map<std::string, mgcfd::LoopTimer> timers;
@@ -183,6 +203,8 @@ int k_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_p
                const double *b_wt, const double *var, double *flux, const DevConsts &c, bool exact);
 int k_validate(cudaStream_t s, int n, const double *test, const double *master, int *d_count);
 int k_fill(cudaStream_t s, long long n, double *a, double v);
+// to_internal: dst[perm[i]] = src[i] (file -> internal); else dst[i] = src[perm[i]] (internal -> file)
+int k_permute_rows(cudaStream_t s, int n, int dim, const double *src, const int *perm, double *dst, bool to_internal);
 int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c);
 
 struct FluxArgs {
@@ -195,6 +217,9 @@ struct FluxArgs {
 int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
 int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);
 int flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact);
+int flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc, bool exact);
+int fast_flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc);
+size_t flux_gather_smem_bytes(int max_loc, bool exact);
 // one-time kernel attribute setup (dynamic shared memory opt-in); returns "" or an error text
 std::string flux_configure();
 // the fast-math translation unit (flux_fast.cu)

@@ -10,6 +10,7 @@ namespace mgcfd {
 
 size_t fast_owner_smem(int max_loc, int max_edges, int max_blob);
 size_t fast_colour_smem(int max_nodes);
+size_t fast_gather_smem(int max_loc);
 
 namespace {
 
@@ -39,6 +40,18 @@ __global__ void fill_kernel(long long n, double *__restrict__ a, double v)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = v;
+}
+
+__global__ void permute_rows_kernel(long long total, int dim, const double *__restrict__ src, const int *__restrict__ perm,
+                                    double *__restrict__ dst, bool to_internal)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long long row = i / dim;
+    int d = (int)(i - row * dim);
+    long long other = (long long)perm[row] * dim + d;
+    if (to_internal) dst[other] = src[i];
+    else dst[i] = src[other];
 }
 
 // misc.h:10-16
@@ -258,6 +271,13 @@ int k_fill(cudaStream_t s, long long n, double *a, double v)
     fill_kernel<<<blocks_for(n), TPB, 0, s>>>(n, a, v);
     return 1;
 }
+int k_permute_rows(cudaStream_t s, int n, int dim, const double *src, const int *perm, double *dst, bool to_internal)
+{
+    if (n == 0) return 0;
+    long long total = (long long)n * dim;
+    permute_rows_kernel<<<blocks_for(total), TPB, 0, s>>>(total, dim, src, perm, dst, to_internal);
+    return 1;
+}
 int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c)
 {
     if (n == 0) return 0;
@@ -375,6 +395,14 @@ int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const
 int flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact_mode)
 {
     return exact_mode ? exact::launch_owner(s, a, p, h) : fast_flux_owner(s, a, p, h);
+}
+int flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc, bool exact_mode)
+{
+    return exact_mode ? exact::launch_gather(s, a, p, n_chunks, max_loc) : fast_flux_gather(s, a, p, n_chunks, max_loc);
+}
+size_t flux_gather_smem_bytes(int max_loc, bool exact_mode)
+{
+    return exact_mode ? exact::gather_smem(max_loc, false) : fast_gather_smem(max_loc);
 }
 std::string flux_configure()
 {

@@ -204,6 +204,8 @@ void plan_colour(LevelHost &L, int block_edges)
 // chunk holds every edge with at least one owned endpoint (cut edges appear in both chunks).
 // Greedy growth under caps on owned nodes, local nodes (owned + halo) and edges; the check
 // before admitting node v is conservative: it assumes all deg(v) edges and neighbours are new.
+// A chunk is only closed when it owns an even number of nodes (the caps on local nodes and edges
+// are therefore soft by one node), so every chunk starts on an even node index.
 // ---------------------------------------------------------------------------------------
 bool plan_owner(LevelHost &L, int max_own, int max_loc, int max_edges, std::string &err)
 {
@@ -236,7 +238,9 @@ bool plan_owner(LevelHost &L, int max_own, int max_loc, int max_edges, std::stri
         int n_own = 0, n_halo = 0, n_edge = 0;
         while (v < no) {
             int deg = adj_ptr[v + 1] - adj_ptr[v];
-            if (n_own > 0 && (n_own + 1 > max_own || n_own + n_halo + 1 + deg > max_loc || n_edge + deg > max_edges))
+            // chunks end on even node counts (the owned run is then a 16-byte aligned bulk-copy source)
+            if (n_own > 0 && n_own % 2 == 0 &&
+                (n_own + 1 > max_own || n_own + n_halo + 1 + deg > max_loc || n_edge + deg > max_edges))
                 break;
             if (halo_stamp[v] == k) n_halo--;      // v was a halo node of this chunk until now
             for (int j = adj_ptr[v]; j < adj_ptr[v + 1]; j++) {

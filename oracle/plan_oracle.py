@@ -139,7 +139,8 @@ def check_colouring(e2n0, order, block_edges, thread_colour, block_colour):
 
 
 def owner_chunks(e2n0, new_of_old, n_owned, max_own, max_loc, max_edges):
-    """returns (chunk_start[], halo lists (internal ids, ascending) per chunk, edge lists (file ids) per chunk)"""
+    """returns (chunk_start[], halo lists (internal ids, ascending) per chunk, edge lists (file ids) per chunk).
+    A chunk is closed only at an even number of owned nodes, so every chunk starts on an even node index."""
     p = np.asarray(new_of_old, dtype=np.int64)
     n = p.shape[0]
     a, b = p[e2n0[:, 0]], p[e2n0[:, 1]]
@@ -155,7 +156,7 @@ def owner_chunks(e2n0, new_of_old, n_owned, max_own, max_loc, max_edges):
         n_own = 0
         while v < n_owned:
             deg = len(inc[v])
-            if n_own > 0 and (n_own + 1 > max_own or n_own + len(halo) + 1 + deg > max_loc or len(elist) + deg > max_edges):
+            if n_own > 0 and n_own % 2 == 0 and (n_own + 1 > max_own or n_own + len(halo) + 1 + deg > max_loc or len(elist) + deg > max_edges):
                 break
             halo.discard(v)
             for e in inc[v]:

@@ -13,7 +13,7 @@ from conftest import mesh0
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["owner", "colour", "atomic"]
+VARIANTS = ["owner", "gather", "colour", "atomic"]
 FLUX_TOL = 1e-12
 
 
@@ -62,7 +62,7 @@ def test_flux_edge_golden(pkg, tiny, golden, variant, exact):
         gpu.set(0, "fluxes", g["in_flux"])
         gpu.compute_flux_edge(0)
         got = gpu.fetch(0, "fluxes")
-    if exact and variant == "owner":
+    if exact and variant in ("owner", "gather"):
         assert np.array_equal(got, g["flux_edge"])
     else:
         # compare the increment, not in_flux + increment, so that the tolerance is not diluted
@@ -86,7 +86,7 @@ def test_flux_edge_from_zero_vs_oracle(pkg, small, meshgen, oracle_port, variant
         gpu.set(0, "variables", var)
         gpu.compute_flux_edge(0)
         got = gpu.fetch(0, "fluxes")
-        if exact and variant == "owner":
+        if exact and variant in ("owner", "gather"):
             assert np.array_equal(got, ref)
         else:
             assert (normwise(got, ref) <= FLUX_TOL).all(), normwise(got, ref)
