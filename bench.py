@@ -51,6 +51,14 @@ def flux_bytes_per_cycle(sizes):
     return RK * sum(32 * sizes[l][1] + 120 * sizes[l][0] for l in visits_per_cycle(len(sizes)))
 
 
+def rk_stage_bytes_per_cycle(sizes):
+    """algorithmic bytes of the fused Runge-Kutta stage launches of one cycle: per stage the flux-edge loop
+    (32*E + 120*N) plus time_step (168*N); the last stage of a visit also does residual (120*N).  The boundary
+    flux, calc_rms and count_bad_vals the kernel also performs are NOT counted (SURVEY.md 8d figures)."""
+    return sum(RK * (32 * sizes[l][1] + 120 * sizes[l][0] + 168 * sizes[l][0]) + 120 * sizes[l][0]
+               for l in visits_per_cycle(len(sizes)))
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -160,10 +168,11 @@ def main():
     ap.add_argument("--mesh", default="m6")
     ap.add_argument("--variant", default="owner", choices=["owner", "gather", "colour", "atomic"])
     ap.add_argument("--exact", action="store_true")
-    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--cpu-cycles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fusion", action="store_true", help="one kernel per op_par_loop call site")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -177,7 +186,7 @@ def main():
     workload = (f"{args.mesh}: {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
                 f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
     config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
-              "arith": "exact" if args.exact else "fast",
+              "arith": "exact" if args.exact else "fast", "fused_schedule": args.variant == "owner" and not args.no_fusion,
               "l2": "no flush between steps: the V-cycle working set (~%d MB) exceeds the 126 MB L2"
                     % (sum(300 * s[0] + 32 * s[1] for s in sizes) // 2**20)}
     nthreads = os.cpu_count() or 1
@@ -210,7 +219,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,
-                    flux_variant=args.variant, exact_arith=args.exact, owner_chunk_nodes=args.chunk)
+                    flux_variant=args.variant, exact_arith=args.exact, owner_chunk_nodes=args.chunk,
+                    fuse=not args.no_fusion)
     stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -242,17 +252,22 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     launches = gpu.kernel_launches() - launches0
-    flux_ms, flux_calls, flux_elems = gpu.timer("compute_flux_edge")
+    fused = args.variant == "owner" and not args.no_fusion
+    flux_ms, flux_calls, flux_elems = gpu.timer("rk_stage" if fused else "compute_flux_edge")
     gpu.timers_enable(0)
 
     edges_step = flux_edges_per_cycle(sizes)
     value = world * edges_step * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peaks()
-    flux_bytes = flux_bytes_per_cycle(sizes) * args.steps
+    flux_bytes = (rk_stage_bytes_per_cycle(sizes) if fused else flux_bytes_per_cycle(sizes)) * args.steps
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"compute_flux_edge_kernel[{args.variant}]", "achieved": achieved, "peak": peak,
+    kname = (f"flux_owner_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
+             if fused else f"compute_flux_edge_kernel[{args.variant}]")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch_L0": 32 * sizes[0][1] + 120 * sizes[0][0],
+                "algorithmic_bytes": ("per stage 32E+120N (flux-edge) + 168N (time_step), + 120N (residual) after the last stage"
+                                      if fused else "32E+120N per launch"),
+                "algorithmic_bytes_per_launch_L0": (32 * sizes[0][1] + 288 * sizes[0][0]) if fused else (32 * sizes[0][1] + 120 * sizes[0][0]),
                 "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
                 "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms,
                 "note": "deck levels are L2-resident sized (L0 flux loop touches ~66 MB); see config.l2"}

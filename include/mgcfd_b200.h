@@ -91,10 +91,12 @@ typedef struct {
 typedef struct {
     int flux_variant;      /* MGCFD_FLUX_*; default MGCFD_FLUX_OWNER */
     int renumber;          /* 1 (default): Hilbert-curve locality renumbering of nodes; 0: keep file order */
-    int owner_chunk_nodes; /* owner variant: max owned nodes per chunk (default 256) */
+    int owner_chunk_nodes; /* owner/gather variants: max owned nodes per chunk (even, <= 256; default 128) */
     int colour_block_edges;/* colour variant: edges per block (default 256) */
     int exact_arith;       /* 1: reference operation order, IEEE div/sqrt, no FMA contraction in the flux kernels */
-    int reserved[11];
+    int no_fusion;         /* 1: mgcfd_run_cycles launches one kernel per call site instead of the fused schedule
+                              (fused Runge-Kutta stage, visit prologue and restrict; owner variant only) */
+    int reserved[10];
 } mgcfd_options;
 
 /* ---- lifetime (op_init / op_exit, euler3d.cpp:126, :824) ---- */

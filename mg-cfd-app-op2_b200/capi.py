@@ -49,7 +49,8 @@ class LevelHost(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("flux_variant", C.c_int), ("renumber", C.c_int), ("owner_chunk_nodes", C.c_int),
-                ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("reserved", C.c_int * 11)]
+                ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("no_fusion", C.c_int),
+                ("reserved", C.c_int * 10)]
 
 
 _lib = None
@@ -137,8 +138,8 @@ class MGCFD:
     """One context = one GPU's share of the mesh.  Methods are the op_par_loop call sites of euler3d.cpp."""
 
     def __init__(self, levels, base_array_index=1, device=0, flux_variant="owner", renumber=True,
-                 exact_arith=False, owner_chunk_nodes=256, colour_block_edges=256, consts=None,
-                 n_owned=None, init=True):
+                 exact_arith=False, owner_chunk_nodes=128, colour_block_edges=256, consts=None,
+                 n_owned=None, init=True, fuse=True):
         """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"])."""
         self.lib = load_library()
         self.n_levels = len(levels)
@@ -149,6 +150,7 @@ class MGCFD:
         opt.exact_arith = int(bool(exact_arith))
         opt.owner_chunk_nodes = int(owner_chunk_nodes)
         opt.colour_block_edges = int(colour_block_edges)
+        opt.no_fusion = int(not fuse)
         self.ctx = C.c_void_p()
         rc = self.lib.mgcfd_create(C.byref(self.ctx), int(device), self.n_levels, C.byref(opt))
         if rc != 0:

@@ -109,7 +109,8 @@ struct LoopScope {
     LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
     {
         if (!ctx->timers_on) return;
-        if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0) return;   // flux-edge launches only
+        if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0 && strcmp(name, "rk_stage") != 0)
+            return;   // flux-edge launches (stand-alone or as the fused Runge-Kutta stage) only
         t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
         e0 = get_event(ctx);
         e1 = get_event(ctx);
@@ -155,7 +156,7 @@ void mgcfd_default_options(mgcfd_options *opt)
     memset(opt, 0, sizeof(*opt));
     opt->flux_variant = MGCFD_FLUX_OWNER;
     opt->renumber = 1;
-    opt->owner_chunk_nodes = 256;
+    opt->owner_chunk_nodes = 128;
     opt->colour_block_edges = 256;
     opt->exact_arith = 0;
 }
@@ -216,6 +217,8 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaMalloc((void **)&ctx->d_min_dt, sizeof(double) * n_levels)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_rms, sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_min_enc, sizeof(unsigned long long) * 2 * n_levels)) != cudaSuccess) return fail("cudaMalloc", e);
+    k_reset_min_slots(ctx->stream, 2 * n_levels, ctx->d_min_enc);
     if ((e = cudaMalloc((void **)&ctx->d_flags, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemset(ctx->d_flags, 0, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, sizeof(double) * 8)) != cudaSuccess) return fail("cudaMallocHost", e);
@@ -231,7 +234,7 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
 
 static void free_level(LevelDev &d)
 {
-    void *ptrs[] = {d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
+    void *ptrs[] = {d.var_alt, d.bnd_ptr, d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
                     d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.perm, d.atomic.nodes, d.atomic.w,
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
                     d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.gather.desc, d.gather.halo_gid,
@@ -253,6 +256,7 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
     if (ctx->d_rms) cudaFree(ctx->d_rms);
+    if (ctx->d_min_enc) cudaFree(ctx->d_min_enc);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -352,6 +356,15 @@ static int upload_bnd(mgcfd_ctx *ctx, int level)
     }
     bu_ptr.push_back((int)idx.size());
     D.n_bnd_unique = (int)bu_node.size();
+    std::vector<int> node_ptr(L.n_owned + 1, 0);      // the same grouping indexed by owned node (fused stage)
+    for (size_t t = 0; t < bu_node.size(); t++) node_ptr[bu_node[t] + 1] = bu_ptr[t + 1] - bu_ptr[t];
+    for (int i = 0; i < L.n_owned; i++) node_ptr[i + 1] += node_ptr[i];
+    {
+        int rc0 = dev_upload(ctx, &D.bnd_ptr, node_ptr);
+        if (rc0) return rc0;
+    }
+    L.bnd_node_ptr = node_ptr;
+    D.owner.valid = false;                             // chunk descriptors carry a has-boundary flag
     int rc;
     if ((rc = dev_upload(ctx, &D.bu_node, bu_node))) return rc;
     if ((rc = dev_upload(ctx, &D.bu_ptr, bu_ptr))) return rc;
@@ -436,6 +449,7 @@ int mgcfd_plan(mgcfd_ctx *ctx)
         const size_t n = L.n_nodes;
         int rc;
         if ((rc = dev_alloc(ctx, &D.var, n * 5))) return rc;
+        if ((rc = dev_alloc(ctx, &D.var_alt, n * 5))) return rc;
         if ((rc = dev_alloc(ctx, &D.old, n * 5))) return rc;
         if ((rc = dev_alloc(ctx, &D.res, n * 5))) return rc;
         if ((rc = dev_alloc(ctx, &D.flux, n * 5))) return rc;
@@ -594,6 +608,8 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         d.n_inc = O.n_inc[k];
         d.blob_off = O.blob_off[k];
         d.blob_bytes = (int)(O.blob_off[k + 1] - O.blob_off[k]);
+        d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] > L.bnd_node_ptr[O.node0[k]] ? 1 : 0;
+        d.pad_ = 0;
         unsigned char *base = blob.data() + d.blob_off;
         double *w0 = reinterpret_cast<double *>(base), *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *g = w2 + d.e_pad;
         uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);
@@ -1007,34 +1023,76 @@ int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
     cudaStream_t s = ctx->stream;
     const bool exact = ctx->opt.exact_arith != 0;
     const DevConsts dc = dev_consts(ctx);
+    // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
+    const bool fused = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && !ctx->opt.no_fusion;
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, s));
     int level = 0, dir = 0, i = 0;
     while (i < n_cycles) {
         LevelHost &L = ctx->H[level];
         LevelDev &D = ctx->D[level];
         const int no = L.n_owned;
-        { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
-        { LoopScope t(ctx, "calculate_dt", level, no); ctx->launches += k_calculate_dt(s, no, D.var, D.cbrt_vol, D.sf); }
-        {
-            LoopScope t(ctx, "get_min_dt", level, no);
-            ctx->launches += k_fill(s, 1, &ctx->d_min_dt[level], DBL_MAX);
-            ctx->launches += k_min_dt(s, no, D.sf, &ctx->d_min_dt[level], ctx->d_flags);
-        }
-        { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor(s, no, D.vol, &ctx->d_min_dt[level], D.sf); }
-        for (int rk = 0; rk < MGCFD_RK; rk++) {
-            int rc = run_flux(ctx, level, false);
-            if (rc) return rc;
-            {
-                LoopScope t(ctx, "compute_bnd_node_flux", level, L.n_bnd);
-                ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+        if (fused) {
+            unsigned long long *slot = &ctx->d_min_enc[2 * level + D.visit_parity];
+            unsigned long long *next = &ctx->d_min_enc[2 * level + (D.visit_parity ^ 1)];
+            D.visit_parity ^= 1;
+            { LoopScope t(ctx, "visit_begin", level, no); ctx->launches += k_visit_begin(s, no, D.var, D.cbrt_vol, D.old, D.sf, slot); }
+            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor_fused(s, no, D.vol, slot, next, D.sf, &ctx->d_min_dt[level], ctx->d_flags); }
+            if (level == 0) ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0);
+            for (int rk = 0; rk < MGCFD_RK; rk++) {
+                if (!D.flux_is_zero) {      // only after a caller poked the fluxes: unfused stage keeps OP_INC semantics
+                    int rc = run_flux(ctx, level, false);
+                    if (rc) return rc;
+                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+                    ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var);
+                    D.flux_is_zero = true;
+                    if (rk == MGCFD_RK - 1) {
+                        ctx->launches += k_residual(s, no, D.old, D.var, D.res);
+                        if (level == 0) { ctx->launches += k_rms(s, no, D.res, ctx->d_rms); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+                    }
+                    continue;
+                }
+                RkStageArgs ra;
+                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
+                ra.d_rms = level == 0 ? ctx->d_rms : nullptr;
+                ra.d_bad = &ctx->d_flags[0];
+                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
+                ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = dc;
+                FluxArgs a;
+                a.n_edges = L.n_edges; a.n_owned = no; a.n_nodes = L.n_nodes;
+                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
+                {
+                    LoopScope t(ctx, "rk_stage", level, L.n_edges);
+                    ctx->launches += flux_owner(s, a, D.owner, L.owner, exact);
+                }
+                if (L.n_nodes > no)   // halo entries of the new buffer are refreshed by the exchange; keep them defined
+                    CK(cudaMemcpyAsync(D.var_alt + (size_t)no * 5, D.var + (size_t)no * 5, (size_t)(L.n_nodes - no) * 40,
+                                       cudaMemcpyDeviceToDevice, s));
+                std::swap(D.var, D.var_alt);
             }
-            { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
-            D.flux_is_zero = true;
-        }
-        { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
-        if (level == 0) {
-            { LoopScope t(ctx, "calc_rms", level, no); ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0); ctx->launches += k_rms(s, no, D.res, ctx->d_rms); }
-            { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+        } else {
+            { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
+            { LoopScope t(ctx, "calculate_dt", level, no); ctx->launches += k_calculate_dt(s, no, D.var, D.cbrt_vol, D.sf); }
+            {
+                LoopScope t(ctx, "get_min_dt", level, no);
+                ctx->launches += k_fill(s, 1, &ctx->d_min_dt[level], DBL_MAX);
+                ctx->launches += k_min_dt(s, no, D.sf, &ctx->d_min_dt[level], ctx->d_flags);
+            }
+            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor(s, no, D.vol, &ctx->d_min_dt[level], D.sf); }
+            for (int rk = 0; rk < MGCFD_RK; rk++) {
+                int rc = run_flux(ctx, level, false);
+                if (rc) return rc;
+                {
+                    LoopScope t(ctx, "compute_bnd_node_flux", level, L.n_bnd);
+                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+                }
+                { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
+                D.flux_is_zero = true;
+            }
+            { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
+            if (level == 0) {
+                { LoopScope t(ctx, "calc_rms", level, no); ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0); ctx->launches += k_rms(s, no, D.res, ctx->d_rms); }
+                { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+            }
         }
         if (nl <= 1) {
             i++;
@@ -1042,9 +1100,14 @@ int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
             level++;
             LevelDev &A = ctx->D[level], &F = ctx->D[level - 1];
             const int nf = ctx->H[level - 1].n_owned;
-            { LoopScope t(ctx, "up_pre", level, nf); ctx->launches += k_up_pre(s, nf, F.mg, A.var, A.up_count); }
-            { LoopScope t(ctx, "up", level, nf); ctx->launches += k_up(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count); }
-            { LoopScope t(ctx, "up_post", level, ctx->H[level].n_owned); ctx->launches += k_up_post(s, ctx->H[level].n_owned, A.var, A.up_count); }
+            if (fused) {
+                LoopScope t(ctx, "restrict", level, nf);
+                ctx->launches += k_restrict_fused(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
+            } else {
+                { LoopScope t(ctx, "up_pre", level, nf); ctx->launches += k_up_pre(s, nf, F.mg, A.var, A.up_count); }
+                { LoopScope t(ctx, "up", level, nf); ctx->launches += k_up(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count); }
+                { LoopScope t(ctx, "up_post", level, ctx->H[level].n_owned); ctx->launches += k_up_post(s, ctx->H[level].n_owned, A.var, A.up_count); }
+            }
             if (level == nl - 1) dir = 1;
         } else {
             level--;

@@ -119,6 +119,47 @@ __device__ __forceinline__ void load5(const double *__restrict__ p, double u[5])
 }
 
 // ------------------------------------------------------------------------------------------
+// compute_bnd_node_flux_kernel body (flux.h:14-39, flux_boundary.elem_func, flux_wall.elem_func) for ONE node:
+// applies the node's boundary entries [j0, j1) (ascending file order) to fl[5].  Shared by the stand-alone
+// boundary kernel and the fused Runge-Kutta stage.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bnd_apply(const double u[5], double fl[5], int j0, int j1,
+                                          const int *__restrict__ b_group, const double *__restrict__ b_wt,
+                                          const DevConsts &c)
+{
+    double rho = u[0], m[3] = {u[1], u[2], u[3]}, E = u[4];
+    double v[3] = {m[0] / rho, m[1] / rho, m[2] / rho};
+    double q2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double p = (GAMMA - 1.0) * (E - 0.5 * rho * q2);
+    double fc[4][3];
+    fc[0][0] = v[0] * m[0] + p; fc[0][1] = v[0] * m[1];     fc[0][2] = v[0] * m[2];
+    fc[1][0] = fc[0][1];        fc[1][1] = v[1] * m[1] + p; fc[1][2] = v[1] * m[2];
+    fc[2][0] = fc[0][2];        fc[2][1] = fc[1][2];        fc[2][2] = v[2] * m[2] + p;
+    double ep = E + p;
+    fc[3][0] = v[0] * ep; fc[3][1] = v[1] * ep; fc[3][2] = v[2] * ep;
+    for (int i = j0; i < j1; i++) {
+        int g = b_group[i];
+        double w[3] = {b_wt[(size_t)i * 3], b_wt[(size_t)i * 3 + 1], b_wt[(size_t)i * 3 + 2]};
+        if (g <= 2) {
+            // pressure-only wall (flux_boundary.elem_func:50-54); "+= 0" only matters for -0.0
+            fl[0] += 0.0;
+            fl[1] += w[0] * p;
+            fl[2] += w[1] * p;
+            fl[3] += w[2] * p;
+            fl[4] += 0.0;
+        } else if (g == 3 || (g >= 4 && g <= 7)) {
+            // far field (flux_wall.elem_func:49-76)
+            double fx = 0.5 * w[0], fy = 0.5 * w[1], fz = 0.5 * w[2];
+            fl[0] += fx * (c.ff_variable[1] + m[0]) + fy * (c.ff_variable[2] + m[1]) + fz * (c.ff_variable[3] + m[2]);
+            fl[4] += fx * (c.ff_fc[4][0] + fc[3][0]) + fy * (c.ff_fc[4][1] + fc[3][1]) + fz * (c.ff_fc[4][2] + fc[3][2]);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                fl[1 + k] += fx * (c.ff_fc[1 + k][0] + fc[k][0]) + fy * (c.ff_fc[1 + k][1] + fc[k][1]) + fz * (c.ff_fc[1 + k][2] + fc[k][2]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // variant 0: thread per edge, fp64 RED with warp aggregation on the sorted (lower) endpoint
 // ------------------------------------------------------------------------------------------
 template <bool STREAM>
@@ -365,11 +406,16 @@ __device__ __forceinline__ void stage_tile(double *raw, uint64_t *bar, int node0
     cp_async_wait_all();
 }
 
-template <bool STREAM, bool OVERWRITE>
+// FUSE: the Runge-Kutta stage in one kernel -- compute_flux_edge + compute_bnd_node_flux + time_step (+ residual,
+// calc_rms, count_bad_vals after the last stage).  The owner of a node holds the node's complete edge-flux sum in
+// registers, so it adds the boundary entries and applies var_new = old + step_factor/(RK+1-rk) * flux on the spot;
+// the fluxes never travel to HBM (they are zero before and after every stage).  var_new goes to the
+// alternate variables buffer because neighbouring chunks still read this stage's input.
+template <bool STREAM, bool OVERWRITE, bool FUSE>
 __global__ void __launch_bounds__(256)
 flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
                   const int *__restrict__ halo_gid, const unsigned char *__restrict__ blob,
-                  const double *__restrict__ var, double *__restrict__ flux)
+                  const double *__restrict__ var, double *__restrict__ flux, RkStageArgs rk)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int NREC = STREAM ? 5 : NF;
@@ -469,12 +515,53 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
                 acc[4] += is_b ? -f4 : f4;
             }
         }
+        if (FUSE && d.has_bnd) {
+            int j0 = rk.bnd_ptr[d.node0 + n], j1 = rk.bnd_ptr[d.node0 + n + 1];
+            if (j1 > j0) {
+                double u[5];
+#pragma unroll
+                for (int v = 0; v < 5; v++) u[v] = raw[n * 5 + v];
+                bnd_apply(u, acc, j0, j1, rk.b_group, rk.b_wt, rk.c);
+            }
+        }
+    }
+    if (n < d.n_own) {
 #pragma unroll
         for (int v = 0; v < 5; v++) raw[n * 5 + v] = acc[v];      // the state tile is dead: reuse it for the output
     }
     __syncthreads();
-    double *out = flux + (size_t)d.node0 * 5;
-    for (int f = tid; f < d.n_own * 5; f += blockDim.x) out[f] = raw[f];
+    if (!FUSE) {
+        double *out = flux + (size_t)d.node0 * 5;
+        for (int f = tid; f < d.n_own * 5; f += blockDim.x) out[f] = raw[f];
+    } else {
+        // time_stepping_kernels.h:66-86 (+ validation.h:27-44,102-115 after the last stage), flat and coalesced
+        const size_t g0 = (size_t)d.node0 * 5;
+        const double denom = (double)(MGCFD_RK + 1 - rk.rk);
+        double sq = 0.0;
+        int bad = 0;
+        for (int f = tid; f < d.n_own * 5; f += blockDim.x) {
+            double factor = rk.sf[d.node0 + f / 5] / denom;
+            double o = rk.old[g0 + f];
+            double vn = __dadd_rn(o, __dmul_rn(factor, raw[f]));
+            rk.var_out[g0 + f] = vn;
+            if (rk.last) {
+                double r = vn - o;
+                rk.res[g0 + f] = r;
+                sq += r * r;
+                bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
+            }
+        }
+        if (rk.last && rk.d_rms) {
+            for (int o = 16; o > 0; o >>= 1) {
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                bad += __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            if ((tid & 31) == 0) {
+                atomicAdd(rk.d_rms, sq);
+                if (bad) atomicAdd(rk.d_bad, bad);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -594,42 +681,12 @@ bnd_flux_kernel(int n_unique, const int *__restrict__ bu_node, const int *__rest
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_unique) return;
     int node = bu_node[t];
-    double u[5];
+    double u[5], fl[5];
     load5(var + (size_t)node * 5, u);
     double *out = flux + (size_t)node * 5;
-    double fl[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) fl[k] = out[k];
-    double rho = u[0], m[3] = {u[1], u[2], u[3]}, E = u[4];
-    double v[3] = {m[0] / rho, m[1] / rho, m[2] / rho};
-    double q2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    double p = (GAMMA - 1.0) * (E - 0.5 * rho * q2);
-    double fc[4][3];
-    fc[0][0] = v[0] * m[0] + p; fc[0][1] = v[0] * m[1];     fc[0][2] = v[0] * m[2];
-    fc[1][0] = fc[0][1];        fc[1][1] = v[1] * m[1] + p; fc[1][2] = v[1] * m[2];
-    fc[2][0] = fc[0][2];        fc[2][1] = fc[1][2];        fc[2][2] = v[2] * m[2] + p;
-    double ep = E + p;
-    fc[3][0] = v[0] * ep; fc[3][1] = v[1] * ep; fc[3][2] = v[2] * ep;
-    for (int i = bu_ptr[t]; i < bu_ptr[t + 1]; i++) {
-        int g = b_group[i];
-        double w[3] = {b_wt[(size_t)i * 3], b_wt[(size_t)i * 3 + 1], b_wt[(size_t)i * 3 + 2]};
-        if (g <= 2) {
-            // pressure-only wall (flux_boundary.elem_func:50-54); "+= 0" only matters for -0.0
-            fl[0] += 0.0;
-            fl[1] += w[0] * p;
-            fl[2] += w[1] * p;
-            fl[3] += w[2] * p;
-            fl[4] += 0.0;
-        } else if (g == 3 || (g >= 4 && g <= 7)) {
-            // far field (flux_wall.elem_func:49-76)
-            double fx = 0.5 * w[0], fy = 0.5 * w[1], fz = 0.5 * w[2];
-            fl[0] += fx * (c.ff_variable[1] + m[0]) + fy * (c.ff_variable[2] + m[1]) + fz * (c.ff_variable[3] + m[2]);
-            fl[4] += fx * (c.ff_fc[4][0] + fc[3][0]) + fy * (c.ff_fc[4][1] + fc[3][1]) + fz * (c.ff_fc[4][2] + fc[3][2]);
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                fl[1 + k] += fx * (c.ff_fc[1 + k][0] + fc[k][0]) + fy * (c.ff_fc[1 + k][1] + fc[k][1]) + fz * (c.ff_fc[1 + k][2] + fc[k][2]);
-        }
-    }
+    bnd_apply(u, fl, bu_ptr[t], bu_ptr[t + 1], b_group, b_wt, c);
 #pragma unroll
     for (int k = 0; k < 5; k++) out[k] = fl[k];
 }
@@ -702,12 +759,17 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
 {
     if (h.n_chunks == 0) return 0;
     size_t smem = owner_smem(h.max_loc, h.max_edges, h.max_blob, a.stream_kernel);
+    RkStageArgs none{};
+#define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux
     if (a.stream_kernel)
-        flux_owner_kernel<true, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<true, false, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
+    else if (a.rk)
+        flux_owner_kernel<false, true, true><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, *a.rk);
     else if (a.overwrite)
-        flux_owner_kernel<false, true><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<false, true, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
     else
-        flux_owner_kernel<false, false><<<h.n_chunks, 256, smem, s>>>(h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux);
+        flux_owner_kernel<false, false, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
+#undef OWNER_ARGS
     return 1;
 }
 
@@ -720,9 +782,10 @@ inline std::string configure()
     if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(" #k "): ") + cudaGetErrorString(e);
     OPT_IN((flux_colour_kernel<true>));
     OPT_IN((flux_colour_kernel<false>));
-    OPT_IN((flux_owner_kernel<true, false>));
-    OPT_IN((flux_owner_kernel<false, true>));
-    OPT_IN((flux_owner_kernel<false, false>));
+    OPT_IN((flux_owner_kernel<true, false, false>));
+    OPT_IN((flux_owner_kernel<false, true, false>));
+    OPT_IN((flux_owner_kernel<false, false, false>));
+    OPT_IN((flux_owner_kernel<false, true, true>));
     OPT_IN((flux_gather_kernel<true, false>));
     OPT_IN((flux_gather_kernel<false, true>));
     OPT_IN((flux_gather_kernel<false, false>));

@@ -64,6 +64,7 @@ struct LevelHost {
     std::vector<double> coords, ewt, bwt;     // file order
     std::vector<int> e2n, b2n, bgroup, mg;    // 0-based, file order (mg empty on the coarsest)
     std::vector<int> new_of_old, old_of_new;  // node renumbering
+    std::vector<int> bnd_node_ptr;            // [n_owned+1] boundary entries per owned internal node
     SortedEdges sorted;
     ColourPlanHost colour;
     OwnerPlanHost owner;
@@ -105,6 +106,7 @@ struct OwnerChunkDesc {         // one per chunk, read by the kernel
     int node0, n_own, n_halo, halo_off;
     int n_edges, e_pad, n_inc, blob_bytes;
     long long blob_off;
+    int has_bnd, pad_;           // some owned node has boundary entries (fused stage)
 };
 
 struct OwnerPlanDev {
@@ -133,6 +135,9 @@ struct GatherPlanDev {
 
 struct LevelDev {
     double *var = nullptr, *old = nullptr, *res = nullptr, *flux = nullptr, *dummy_flux = nullptr;
+    double *var_alt = nullptr;     // second variables buffer: the fused stage writes var_new here, then the two swap
+    int *bnd_ptr = nullptr;        // [n_owned+1] boundary entry range per owned node (fused stage)
+    int visit_parity = 0;          // which min_dt slot the next visit reduces into
     double *vol = nullptr, *sf = nullptr, *coords = nullptr;
     int *up_count = nullptr;       // p_up_scratch payload
     int *mg = nullptr;             // internal fine node -> internal coarse node (level+1)
@@ -171,6 +176,7 @@ struct mgcfd_ctx {
     std::string err;
     // device scalars
     double *d_min_dt = nullptr;      // [n_levels] scratch for reductions
+    unsigned long long *d_min_enc = nullptr;   // [n_levels][2] order-encoded min_dt slots of the fused path
     double *d_rms = nullptr;
     int *d_flags = nullptr;          // [0]=bad value count, [1]=min_dt<0 flag, [2]=validate count
     double *h_pinned = nullptr;      // pinned host scratch (8 doubles)
@@ -206,6 +212,27 @@ int k_fill(cudaStream_t s, long long n, double *a, double v);
 // to_internal: dst[perm[i]] = src[i] (file -> internal); else dst[i] = src[perm[i]] (internal -> file)
 int k_permute_rows(cudaStream_t s, int n, int dim, const double *src, const int *perm, double *dst, bool to_internal);
 int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c);
+// fused node kernels of mgcfd_run_cycles
+int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
+                  unsigned long long *min_slot);
+int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
+                        double *sf, double *d_min_out, int *d_flags);
+int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
+                     double *var_above, int *count_above);
+int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots);
+
+// extra arguments of the fused Runge-Kutta stage (flux + boundary flux + time_step [+ residual, rms, bad values])
+struct RkStageArgs {
+    const double *old, *sf;
+    double *var_out, *res;
+    double *d_rms;               // non-null on level 0: sum of squared residuals / bad-value count after the last stage
+    int *d_bad;
+    const int *bnd_ptr;          // per owned node: range into the boundary entry arrays
+    const int *b_group;
+    const double *b_wt;
+    int rk, last;
+    DevConsts c;
+};
 
 struct FluxArgs {
     int n_edges = 0, n_owned = 0, n_nodes = 0;
@@ -213,6 +240,7 @@ struct FluxArgs {
     double *flux = nullptr;
     bool stream_kernel = false;     // unstructured_stream_kernel body instead of the flux body
     bool overwrite = false;         // owner variant: flux known to be zero -> plain store, no read
+    const RkStageArgs *rk = nullptr; // owner variant: fuse the rest of the Runge-Kutta stage into the kernel
 };
 int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
 int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);

@@ -4,6 +4,8 @@
 // (double division and sqrt are IEEE-rounded on the device).  They are all bandwidth-bound
 // streaming kernels; contraction would not make them faster.
 #define MGCFD_EXACT 1
+#include <cfloat>
+
 #include "flux_kernels.cuh"
 
 namespace mgcfd {
@@ -115,6 +117,83 @@ __global__ void finish_min_kernel(unsigned long long *d_min, int *d_flags)
 __global__ void encode_min_kernel(unsigned long long *d_min)
 {
     *d_min = enc_min(*reinterpret_cast<double *>(d_min));
+}
+
+// fused start of a level visit: copy_double_kernel + calculate_dt_kernel + get_min_dt_kernel (euler3d.cpp:467-479)
+__global__ void visit_begin_kernel(int n, const double *__restrict__ var, const double *__restrict__ cbrt_vol,
+                                   double *__restrict__ old, double *__restrict__ dt, unsigned long long *__restrict__ min_slot)
+{
+    __shared__ unsigned long long smin[TPB / 32];
+    unsigned long long m = ~0ull;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double u[5];
+#pragma unroll
+        for (int v = 0; v < 5; v++) { u[v] = var[(size_t)i * 5 + v]; old[(size_t)i * 5 + v] = u[v]; }
+        double rho = u[0];
+        double vx = u[1] / rho, vy = u[2] / rho, vz = u[3] / rho;
+        double q2 = vx * vx + vy * vy + vz * vz;
+        double p = (1.4 - 1.0) * (u[4] - 0.5 * rho * q2);
+        double c = sqrt(1.4 * p / rho);
+        double d = 0.5 * (cbrt_vol[i] / (sqrt(q2) + c));
+        dt[i] = d;
+        if (d == d) m = enc_min(d);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        if (t < m) m = t;
+    }
+    if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TPB / 32; w++)
+            if (smin[w] < m) m = smin[w];
+        atomicMin(min_slot, m);
+    }
+}
+
+// compute_step_factor_kernel reading the reduced minimum from its slot; also re-arms the other slot for the next
+// visit of this level, publishes min_dt and raises the deferred min_dt < 0 flag (euler3d.cpp:480)
+__global__ void step_factor_fused_kernel(int n, const double *__restrict__ vol, const unsigned long long *__restrict__ min_slot,
+                                         unsigned long long *__restrict__ next_slot, double *__restrict__ sf,
+                                         double *__restrict__ d_min_out, int *__restrict__ d_flags)
+{
+    const double m = dec_min(*min_slot);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        *next_slot = enc_min(DBL_MAX);
+        *d_min_out = m;
+        if (m < 0.0f) d_flags[1] = 1;
+    }
+    if (i < n) sf[i] = m / vol[i];
+}
+
+__global__ void reset_min_slots_kernel(int n, unsigned long long *slots)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slots[i] = enc_min(DBL_MAX);
+}
+
+// up_pre + up + up_post (mg.h:29-64) in one gather: a coarse node with children becomes their average, summed from
+// 0.0 in ascending file order exactly as the three loops do; a childless coarse node is left untouched (x * 1.0 == x)
+__global__ void restrict_fused_kernel(int n_coarse, const int *__restrict__ child_ptr, const int *__restrict__ child_idx,
+                                      const double *__restrict__ var, double *__restrict__ var_above,
+                                      int *__restrict__ count_above)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_coarse) return;
+    int j0 = child_ptr[p], j1 = child_ptr[p + 1];
+    if (j0 == j1) return;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = j0; j < j1; j++) {
+        const double *u = var + (size_t)child_idx[j] * 5;
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] += u[v];
+    }
+    double avg = 1.0 / (double)(j1 - j0);
+#pragma unroll
+    for (int v = 0; v < 5; v++) var_above[(size_t)p * 5 + v] = acc[v] * avg;
+    count_above[p] = j1 - j0;
 }
 
 // time_stepping_kernels.h:43-64 (only line :63 has an effect)
@@ -304,6 +383,31 @@ int k_min_dt(cudaStream_t s, int n, const double *sf, double *d_min, int *d_flag
     }
     finish_min_kernel<<<1, 1, 0, s>>>(u, d_flags);
     return launches;
+}
+int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
+                  unsigned long long *min_slot)
+{
+    if (n == 0) return 0;
+    visit_begin_kernel<<<blocks_for(n), TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot);
+    return 1;
+}
+int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
+                        double *sf, double *d_min_out, int *d_flags)
+{
+    step_factor_fused_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, vol, min_slot, next_slot, sf, d_min_out, d_flags);
+    return 1;
+}
+int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots)
+{
+    reset_min_slots_kernel<<<blocks_for(n), TPB, 0, s>>>(n, slots);
+    return 1;
+}
+int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
+                     double *var_above, int *count_above)
+{
+    if (n_coarse == 0) return 0;
+    restrict_fused_kernel<<<blocks_for(n_coarse), TPB, 0, s>>>(n_coarse, child_ptr, child_idx, var, var_above, count_above);
+    return 1;
 }
 int k_step_factor(cudaStream_t s, int n, const double *vol, const double *d_min, double *sf)
 {

@@ -53,12 +53,44 @@ def test_cycles_exact_mode_bit_identical(pkg, meshgen, golden, name, cycles, var
         check_levels(gpu, [g[f"var_L{l}"] for l in range(len(mesh["levels"]))], None, exact=True)
 
 
-def test_loopwise_equals_device_driven(pkg, meshgen):
+@pytest.mark.parametrize("exact", [True, False])
+def test_loopwise_equals_device_driven(pkg, meshgen, exact):
+    """call site by call site (host checks included) == device-driven unfused == device-driven fused schedule.
+    Bit for bit in the exact build; in the fast build the fused Runge-Kutta stage may contract differently from
+    the stand-alone kernels, so the fused run is compared at 1e-13 normwise."""
     mesh = meshgen.make_multigrid("small")
-    with pkg.MGCFD(mesh["levels"]) as a, pkg.MGCFD(mesh["levels"]) as b:
+    with pkg.MGCFD(mesh["levels"], exact_arith=exact) as a, pkg.MGCFD(mesh["levels"], exact_arith=exact) as b, \
+            pkg.MGCFD(mesh["levels"], exact_arith=exact, fuse=False) as c:
         a.run_cycles(3)
         rms, min_dt = b.run_cycles_loopwise(3)
+        c.run_cycles(3)
         assert rms > 0 and min_dt > 0
+        for l in range(len(mesh["levels"])):
+            ref = b.fetch(l, "variables")
+            assert np.array_equal(c.fetch(l, "variables"), ref)
+            assert np.array_equal(c.fetch(l, "residuals"), b.fetch(l, "residuals"))
+            if exact:
+                assert np.array_equal(a.fetch(l, "variables"), ref)
+                assert np.array_equal(a.fetch(l, "residuals"), b.fetch(l, "residuals"))
+                assert np.array_equal(a.fetch(l, "old_variables"), b.fetch(l, "old_variables"))
+                assert np.array_equal(a.fetch(l, "step_factors"), b.fetch(l, "step_factors"))
+                if l > 0:
+                    assert np.array_equal(a.fetch(l, "up_scratch"), b.fetch(l, "up_scratch"))
+            else:
+                assert (normwise(a.fetch(l, "variables"), ref) <= 1e-13).all()
+            assert not a.fetch(l, "fluxes").any() and not b.fetch(l, "fluxes").any()
+
+
+def test_fused_schedule_after_poked_fluxes(pkg, meshgen):
+    """a caller that left non-zero fluxes behind still gets OP_INC semantics from the fused schedule"""
+    mesh = meshgen.make_multigrid("tiny")
+    rng = np.random.default_rng(3)
+    with pkg.MGCFD(mesh["levels"], exact_arith=True) as a, pkg.MGCFD(mesh["levels"], exact_arith=True, fuse=False) as b:
+        f = rng.uniform(-1e-9, 1e-9, size=(a.sizes[0][0], 5))
+        a.set(0, "fluxes", f)
+        b.set(0, "fluxes", f)
+        a.run_cycles(2)
+        b.run_cycles(2)
         for l in range(len(mesh["levels"])):
             assert np.array_equal(a.fetch(l, "variables"), b.fetch(l, "variables"))
 
