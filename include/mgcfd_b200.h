@@ -85,7 +85,18 @@ typedef struct {
     const int    *bnd_node_to_node;    /* [n_bnd_nodes] op_decl_map_hdf5 :274, base_array_index-based */
     const int    *bnd_node_to_group;   /* [n_bnd_nodes] op_decl_dat_hdf5 :276 */
     const double *bnd_node_weights;    /* [n_bnd_nodes*3] op_decl_dat_hdf5 :306 */
-    const int    *node_to_mg_node;     /* [n_nodes] map into level+1 (op_decl_map_hdf5 :283), NULL on the coarsest */
+    const int    *node_to_mg_node;     /* [n_nodes] map into level+1 (op_decl_map_hdf5 :283), NULL on the coarsest;
+                                          on a partition a HALO node whose parent is not on this rank holds base-1 */
+    /* ---- partition only (all NULL / 0 on one GPU); OP2 keeps these inside op_set / op_map after op_partition ---- */
+    const int    *global_node_id;      /* [n_nodes] file index of each local node in the undecomposed mesh; fixes the
+                                          summation order of restrict to the undecomposed one */
+    int           n_neighbours;        /* ranks this rank exchanges halos with on this level */
+    int           pad_;
+    const int    *neighbour_rank;      /* [n_neighbours] ascending */
+    const int    *export_ptr;          /* [n_neighbours+1] into export_idx */
+    const int    *export_idx;          /* local (file) indices of owned nodes sent to each neighbour, in the
+                                          neighbour's import order */
+    const int    *import_ptr;          /* [n_neighbours+1] offsets, in nodes, into the halo range [n_owned, n_nodes) */
 } mgcfd_level_host;
 
 typedef struct {
@@ -96,7 +107,8 @@ typedef struct {
     int exact_arith;       /* 1: reference operation order, IEEE div/sqrt, no FMA contraction in the flux kernels */
     int no_fusion;         /* 1: mgcfd_run_cycles launches one kernel per call site instead of the fused schedule
                               (fused Runge-Kutta stage, visit prologue and restrict; owner variant only) */
-    int reserved[10];
+    int rank, n_ranks;     /* position of this context in a multi-GPU run (default 0 of 1) */
+    int reserved[8];
 } mgcfd_options;
 
 /* ---- lifetime (op_init / op_exit, euler3d.cpp:126, :824) ---- */
@@ -140,6 +152,38 @@ int mgcfd_loop_up_pre(mgcfd_ctx *ctx, int level_above);                         
 int mgcfd_loop_up(mgcfd_ctx *ctx, int level_above);                             /* :585-588 */
 int mgcfd_loop_up_post(mgcfd_ctx *ctx, int level_above);                        /* :590-592 */
 int mgcfd_loop_down(mgcfd_ctx *ctx, int level);                                 /* :626-631 prolong level+1 -> level */
+
+/* ---- domain decomposition (op_partition, euler3d.cpp:340-375; OP2 derives the halo lists internally) ----
+ * Host-side and deterministic; every rank calls these on the undecomposed mesh and builds its own local mesh. */
+typedef struct mgcfd_local_mesh mgcfd_local_mesh;
+/* recursive coordinate bisection of level-0 nodes (the reference offers "INERTIAL"/"GEOM" methods, :373-375) */
+int mgcfd_partition_rcb(int n_nodes, const double *node_coordinates, int n_parts, int *part_out);
+/* coarse node -> owner of its lowest-numbered child; childless -> owner of the nearest edge neighbour with children */
+int mgcfd_partition_coarse(int n_fine, const int *fine_part, const int *fine_to_coarse, int base_array_index, int n_coarse,
+                           int n_coarse_edges, const int *coarse_edge_to_node, const double *coarse_coordinates,
+                           int *coarse_part_out);
+/* this rank's share of every level: [owned | import halo] nodes, edges with an owned endpoint, boundary entries of
+ * owned nodes, 0-based local maps, export/import lists.  part[l][n] = owner of node n of level l. */
+int mgcfd_local_mesh_build(int n_levels, const mgcfd_level_host *global_levels, int base_array_index,
+                           const int *const *part, int rank, int n_ranks, mgcfd_local_mesh **out);
+const mgcfd_level_host *mgcfd_local_mesh_level(const mgcfd_local_mesh *m, int level);   /* pass to mgcfd_decl_level(.., base 0) */
+/* what: "global_node" "global_edge" "global_bnd" "neighbour_rank" "export_ptr" "export_idx" "import_ptr"
+ * "edge_to_node" "node_to_mg_node"; returns the element count (out may be NULL) */
+long long mgcfd_local_mesh_query(const mgcfd_local_mesh *m, int level, const char *what, int *out, long long capacity);
+void mgcfd_local_mesh_free(mgcfd_local_mesh *m);
+
+/* ---- multi-GPU execution.  Halo exchange of `variables` after every Runge-Kutta stage / restrict / prolong and
+ * of `residuals` after every visit (OP2: dirty-bit halo exchanges inside op_par_loop), min_dt all-reduce(MIN).
+ * Two transports:
+ *   group  one process drives several contexts (one per GPU, or several on one GPU for tests): packed export
+ *          buffers are pulled by the neighbour with peer copies, ordered by CUDA events;
+ *   NCCL   one process per GPU (torchrun): grouped ncclSend/ncclRecv per neighbour + ncclAllReduce(min);
+ *          the 128-byte unique id is created on rank 0 and distributed by the launcher. ---- */
+int mgcfd_group_run_cycles(mgcfd_ctx **ranks, int n_ranks, int n_cycles);
+int mgcfd_nccl_unique_id(void *id_out_128);
+int mgcfd_comm_init_nccl(mgcfd_ctx *ctx, int n_ranks, int rank, const void *unique_id_128);
+/* bytes this rank has sent in halo exchanges so far */
+long long mgcfd_halo_bytes_sent(const mgcfd_ctx *ctx);
 
 /* ---- whole V-cycles on the device: the schedule of euler3d.cpp:458-641 with the per-visit host
  * checks (:480, :544) deferred to one flag read per call.  Results equal the loop-by-loop path. ---- */

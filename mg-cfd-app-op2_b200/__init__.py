@@ -6,4 +6,5 @@ level-file layout), host/ (native euler3d driver).  Nothing here imports oracle/
 """
 from . import meshgen  # noqa: F401
 from . import capi  # noqa: F401
-from .capi import MGCFD, MgcfdError, PinnedArray, load_library, farfield_consts  # noqa: F401
+from .capi import (MGCFD, MgcfdError, PinnedArray, LocalMesh, load_library, farfield_consts,  # noqa: F401
+                   partition_levels, group_run_cycles, nccl_unique_id)

@@ -44,13 +44,14 @@ class LevelHost(C.Structure):
     _fields_ = [("n_nodes", C.c_int), ("n_edges", C.c_int), ("n_bnd_nodes", C.c_int), ("n_owned_nodes", C.c_int),
                 ("node_coordinates", _dp), ("edge_to_node", _ip), ("edge_weights", _dp),
                 ("bnd_node_to_node", _ip), ("bnd_node_to_group", _ip), ("bnd_node_weights", _dp),
-                ("node_to_mg_node", _ip)]
+                ("node_to_mg_node", _ip), ("global_node_id", _ip), ("n_neighbours", C.c_int), ("pad_", C.c_int),
+                ("neighbour_rank", _ip), ("export_ptr", _ip), ("export_idx", _ip), ("import_ptr", _ip)]
 
 
 class Options(C.Structure):
     _fields_ = [("flux_variant", C.c_int), ("renumber", C.c_int), ("owner_chunk_nodes", C.c_int),
                 ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("no_fusion", C.c_int),
-                ("reserved", C.c_int * 10)]
+                ("rank", C.c_int), ("n_ranks", C.c_int), ("reserved", C.c_int * 8)]
 
 
 _lib = None
@@ -79,6 +80,13 @@ def load_library():
     lib.mgcfd_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     lib.mgcfd_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.mgcfd_host_free.argtypes = [C.c_void_p]
+    lib.mgcfd_local_mesh_level.restype = C.POINTER(LevelHost)
+    lib.mgcfd_local_mesh_level.argtypes = [C.c_void_p, C.c_int]
+    lib.mgcfd_local_mesh_query.restype = C.c_longlong
+    lib.mgcfd_local_mesh_query.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _ip, C.c_longlong]
+    lib.mgcfd_local_mesh_free.argtypes = [C.c_void_p]
+    lib.mgcfd_halo_bytes_sent.restype = C.c_longlong
+    lib.mgcfd_halo_bytes_sent.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -97,10 +105,22 @@ ABI_SYMBOLS = [
     "mgcfd_plan_query", "mgcfd_timers_enable", "mgcfd_timers_reset", "mgcfd_timers_get",
     "mgcfd_kernel_launches", "mgcfd_set_flux_variant", "mgcfd_stream", "mgcfd_device_ptr",
     "mgcfd_host_alloc", "mgcfd_host_free",
+    "mgcfd_partition_rcb", "mgcfd_partition_coarse", "mgcfd_local_mesh_build", "mgcfd_local_mesh_level",
+    "mgcfd_local_mesh_query", "mgcfd_local_mesh_free", "mgcfd_group_run_cycles", "mgcfd_nccl_unique_id",
+    "mgcfd_comm_init_nccl", "mgcfd_halo_bytes_sent",
 ]
 
 _DAT_DIMS = {"variables": 5, "old_variables": 5, "residuals": 5, "fluxes": 5, "dummy_fluxes": 5,
              "volumes": 1, "step_factors": 1, "node_coordinates": 3}
+
+
+def nccl_unique_id():
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.mgcfd_nccl_unique_id(buf)
+    if rc != 0:
+        raise MgcfdError(rc, "mgcfd_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 def farfield_consts(mesh_name=0):
@@ -134,15 +154,115 @@ class PinnedArray:
             self.ptr = C.c_void_p()
 
 
+def _level_struct(lev, keep):
+    """mgcfd_level_host for a dict of the reference's datasets; `keep` collects the arrays that must stay alive."""
+    coords = _as(lev["node_coordinates"], np.float64)
+    e2n = _as(lev["edge-->node"], np.int32)
+    ewt = _as(lev["edge_weights"], np.float64)
+    b2n = _as(lev["bnd_node-->node"], np.int32)
+    bgr = _as(lev["bnd_node-->group"], np.int32)
+    bwt = _as(lev["bnd_node_weights"], np.float64)
+    mg = _as(lev["node-->mg_node"], np.int32) if "node-->mg_node" in lev else None
+    keep.extend([coords, e2n, ewt, b2n, bgr, bwt, mg])
+    h = LevelHost()
+    h.n_nodes, h.n_edges, h.n_bnd_nodes = coords.shape[0], e2n.shape[0], b2n.shape[0]
+    h.n_owned_nodes = h.n_nodes
+    h.node_coordinates = coords.ctypes.data_as(_dp)
+    h.edge_to_node = e2n.ctypes.data_as(_ip)
+    h.edge_weights = ewt.ctypes.data_as(_dp)
+    h.bnd_node_to_node = b2n.ctypes.data_as(_ip)
+    h.bnd_node_to_group = bgr.ctypes.data_as(_ip)
+    h.bnd_node_weights = bwt.ctypes.data_as(_dp)
+    h.node_to_mg_node = mg.ctypes.data_as(_ip) if mg is not None else _ip()
+    return h
+
+
+def partition_levels(levels, base_array_index, n_ranks):
+    """Owner rank of every node of every level (op_partition, euler3d.cpp:340-375): recursive coordinate bisection
+    on level 0, coarse nodes follow their lowest-numbered child."""
+    lib = load_library()
+    parts = []
+    for l, lev in enumerate(levels):
+        coords = _as(lev["node_coordinates"], np.float64)
+        part = np.empty(coords.shape[0], dtype=np.int32)
+        if l == 0:
+            rc = lib.mgcfd_partition_rcb(coords.shape[0], coords.ctypes.data_as(_dp), int(n_ranks), part.ctypes.data_as(_ip))
+        else:
+            fine = levels[l - 1]
+            f2c = _as(fine["node-->mg_node"], np.int32)
+            e2n = _as(lev["edge-->node"], np.int32)
+            rc = lib.mgcfd_partition_coarse(f2c.shape[0], parts[l - 1].ctypes.data_as(_ip), f2c.ctypes.data_as(_ip),
+                                            int(base_array_index), coords.shape[0], e2n.shape[0], e2n.ctypes.data_as(_ip),
+                                            coords.ctypes.data_as(_dp), part.ctypes.data_as(_ip))
+        if rc != 0:
+            raise MgcfdError(rc, "partitioning failed")
+        parts.append(part)
+    return parts
+
+
+class LocalMesh:
+    """One rank's share of a partitioned deck: [owned | import halo] nodes, edges with an owned endpoint, boundary
+    entries of owned nodes, export/import lists (mgcfd_local_mesh_build)."""
+
+    def __init__(self, levels, base_array_index, parts, rank, n_ranks):
+        self.lib = load_library()
+        self.n_levels, self.rank, self.n_ranks = len(levels), int(rank), int(n_ranks)
+        keep = []
+        glob = (LevelHost * len(levels))(*[_level_struct(lev, keep) for lev in levels])
+        parts = [_as(p, np.int32) for p in parts]
+        pp = (_ip * len(levels))(*[p.ctypes.data_as(_ip) for p in parts])
+        self.handle = C.c_void_p()
+        rc = self.lib.mgcfd_local_mesh_build(len(levels), glob, int(base_array_index), pp, self.rank, self.n_ranks,
+                                             C.byref(self.handle))
+        if rc != 0:
+            raise MgcfdError(rc, "mgcfd_local_mesh_build failed")
+
+    def level(self, l):
+        return self.lib.mgcfd_local_mesh_level(self.handle, l)
+
+    def query(self, l, what):
+        n = self.lib.mgcfd_local_mesh_query(self.handle, l, what.encode(), None, 0)
+        if n < 0:
+            raise MgcfdError(int(n), f"local_mesh_query({what})")
+        out = np.empty(n, dtype=np.int32)
+        self.lib.mgcfd_local_mesh_query(self.handle, l, what.encode(), out.ctypes.data_as(_ip), n)
+        return out
+
+    def sizes(self, l):
+        v = self.level(l).contents
+        return v.n_nodes, v.n_edges, v.n_bnd_nodes, v.n_owned_nodes
+
+    def free(self):
+        if self.handle and self.handle.value:
+            self.lib.mgcfd_local_mesh_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def group_run_cycles(ranks, n_cycles):
+    """V-cycles over several contexts driven by this process (one per GPU, or several on one GPU)."""
+    lib = load_library()
+    arr = (C.c_void_p * len(ranks))(*[r.ctx for r in ranks])
+    rc = lib.mgcfd_group_run_cycles(arr, len(ranks), int(n_cycles))
+    if rc != 0:
+        raise MgcfdError(rc, lib.mgcfd_last_error(ranks[0].ctx).decode())
+
+
 class MGCFD:
     """One context = one GPU's share of the mesh.  Methods are the op_par_loop call sites of euler3d.cpp."""
 
-    def __init__(self, levels, base_array_index=1, device=0, flux_variant="owner", renumber=True,
+    def __init__(self, levels=None, base_array_index=1, device=0, flux_variant="owner", renumber=True,
                  exact_arith=False, owner_chunk_nodes=128, colour_block_edges=256, consts=None,
-                 n_owned=None, init=True, fuse=True):
-        """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"])."""
+                 init=True, fuse=True, local_mesh=None):
+        """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"]), or
+        local_mesh: a LocalMesh (this rank's share of a partitioned deck)."""
         self.lib = load_library()
-        self.n_levels = len(levels)
+        self.n_levels = local_mesh.n_levels if local_mesh is not None else len(levels)
         opt = Options()
         self.lib.mgcfd_default_options(C.byref(opt))
         opt.flux_variant = FLUX_VARIANTS[flux_variant] if isinstance(flux_variant, str) else int(flux_variant)
@@ -151,36 +271,38 @@ class MGCFD:
         opt.owner_chunk_nodes = int(owner_chunk_nodes)
         opt.colour_block_edges = int(colour_block_edges)
         opt.no_fusion = int(not fuse)
+        opt.rank = local_mesh.rank if local_mesh is not None else 0
+        opt.n_ranks = local_mesh.n_ranks if local_mesh is not None else 1
+        self.rank, self.n_ranks = opt.rank, opt.n_ranks
         self.ctx = C.c_void_p()
         rc = self.lib.mgcfd_create(C.byref(self.ctx), int(device), self.n_levels, C.byref(opt))
         if rc != 0:
             raise MgcfdError(rc, self.lib.mgcfd_last_error(None).decode())
         self.consts = consts if consts is not None else farfield_consts()
         self._ck(self.lib.mgcfd_decl_consts(self.ctx, C.byref(self.consts)))
-        self.sizes = []
-        for l, lev in enumerate(levels):
-            coords = _as(lev["node_coordinates"], np.float64)
-            e2n = _as(lev["edge-->node"], np.int32)
-            ewt = _as(lev["edge_weights"], np.float64)
-            b2n = _as(lev["bnd_node-->node"], np.int32)
-            bgr = _as(lev["bnd_node-->group"], np.int32)
-            bwt = _as(lev["bnd_node_weights"], np.float64)
-            mg = _as(lev["node-->mg_node"], np.int32) if "node-->mg_node" in lev else None
-            h = LevelHost()
-            h.n_nodes, h.n_edges, h.n_bnd_nodes = coords.shape[0], e2n.shape[0], b2n.shape[0]
-            h.n_owned_nodes = h.n_nodes if n_owned is None else int(n_owned[l])
-            h.node_coordinates = coords.ctypes.data_as(_dp)
-            h.edge_to_node = e2n.ctypes.data_as(_ip)
-            h.edge_weights = ewt.ctypes.data_as(_dp)
-            h.bnd_node_to_node = b2n.ctypes.data_as(_ip)
-            h.bnd_node_to_group = bgr.ctypes.data_as(_ip)
-            h.bnd_node_weights = bwt.ctypes.data_as(_dp)
-            h.node_to_mg_node = mg.ctypes.data_as(_ip) if mg is not None else _ip()
-            self._ck(self.lib.mgcfd_decl_level(self.ctx, l, C.byref(h), int(base_array_index)))
+        self.sizes, self.n_owned = [], []
+        keep = []
+        for l in range(self.n_levels):
+            if local_mesh is not None:
+                hp = local_mesh.level(l)
+                h = hp.contents
+                self._ck(self.lib.mgcfd_decl_level(self.ctx, l, hp, 0))          # local maps are 0-based
+            else:
+                h = _level_struct(levels[l], keep)
+                self._ck(self.lib.mgcfd_decl_level(self.ctx, l, C.byref(h), int(base_array_index)))
             self.sizes.append((h.n_nodes, h.n_edges, h.n_bnd_nodes))
+            self.n_owned.append(h.n_owned_nodes)
         self._ck(self.lib.mgcfd_plan(self.ctx))
         if init:
             self.init_loops()
+
+    def comm_init_nccl(self, unique_id):
+        """unique_id: the 128 bytes mgcfd_nccl_unique_id() produced on rank 0"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.mgcfd_comm_init_nccl(self.ctx, self.n_ranks, self.rank, buf))
+
+    def halo_bytes_sent(self):
+        return int(self.lib.mgcfd_halo_bytes_sent(self.ctx))
 
     # ---- plumbing
     def _ck(self, rc):

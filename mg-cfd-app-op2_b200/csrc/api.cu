@@ -40,7 +40,7 @@ static std::string g_create_error;
         }                                                                                                \
     } while (0)
 
-static int check_launch(mgcfd_ctx *ctx, const char *what)
+int mgcfd::api_check_launch(mgcfd_ctx *ctx, const char *what)
 {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -72,7 +72,7 @@ static int dev_upload(mgcfd_ctx *ctx, T **p, const std::vector<T> &h)
     return MGCFD_OK;
 }
 
-static DevConsts dev_consts(const mgcfd_ctx *ctx)
+DevConsts mgcfd::api_dev_consts(const mgcfd_ctx *ctx)
 {
     DevConsts c;
     c.smoothing = ctx->consts.smoothing_coefficient;
@@ -90,42 +90,7 @@ static DevConsts dev_consts(const mgcfd_ctx *ctx)
 // ------------------------------------------------------------------------------------------
 // timers
 // ------------------------------------------------------------------------------------------
-struct LoopScope {
-    mgcfd_ctx *ctx;
-    LoopTimer *t = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    long long elems;
-    static cudaEvent_t get_event(mgcfd_ctx *ctx)
-    {
-        if (!ctx->event_pool.empty()) {
-            cudaEvent_t e = ctx->event_pool.back();
-            ctx->event_pool.pop_back();
-            return e;
-        }
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        return e;
-    }
-    LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
-    {
-        if (!ctx->timers_on) return;
-        if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0 && strcmp(name, "rk_stage") != 0)
-            return;   // flux-edge launches (stand-alone or as the fused Runge-Kutta stage) only
-        t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
-        e0 = get_event(ctx);
-        e1 = get_event(ctx);
-        cudaEventRecord(e0, ctx->stream);
-    }
-    ~LoopScope()
-    {
-        if (!t) return;
-        cudaEventRecord(e1, ctx->stream);
-        t->pending.push_back({e0, e1});
-        t->pending_elems.push_back(elems);
-    }
-};
-
-static void timers_collect(mgcfd_ctx *ctx)
+void mgcfd::timers_collect(mgcfd_ctx *ctx)
 {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->timers) {
@@ -181,6 +146,9 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
         if (ctx->opt.colour_block_edges <= 0 || ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
         ctx->H.resize(n_levels);
         ctx->D.resize(n_levels);
+        ctx->halo.resize(n_levels);
+        ctx->n_ranks = std::max(1, ctx->opt.n_ranks);
+        ctx->rank = ctx->opt.rank;
         *out = ctx;
         return MGCFD_OK;
     }
@@ -209,6 +177,10 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     if (ctx->opt.colour_block_edges > 256) ctx->opt.colour_block_edges = 256;
     ctx->H.resize(n_levels);
     ctx->D.resize(n_levels);
+    ctx->halo.resize(n_levels);
+    ctx->n_ranks = std::max(1, ctx->opt.n_ranks);
+    ctx->rank = ctx->opt.rank;
+    if (ctx->rank < 0 || ctx->rank >= ctx->n_ranks) { g_create_error = "mgcfd_create: rank out of range"; delete ctx; return MGCFD_ERR_ARG; }
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         delete ctx;
@@ -222,6 +194,9 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     if ((e = cudaMalloc((void **)&ctx->d_flags, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemset(ctx->d_flags, 0, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMallocHost((void **)&ctx->h_pinned, sizeof(double) * 8)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     std::string ce = flux_configure();
     if (!ce.empty()) {
         g_create_error = ce;
@@ -254,6 +229,12 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     for (auto &kv : ctx->timers)
         for (auto &p : kv.second.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_pack, ctx->ev_done, ctx->ev_k1})
+        if (e) cudaEventDestroy(e);
+    for (auto &h : ctx->halo) {
+        if (h.d_export_idx) cudaFree(h.d_export_idx);
+        if (h.sendbuf) cudaFree(h.sendbuf);
+    }
     if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
     if (ctx->d_rms) cudaFree(ctx->d_rms);
     if (ctx->d_min_enc) cudaFree(ctx->d_min_enc);
@@ -333,6 +314,22 @@ int mgcfd_decl_level(mgcfd_ctx *ctx, int level, const mgcfd_level_host *lv, int 
         REQUIRE(level + 1 < ctx->n_levels, "node-->mg_node given on the coarsest level");
         L.mg.resize(n);
         for (size_t i = 0; i < n; i++) L.mg[i] = lv->node_to_mg_node[i] - base;   // range-checked in mgcfd_plan
+    }
+    if (lv->global_node_id) L.global_node.assign(lv->global_node_id, lv->global_node_id + n);
+    if (lv->n_neighbours > 0) {
+        REQUIRE(ctx->n_ranks > 1, "halo lists given to a context created with n_ranks == 1");
+        REQUIRE(lv->neighbour_rank && lv->export_ptr && lv->import_ptr, "null halo list");
+        const int nn = lv->n_neighbours;
+        L.nbr_rank.assign(lv->neighbour_rank, lv->neighbour_rank + nn);
+        L.export_ptr.assign(lv->export_ptr, lv->export_ptr + nn + 1);
+        L.import_ptr.assign(lv->import_ptr, lv->import_ptr + nn + 1);
+        REQUIRE(L.import_ptr[nn] == L.n_nodes - L.n_owned, "import lists do not cover the halo range");
+        REQUIRE(L.export_ptr[nn] == 0 || lv->export_idx, "null export list");
+        L.export_idx.assign(lv->export_idx, lv->export_idx + L.export_ptr[nn]);
+        for (int q : L.nbr_rank) REQUIRE(q >= 0 && q < ctx->n_ranks && q != ctx->rank, "neighbour rank out of range");
+        for (int v : L.export_idx) REQUIRE(v >= 0 && v < L.n_owned, "export index is not an owned node");
+    } else {
+        REQUIRE(L.n_owned == L.n_nodes, "halo nodes without import lists");
     }
     return MGCFD_OK;
 }
@@ -414,7 +411,7 @@ static int upload_node_dat(mgcfd_ctx *ctx, int level, double *dst, const double 
     CK(cudaMemcpyAsync(ctx->d_stage, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->launches += k_permute_rows(ctx->stream, L.n_nodes, dim, static_cast<const double *>(ctx->d_stage), ctx->D[level].perm, dst, true);
     CK(cudaStreamSynchronize(ctx->stream));
-    return check_launch(ctx, "permute_rows");
+    return api_check_launch(ctx, "permute_rows");
 }
 
 static int download_node_dat(mgcfd_ctx *ctx, int level, const double *src, double *dst_file_order, int dim)
@@ -429,7 +426,7 @@ static int download_node_dat(mgcfd_ctx *ctx, int level, const double *src, doubl
     CK(cudaMemcpyAsync(pinned ? (void *)dst_file_order : ctx->h_stage, ctx->d_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (!pinned) memcpy(dst_file_order, ctx->h_stage, bytes);
-    return check_launch(ctx, "permute_rows");
+    return api_check_launch(ctx, "permute_rows");
 }
 
 int mgcfd_plan(mgcfd_ctx *ctx)
@@ -466,23 +463,54 @@ int mgcfd_plan(mgcfd_ctx *ctx)
             LevelHost &Cs = ctx->H[l + 1];
             std::vector<int> mg(n);
             for (size_t i = 0; i < n; i++) {
-                int p = L.mg[L.old_of_new[i]];
+                int f = L.old_of_new[i], p = L.mg[f];
+                if (p == -1 && f >= L.n_owned) { mg[i] = -1; continue; }   // halo node whose parent lives elsewhere
                 REQUIRE(p >= 0 && p < Cs.n_nodes, "node-->mg_node entry out of range");
                 mg[i] = Cs.new_of_old[p];
             }
             if ((rc = dev_upload(ctx, &D.mg, mg))) return rc;
-            // restrict gather lists on the coarse level: children in ascending fine FILE order
+            // restrict gather lists of the OWNED coarse nodes: children (owned or halo) in ascending file order of
+            // the undecomposed mesh, which is the order OP2-seq applies the increments in
+            std::vector<int> forder(L.n_nodes);
+            std::iota(forder.begin(), forder.end(), 0);
+            if (!L.global_node.empty())
+                std::stable_sort(forder.begin(), forder.end(), [&](int x, int y) { return L.global_node[x] < L.global_node[y]; });
+            auto parent_of = [&](int f) {
+                int p = L.mg[f];
+                if (p < 0) return -1;
+                p = Cs.new_of_old[p];
+                return p < Cs.n_owned ? p : -1;
+            };
             std::vector<int> cptr(Cs.n_nodes + 1, 0), cidx;
-            for (int f = 0; f < L.n_nodes; f++)
-                if (L.new_of_old[f] < L.n_owned) cptr[Cs.new_of_old[L.mg[f]] + 1]++;
+            for (int f : forder) {
+                int p = parent_of(f);
+                if (p >= 0) cptr[p + 1]++;
+            }
             for (int p = 0; p < Cs.n_nodes; p++) cptr[p + 1] += cptr[p];
             cidx.resize(cptr[Cs.n_nodes]);
             std::vector<int> fill(cptr.begin(), cptr.end() - 1);
-            for (int f = 0; f < L.n_nodes; f++)
-                if (L.new_of_old[f] < L.n_owned) cidx[fill[Cs.new_of_old[L.mg[f]]]++] = L.new_of_old[f];
+            for (int f : forder) {
+                int p = parent_of(f);
+                if (p >= 0) cidx[fill[p]++] = L.new_of_old[f];
+            }
             LevelDev &DC = ctx->D[l + 1];
             if ((rc = dev_upload(ctx, &DC.child_ptr, cptr))) return rc;
             if ((rc = dev_upload(ctx, &DC.child_idx, cidx))) return rc;
+        }
+    }
+    for (int l = 0; l < ctx->n_levels; l++) {
+        LevelHost &L = ctx->H[l];
+        HaloLevel &Hd = ctx->halo[l];
+        Hd.nbr_rank = L.nbr_rank;
+        Hd.exp_ptr = L.export_ptr;
+        Hd.imp_ptr = L.import_ptr;
+        Hd.n_export = (int)L.export_idx.size();
+        if (Hd.n_export) {
+            std::vector<int> idx(L.export_idx.size());
+            for (size_t i = 0; i < idx.size(); i++) idx[i] = L.new_of_old[L.export_idx[i]];
+            int rc;
+            if ((rc = dev_upload(ctx, &Hd.d_export_idx, idx))) return rc;
+            if ((rc = dev_alloc(ctx, &Hd.sendbuf, (size_t)Hd.n_export * 5))) return rc;
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -712,7 +740,7 @@ static int ensure_gather(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
-static int ensure_flux_plan(mgcfd_ctx *ctx, int level)
+extern "C++" int mgcfd::api_ensure_flux_plan(mgcfd_ctx *ctx, int level)
 {
     switch (ctx->opt.flux_variant) {
     case MGCFD_FLUX_GATHER: return ensure_gather(ctx, level);
@@ -738,8 +766,8 @@ int mgcfd_loop_initialize_variables(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();
     LoopScope t(ctx, "initialize_variables", level, ctx->H[level].n_nodes);
-    ctx->launches += k_init_vars(ctx->stream, ctx->H[level].n_nodes, ctx->D[level].var, dev_consts(ctx));
-    return check_launch(ctx, "initialize_variables_kernel");
+    ctx->launches += k_init_vars(ctx->stream, ctx->H[level].n_nodes, ctx->D[level].var, api_dev_consts(ctx));
+    return api_check_launch(ctx, "initialize_variables_kernel");
 }
 
 int mgcfd_loop_zero_fluxes(mgcfd_ctx *ctx, int level)
@@ -747,7 +775,7 @@ int mgcfd_loop_zero_fluxes(mgcfd_ctx *ctx, int level)
     CHECK_LEVEL(level); CHECK_PLANNED();
     ctx->launches += k_fill(ctx->stream, (long long)ctx->H[level].n_nodes * 5, ctx->D[level].flux, 0.0);
     ctx->D[level].flux_is_zero = true;
-    return check_launch(ctx, "zero_5d_array_kernel");
+    return api_check_launch(ctx, "zero_5d_array_kernel");
 }
 
 static int upload_volumes(mgcfd_ctx *ctx, int level, const std::vector<double> &vol_file_order)
@@ -821,7 +849,7 @@ int mgcfd_loop_copy_double(mgcfd_ctx *ctx, int level)
     CHECK_LEVEL(level); CHECK_PLANNED();
     LoopScope t(ctx, "copy_double", level, ctx->H[level].n_owned);
     ctx->launches += k_copy(ctx->stream, ctx->H[level].n_owned, ctx->D[level].var, ctx->D[level].old);
-    return check_launch(ctx, "copy_double_kernel");
+    return api_check_launch(ctx, "copy_double_kernel");
 }
 
 int mgcfd_loop_calculate_dt(mgcfd_ctx *ctx, int level)
@@ -830,7 +858,7 @@ int mgcfd_loop_calculate_dt(mgcfd_ctx *ctx, int level)
     LoopScope t(ctx, "calculate_dt", level, ctx->H[level].n_owned);
     ctx->launches += k_calculate_dt(ctx->stream, ctx->H[level].n_owned, ctx->D[level].var, ctx->D[level].cbrt_vol,
                                     ctx->D[level].sf);
-    return check_launch(ctx, "calculate_dt_kernel");
+    return api_check_launch(ctx, "calculate_dt_kernel");
 }
 
 int mgcfd_loop_get_min_dt(mgcfd_ctx *ctx, int level, double *min_dt)
@@ -846,7 +874,7 @@ int mgcfd_loop_get_min_dt(mgcfd_ctx *ctx, int level, double *min_dt)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     *min_dt = ctx->h_pinned[1];
-    return check_launch(ctx, "get_min_dt_kernel");
+    return api_check_launch(ctx, "get_min_dt_kernel");
 }
 
 int mgcfd_loop_compute_step_factor(mgcfd_ctx *ctx, int level, const double *min_dt)
@@ -858,12 +886,12 @@ int mgcfd_loop_compute_step_factor(mgcfd_ctx *ctx, int level, const double *min_
     CK(cudaMemcpyAsync(&ctx->d_min_dt[level], &ctx->h_pinned[2], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // h_pinned[2] is reused by the next call
     ctx->launches += k_step_factor(ctx->stream, ctx->H[level].n_owned, ctx->D[level].vol, &ctx->d_min_dt[level], ctx->D[level].sf);
-    return check_launch(ctx, "compute_step_factor_kernel");
+    return api_check_launch(ctx, "compute_step_factor_kernel");
 }
 
-static int run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel)
+extern "C++" int mgcfd::api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel)
 {
-    int rc = ensure_flux_plan(ctx, level);
+    int rc = api_ensure_flux_plan(ctx, level);
     if (rc) return rc;
     LevelHost &L = ctx->H[level];
     LevelDev &D = ctx->D[level];
@@ -890,19 +918,19 @@ static int run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel)
     case MGCFD_FLUX_GATHER: ctx->launches += flux_gather(ctx->stream, a, D.gather, L.owner.n_chunks, L.owner.max_loc, exact); break;
     }
     if (!stream_kernel) D.flux_is_zero = false;
-    return check_launch(ctx, "compute_flux_edge_kernel");
+    return api_check_launch(ctx, "compute_flux_edge_kernel");
 }
 
 int mgcfd_loop_compute_flux_edge(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();
-    return run_flux(ctx, level, false);
+    return api_run_flux(ctx, level, false);
 }
 
 int mgcfd_loop_unstructured_stream(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();
-    return run_flux(ctx, level, true);
+    return api_run_flux(ctx, level, true);
 }
 
 int mgcfd_loop_compute_bnd_node_flux(mgcfd_ctx *ctx, int level)
@@ -911,9 +939,9 @@ int mgcfd_loop_compute_bnd_node_flux(mgcfd_ctx *ctx, int level)
     LevelDev &D = ctx->D[level];
     LoopScope t(ctx, "compute_bnd_node_flux", level, ctx->H[level].n_bnd);
     ctx->launches += k_bnd_flux(ctx->stream, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux,
-                                dev_consts(ctx), ctx->opt.exact_arith != 0);
+                                api_dev_consts(ctx), ctx->opt.exact_arith != 0);
     D.flux_is_zero = false;
-    return check_launch(ctx, "compute_bnd_node_flux_kernel");
+    return api_check_launch(ctx, "compute_bnd_node_flux_kernel");
 }
 
 int mgcfd_loop_time_step(mgcfd_ctx *ctx, int level, const int *rk)
@@ -924,7 +952,7 @@ int mgcfd_loop_time_step(mgcfd_ctx *ctx, int level, const int *rk)
     LoopScope t(ctx, "time_step", level, ctx->H[level].n_owned);
     ctx->launches += k_time_step(ctx->stream, ctx->H[level].n_owned, *rk, D.sf, D.flux, D.old, D.var);
     D.flux_is_zero = true;
-    return check_launch(ctx, "time_step_kernel");
+    return api_check_launch(ctx, "time_step_kernel");
 }
 
 int mgcfd_loop_residual(mgcfd_ctx *ctx, int level)
@@ -933,7 +961,7 @@ int mgcfd_loop_residual(mgcfd_ctx *ctx, int level)
     LevelDev &D = ctx->D[level];
     LoopScope t(ctx, "residual", level, ctx->H[level].n_owned);
     ctx->launches += k_residual(ctx->stream, ctx->H[level].n_owned, D.old, D.var, D.res);
-    return check_launch(ctx, "residual_kernel");
+    return api_check_launch(ctx, "residual_kernel");
 }
 
 int mgcfd_loop_calc_rms(mgcfd_ctx *ctx, int level, double *rms)
@@ -949,7 +977,7 @@ int mgcfd_loop_calc_rms(mgcfd_ctx *ctx, int level, double *rms)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     *rms = ctx->h_pinned[4];
-    return check_launch(ctx, "calc_rms_kernel");
+    return api_check_launch(ctx, "calc_rms_kernel");
 }
 
 int mgcfd_loop_count_bad_vals(mgcfd_ctx *ctx, int level, int *count)
@@ -966,7 +994,7 @@ int mgcfd_loop_count_bad_vals(mgcfd_ctx *ctx, int level, int *count)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     *count = hp[1];
-    return check_launch(ctx, "count_bad_vals");
+    return api_check_launch(ctx, "count_bad_vals");
 }
 
 int mgcfd_loop_up_pre(mgcfd_ctx *ctx, int la)
@@ -975,7 +1003,7 @@ int mgcfd_loop_up_pre(mgcfd_ctx *ctx, int la)
     REQUIRE(la >= 1, "up_pre needs a finer level below");
     LoopScope t(ctx, "up_pre", la, ctx->H[la - 1].n_owned);
     ctx->launches += k_up_pre(ctx->stream, ctx->H[la - 1].n_owned, ctx->D[la - 1].mg, ctx->D[la].var, ctx->D[la].up_count);
-    return check_launch(ctx, "up_pre_kernel");
+    return api_check_launch(ctx, "up_pre_kernel");
 }
 
 int mgcfd_loop_up(mgcfd_ctx *ctx, int la)
@@ -985,7 +1013,7 @@ int mgcfd_loop_up(mgcfd_ctx *ctx, int la)
     LoopScope t(ctx, "up", la, ctx->H[la - 1].n_owned);
     ctx->launches += k_up(ctx->stream, ctx->H[la].n_nodes, ctx->D[la].child_ptr, ctx->D[la].child_idx, ctx->D[la - 1].var,
                           ctx->D[la].var, ctx->D[la].up_count);
-    return check_launch(ctx, "up_kernel");
+    return api_check_launch(ctx, "up_kernel");
 }
 
 int mgcfd_loop_up_post(mgcfd_ctx *ctx, int la)
@@ -994,7 +1022,7 @@ int mgcfd_loop_up_post(mgcfd_ctx *ctx, int la)
     REQUIRE(la >= 1, "up_post needs a finer level below");
     LoopScope t(ctx, "up_post", la, ctx->H[la].n_owned);
     ctx->launches += k_up_post(ctx->stream, ctx->H[la].n_owned, ctx->D[la].var, ctx->D[la].up_count);
-    return check_launch(ctx, "up_post_kernel");
+    return api_check_launch(ctx, "up_post_kernel");
 }
 
 int mgcfd_loop_down(mgcfd_ctx *ctx, int level)
@@ -1004,126 +1032,7 @@ int mgcfd_loop_down(mgcfd_ctx *ctx, int level)
     LevelDev &D = ctx->D[level], &A = ctx->D[level + 1];
     LoopScope t(ctx, "down", level, ctx->H[level].n_owned);
     ctx->launches += k_down(ctx->stream, ctx->H[level].n_owned, D.mg, D.var, D.res, D.coords, A.res, A.coords);
-    return check_launch(ctx, "down_kernel");
-}
-
-// ------------------------------------------------------------------------------------------
-// whole cycles without host round trips (euler3d.cpp:458-641)
-// ------------------------------------------------------------------------------------------
-int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
-{
-    REQUIRE(ctx, "null ctx");
-    CHECK_PLANNED();
-    REQUIRE(n_cycles >= 0, "negative cycle count");
-    const int nl = ctx->n_levels;
-    for (int l = 0; l < nl; l++) {
-        int rc = ensure_flux_plan(ctx, l);
-        if (rc) return rc;
-    }
-    cudaStream_t s = ctx->stream;
-    const bool exact = ctx->opt.exact_arith != 0;
-    const DevConsts dc = dev_consts(ctx);
-    // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
-    const bool fused = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && !ctx->opt.no_fusion;
-    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, s));
-    int level = 0, dir = 0, i = 0;
-    while (i < n_cycles) {
-        LevelHost &L = ctx->H[level];
-        LevelDev &D = ctx->D[level];
-        const int no = L.n_owned;
-        if (fused) {
-            unsigned long long *slot = &ctx->d_min_enc[2 * level + D.visit_parity];
-            unsigned long long *next = &ctx->d_min_enc[2 * level + (D.visit_parity ^ 1)];
-            D.visit_parity ^= 1;
-            { LoopScope t(ctx, "visit_begin", level, no); ctx->launches += k_visit_begin(s, no, D.var, D.cbrt_vol, D.old, D.sf, slot); }
-            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor_fused(s, no, D.vol, slot, next, D.sf, &ctx->d_min_dt[level], ctx->d_flags); }
-            if (level == 0) ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0);
-            for (int rk = 0; rk < MGCFD_RK; rk++) {
-                if (!D.flux_is_zero) {      // only after a caller poked the fluxes: unfused stage keeps OP_INC semantics
-                    int rc = run_flux(ctx, level, false);
-                    if (rc) return rc;
-                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
-                    ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var);
-                    D.flux_is_zero = true;
-                    if (rk == MGCFD_RK - 1) {
-                        ctx->launches += k_residual(s, no, D.old, D.var, D.res);
-                        if (level == 0) { ctx->launches += k_rms(s, no, D.res, ctx->d_rms); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
-                    }
-                    continue;
-                }
-                RkStageArgs ra;
-                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
-                ra.d_rms = level == 0 ? ctx->d_rms : nullptr;
-                ra.d_bad = &ctx->d_flags[0];
-                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
-                ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = dc;
-                FluxArgs a;
-                a.n_edges = L.n_edges; a.n_owned = no; a.n_nodes = L.n_nodes;
-                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
-                {
-                    LoopScope t(ctx, "rk_stage", level, L.n_edges);
-                    ctx->launches += flux_owner(s, a, D.owner, L.owner, exact);
-                }
-                if (L.n_nodes > no)   // halo entries of the new buffer are refreshed by the exchange; keep them defined
-                    CK(cudaMemcpyAsync(D.var_alt + (size_t)no * 5, D.var + (size_t)no * 5, (size_t)(L.n_nodes - no) * 40,
-                                       cudaMemcpyDeviceToDevice, s));
-                std::swap(D.var, D.var_alt);
-            }
-        } else {
-            { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
-            { LoopScope t(ctx, "calculate_dt", level, no); ctx->launches += k_calculate_dt(s, no, D.var, D.cbrt_vol, D.sf); }
-            {
-                LoopScope t(ctx, "get_min_dt", level, no);
-                ctx->launches += k_fill(s, 1, &ctx->d_min_dt[level], DBL_MAX);
-                ctx->launches += k_min_dt(s, no, D.sf, &ctx->d_min_dt[level], ctx->d_flags);
-            }
-            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor(s, no, D.vol, &ctx->d_min_dt[level], D.sf); }
-            for (int rk = 0; rk < MGCFD_RK; rk++) {
-                int rc = run_flux(ctx, level, false);
-                if (rc) return rc;
-                {
-                    LoopScope t(ctx, "compute_bnd_node_flux", level, L.n_bnd);
-                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
-                }
-                { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
-                D.flux_is_zero = true;
-            }
-            { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
-            if (level == 0) {
-                { LoopScope t(ctx, "calc_rms", level, no); ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0); ctx->launches += k_rms(s, no, D.res, ctx->d_rms); }
-                { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
-            }
-        }
-        if (nl <= 1) {
-            i++;
-        } else if (dir == 0) {
-            level++;
-            LevelDev &A = ctx->D[level], &F = ctx->D[level - 1];
-            const int nf = ctx->H[level - 1].n_owned;
-            if (fused) {
-                LoopScope t(ctx, "restrict", level, nf);
-                ctx->launches += k_restrict_fused(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
-            } else {
-                { LoopScope t(ctx, "up_pre", level, nf); ctx->launches += k_up_pre(s, nf, F.mg, A.var, A.up_count); }
-                { LoopScope t(ctx, "up", level, nf); ctx->launches += k_up(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count); }
-                { LoopScope t(ctx, "up_post", level, ctx->H[level].n_owned); ctx->launches += k_up_post(s, ctx->H[level].n_owned, A.var, A.up_count); }
-            }
-            if (level == nl - 1) dir = 1;
-        } else {
-            level--;
-            LevelDev &F = ctx->D[level], &A = ctx->D[level + 1];
-            { LoopScope t(ctx, "down", level, ctx->H[level].n_owned); ctx->launches += k_down(s, ctx->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords); }
-            if (level == 0) { dir = 0; i++; }
-        }
-    }
-    int rc = check_launch(ctx, "mgcfd_run_cycles");
-    if (rc) return rc;
-    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
-    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
-    if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
-    return MGCFD_OK;
+    return api_check_launch(ctx, "down_kernel");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1229,7 +1138,7 @@ int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master, int *n
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_master);
     *n_diff = hp[0];
-    return check_launch(ctx, "identify_differences");
+    return api_check_launch(ctx, "identify_differences");
 }
 
 static long long emit(const std::vector<int> &v, int *out, long long cap)

@@ -1,0 +1,470 @@
+// cycle.cu -- whole multigrid V-cycles on the device (the schedule of euler3d.cpp:458-641 with the per-visit host
+// checks deferred), on one context or on a set of ranks with halo exchange.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <dlfcn.h>
+
+#include <nccl.h>
+
+#include "internal.h"
+
+using namespace mgcfd;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return MGCFD_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                               \
+    do {                                                                                                 \
+        if (!(cond)) {                                                                                   \
+            ctx->err = (msg);                                                                            \
+            return MGCFD_ERR_ARG;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// one context, no communication
+// ------------------------------------------------------------------------------------------
+int mgcfd::cycle_run_single(mgcfd_ctx *ctx, int n_cycles)
+{
+    const int nl = ctx->n_levels;
+    for (int l = 0; l < nl; l++) {
+        int rc = api_ensure_flux_plan(ctx, l);
+        if (rc) return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    const bool exact = ctx->opt.exact_arith != 0;
+    const DevConsts dc = api_dev_consts(ctx);
+    // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
+    const bool fused = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && !ctx->opt.no_fusion;
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, s));
+    int level = 0, dir = 0, i = 0;
+    while (i < n_cycles) {
+        LevelHost &L = ctx->H[level];
+        LevelDev &D = ctx->D[level];
+        const int no = L.n_owned;
+        if (fused) {
+            unsigned long long *slot = &ctx->d_min_enc[2 * level + D.visit_parity];
+            unsigned long long *next = &ctx->d_min_enc[2 * level + (D.visit_parity ^ 1)];
+            D.visit_parity ^= 1;
+            { LoopScope t(ctx, "visit_begin", level, no); ctx->launches += k_visit_begin(s, no, D.var, D.cbrt_vol, D.old, D.sf, slot); }
+            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor_fused(s, no, D.vol, slot, next, D.sf, &ctx->d_min_dt[level], ctx->d_flags); }
+            if (level == 0) ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0);
+            for (int rk = 0; rk < MGCFD_RK; rk++) {
+                if (!D.flux_is_zero) {      // only after a caller poked the fluxes: unfused stage keeps OP_INC semantics
+                    int rc = api_run_flux(ctx, level, false);
+                    if (rc) return rc;
+                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+                    ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var);
+                    D.flux_is_zero = true;
+                    if (rk == MGCFD_RK - 1) {
+                        ctx->launches += k_residual(s, no, D.old, D.var, D.res);
+                        if (level == 0) { ctx->launches += k_rms(s, no, D.res, ctx->d_rms); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+                    }
+                    continue;
+                }
+                RkStageArgs ra;
+                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
+                ra.d_rms = level == 0 ? ctx->d_rms : nullptr;
+                ra.d_bad = &ctx->d_flags[0];
+                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
+                ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = dc;
+                FluxArgs a;
+                a.n_edges = L.n_edges; a.n_owned = no; a.n_nodes = L.n_nodes;
+                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
+                {
+                    LoopScope t(ctx, "rk_stage", level, L.n_edges);
+                    ctx->launches += flux_owner(s, a, D.owner, L.owner, exact);
+                }
+                if (L.n_nodes > no)   // halo entries of the new buffer are refreshed by the exchange; keep them defined
+                    CK(cudaMemcpyAsync(D.var_alt + (size_t)no * 5, D.var + (size_t)no * 5, (size_t)(L.n_nodes - no) * 40,
+                                       cudaMemcpyDeviceToDevice, s));
+                std::swap(D.var, D.var_alt);
+            }
+        } else {
+            { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
+            { LoopScope t(ctx, "calculate_dt", level, no); ctx->launches += k_calculate_dt(s, no, D.var, D.cbrt_vol, D.sf); }
+            {
+                LoopScope t(ctx, "get_min_dt", level, no);
+                ctx->launches += k_fill(s, 1, &ctx->d_min_dt[level], DBL_MAX);
+                ctx->launches += k_min_dt(s, no, D.sf, &ctx->d_min_dt[level], ctx->d_flags);
+            }
+            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor(s, no, D.vol, &ctx->d_min_dt[level], D.sf); }
+            for (int rk = 0; rk < MGCFD_RK; rk++) {
+                int rc = api_run_flux(ctx, level, false);
+                if (rc) return rc;
+                {
+                    LoopScope t(ctx, "compute_bnd_node_flux", level, L.n_bnd);
+                    ctx->launches += k_bnd_flux(s, D.n_bnd_unique, D.bu_node, D.bu_ptr, D.b_group, D.b_wt, D.var, D.flux, dc, exact);
+                }
+                { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
+                D.flux_is_zero = true;
+            }
+            { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
+            if (level == 0) {
+                { LoopScope t(ctx, "calc_rms", level, no); ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0); ctx->launches += k_rms(s, no, D.res, ctx->d_rms); }
+                { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
+            }
+        }
+        if (nl <= 1) {
+            i++;
+        } else if (dir == 0) {
+            level++;
+            LevelDev &A = ctx->D[level], &F = ctx->D[level - 1];
+            const int nf = ctx->H[level - 1].n_owned;
+            if (fused) {
+                LoopScope t(ctx, "restrict", level, nf);
+                ctx->launches += k_restrict_fused(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
+            } else {
+                { LoopScope t(ctx, "up_pre", level, nf); ctx->launches += k_up_pre(s, nf, F.mg, A.var, A.up_count); }
+                { LoopScope t(ctx, "up", level, nf); ctx->launches += k_up(s, ctx->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count); }
+                { LoopScope t(ctx, "up_post", level, ctx->H[level].n_owned); ctx->launches += k_up_post(s, ctx->H[level].n_owned, A.var, A.up_count); }
+            }
+            if (level == nl - 1) dir = 1;
+        } else {
+            level--;
+            LevelDev &F = ctx->D[level], &A = ctx->D[level + 1];
+            { LoopScope t(ctx, "down", level, ctx->H[level].n_owned); ctx->launches += k_down(s, ctx->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords); }
+            if (level == 0) { dir = 0; i++; }
+        }
+    }
+    int rc = api_check_launch(ctx, "mgcfd_run_cycles");
+    if (rc) return rc;
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
+    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
+    if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
+    return MGCFD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily from whatever libnccl.so.2 the process already has (torch's when launched by torchrun)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load()
+    {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define SYM(f, name) f = reinterpret_cast<decltype(f)>(dlsym(handle, name)); if (!f) { error = std::string("dlsym ") + name; return false; }
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+        SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+        SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return true;
+    }
+} g_nccl;
+
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) {                                                                         \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_);                            \
+            return MGCFD_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+enum { DAT_VAR = 0, DAT_RES = 1 };
+
+inline double *dat_ptr(mgcfd_ctx *c, int level, int which) { return which == DAT_VAR ? c->D[level].var : c->D[level].res; }
+
+// pack this rank's export rows of `which` on its stream
+int pack_exports(mgcfd_ctx *ctx, int level, int which)
+{
+    HaloLevel &H = ctx->halo[level];
+    if (H.n_export == 0) return MGCFD_OK;
+    ctx->launches += k_pack_rows(ctx->stream, H.n_export, H.d_export_idx, dat_ptr(ctx, level, which), H.sendbuf);
+    ctx->halo_bytes += (long long)H.n_export * 40;
+    return api_check_launch(ctx, "pack_rows");
+}
+
+// single-process group: every rank packs, then pulls its imports from the neighbours' send buffers
+int exchange_group(mgcfd_ctx **R, int n, int level, int which)
+{
+    for (int r = 0; r < n; r++) {
+        mgcfd_ctx *ctx = R[r];
+        CK(cudaSetDevice(ctx->device));
+        int rc = pack_exports(ctx, level, which);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_pack, ctx->stream));
+    }
+    for (int q = 0; q < n; q++) {
+        mgcfd_ctx *ctx = R[q];
+        CK(cudaSetDevice(ctx->device));
+        HaloLevel &H = ctx->halo[level];
+        const int no = ctx->H[level].n_owned;
+        for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+            int cnt = H.imp_ptr[k + 1] - H.imp_ptr[k];
+            if (cnt == 0) continue;
+            mgcfd_ctx *src = R[H.nbr_rank[k]];
+            HaloLevel &S = src->halo[level];
+            size_t kq = std::find(S.nbr_rank.begin(), S.nbr_rank.end(), ctx->rank) - S.nbr_rank.begin();
+            if (kq == S.nbr_rank.size() || S.exp_ptr[kq + 1] - S.exp_ptr[kq] != cnt) {
+                ctx->err = "halo lists of the ranks do not match";
+                return MGCFD_ERR_ARG;
+            }
+            CK(cudaStreamWaitEvent(ctx->stream, src->ev_pack, 0));
+            CK(cudaMemcpyAsync(dat_ptr(ctx, level, which) + (size_t)(no + H.imp_ptr[k]) * 5, S.sendbuf + (size_t)S.exp_ptr[kq] * 5,
+                               (size_t)cnt * 40, cudaMemcpyDefault, ctx->stream));
+        }
+        CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+    }
+    for (int r = 0; r < n; r++) {       // a send buffer may only be repacked after every neighbour has pulled from it
+        mgcfd_ctx *ctx = R[r];
+        CK(cudaSetDevice(ctx->device));
+        for (int q : ctx->halo[level].nbr_rank) CK(cudaStreamWaitEvent(ctx->stream, R[q]->ev_done, 0));
+    }
+    return MGCFD_OK;
+}
+
+// one process per GPU: grouped ncclSend / ncclRecv per neighbour, receiving straight into the halo range
+int exchange_nccl(mgcfd_ctx *ctx, int level, int which)
+{
+    HaloLevel &H = ctx->halo[level];
+    if (H.nbr_rank.empty()) return MGCFD_OK;
+    int rc = pack_exports(ctx, level, which);
+    if (rc) return rc;
+    ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+    const int no = ctx->H[level].n_owned;
+    NCK(g_nccl.GroupStart());
+    for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+        int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
+        if (ns) NCK(g_nccl.Send(H.sendbuf + (size_t)H.exp_ptr[k] * 5, (size_t)ns * 5, ncclDouble, H.nbr_rank[k], comm, ctx->stream));
+        if (nr) NCK(g_nccl.Recv(dat_ptr(ctx, level, which) + (size_t)(no + H.imp_ptr[k]) * 5, (size_t)nr * 5, ncclDouble,
+                                H.nbr_rank[k], comm, ctx->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    return MGCFD_OK;
+}
+
+int exchange(mgcfd_ctx **R, int n, int level, int which)
+{
+    if (n == 1 && R[0]->nccl_comm) return exchange_nccl(R[0], level, which);
+    if (n == 1) return MGCFD_OK;
+    return exchange_group(R, n, level, which);
+}
+
+// the fused schedule over a set of ranks in lock step
+int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
+{
+    mgcfd_ctx *ctx = R[0];
+    const int nl = ctx->n_levels;
+    const bool nccl = n == 1 && ctx->nccl_comm;
+    for (int r = 0; r < n; r++) {
+        mgcfd_ctx *c = R[r];
+        if (!c->planned || c->device < 0 || c->n_levels != nl) { ctx->err = "ranks are not planned alike"; return MGCFD_ERR_ARG; }
+        if (c->opt.flux_variant != MGCFD_FLUX_OWNER || c->opt.no_fusion) {
+            ctx->err = "multi-GPU runs use the fused owner schedule (flux_variant owner, no_fusion 0)";
+            return MGCFD_ERR_ARG;
+        }
+        cudaSetDevice(c->device);
+        for (int l = 0; l < nl; l++) {
+            int rc = api_ensure_flux_plan(c, l);
+            if (rc) { ctx->err = c->err; return rc; }
+            if (!c->D[l].flux_is_zero) { ctx->err = "fluxes must be zero before a multi-GPU run"; return MGCFD_ERR_ARG; }
+        }
+        if (cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 4, c->stream) != cudaSuccess) return MGCFD_ERR_CUDA;
+    }
+    int level = 0, dir = 0, i = 0, rc;
+    // halos of the start state (a caller may have set variables on the owned nodes only)
+    for (int l = 0; l < nl; l++)
+        if ((rc = exchange(R, n, l, DAT_VAR))) return rc;
+    while (i < n_cycles) {
+        // ---- visit prologue: copy, dt, local min (euler3d.cpp:467-479)
+        for (int r = 0; r < n; r++) {
+            mgcfd_ctx *c = R[r];
+            cudaSetDevice(c->device);
+            LevelDev &D = c->D[level];
+            unsigned long long *slot = &c->d_min_enc[2 * level + D.visit_parity];
+            LoopScope t(c, "visit_begin", level, c->H[level].n_owned);
+            c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot);
+            if (n > 1) cudaEventRecord(c->ev_k1, c->stream);
+        }
+        // ---- global minimum + step factor (euler3d.cpp:477-489)
+        for (int r = 0; r < n; r++) {
+            mgcfd_ctx *c = R[r];
+            cudaSetDevice(c->device);
+            LevelDev &D = c->D[level];
+            unsigned long long *slot = &c->d_min_enc[2 * level + D.visit_parity];
+            unsigned long long *next = &c->d_min_enc[2 * level + (D.visit_parity ^ 1)];
+            const int no = c->H[level].n_owned;
+            LoopScope t(c, "compute_step_factor", level, no);
+            if (nccl) {
+                ctx = c;
+                NCK(g_nccl.AllReduce(slot, slot, 1, ncclUint64, ncclMin, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+                c->launches += k_step_factor_fused(c->stream, no, D.vol, slot, next, D.sf, &c->d_min_dt[level], c->d_flags);
+            } else {
+                MinSlots ms;
+                ms.n = n;
+                for (int q = 0; q < n; q++) {
+                    ms.p[q] = &R[q]->d_min_enc[2 * level + R[q]->D[level].visit_parity];
+                    if (q != r) cudaStreamWaitEvent(c->stream, R[q]->ev_k1, 0);
+                }
+                c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags);
+            }
+            if (level == 0) c->launches += k_fill(c->stream, 1, c->d_rms, 0.0);
+        }
+        for (int r = 0; r < n; r++) R[r]->D[level].visit_parity ^= 1;
+        // ---- three fused Runge-Kutta stages, halo exchange of the new variables after each (euler3d.cpp:492-531)
+        for (int rk = 0; rk < MGCFD_RK; rk++) {
+            for (int r = 0; r < n; r++) {
+                mgcfd_ctx *c = R[r];
+                cudaSetDevice(c->device);
+                LevelHost &L = c->H[level];
+                LevelDev &D = c->D[level];
+                RkStageArgs ra;
+                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
+                ra.d_rms = level == 0 ? c->d_rms : nullptr;
+                ra.d_bad = &c->d_flags[0];
+                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
+                ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = api_dev_consts(c);
+                FluxArgs a;
+                a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
+                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
+                {
+                    LoopScope t(c, "rk_stage", level, L.n_edges);
+                    c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
+                }
+                if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
+                std::swap(D.var, D.var_alt);
+            }
+            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+        }
+        if (level >= 1 && (rc = exchange(R, n, level, DAT_RES))) return rc;      // prolong of level-1 reads res[level] parents
+        if (nl <= 1) {
+            i++;
+        } else if (dir == 0) {
+            level++;
+            for (int r = 0; r < n; r++) {
+                mgcfd_ctx *c = R[r];
+                cudaSetDevice(c->device);
+                LevelDev &A = c->D[level], &F = c->D[level - 1];
+                LoopScope t(c, "restrict", level, c->H[level - 1].n_owned);
+                c->launches += k_restrict_fused(c->stream, c->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
+            }
+            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+            if (level == nl - 1) dir = 1;
+        } else {
+            level--;
+            for (int r = 0; r < n; r++) {
+                mgcfd_ctx *c = R[r];
+                cudaSetDevice(c->device);
+                LevelDev &F = c->D[level], &A = c->D[level + 1];
+                LoopScope t(c, "down", level, c->H[level].n_owned);
+                c->launches += k_down(c->stream, c->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords);
+            }
+            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+            if (level == 0) { dir = 0; i++; }
+        }
+    }
+    // deferred checks (euler3d.cpp:480, :544): any rank's flag fails the run
+    int bad = 0, neg = 0;
+    for (int r = 0; r < n; r++) {
+        mgcfd_ctx *c = R[r];
+        cudaSetDevice(c->device);
+        if ((rc = api_check_launch(c, "mgcfd_run_cycles"))) { ctx->err = c->err; return rc; }
+        int *hp = reinterpret_cast<int *>(&c->h_pinned[6]);
+        if (cudaMemcpyAsync(hp, c->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            ctx->err = std::string("run_ranks: ") + cudaGetErrorString(cudaGetLastError());
+            return MGCFD_ERR_CUDA;
+        }
+        bad += hp[0];
+        neg += hp[1];
+    }
+    ctx = R[0];
+    if (neg) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
+    if (bad > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
+    return MGCFD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
+{
+    if (!ctx) return MGCFD_ERR_ARG;
+    REQUIRE(ctx->planned, "mgcfd_plan() has not been called");
+    if (ctx->device < 0) { ctx->err = "planning-only context (device -1): compute entry points need a CUDA device"; return MGCFD_ERR_NODEVICE; }
+    REQUIRE(n_cycles >= 0, "negative cycle count");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) return run_ranks(&ctx, 1, n_cycles);
+    REQUIRE(ctx->n_ranks == 1, "a partitioned context needs mgcfd_comm_init_nccl() or mgcfd_group_run_cycles()");
+    return cycle_run_single(ctx, n_cycles);
+}
+
+int mgcfd_group_run_cycles(mgcfd_ctx **ranks, int n_ranks, int n_cycles)
+{
+    if (!ranks || n_ranks < 1 || n_ranks > 16 || !ranks[0]) return MGCFD_ERR_ARG;
+    mgcfd_ctx *ctx = ranks[0];
+    REQUIRE(n_cycles >= 0, "negative cycle count");
+    for (int r = 0; r < n_ranks; r++) {
+        REQUIRE(ranks[r] && ranks[r]->rank == r && ranks[r]->n_ranks == n_ranks, "ranks[r] must be the context of rank r of n_ranks");
+        REQUIRE(!ranks[r]->nccl_comm, "group runs and NCCL contexts do not mix");
+    }
+    if (n_ranks == 1) return mgcfd_run_cycles(ctx, n_cycles);
+    // peer access between the devices of the group (same-device groups need none)
+    for (int a = 0; a < n_ranks; a++)
+        for (int b = 0; b < n_ranks; b++) {
+            if (ranks[a]->device == ranks[b]->device) continue;
+            cudaSetDevice(ranks[a]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ranks[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                return MGCFD_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+    return run_ranks(ranks, n_ranks, n_cycles);
+}
+
+int mgcfd_nccl_unique_id(void *id_out_128)
+{
+    if (!id_out_128 || !g_nccl.load()) return MGCFD_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return MGCFD_ERR_CUDA;
+    memcpy(id_out_128, &id, sizeof(id));
+    return MGCFD_OK;
+}
+
+int mgcfd_comm_init_nccl(mgcfd_ctx *ctx, int n_ranks, int rank, const void *unique_id_128)
+{
+    if (!ctx) return MGCFD_ERR_ARG;
+    REQUIRE(unique_id_128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad arguments");
+    REQUIRE(ctx->rank == rank && ctx->n_ranks == n_ranks, "context was not created for this rank");
+    if (!g_nccl.load()) { ctx->err = g_nccl.error; return MGCFD_ERR_CUDA; }
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof(id));
+    ncclComm_t comm;
+    NCK(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+    ctx->nccl_comm = comm;
+    return MGCFD_OK;
+}
+
+long long mgcfd_halo_bytes_sent(const mgcfd_ctx *ctx) { return ctx ? ctx->halo_bytes : 0; }
+
+}  // extern "C"

@@ -1,6 +1,7 @@
 // internal.h -- shared declarations of libmgcfd_b200 (not part of the public C-ABI).
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -65,6 +66,8 @@ struct LevelHost {
     std::vector<int> e2n, b2n, bgroup, mg;    // 0-based, file order (mg empty on the coarsest)
     std::vector<int> new_of_old, old_of_new;  // node renumbering
     std::vector<int> bnd_node_ptr;            // [n_owned+1] boundary entries per owned internal node
+    std::vector<int> global_node;             // partition: file index in the undecomposed mesh (else empty)
+    std::vector<int> nbr_rank, export_ptr, export_idx, import_ptr;   // partition: halo lists in local file numbering
     SortedEdges sorted;
     ColourPlanHost colour;
     OwnerPlanHost owner;
@@ -156,6 +159,14 @@ struct LevelDev {
     bool flux_is_zero = false;     // tracked so that the owner variant may overwrite instead of accumulate
 };
 
+// halo exchange lists of one level (internal node numbering; halo nodes keep their file positions)
+struct HaloLevel {
+    std::vector<int> nbr_rank, exp_ptr, imp_ptr;
+    int *d_export_idx = nullptr;     // internal indices of exported owned nodes, concatenated per neighbour
+    double *sendbuf = nullptr;       // [n_export][5]
+    int n_export = 0;
+};
+
 struct LoopTimer {
     double ms = 0.0;
     long long calls = 0, elements = 0;
@@ -186,9 +197,60 @@ struct mgcfd_ctx {
     int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only
     std::map<std::string, mgcfd::LoopTimer> timers;
     std::vector<cudaEvent_t> event_pool;
+    // multi-GPU
+    std::vector<mgcfd::HaloLevel> halo;
+    int rank = 0, n_ranks = 1;
+    void *nccl_comm = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_done = nullptr, ev_k1 = nullptr;
+    long long halo_bytes = 0;
 };
 
 namespace mgcfd {
+
+// helpers of api.cu used by the cycle driver (cycle.cu)
+int api_check_launch(mgcfd_ctx *ctx, const char *what);
+DevConsts api_dev_consts(const mgcfd_ctx *ctx);
+int api_ensure_flux_plan(mgcfd_ctx *ctx, int level);
+int api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel);
+void timers_collect(mgcfd_ctx *ctx);
+int cycle_run_single(mgcfd_ctx *ctx, int n_cycles);
+
+// per-call-site device timer (CUDA events on the context's stream)
+struct LoopScope {
+    mgcfd_ctx *ctx;
+    LoopTimer *t = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    long long elems;
+    static cudaEvent_t get_event(mgcfd_ctx *ctx)
+    {
+        if (!ctx->event_pool.empty()) {
+            cudaEvent_t e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
+    {
+        if (!ctx->timers_on) return;
+        if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0 && strcmp(name, "rk_stage") != 0)
+            return;   // flux-edge launches (stand-alone or as the fused Runge-Kutta stage) only
+        t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
+        e0 = get_event(ctx);
+        e1 = get_event(ctx);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~LoopScope()
+    {
+        if (!t) return;
+        cudaEventRecord(e1, ctx->stream);
+        t->pending.push_back({e0, e1});
+        t->pending_elems.push_back(elems);
+    }
+};
+
 
 // kernels.cu / flux_*.cu launchers.  All enqueue on `s` and return the number of kernels launched.
 int k_copy(cudaStream_t s, int n, const double *var, double *old);
@@ -220,6 +282,10 @@ int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long 
 int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
                      double *var_above, int *count_above);
 int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots);
+struct MinSlots { const unsigned long long *p[16]; int n; };
+int k_step_factor_group(cudaStream_t s, int n, const double *vol, MinSlots slots, unsigned long long *next_slot, double *sf,
+                        double *d_min_out, int *d_flags);
+int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double *dst);
 
 // extra arguments of the fused Runge-Kutta stage (flux + boundary flux + time_step [+ residual, rms, bad values])
 struct RkStageArgs {

@@ -168,6 +168,33 @@ __global__ void step_factor_fused_kernel(int n, const double *__restrict__ vol, 
     if (i < n) sf[i] = m / vol[i];
 }
 
+// the same with the minimum taken over the slots of all ranks of a single-process group (peer-mapped pointers)
+__global__ void step_factor_group_kernel(int n, const double *__restrict__ vol, MinSlots slots,
+                                         unsigned long long *__restrict__ next_slot, double *__restrict__ sf,
+                                         double *__restrict__ d_min_out, int *__restrict__ d_flags)
+{
+    unsigned long long u = ~0ull;
+    for (int r = 0; r < slots.n; r++) {
+        unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(slots.p[r]);
+        if (t < u) u = t;
+    }
+    const double m = dec_min(u);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        *next_slot = enc_min(DBL_MAX);
+        *d_min_out = m;
+        if (m < 0.0f) d_flags[1] = 1;
+    }
+    if (i < n) sf[i] = m / vol[i];
+}
+
+// halo export: gather the rows of the exported owned nodes into a contiguous send buffer
+__global__ void pack_rows_kernel(int n5, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n5) dst[i] = src[(size_t)idx[i / 5] * 5 + i % 5];
+}
+
 __global__ void reset_min_slots_kernel(int n, unsigned long long *slots)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,6 +422,18 @@ int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long 
                         double *sf, double *d_min_out, int *d_flags)
 {
     step_factor_fused_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, vol, min_slot, next_slot, sf, d_min_out, d_flags);
+    return 1;
+}
+int k_step_factor_group(cudaStream_t s, int n, const double *vol, MinSlots slots, unsigned long long *next_slot, double *sf,
+                        double *d_min_out, int *d_flags)
+{
+    step_factor_group_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, vol, slots, next_slot, sf, d_min_out, d_flags);
+    return 1;
+}
+int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double *dst)
+{
+    if (n == 0) return 0;
+    pack_rows_kernel<<<blocks_for((long long)n * 5), TPB, 0, s>>>(n * 5, idx, src, dst);
     return 1;
 }
 int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots)

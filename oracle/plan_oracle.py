@@ -174,3 +174,119 @@ def owner_chunks(e2n0, new_of_old, n_owned, max_own, max_loc, max_edges):
         halos.append(halo)
         edges.append(elist)
     return starts, halos, edges
+
+
+# ---------------------------------------------------------------------------------------------------
+# domain decomposition (restates mg-cfd-app-op2_b200/csrc/partition.cpp from its specification)
+# ---------------------------------------------------------------------------------------------------
+def rcb(coords, n_parts):
+    """recursive coordinate bisection: median split of the longest bounding-box axis, ties by index, shares
+    proportional to the rank counts of the halves (left half gets floor(parts/2) ranks)"""
+    part = np.empty(coords.shape[0], dtype=np.int32)
+
+    def rec(ids, p0, p1):
+        if p1 - p0 == 1:
+            part[ids] = p0
+            return
+        c = coords[ids]
+        ext = c.max(axis=0) - c.min(axis=0) if ids.size else np.zeros(3)
+        axis = 0
+        for d in (1, 2):
+            if ext[d] > ext[axis]:
+                axis = d
+        order = ids[np.lexsort((ids, c[:, axis]))] if ids.size else ids
+        left_parts = (p1 - p0) // 2
+        n_left = (order.size * left_parts) // (p1 - p0)
+        rec(order[:n_left], p0, p0 + left_parts)
+        rec(order[n_left:], p0 + left_parts, p1)
+
+    rec(np.arange(coords.shape[0], dtype=np.int64), 0, n_parts)
+    return part
+
+
+def coarse_part(fine_part, fine_to_coarse0, n_coarse, coarse_e2n0, coarse_coords):
+    part = np.full(n_coarse, -1, dtype=np.int32)
+    parents, first = np.unique(fine_to_coarse0, return_index=True)     # first occurrence = lowest-numbered child
+    part[parents] = fine_part[first]
+    orphans = np.nonzero(part < 0)[0]
+    if orphans.size:
+        resolved = {}
+        orphan_set = set(orphans.tolist())
+        nbrs = {int(o): [] for o in orphans}
+        for a, b in coarse_e2n0.tolist():
+            if a in orphan_set and b not in orphan_set:
+                nbrs[a].append(b)
+            if b in orphan_set and a not in orphan_set:
+                nbrs[b].append(a)
+        for o in orphans.tolist():
+            best, best_d = -1, 0.0
+            for nb in nbrs[o]:
+                t = coarse_coords[o] - coarse_coords[nb]
+                d2 = 0.0
+                for k in range(3):
+                    d2 += float(t[k]) * float(t[k])
+                if best < 0 or d2 < best_d or (d2 == best_d and nb < best):
+                    best, best_d = nb, d2
+            resolved[o] = int(part[best]) if best >= 0 else 0
+        for o, r in resolved.items():
+            part[o] = r
+    return part
+
+
+def partition_levels(levels0, n_ranks):
+    parts = [rcb(np.asarray(levels0[0]["node_coordinates"]), n_ranks)]
+    for l in range(1, len(levels0)):
+        parts.append(coarse_part(parts[l - 1], levels0[l - 1]["node-->mg_node"].reshape(-1),
+                                 levels0[l]["node_coordinates"].shape[0], levels0[l]["edge-->node"],
+                                 np.asarray(levels0[l]["node_coordinates"])))
+    return parts
+
+
+def local_mesh(levels0, parts, rank):
+    """per level: dict(global_node, n_owned, global_edge, global_bnd, e2n (local), mg (local or -1),
+    neighbour_rank, export lists (global ids per neighbour), import lists (global ids per neighbour))"""
+    nl = len(levels0)
+    needs = [set() for _ in range(nl)]                 # (q, n): rank q reads remote node n of level l
+    for l, lev in enumerate(levels0):
+        p = parts[l]
+        e = lev["edge-->node"]
+        cut = p[e[:, 0]] != p[e[:, 1]]
+        for a, b in e[cut].tolist():
+            needs[l].add((int(p[a]), b))
+            needs[l].add((int(p[b]), a))
+        if l + 1 < nl:
+            mg = lev["node-->mg_node"].reshape(-1)
+            pc = parts[l + 1][mg]
+            diff = np.nonzero(pc != p)[0]
+            for f in diff.tolist():
+                needs[l].add((int(pc[f]), f))                       # restrict on the parent's rank reads the child
+                needs[l + 1].add((int(p[f]), int(mg[f])))           # prolong on the child's rank reads the parent
+    out = []
+    for l, lev in enumerate(levels0):
+        p = parts[l]
+        owned = np.nonzero(p == rank)[0]
+        halo = sorted((n for q, n in needs[l] if q == rank), key=lambda n: (int(p[n]), n))
+        exports = sorted((q, n) for q, n in needs[l] if q != rank and p[n] == rank)
+        nbrs = sorted({int(p[n]) for n in halo} | {q for q, _ in exports})
+        global_node = np.concatenate([owned, np.array(halo, dtype=np.int64)]).astype(np.int64)
+        local_of = np.full(p.shape[0], -1, dtype=np.int64)
+        local_of[global_node] = np.arange(global_node.size)
+        e = lev["edge-->node"]
+        emask = (p[e[:, 0]] == rank) | (p[e[:, 1]] == rank)
+        b2n = lev["bnd_node-->node"].reshape(-1)
+        bmask = p[b2n] == rank
+        d = {
+            "global_node": global_node, "n_owned": owned.size,
+            "global_edge": np.nonzero(emask)[0], "global_bnd": np.nonzero(bmask)[0],
+            "e2n": local_of[e[emask]],
+            "neighbour_rank": nbrs,
+            "exports": {q: [n for qq, n in exports if qq == q] for q in nbrs},
+            "imports": {q: [n for n in halo if p[n] == q] for q in nbrs},
+        }
+        out.append(d)
+    for l in range(nl - 1):
+        mg = levels0[l]["node-->mg_node"].reshape(-1)
+        local_coarse = np.full(parts[l + 1].shape[0], -1, dtype=np.int64)
+        local_coarse[out[l + 1]["global_node"]] = np.arange(out[l + 1]["global_node"].size)
+        out[l]["mg"] = local_coarse[mg[out[l]["global_node"]]]
+    return out

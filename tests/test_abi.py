@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layouts_match_header(pkg):
     assert ctypes.sizeof(pkg.capi.Consts) == 8 * 18 + 8
-    assert ctypes.sizeof(pkg.capi.LevelHost) == 16 + 7 * 8
+    assert ctypes.sizeof(pkg.capi.LevelHost) == 16 + 7 * 8 + 8 + 8 + 4 * 8
     assert ctypes.sizeof(pkg.capi.Options) == 16 * 4
 
 

@@ -1,0 +1,77 @@
+"""Partition / halo index sets (BASELINE.json north_star: bit-exact partition/halo index sets): the C++ partitioner
+against the independent restatement in oracle/plan_oracle.py, plus the invariants of SURVEY.md 4.3-3.  Host code
+only -- runs without a GPU."""
+import numpy as np
+import pytest
+
+from conftest import mesh0
+
+
+@pytest.fixture(scope="module")
+def plan_oracle():
+    import plan_oracle
+    return plan_oracle
+
+
+@pytest.mark.parametrize("name,n_ranks", [("tiny", 2), ("small", 2), ("small", 3), ("small", 4), ("small", 8), ("medium", 8)])
+def test_partition_and_local_meshes_bit_exact(pkg, meshgen, plan_oracle, name, n_ranks):
+    mesh = meshgen.make_multigrid(name)
+    lev0 = mesh0(meshgen, name)
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], n_ranks)
+    ref_parts = plan_oracle.partition_levels(lev0, n_ranks)
+    for a, b in zip(parts, ref_parts):
+        assert np.array_equal(a, b)
+    sizes = np.bincount(parts[0], minlength=n_ranks)
+    assert sizes.max() - sizes.min() <= n_ranks                 # bisection balances level 0
+    locals_ = []
+    for r in range(n_ranks):
+        lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, n_ranks)
+        ref = plan_oracle.local_mesh(lev0, ref_parts, r)
+        for l in range(len(lev0)):
+            n_nodes, n_edges, n_bnd, n_owned = lm.sizes(l)
+            gn = lm.query(l, "global_node")
+            assert np.array_equal(gn, ref[l]["global_node"]) and n_owned == ref[l]["n_owned"]
+            assert np.array_equal(lm.query(l, "global_edge"), ref[l]["global_edge"])
+            assert np.array_equal(lm.query(l, "global_bnd"), ref[l]["global_bnd"])
+            assert np.array_equal(lm.query(l, "edge_to_node").reshape(-1, 2), ref[l]["e2n"])
+            if l + 1 < len(lev0):
+                assert np.array_equal(lm.query(l, "node_to_mg_node"), ref[l]["mg"])
+            nbr = lm.query(l, "neighbour_rank")
+            assert list(nbr) == ref[l]["neighbour_rank"]
+            ep, ei, ip = lm.query(l, "export_ptr"), lm.query(l, "export_idx"), lm.query(l, "import_ptr")
+            for k, q in enumerate(nbr):
+                assert list(gn[ei[ep[k]:ep[k + 1]]]) == ref[l]["exports"][q]
+                assert list(gn[n_owned + ip[k]:n_owned + ip[k + 1]]) == ref[l]["imports"][q]
+        locals_.append(lm)
+    # invariants across ranks
+    for l, lev in enumerate(lev0):
+        e = lev["edge-->node"]
+        seen_edges = np.zeros(e.shape[0], dtype=np.int64)
+        owned_total = 0
+        for r, lm in enumerate(locals_):
+            gn, ge = lm.query(l, "global_node"), lm.query(l, "global_edge")
+            n_owned = lm.sizes(l)[3]
+            owned_total += n_owned
+            seen_edges[ge] += 1
+            assert np.isin(e[ge].ravel(), gn).all()             # owned + halo covers every referenced node
+            nbr, ep, ei, ip = (lm.query(l, k) for k in ("neighbour_rank", "export_ptr", "export_idx", "import_ptr"))
+            for k, q in enumerate(nbr):                         # my exports to q are exactly q's imports from me
+                other = locals_[q]
+                onbr, oip = other.query(l, "neighbour_rank"), other.query(l, "import_ptr")
+                kk = list(onbr).index(r)
+                ogn, ono = other.query(l, "global_node"), other.sizes(l)[3]
+                assert np.array_equal(gn[ei[ep[k]:ep[k + 1]]], ogn[ono + oip[kk]:ono + oip[kk + 1]])
+        assert owned_total == lev["node_coordinates"].shape[0]
+        cut = parts[l][e[:, 0]] != parts[l][e[:, 1]]
+        assert np.array_equal(seen_edges, 1 + cut)              # cut edges execute on both owners, others once
+
+
+def test_single_rank_partition_is_the_whole_mesh(pkg, meshgen):
+    mesh = meshgen.make_multigrid("tiny")
+    parts = pkg.partition_levels(mesh["levels"], 1, 1)
+    lm = pkg.LocalMesh(mesh["levels"], 1, parts, 0, 1)
+    for l, lev in enumerate(mesh["levels"]):
+        n = lev["node_coordinates"].shape[0]
+        assert lm.sizes(l) == (n, lev["edge-->node"].shape[0], lev["bnd_node-->node"].shape[0], n)
+        assert np.array_equal(lm.query(l, "global_node"), np.arange(n))
+        assert lm.query(l, "neighbour_rank").size == 0
