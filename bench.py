@@ -180,10 +180,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = ge.load_package()
-    mesh = pkg.meshgen.make_multigrid(args.mesh)
+    if world > 1:
+        # weak scaling: the deck grows with the GPU count along x, so every rank's share stays about one --mesh deck
+        mesh_name, dims, seed0 = pkg.meshgen.CONFIGS[args.mesh]
+        dims = [(nx * world, ny, nz, None if ne is None else ne * world) for nx, ny, nz, ne in dims]
+        mesh = pkg.meshgen.make_multigrid((mesh_name, dims, seed0))
+    else:
+        mesh = pkg.meshgen.make_multigrid(args.mesh)
     levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
     sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
-    workload = (f"{args.mesh}: {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
+    workload = (f"{args.mesh}{' x%d along x (weak scaling, recursive-bisection partition, 1 rank per GPU)' % world if world > 1 else ''}"
+                f": {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
                 f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
     config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
               "arith": "exact" if args.exact else "fast", "fused_schedule": args.variant == "owner" and not args.no_fusion,
@@ -218,9 +225,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,
-                    flux_variant=args.variant, exact_arith=args.exact, owner_chunk_nodes=args.chunk,
-                    fuse=not args.no_fusion)
+    if world > 1:
+        parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world)
+        lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
+        gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant="owner", exact_arith=args.exact,
+                        owner_chunk_nodes=args.chunk)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        gpu.comm_init_nccl(bytes(uid.cpu().numpy().tobytes()))
+        local_sizes = [(lm.sizes(l)[0], lm.sizes(l)[1], lm.sizes(l)[2]) for l in range(len(sizes))]
+    else:
+        gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,
+                        flux_variant=args.variant, exact_arith=args.exact, owner_chunk_nodes=args.chunk,
+                        fuse=not args.no_fusion)
+        local_sizes = sizes
     stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -252,14 +272,15 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     launches = gpu.kernel_launches() - launches0
-    fused = args.variant == "owner" and not args.no_fusion
+    fused = world > 1 or (args.variant == "owner" and not args.no_fusion)
     flux_ms, flux_calls, flux_elems = gpu.timer("rk_stage" if fused else "compute_flux_edge")
     gpu.timers_enable(0)
 
-    edges_step = flux_edges_per_cycle(sizes)
-    value = world * edges_step * args.steps / (ms * 1e-3)
+    edges_step = flux_edges_per_cycle(sizes)          # edges of the whole (undecomposed) deck, cut edges counted once
+    value = edges_step * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peaks()
-    flux_bytes = (rk_stage_bytes_per_cycle(sizes) if fused else flux_bytes_per_cycle(sizes)) * args.steps
+    # per-GPU roofline: this rank's launches move this rank's edges (owned + recomputed cut edges) and nodes
+    flux_bytes = (rk_stage_bytes_per_cycle(local_sizes) if fused else flux_bytes_per_cycle(local_sizes)) * args.steps
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
     kname = (f"flux_owner_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
              if fused else f"compute_flux_edge_kernel[{args.variant}]")
@@ -267,7 +288,7 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes": ("per stage 32E+120N (flux-edge) + 168N (time_step), + 120N (residual) after the last stage"
                                       if fused else "32E+120N per launch"),
-                "algorithmic_bytes_per_launch_L0": (32 * sizes[0][1] + 288 * sizes[0][0]) if fused else (32 * sizes[0][1] + 120 * sizes[0][0]),
+                "algorithmic_bytes_per_launch_L0": (32 * local_sizes[0][1] + 288 * local_sizes[0][0]) if fused else (32 * local_sizes[0][1] + 120 * local_sizes[0][0]),
                 "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
                 "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms,
                 "note": "deck levels are L2-resident sized (L0 flux loop touches ~66 MB); see config.l2"}
@@ -275,7 +296,7 @@ def main():
     # end-to-end through the C-ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        pinned = [pkg.PinnedArray((s[0], 5)) for s in sizes]       # the caller's page-locked host buffers
+        pinned = [pkg.PinnedArray((s[0], 5)) for s in local_sizes]       # the caller's page-locked host buffers
         for l in range(len(sizes)):
             gpu.fetch_into(l, "variables", pinned[l].array)
         n_e2e = max(3, min(args.steps, 10))
@@ -292,8 +313,8 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         for p_ in pinned:
             p_.free()
-        nbytes = sum(s[0] * 40 for s in sizes)
-        e2e = {"value": world * edges_step * n_e2e / dt, "unit": "edges/s", "h2d_bytes_per_step": nbytes,
+        nbytes = sum(s[0] * 40 for s in local_sizes) * world
+        e2e = {"value": edges_step * n_e2e / dt, "unit": "edges/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
                "what": "per step: mgcfd_set_dat(variables) for every level from page-locked host arrays, mgcfd_run_cycles(1), "
                        "mgcfd_fetch_dat(variables) for every level back into them; wall clock around the loop"}
@@ -307,12 +328,14 @@ def main():
                "sample": f"{args.cpu_cycles} full V-cycles (+1 warm-up) of the same deck with the GPU run's node/edge ordering, "
                          f"{r['lib']}, OpenMP block-coloured; flux kernel alone {r['flux_kernel_edges_per_s']:.3e} edges/s",
                "mg_cycles_per_s": r["cycles_per_s"]}
+    halo_bytes = gpu.halo_bytes_sent()
     gpu.close()
     if rank == 0:
+        config["halo_bytes_sent_rank0"] = halo_bytes
         line = {"metric": "mg_cycle_flux_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config, "mg_cycles_per_s": world * args.steps / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu,
+                "config": config, "mg_cycles_per_s": args.steps / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
