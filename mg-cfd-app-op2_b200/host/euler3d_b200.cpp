@@ -1,0 +1,448 @@
+// euler3d_b200.cpp -- native host driver: the reference's euler3d.cpp main() restated over the C-ABI of
+// libmgcfd_b200 (include/mgcfd_b200.h).  Same command line (config.h:107-127), same input deck (io.h:28-205), same
+// initialisation and V-cycle schedule (euler3d.cpp:413-441, 458-641), same -v validation (euler3d.cpp:658-718) and
+// output naming (euler3d.cpp:720-779).  Level files are MGCFDBIN containers holding the reference's HDF5 dataset
+// names (see meshgen.py); a build with libhdf5 would only swap read_level().
+//
+//   euler3d_b200 -i input.dat [-d dir] [-o prefix] [-g cycles] [-v] [-b] [-I n] [-m partitioner] [-r method]
+//                [--renumber] [--output-variables] [--output-fluxes] [--output-step-factors]
+//                [--gpus N] [--same-device] [--variant owner|gather|colour|atomic] [--exact] [--loopwise]
+#include <getopt.h>
+#include <sys/time.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "mgcfd_b200.h"
+
+namespace {
+
+struct Dataset {
+    int dtype = 0;                       // 0 float64, 1 int32
+    std::vector<uint64_t> dims;
+    std::vector<unsigned char> bytes;
+    const double *f64() const { return reinterpret_cast<const double *>(bytes.data()); }
+    const int *i32() const { return reinterpret_cast<const int *>(bytes.data()); }
+};
+typedef std::map<std::string, Dataset> Container;
+
+bool read_container(const std::string &path, Container &out, std::string &err)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { err = "cannot open " + path; return false; }
+    char magic[8];
+    uint32_t version = 0, n = 0;
+    f.read(magic, 8);
+    f.read(reinterpret_cast<char *>(&version), 4);
+    f.read(reinterpret_cast<char *>(&n), 4);
+    if (!f || memcmp(magic, "MGCFDBIN", 8) != 0) {
+        err = path + ": not an MGCFDBIN container (HDF5 level files need a libhdf5 build; none exists in this image)";
+        return false;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t len = 0, dtype = 0, ndim = 0;
+        f.read(reinterpret_cast<char *>(&len), 4);
+        std::string name(len, '\0');
+        f.read(&name[0], len);
+        f.read(reinterpret_cast<char *>(&dtype), 4);
+        f.read(reinterpret_cast<char *>(&ndim), 4);
+        Dataset d;
+        d.dtype = (int)dtype;
+        d.dims.resize(ndim);
+        f.read(reinterpret_cast<char *>(d.dims.data()), 8 * ndim);
+        uint64_t nbytes = 0;
+        f.read(reinterpret_cast<char *>(&nbytes), 8);
+        f.seekg((8 - f.tellg() % 8) % 8, std::ios::cur);
+        d.bytes.resize(nbytes);
+        f.read(reinterpret_cast<char *>(d.bytes.data()), (std::streamsize)nbytes);
+        if (!f) { err = path + ": truncated dataset " + name; return false; }
+        out[name] = std::move(d);
+    }
+    return true;
+}
+
+bool write_container(const std::string &path, const std::string &name, const double *data, uint64_t rows, uint64_t cols)
+{
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    uint32_t version = 1, n = 1, len = (uint32_t)name.size(), dtype = 0, ndim = cols > 1 ? 2 : 1;
+    uint64_t dims[2] = {rows, cols}, nbytes = rows * cols * 8;
+    f.write("MGCFDBIN", 8);
+    f.write(reinterpret_cast<char *>(&version), 4);
+    f.write(reinterpret_cast<char *>(&n), 4);
+    f.write(reinterpret_cast<char *>(&len), 4);
+    f.write(name.data(), len);
+    f.write(reinterpret_cast<char *>(&dtype), 4);
+    f.write(reinterpret_cast<char *>(&ndim), 4);
+    f.write(reinterpret_cast<char *>(dims), 8 * ndim);
+    f.write(reinterpret_cast<char *>(&nbytes), 8);
+    static const char zeros[8] = {0};
+    f.write(zeros, (8 - f.tellp() % 8) % 8);
+    f.write(reinterpret_cast<const char *>(data), (std::streamsize)nbytes);
+    return (bool)f;
+}
+
+std::string trim(const std::string &s)
+{
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+struct Deck {
+    int size = 0, levels = 0, base = 1, mesh_name = -1;     // base_array_index defaults to 1 (euler3d.cpp:92)
+    std::vector<std::string> files;
+};
+
+// io.h:28-205: "key = value" lines, '#' comments, a [levels] section of "<index> = <file>" lines
+bool read_input_dat(const std::string &path, Deck &d, std::string &err)
+{
+    std::ifstream f(path);
+    if (!f) { err = "Error: Could not open input file '" + path + "'"; return false; }
+    std::string line;
+    bool have_size = false, have_levels = false, have_name = false, have_files = false;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line[0] == '#') continue;
+        if (!line.empty() && line[0] == '[') {
+            std::string sec = trim(line);
+            int count = sec == "[levels]" ? d.levels : (sec == "[mg_mapping]" ? d.levels - 1 : 0);
+            if (sec == "[levels]") {
+                if (!have_levels) { err = "Need to know number of levels before parsing level filenames"; return false; }
+                d.files.assign(d.levels, "");
+                have_files = true;
+            }
+            for (int i = 0; i < count; i++) {
+                if (!std::getline(f, line)) { err = "Have reached EOF before reading all filenames"; return false; }
+                size_t eq = line.find('=');
+                if (eq == std::string::npos) { err = "Was expecting a key-value pair following " + sec; return false; }
+                int idx = atoi(trim(line.substr(0, eq)).c_str());
+                if (sec == "[levels]" && idx >= 0 && idx < d.levels) d.files[idx] = trim(line.substr(eq + 1));
+            }
+            continue;
+        }
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) continue;
+        std::string key = trim(line.substr(0, eq)), value = trim(line.substr(eq + 1));
+        if (key == "size") { d.size = atoi(value.c_str()); have_size = true; }
+        else if (key == "num_levels") { d.levels = atoi(value.c_str()); have_levels = true; }
+        else if (key == "base_array_index") d.base = atoi(value.c_str());
+        else if (key == "mesh_name") {
+            // const.h:48-51
+            if (value == "fvcorr") d.mesh_name = 0;
+            else if (value == "la_cascade") d.mesh_name = 1;
+            else if (value == "rotor37") d.mesh_name = 2;
+            else if (value == "m6wing") d.mesh_name = 3;
+            else { err = "Unknown mesh_name '" + value + "'"; return false; }
+            have_name = true;
+        }
+    }
+    if (!have_size) { err = "size not present"; return false; }
+    if (!have_levels) { err = "number of levels not present"; return false; }
+    if (!have_name) { err = "mesh name not present"; return false; }
+    if (!have_files) { err = "mesh filenames not present"; return false; }
+    return true;
+}
+
+double wall()
+{
+    timeval t;
+    gettimeofday(&t, nullptr);
+    return t.tv_sec + 1e-6 * t.tv_usec;
+}
+
+struct Config {                               // config.h:64-103, defaults :129-165
+    std::string input_file, input_dir, prefix, variant = "owner";
+    int cycles = 25, flow_interval = 0, gpus = 1;
+    bool validate = false, mem_bound = false, renumber = true, exact = false, loopwise = false, same_device = false;
+    int out_vars = 0, out_fluxes = 0, out_sf = 0;
+};
+
+#define CHECK(call)                                                                                  \
+    do {                                                                                             \
+        int rc_ = (call);                                                                            \
+        if (rc_ != MGCFD_OK) {                                                                       \
+            fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, mgcfd_last_error(ctx));             \
+            return 1;                                                                                \
+        }                                                                                            \
+    } while (0)
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    Config conf;
+    static option long_opts[] = {
+        {"help", no_argument, nullptr, 'h'}, {"config-filepath", required_argument, nullptr, 'c'},
+        {"legacy-mode", no_argument, nullptr, 'l'}, {"input-file", required_argument, nullptr, 'i'},
+        {"input-directory", required_argument, nullptr, 'd'}, {"papi-config-file", required_argument, nullptr, 'p'},
+        {"output-file-prefix", required_argument, nullptr, 'o'}, {"num-cycles", required_argument, nullptr, 'g'},
+        {"partitioner", required_argument, nullptr, 'm'}, {"partitioner-method", required_argument, nullptr, 'r'},
+        {"renumber", no_argument, nullptr, 'n'}, {"validate", no_argument, nullptr, 'v'},
+        {"measure-mem-bound", no_argument, nullptr, 'b'}, {"output-variables", no_argument, &conf.out_vars, 1},
+        {"output-fluxes", no_argument, &conf.out_fluxes, 1}, {"output-step-factors", no_argument, &conf.out_sf, 1},
+        {"output-flow-interval", required_argument, nullptr, 'I'}, {"gpus", required_argument, nullptr, 1001},
+        {"variant", required_argument, nullptr, 1002}, {"exact", no_argument, nullptr, 1003},
+        {"loopwise", no_argument, nullptr, 1004}, {"same-device", no_argument, nullptr, 1005}, {nullptr, 0, nullptr, 0}};
+    int opt;
+    while ((opt = getopt_long(argc, argv, "hc:li:d:p:o:g:m:r:vbI:", long_opts, nullptr)) != -1) {
+        switch (opt) {
+        case 'i': conf.input_file = optarg; break;
+        case 'd': conf.input_dir = optarg; break;
+        case 'o': conf.prefix = optarg; break;
+        case 'g': conf.cycles = atoi(optarg); break;
+        case 'v': conf.validate = true; break;
+        case 'b': conf.mem_bound = true; break;
+        case 'I': conf.flow_interval = atoi(optarg); break;
+        case 'n': conf.renumber = true; break;
+        case 'm': case 'r': case 'c': case 'p': break;       // OP2 partitioner / PAPI selections: accepted, not used
+        case 'l': fprintf(stderr, "legacy mode (renumbered dataset names) is not supported\n"); return 1;
+        case 1001: conf.gpus = atoi(optarg); break;
+        case 1002: conf.variant = optarg; break;
+        case 1003: conf.exact = true; break;
+        case 1004: conf.loopwise = true; break;
+        case 1005: conf.same_device = true; break;       // all ranks of --gpus N on device 0 (tests on a one-GPU box)
+        case 0: break;
+        case 'h':
+        default:
+            printf("usage: %s -i input.dat [-d dir] [-o prefix] [-g cycles] [-v] [-b] [-I n] [--output-variables] "
+                   "[--output-fluxes] [--output-step-factors] [--gpus N] [--variant owner|gather|colour|atomic] "
+                   "[--exact] [--loopwise]\n", argv[0]);
+            return opt == 'h' ? 0 : 1;
+        }
+    }
+    if (conf.input_file.empty()) { printf("ERROR: input_file not set\n"); return 1; }
+    const std::string dir = conf.input_dir.empty() ? "" : conf.input_dir + "/";
+    Deck deck;
+    std::string err;
+    if (!read_input_dat(dir + conf.input_file, deck, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    const int levels = deck.levels;
+
+    printf("-----------------------------------------------------\nLoading level files ...\n");
+    std::vector<Container> files(levels);
+    std::vector<mgcfd_level_host> lv(levels);
+    for (int i = 0; i < levels; i++) {
+        printf("Loading level %d / %d\n", i + 1, levels);
+        if (!read_container(dir + deck.files[i], files[i], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        Container &c = files[i];
+        for (const char *need : {"node_coordinates", "edge-->node", "edge_weights", "bnd_node-->node", "bnd_node-->group",
+                                 "bnd_node_weights"})
+            if (!c.count(need)) { fprintf(stderr, "%s: dataset %s missing\n", deck.files[i].c_str(), need); return 1; }
+        mgcfd_level_host &h = lv[i];
+        memset(&h, 0, sizeof(h));
+        h.n_nodes = h.n_owned_nodes = (int)c["node_coordinates"].dims[0];
+        h.n_edges = (int)c["edge-->node"].dims[0];
+        h.n_bnd_nodes = (int)c["bnd_node-->node"].dims[0];
+        h.node_coordinates = c["node_coordinates"].f64();
+        h.edge_to_node = c["edge-->node"].i32();
+        h.edge_weights = c["edge_weights"].f64();
+        h.bnd_node_to_node = c["bnd_node-->node"].i32();
+        h.bnd_node_to_group = c["bnd_node-->group"].i32();
+        h.bnd_node_weights = c["bnd_node_weights"].f64();
+        if (i + 1 < levels) {
+            if (!c.count("node-->mg_node")) { fprintf(stderr, "%s: dataset node-->mg_node missing\n", deck.files[i].c_str()); return 1; }
+            h.node_to_mg_node = c["node-->mg_node"].i32();
+        }
+    }
+    // -v: solution.variables.L<l>.cycles=<g> with dataset p_variables_result_L<l> (euler3d.cpp:314-335)
+    std::vector<Container> solution(levels);
+    std::vector<const double *> variables_correct(levels, nullptr);
+    if (conf.validate)
+        for (int i = 0; i < levels; i++) {
+            std::string p = dir + "solution.variables.L" + std::to_string(i) + ".cycles=" + std::to_string(conf.cycles) + ".mgb";
+            std::string name = "p_variables_result_L" + std::to_string(i);
+            if (read_container(p, solution[i], err) && solution[i].count(name)) variables_correct[i] = solution[i][name].f64();
+            else printf("Cannot find level %d solution file: %s\n", i, p.c_str());
+        }
+
+    // ---- contexts: one per GPU (domain decomposition when --gpus > 1), euler3d.cpp:340-409
+    const int P = conf.gpus;
+    mgcfd_options o;
+    mgcfd_default_options(&o);
+    o.renumber = conf.renumber;
+    o.exact_arith = conf.exact;
+    o.flux_variant = conf.variant == "atomic" ? MGCFD_FLUX_ATOMIC : conf.variant == "colour" ? MGCFD_FLUX_COLOUR
+                   : conf.variant == "gather" ? MGCFD_FLUX_GATHER : MGCFD_FLUX_OWNER;
+    std::vector<mgcfd_ctx *> R(P, nullptr);
+    std::vector<mgcfd_local_mesh *> LM(P, nullptr);
+    std::vector<std::vector<int>> part(levels);
+    mgcfd_ctx *ctx = nullptr;
+    mgcfd_consts consts;
+    mgcfd_compute_farfield_consts(&consts);                       // euler3d.cpp:157-189
+    consts.mesh_name = deck.mesh_name;
+    if (P > 1) {
+        printf("-----------------------------------------------------\nPartitioning ...\n");
+        std::vector<const int *> pp(levels);
+        for (int l = 0; l < levels; l++) {
+            part[l].resize(lv[l].n_nodes);
+            int rc = l == 0 ? mgcfd_partition_rcb(lv[0].n_nodes, lv[0].node_coordinates, P, part[0].data())
+                            : mgcfd_partition_coarse(lv[l - 1].n_nodes, part[l - 1].data(), lv[l - 1].node_to_mg_node, deck.base,
+                                                     lv[l].n_nodes, lv[l].n_edges, lv[l].edge_to_node, lv[l].node_coordinates,
+                                                     part[l].data());
+            if (rc) { fprintf(stderr, "partitioning failed\n"); return 1; }
+            pp[l] = part[l].data();
+        }
+        for (int r = 0; r < P; r++)
+            if (mgcfd_local_mesh_build(levels, lv.data(), deck.base, pp.data(), r, P, &LM[r])) { fprintf(stderr, "local mesh failed\n"); return 1; }
+        printf("PARTITIONING COMPLETE\n");
+    }
+    for (int r = 0; r < P; r++) {
+        o.rank = r;
+        o.n_ranks = P;
+        if (mgcfd_create(&R[r], conf.same_device ? 0 : r, levels, &o) != MGCFD_OK) { fprintf(stderr, "mgcfd_create: %s\n", mgcfd_last_error(nullptr)); return 1; }
+        ctx = R[r];
+        CHECK(mgcfd_decl_consts(ctx, &consts));                  // op_decl_const x7, :232-238
+        for (int i = 0; i < levels; i++) {
+            if (P > 1) CHECK(mgcfd_decl_level(ctx, i, mgcfd_local_mesh_level(LM[r], i), 0));
+            else CHECK(mgcfd_decl_level(ctx, i, &lv[i], deck.base));
+        }
+        CHECK(mgcfd_plan(ctx));
+        for (int i = 0; i < levels; i++) {                       // :413-432
+            CHECK(mgcfd_loop_initialize_variables(ctx, i));
+            CHECK(mgcfd_loop_zero_fluxes(ctx, i));
+            CHECK(mgcfd_loop_zero_volumes(ctx, i));
+            CHECK(mgcfd_loop_calculate_cell_volumes(ctx, i));
+        }
+        for (int l = 0; l < levels; l++) {                       // :436-441
+            CHECK(mgcfd_loop_dampen_ewt_edges(ctx, l));
+            CHECK(mgcfd_loop_dampen_ewt_bnd(ctx, l));
+        }
+    }
+    ctx = R[0];
+
+    printf("-----------------------------------------------------\nCompute beginning\n");
+    double t1 = wall();
+    if (P > 1 || !conf.loopwise) {
+        // device-driven schedule (host checks of :480 and :544 deferred to the end of the run)
+        if (conf.flow_interval > 0 || conf.mem_bound) printf("note: -I / -b need --loopwise on one GPU; ignored\n");
+        for (int i = 0; i < conf.cycles; i++) printf("Performing MG cycle %d / %d\n", i + 1, conf.cycles);
+        int rc = P > 1 ? mgcfd_group_run_cycles(R.data(), P, conf.cycles) : mgcfd_run_cycles(ctx, conf.cycles);
+        if (rc == MGCFD_ERR_MIN_DT) { printf("Fatal error during 'step factor' calculation\n"); return 1; }
+        if (rc == MGCFD_ERR_BAD_VALS) { printf("Bad variable values detected, aborting\n"); return 1; }
+        if (rc) { fprintf(stderr, "run failed (%d): %s\n", rc, mgcfd_last_error(ctx)); return 1; }
+    } else {
+        // euler3d.cpp:458-641, call site by call site
+        int level = 0, mg_dir = 0, i = 0, bad_val_count = 0;
+        double rms = 0.0, min_dt;
+        while (i < conf.cycles) {
+            if (level == 0) printf("Performing MG cycle %d / %d\n", i + 1, conf.cycles);
+            CHECK(mgcfd_loop_copy_double(ctx, level));
+            CHECK(mgcfd_loop_calculate_dt(ctx, level));
+            min_dt = std::numeric_limits<double>::max();
+            CHECK(mgcfd_loop_get_min_dt(ctx, level, &min_dt));
+            if (min_dt < 0.0f) { printf("Fatal error during 'step factor' calculation, min_dt = %.5e\n", min_dt); return 1; }
+            CHECK(mgcfd_loop_compute_step_factor(ctx, level, &min_dt));
+            for (int rkCycle = 0; rkCycle < MGCFD_RK; rkCycle++) {
+                CHECK(mgcfd_loop_compute_flux_edge(ctx, level));
+                CHECK(mgcfd_loop_compute_bnd_node_flux(ctx, level));
+                CHECK(mgcfd_loop_time_step(ctx, level, &rkCycle));
+                if (conf.mem_bound) CHECK(mgcfd_loop_unstructured_stream(ctx, level));
+            }
+            CHECK(mgcfd_loop_residual(ctx, level));
+            if (level == 0) {
+                rms = 0.0;
+                CHECK(mgcfd_loop_calc_rms(ctx, level, &rms));
+                rms = sqrt(rms / double(lv[level].n_nodes));
+                bad_val_count = 0;
+                CHECK(mgcfd_loop_count_bad_vals(ctx, level, &bad_val_count));
+                if (bad_val_count > 0) { printf("Bad variable values detected, aborting\n"); return 1; }
+            }
+            if (conf.flow_interval > 0 && ((i + 1) % conf.flow_interval) == 0 && level == 0) {      // :552-571
+                std::vector<double> v((size_t)lv[0].n_nodes * 5);
+                CHECK(mgcfd_fetch_dat(ctx, 0, "variables", v.data()));
+                write_container(conf.prefix + "variables.L0.cycle=" + std::to_string(i + 1) + ".mgb", "p_variables", v.data(),
+                                lv[0].n_nodes, 5);
+            }
+            if (levels <= 1) {
+                i++;
+            } else if (mg_dir == 0) {
+                level++;
+                CHECK(mgcfd_loop_up_pre(ctx, level));
+                CHECK(mgcfd_loop_up(ctx, level));
+                CHECK(mgcfd_loop_up_post(ctx, level));
+                if (level == levels - 1) mg_dir = 1;
+            } else {
+                level--;
+                CHECK(mgcfd_loop_down(ctx, level));
+                if (level == 0) { mg_dir = 0; i++; }
+            }
+        }
+    }
+    for (int r = 0; r < P; r++) mgcfd_sync(R[r]);
+    printf("\nCompute complete\n");
+    printf("Max total runtime = %f\n", wall() - t1);
+
+    // assemble file-order results (ranks return [owned | halo] in their local order)
+    std::vector<std::vector<double>> vars(levels);
+    auto fetch_all = [&](const char *dat, int l, int dim, std::vector<double> &out) -> int {
+        out.assign((size_t)lv[l].n_nodes * dim, 0.0);
+        if (P == 1) return mgcfd_fetch_dat(R[0], l, dat, out.data());
+        for (int r = 0; r < P; r++) {
+            const mgcfd_level_host *h = mgcfd_local_mesh_level(LM[r], l);
+            std::vector<double> loc((size_t)h->n_nodes * dim);
+            int rc = mgcfd_fetch_dat(R[r], l, dat, loc.data());
+            if (rc) return rc;
+            for (int i = 0; i < h->n_owned_nodes; i++)
+                for (int d = 0; d < dim; d++) out[(size_t)h->global_node_id[i] * dim + d] = loc[(size_t)i * dim + d];
+        }
+        return MGCFD_OK;
+    };
+
+    if (conf.validate) {                                                                     // :658-718
+        printf("-----------------------------------------------------\n");
+        printf("Looking for NaN and infinity values ...");
+        bool failed = false;
+        for (int l = 0; l < levels && !failed; l++) {
+            CHECK(fetch_all("variables", l, 5, vars[l]));
+            int bad = 0;
+            for (double v : vars[l]) bad += (std::isnan(v) || std::isinf(v)) ? 1 : 0;
+            if (bad > 0) { printf("\nValue check of MG level %d failed: %d bad values detected\n", l, bad); failed = true; }
+        }
+        if (!failed) {
+            printf(" None found\nValidating result against solution ...");
+            bool validation_failed = false;
+            for (int l = 0; l < levels; l++) {
+                if (!variables_correct[l]) { printf("\n- Do not have solution for level %d, cannot validate\n", l); validation_failed = true; continue; }
+                int count = 0;
+                if (P == 1) {
+                    CHECK(mgcfd_validate_level(ctx, l, variables_correct[l], &count));        // identify_differences + count_non_zeros on the device
+                } else {
+                    for (size_t k = 0; k < vars[l].size(); k++) {                            // validation.h:65-88
+                        double tol = fabs(variables_correct[l][k] * 10.0e-8);
+                        if (tol < 3.0e-19) tol = 3.0e-19;
+                        if (fabs(vars[l][k] - variables_correct[l][k]) > tol) count++;
+                    }
+                }
+                if (count > lv[l].n_nodes / 5000) {
+                    validation_failed = true;
+                    printf("\nValidation of MG level %d failed: %d incorrect values in 'variables' array\n", l, count);
+                    break;
+                }
+            }
+            printf(validation_failed ? "Validation failed\n" : " Result correct\nValidation passed\n");
+        }
+    }
+    if (conf.out_vars || conf.out_fluxes || conf.out_sf) {                                    // :720-779
+        printf("-----------------------------------------------------\nWriting out data...\n");
+        for (int l = 0; l < levels; l++) {
+            std::string suffix = ".L" + std::to_string(l) + ".cycles=" + std::to_string(conf.cycles) + ".mgb";
+            std::vector<double> buf;
+            if (conf.out_sf) { CHECK(fetch_all("step_factors", l, 1, buf)); write_container(conf.prefix + "step_factors" + suffix, "p_step_factors_result_L" + std::to_string(l), buf.data(), lv[l].n_nodes, 1); }
+            if (conf.out_fluxes) { CHECK(fetch_all("fluxes", l, 5, buf)); write_container(conf.prefix + "fluxes" + suffix, "p_fluxes_result_L" + std::to_string(l), buf.data(), lv[l].n_nodes, 5); }
+            if (conf.out_vars) { CHECK(fetch_all("variables", l, 5, buf)); write_container(conf.prefix + "variables" + suffix, "p_variables_result_L" + std::to_string(l), buf.data(), lv[l].n_nodes, 5); }
+        }
+    }
+    printf("-----------------------------------------------------\nWinding down\n");
+    for (int r = 0; r < P; r++) {
+        mgcfd_destroy(R[r]);
+        if (LM[r]) mgcfd_local_mesh_free(LM[r]);
+    }
+    return 0;
+}

@@ -207,3 +207,77 @@ def zero_based(level, base=1):
         if key in out:
             out[key] = np.ascontiguousarray(out[key] - base, dtype=np.int32)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# deck files.  The reference reads HDF5 level files (euler3d.cpp:248-312); no HDF5 library exists in this image
+# (SURVEY.md 7.3-H1), so decks are stored in a minimal container holding the SAME dataset names, shapes and dtypes:
+#   "MGCFDBIN" | u32 version=1 | u32 n_datasets | per dataset: u32 name_len, name, u32 dtype (0 float64, 1 int32),
+#   u32 ndim, u64 dims[ndim], u64 nbytes, zero padding to an 8-byte boundary, raw little-endian data
+# read by host/euler3d_b200.cpp and by read_container() below.
+# ---------------------------------------------------------------------------------------------------
+import os
+import struct
+
+_MAGIC = b"MGCFDBIN"
+
+
+def write_container(path, datasets):
+    with open(path, "wb") as f:
+        f.write(_MAGIC + struct.pack("<II", 1, len(datasets)))
+        for name, arr in datasets.items():
+            a = np.ascontiguousarray(arr)
+            if a.dtype == np.float64:
+                code = 0
+            elif a.dtype == np.int32:
+                code = 1
+            else:
+                raise TypeError(f"{name}: only float64 / int32 datasets exist in MG-CFD decks")
+            nb = name.encode()
+            f.write(struct.pack("<I", len(nb)) + nb + struct.pack("<II", code, a.ndim))
+            f.write(struct.pack(f"<{a.ndim}Q", *a.shape) + struct.pack("<Q", a.nbytes))
+            f.write(b"\0" * (-f.tell() % 8))
+            f.write(a.tobytes())
+
+
+def read_container(path):
+    out = {}
+    with open(path, "rb") as f:
+        if f.read(8) != _MAGIC:
+            raise ValueError(f"{path}: not an MGCFDBIN container")
+        _, n = struct.unpack("<II", f.read(8))
+        for _ in range(n):
+            (ln,) = struct.unpack("<I", f.read(4))
+            name = f.read(ln).decode()
+            code, ndim = struct.unpack("<II", f.read(8))
+            dims = struct.unpack(f"<{ndim}Q", f.read(8 * ndim))
+            (nbytes,) = struct.unpack("<Q", f.read(8))
+            f.read(-f.tell() % 8)
+            out[name] = np.frombuffer(f.read(nbytes), dtype=np.float64 if code == 0 else np.int32).reshape(dims).copy()
+    return out
+
+
+def write_deck(directory, mesh, stem="mesh"):
+    """input.dat (io.h:28-205 format) + one level file per multigrid level"""
+    os.makedirs(directory, exist_ok=True)
+    names = []
+    for l, lev in enumerate(mesh["levels"]):
+        names.append(f"{stem}.L{l}.mgb")
+        write_container(os.path.join(directory, names[-1]), lev)
+    with open(os.path.join(directory, "input.dat"), "w") as f:
+        f.write("# synthetic MG-CFD deck (meshgen.py)\n")
+        f.write(f"size = {mesh['levels'][0]['node_coordinates'].shape[0]}\n")
+        f.write(f"num_levels = {len(names)}\n")
+        f.write(f"base_array_index = {mesh['base_array_index']}\n")
+        f.write(f"mesh_name = {mesh['mesh_name']}\n")
+        f.write("[levels]\n")
+        for l, n in enumerate(names):
+            f.write(f"{l} = {n}\n")
+    return os.path.join(directory, "input.dat")
+
+
+def write_solution(directory, level, cycles, variables, prefix="solution."):
+    """solution.variables.L<l>.cycles=<g> with dataset p_variables_result_L<l> (euler3d.cpp:315-327, 765-771)"""
+    path = os.path.join(directory, f"{prefix}variables.L{level}.cycles={cycles}.mgb")
+    write_container(path, {f"p_variables_result_L{level}": np.ascontiguousarray(variables, dtype=np.float64)})
+    return path

@@ -1,0 +1,53 @@
+"""The native driver (host/euler3d_b200.cpp = euler3d.cpp's main() over the C-ABI) end to end: reads a deck, runs
+N cycles, validates with the reference's -v criterion against the solution files, writes --output-variables."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "mg-cfd-app-op2_b200", "euler3d_b200")
+
+
+def make_deck(tmp_path, meshgen, golden):
+    mesh = meshgen.make_multigrid("small")
+    meshgen.write_deck(str(tmp_path), mesh)
+    g = golden("small_cycles10.npz")
+    for l in range(len(mesh["levels"])):
+        meshgen.write_solution(str(tmp_path), l, 10, g[f"var_L{l}"])
+    return mesh, g
+
+
+@pytest.mark.parametrize("extra", [[], ["--loopwise"], ["--loopwise", "-b", "--variant", "colour"], ["--exact"],
+                                   ["--gpus", "2", "--same-device"], ["--gpus", "4", "--same-device", "--exact"]])
+def test_driver_validates(tmp_path, meshgen, golden, extra):
+    mesh, g = make_deck(tmp_path, meshgen, golden)
+    out = os.path.join(str(tmp_path), "out.")
+    cmd = [EXE, "-i", "input.dat", "-d", str(tmp_path), "-g", "10", "-v", "--output-variables", "-o", out] + extra
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Validation passed" in p.stdout and "Max total runtime" in p.stdout
+    for l in range(len(mesh["levels"])):
+        got = meshgen.read_container(f"{out}variables.L{l}.cycles=10.mgb")[f"p_variables_result_L{l}"]
+        ref = g[f"var_L{l}"]
+        if "--exact" in extra:
+            assert np.array_equal(got, ref)
+        else:
+            assert (np.abs(got - ref).max(axis=0) <= 1e-10 * np.abs(ref).max(axis=0)).all()
+
+
+def test_driver_reports_failed_validation(tmp_path, meshgen, golden):
+    mesh, g = make_deck(tmp_path, meshgen, golden)
+    meshgen.write_solution(str(tmp_path), 0, 10, g["var_L0"] * (1 + 1e-5))
+    p = subprocess.run([EXE, "-i", "input.dat", "-d", str(tmp_path), "-g", "10", "-v"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "Validation failed" in p.stdout and "Validation passed" not in p.stdout
+
+
+def test_driver_argument_errors(tmp_path):
+    p = subprocess.run([EXE], capture_output=True, text=True)
+    assert p.returncode == 1 and "input_file not set" in p.stdout
+    p = subprocess.run([EXE, "-i", "missing.dat", "-d", str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 1 and "Could not open input file" in p.stderr
