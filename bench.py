@@ -274,6 +274,10 @@ def main():
     launches = gpu.kernel_launches() - launches0
     fused = world > 1 or (args.variant == "owner" and not args.no_fusion)
     flux_ms, flux_calls, flux_elems = gpu.timer("rk_stage" if fused else "compute_flux_edge")
+    per_level = []
+    for l in range(len(sizes)):
+        ms_l, calls_l, _ = gpu.timer("rk_stage" if fused else "compute_flux_edge", l)
+        per_level.append(round(1e3 * ms_l / max(calls_l, 1), 2))
     gpu.timers_enable(0)
 
     edges_step = flux_edges_per_cycle(sizes)          # edges of the whole (undecomposed) deck, cut edges counted once
@@ -284,14 +288,23 @@ def main():
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
     kname = (f"flux_owner_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
              if fused else f"compute_flux_edge_kernel[{args.variant}]")
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if fused and world == 1 and args.mesh == "m6" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]      # ncu --set full capture of the level-0 launch
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch (profiles/r01_traffic.json)",
+                "peak_source": peak_src,
                 "algorithmic_bytes": ("per stage 32E+120N (flux-edge) + 168N (time_step), + 120N (residual) after the last stage"
                                       if fused else "32E+120N per launch"),
                 "algorithmic_bytes_per_launch_L0": (32 * local_sizes[0][1] + 288 * local_sizes[0][0]) if fused else (32 * local_sizes[0][1] + 120 * local_sizes[0][0]),
                 "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
                 "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms,
-                "note": "deck levels are L2-resident sized (L0 flux loop touches ~66 MB); see config.l2"}
+                "per_level_avg_launch_us": per_level,
+                "note": "achieved = algorithmic bytes of all timed launches / their summed CUDA-event time; M6 levels are "
+                        "L2-resident sized, see config.l2"}
 
     # end-to-end through the C-ABI with host buffers
     e2e = None

@@ -356,6 +356,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
         : "memory");
 }
 
+__device__ __forceinline__ double flip_sign(double x, int sign_mask)
+{
+    return __hiloint2double(__double2hiint(x) ^ sign_mask, __double2loint(x));
+}
 __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -425,15 +429,24 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     double *Fx = reinterpret_cast<double *>(sblob + max_blob);          // flux planes 4..NFL-1
     double *raw = Fx + (size_t)(NFL - 4) * max_edges;                   // conserved variables, AoS [max_loc][5]
     double *der = raw + (size_t)max_loc * 5;                            // p, |v|+c, 1/rho planes (fast build only)
+    // FUSE: old_variables tile [max_own][5] and step factors [max_own], both 16-byte aligned bulk-copy targets
+    double *told = raw + (((size_t)NREC * max_loc + 1) & ~(size_t)1);
+    double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
     const OwnerChunkDesc d = descs[blockIdx.x];
     const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
+    const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
 
     // 1. bulk async copies (TMA 1-D) of the chunk's blob and of the owned nodes' conserved variables; 2. halo nodes
     //    by 8-byte async copies straight into the tile
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)d.blob_bytes + owned_bulk_bytes(d.n_own));
+        mbar_expect_tx(bar, (uint32_t)d.blob_bytes + owned_bulk_bytes(d.n_own) + old_bulk + sf_bulk);
         bulk_g2s(sblob, blob + d.blob_off, (uint32_t)d.blob_bytes, bar);
+        if (FUSE) {
+            // the update's operands are fetched now and land while the fluxes are being computed
+            if (old_bulk) bulk_g2s(told, rk.old + (size_t)d.node0 * 5, old_bulk, bar);
+            if (sf_bulk) bulk_g2s(tsf, rk.sf + d.node0, sf_bulk, bar);
+        }
     }
     stage_tile(raw, bar, d.node0, d.n_own, d.n_halo, halo_gid + d.halo_off, var, tid, blockDim.x);
     __syncthreads();          // halo tile complete; mbarrier initialisation visible to all threads
@@ -507,12 +520,13 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
                     acc[0] += w0[e]; acc[1] += w1[e]; acc[2] += w2[e]; acc[3] += gg[e]; acc[4] += Fx[e];
                 }
             } else {
-                double f0 = w0[e], f1 = w1[e], f2 = w2[e], f3 = gg[e], f4 = Fx[e];
-                acc[0] += is_b ? -f0 : f0;
-                acc[1] += is_b ? -f1 : f1;
-                acc[2] += is_b ? -f2 : f2;
-                acc[3] += is_b ? -f3 : f3;
-                acc[4] += is_b ? -f4 : f4;
+                // end b receives the negated vector: flip the sign bit instead of selecting between f and -f
+                const int sgn = is_b ? (int)0x80000000 : 0;
+                acc[0] += flip_sign(w0[e], sgn);
+                acc[1] += flip_sign(w1[e], sgn);
+                acc[2] += flip_sign(w2[e], sgn);
+                acc[3] += flip_sign(gg[e], sgn);
+                acc[4] += flip_sign(Fx[e], sgn);
             }
         }
         if (FUSE && d.has_bnd) {
@@ -539,9 +553,11 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
         const double denom = (double)(MGCFD_RK + 1 - rk.rk);
         double sq = 0.0;
         int bad = 0;
+        const int old_n = (int)(old_bulk >> 3), sf_n = (int)(sf_bulk >> 3);    // an odd last chunk has one tail element
         for (int f = tid; f < d.n_own * 5; f += blockDim.x) {
-            double factor = rk.sf[d.node0 + f / 5] / denom;
-            double o = rk.old[g0 + f];
+            int node = f / 5;
+            double factor = (node < sf_n ? tsf[node] : rk.sf[d.node0 + node]) / denom;
+            double o = f < old_n ? told[f] : rk.old[g0 + f];
             double vn = __dadd_rn(o, __dmul_rn(factor, raw[f]));
             rk.var_out[g0 + f] = vn;
             if (rk.last) {
@@ -703,10 +719,11 @@ inline int launch_bnd(cudaStream_t s, int n_unique, const int *bu_node, const in
 // launchers
 // ------------------------------------------------------------------------------------------
 inline size_t colour_smem(int max_nodes, bool stream) { return (size_t)((stream ? 5 : NF) + 5) * max_nodes * sizeof(double); }
-inline size_t owner_smem(int max_loc, int max_edges, int max_blob, bool stream)
+inline size_t owner_smem(int max_loc, int max_edges, int max_blob, bool stream, int fuse_max_own = 0)
 {
     return 16 + (size_t)max_blob +
-           ((size_t)(stream ? 5 : NF) * max_loc + (size_t)((stream ? 10 : NFLUX) - 4) * max_edges) * sizeof(double);
+           ((size_t)(stream ? 5 : NF) * max_loc + (size_t)((stream ? 10 : NFLUX) - 4) * max_edges + (size_t)fuse_max_own * 6 + 4) *
+               sizeof(double);
 }
 
 inline int launch_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p)
@@ -763,8 +780,12 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
 #define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux
     if (a.stream_kernel)
         flux_owner_kernel<true, false, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
-    else if (a.rk)
-        flux_owner_kernel<false, true, true><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, *a.rk);
+    else if (a.rk) {
+        RkStageArgs ra = *a.rk;
+        ra.max_own = h.max_own;
+        size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.max_blob, false, h.max_own);
+        flux_owner_kernel<false, true, true><<<h.n_chunks, 256, fsmem, s>>>(OWNER_ARGS, ra);
+    }
     else if (a.overwrite)
         flux_owner_kernel<false, true, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
     else

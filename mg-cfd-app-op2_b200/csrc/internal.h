@@ -297,6 +297,7 @@ struct RkStageArgs {
     const int *b_group;
     const double *b_wt;
     int rk, last;
+    int max_own, pad_;           // filled by the launcher: tile sizes of the prefetched update operands
     DevConsts c;
 };
 

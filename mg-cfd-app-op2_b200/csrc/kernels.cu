@@ -556,7 +556,8 @@ std::string flux_configure()
 size_t flux_owner_smem_bytes(int max_loc, int max_edges, int max_blob, bool exact_mode)
 {
     size_t stream = exact::owner_smem(max_loc, max_edges, max_blob, true);
-    size_t body = exact_mode ? exact::owner_smem(max_loc, max_edges, max_blob, false) : fast_owner_smem(max_loc, max_edges, max_blob);
+    size_t body = (exact_mode ? exact::owner_smem(max_loc, max_edges, max_blob, false) : fast_owner_smem(max_loc, max_edges, max_blob)) +
+                  (size_t)256 * 6 * sizeof(double);      // + the fused stage's old_variables / step_factor tiles
     return stream > body ? stream : body;
 }
 size_t flux_colour_smem_bytes(int max_nodes, bool exact_mode)
