@@ -108,7 +108,9 @@ typedef struct {
     int no_fusion;         /* 1: mgcfd_run_cycles launches one kernel per call site instead of the fused schedule
                               (fused Runge-Kutta stage, visit prologue and restrict; owner variant only) */
     int rank, n_ranks;     /* position of this context in a multi-GPU run (default 0 of 1) */
-    int reserved[8];
+    int no_graphs;         /* 1: mgcfd_run_cycles enqueues every launch; 0 (default): each cycle replays as a
+                              captured CUDA graph (also with NCCL: halo exchanges and the all-reduce are captured) */
+    int reserved[7];
 } mgcfd_options;
 
 /* ---- lifetime (op_init / op_exit, euler3d.cpp:126, :824) ---- */

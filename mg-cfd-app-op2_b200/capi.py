@@ -51,7 +51,7 @@ class LevelHost(C.Structure):
 class Options(C.Structure):
     _fields_ = [("flux_variant", C.c_int), ("renumber", C.c_int), ("owner_chunk_nodes", C.c_int),
                 ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("no_fusion", C.c_int),
-                ("rank", C.c_int), ("n_ranks", C.c_int), ("reserved", C.c_int * 8)]
+                ("rank", C.c_int), ("n_ranks", C.c_int), ("no_graphs", C.c_int), ("reserved", C.c_int * 7)]
 
 
 _lib = None
@@ -258,7 +258,7 @@ class MGCFD:
 
     def __init__(self, levels=None, base_array_index=1, device=0, flux_variant="owner", renumber=True,
                  exact_arith=False, owner_chunk_nodes=128, colour_block_edges=256, consts=None,
-                 init=True, fuse=True, local_mesh=None):
+                 init=True, fuse=True, local_mesh=None, graphs=True):
         """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"]), or
         local_mesh: a LocalMesh (this rank's share of a partitioned deck)."""
         self.lib = load_library()
@@ -271,6 +271,7 @@ class MGCFD:
         opt.owner_chunk_nodes = int(owner_chunk_nodes)
         opt.colour_block_edges = int(colour_block_edges)
         opt.no_fusion = int(not fuse)
+        opt.no_graphs = int(not graphs)
         opt.rank = local_mesh.rank if local_mesh is not None else 0
         opt.n_ranks = local_mesh.n_ranks if local_mesh is not None else 1
         self.rank, self.n_ranks = opt.rank, opt.n_ranks

@@ -197,6 +197,9 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     if ((e = cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_prod, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     std::string ce = flux_configure();
     if (!ce.empty()) {
         g_create_error = ce;
@@ -225,15 +228,18 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     if (ctx->device < 0) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cycle_drop_graphs(ctx);
     for (auto &d : ctx->D) free_level(d);
     for (auto &kv : ctx->timers)
         for (auto &p : kv.second.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    for (cudaEvent_t e : {ctx->ev_pack, ctx->ev_done, ctx->ev_k1})
+    if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    for (cudaEvent_t e : {ctx->ev_pack, ctx->ev_done, ctx->ev_k1, ctx->ev_prod, ctx->ev_ready})
         if (e) cudaEventDestroy(e);
     for (auto &h : ctx->halo) {
         if (h.d_export_idx) cudaFree(h.d_export_idx);
         if (h.sendbuf) cudaFree(h.sendbuf);
+        if (h.d_chunk_list) cudaFree(h.d_chunk_list);
     }
     if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
     if (ctx->d_rms) cudaFree(ctx->d_rms);
@@ -548,6 +554,7 @@ static int ensure_atomic(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.atomic.nodes, nodes))) return rc;
     if ((rc = dev_upload(ctx, &D.atomic.w, w))) return rc;
     D.atomic.valid = true;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 
@@ -589,6 +596,7 @@ static int ensure_colour(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.colour.ecol, C.ecol))) return rc;
     if ((rc = dev_upload(ctx, &D.colour.w, w))) return rc;
     D.colour.valid = true;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 
@@ -622,6 +630,23 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
         return MGCFD_ERR_PLAN;
+    }
+    if (ctx->n_ranks > 1) {
+        // chunks that own exported nodes run first so that the halo exchange overlaps the remaining (interior) chunks
+        HaloLevel &Hd = ctx->halo[level];
+        std::vector<char> exported(L.n_owned, 0);
+        for (int f : L.export_idx) exported[L.new_of_old[f]] = 1;
+        std::vector<int> first, rest;
+        for (int k = 0; k < O.n_chunks; k++) {
+            bool b = false;
+            for (int v = O.node0[k]; v < O.node0[k + 1] && !b; v++) b = exported[v];
+            (b ? first : rest).push_back(k);
+        }
+        Hd.n_boundary_chunks = (int)first.size();
+        Hd.n_chunks = O.n_chunks;
+        first.insert(first.end(), rest.begin(), rest.end());
+        int rcl = dev_upload(ctx, &Hd.d_chunk_list, first);
+        if (rcl) return rcl;
     }
     std::vector<OwnerChunkDesc> desc(O.n_chunks);
     std::vector<unsigned char> blob((size_t)O.blob_off[O.n_chunks], 0);
@@ -658,6 +683,7 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.owner.blob, blob))) return rc;
     D.owner.blob_bytes = (long long)blob.size();
     D.owner.valid = true;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 
@@ -737,6 +763,7 @@ static int ensure_gather(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.gather.g, g))) return rc;
     D.gather.n_ent = (long long)ent.size();
     D.gather.valid = true;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 
@@ -756,6 +783,7 @@ int mgcfd_set_flux_variant(mgcfd_ctx *ctx, int variant)
 {
     REQUIRE(ctx && variant >= 0 && variant < MGCFD_FLUX_NVARIANTS, "unknown flux variant");
     ctx->opt.flux_variant = variant;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 

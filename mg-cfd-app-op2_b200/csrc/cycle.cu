@@ -31,19 +31,94 @@ using namespace mgcfd;
 // ------------------------------------------------------------------------------------------
 // one context, no communication
 // ------------------------------------------------------------------------------------------
+// CUDA-graph replay of the enqueue functions below.  A graph holds ONE cycle.  A cycle flips the variables double
+// buffer and the min_dt slot parity of the levels it visits an odd number of times, so graphs are keyed by that
+// parity state, and each graph remembers the state it leaves behind (applied to the host bookkeeping on replay).
+namespace {
+unsigned parity_state(mgcfd_ctx *ctx)
+{
+    unsigned s = 0;
+    for (int l = 0; l < ctx->n_levels; l++) s |= ((unsigned)ctx->D[l].visit_parity | ((unsigned)ctx->D[l].var_flip << 1)) << (2 * l);
+    return s;
+}
+
+template <typename Enqueue>
+int run_with_graph(mgcfd_ctx *ctx, int n_cycles, Enqueue enqueue)
+{
+    bool usable = !ctx->opt.no_graphs && !ctx->timers_on && n_cycles >= 1 && ctx->n_levels <= 15;
+    for (int l = 0; l < ctx->n_levels && usable; l++) usable = ctx->D[l].flux_is_zero;
+    if (!usable) return enqueue(n_cycles);
+    for (int i = 0; i < n_cycles; i++) {
+        const unsigned key = parity_state(ctx);
+        auto it = ctx->graphs.find(key);
+        if (it == ctx->graphs.end()) {
+            GraphEntry g;
+            long long l0 = ctx->launches, h0 = ctx->halo_bytes;
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue(1);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return MGCFD_ERR_CUDA; }
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return MGCFD_ERR_CUDA; }
+            g.launches = ctx->launches - l0;
+            g.halo_bytes = ctx->halo_bytes - h0;
+            ctx->launches = l0;              // capturing enqueues nothing; the replay below does
+            ctx->halo_bytes = h0;
+            for (int l = 0; l < ctx->n_levels; l++)
+                g.after.push_back({ctx->D[l].var, ctx->D[l].var_alt, ctx->D[l].visit_parity, ctx->D[l].var_flip});
+            it = ctx->graphs.emplace(key, g).first;
+        }
+        CK(cudaGraphLaunch(it->second.exec, ctx->stream));
+        ctx->launches += it->second.launches;
+        ctx->halo_bytes += it->second.halo_bytes;
+        for (int l = 0; l < ctx->n_levels; l++) {
+            const GraphEntry::LevelState &st = it->second.after[l];
+            ctx->D[l].var = st.var; ctx->D[l].var_alt = st.var_alt;
+            ctx->D[l].visit_parity = st.visit_parity; ctx->D[l].var_flip = st.var_flip;
+        }
+    }
+    return MGCFD_OK;
+}
+
+int finish_run(mgcfd_ctx *ctx)
+{
+    int rc = api_check_launch(ctx, "mgcfd_run_cycles");
+    if (rc) return rc;
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
+    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
+    if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
+    return MGCFD_OK;
+}
+}  // namespace
+
+static int enqueue_single(mgcfd_ctx *ctx, int n_cycles);
+
 int mgcfd::cycle_run_single(mgcfd_ctx *ctx, int n_cycles)
 {
-    const int nl = ctx->n_levels;
-    for (int l = 0; l < nl; l++) {
+    for (int l = 0; l < ctx->n_levels; l++) {
         int rc = api_ensure_flux_plan(ctx, l);
         if (rc) return rc;
     }
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, ctx->stream));
+    int rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_single(ctx, k); });
+    if (rc) return rc;
+    return finish_run(ctx);
+}
+
+// the schedule of euler3d.cpp:458-641 for n_cycles cycles: enqueue only, no host synchronisation
+static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
+{
+    const int nl = ctx->n_levels;
     cudaStream_t s = ctx->stream;
     const bool exact = ctx->opt.exact_arith != 0;
     const DevConsts dc = api_dev_consts(ctx);
     // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
     const bool fused = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && !ctx->opt.no_fusion;
-    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, s));
     int level = 0, dir = 0, i = 0;
     while (i < n_cycles) {
         LevelHost &L = ctx->H[level];
@@ -86,6 +161,7 @@ int mgcfd::cycle_run_single(mgcfd_ctx *ctx, int n_cycles)
                     CK(cudaMemcpyAsync(D.var_alt + (size_t)no * 5, D.var + (size_t)no * 5, (size_t)(L.n_nodes - no) * 40,
                                        cudaMemcpyDeviceToDevice, s));
                 std::swap(D.var, D.var_alt);
+                D.var_flip ^= 1;
             }
         } else {
             { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
@@ -134,16 +210,8 @@ int mgcfd::cycle_run_single(mgcfd_ctx *ctx, int n_cycles)
             if (level == 0) { dir = 0; i++; }
         }
     }
-    int rc = api_check_launch(ctx, "mgcfd_run_cycles");
-    if (rc) return rc;
-    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
-    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
-    if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
     return MGCFD_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------
 // NCCL, loaded lazily from whatever libnccl.so.2 the process already has (torch's when launched by torchrun)
@@ -189,12 +257,16 @@ enum { DAT_VAR = 0, DAT_RES = 1 };
 
 inline double *dat_ptr(mgcfd_ctx *c, int level, int which) { return which == DAT_VAR ? c->D[level].var : c->D[level].res; }
 
-// pack this rank's export rows of `which` on its stream
+// ---- halo exchange.  Every transfer runs on the rank's communication stream:
+//   producer kernel (main stream) -> ev_prod -> [comm stream: pack exports, move, land in the halo range] -> ev_ready
+// and the main stream waits for ev_ready only before the next kernel that reads halo data, so whatever is queued on
+// the main stream in between (the interior chunks of the same Runge-Kutta stage) overlaps the exchange.
+
 int pack_exports(mgcfd_ctx *ctx, int level, int which)
 {
     HaloLevel &H = ctx->halo[level];
     if (H.n_export == 0) return MGCFD_OK;
-    ctx->launches += k_pack_rows(ctx->stream, H.n_export, H.d_export_idx, dat_ptr(ctx, level, which), H.sendbuf);
+    ctx->launches += k_pack_rows(ctx->comm_stream, H.n_export, H.d_export_idx, dat_ptr(ctx, level, which), H.sendbuf);
     ctx->halo_bytes += (long long)H.n_export * 40;
     return api_check_launch(ctx, "pack_rows");
 }
@@ -205,9 +277,10 @@ int exchange_group(mgcfd_ctx **R, int n, int level, int which)
     for (int r = 0; r < n; r++) {
         mgcfd_ctx *ctx = R[r];
         CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
         int rc = pack_exports(ctx, level, which);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_pack, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_pack, ctx->comm_stream));
     }
     for (int q = 0; q < n; q++) {
         mgcfd_ctx *ctx = R[q];
@@ -224,16 +297,17 @@ int exchange_group(mgcfd_ctx **R, int n, int level, int which)
                 ctx->err = "halo lists of the ranks do not match";
                 return MGCFD_ERR_ARG;
             }
-            CK(cudaStreamWaitEvent(ctx->stream, src->ev_pack, 0));
+            CK(cudaStreamWaitEvent(ctx->comm_stream, src->ev_pack, 0));
             CK(cudaMemcpyAsync(dat_ptr(ctx, level, which) + (size_t)(no + H.imp_ptr[k]) * 5, S.sendbuf + (size_t)S.exp_ptr[kq] * 5,
-                               (size_t)cnt * 40, cudaMemcpyDefault, ctx->stream));
+                               (size_t)cnt * 40, cudaMemcpyDefault, ctx->comm_stream));
         }
-        CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_done, ctx->comm_stream));
     }
     for (int r = 0; r < n; r++) {       // a send buffer may only be repacked after every neighbour has pulled from it
         mgcfd_ctx *ctx = R[r];
         CK(cudaSetDevice(ctx->device));
-        for (int q : ctx->halo[level].nbr_rank) CK(cudaStreamWaitEvent(ctx->stream, R[q]->ev_done, 0));
+        for (int q : ctx->halo[level].nbr_rank) CK(cudaStreamWaitEvent(ctx->comm_stream, R[q]->ev_done, 0));
+        CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
     }
     return MGCFD_OK;
 }
@@ -242,28 +316,62 @@ int exchange_group(mgcfd_ctx **R, int n, int level, int which)
 int exchange_nccl(mgcfd_ctx *ctx, int level, int which)
 {
     HaloLevel &H = ctx->halo[level];
-    if (H.nbr_rank.empty()) return MGCFD_OK;
-    int rc = pack_exports(ctx, level, which);
-    if (rc) return rc;
-    ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
-    const int no = ctx->H[level].n_owned;
-    NCK(g_nccl.GroupStart());
-    for (size_t k = 0; k < H.nbr_rank.size(); k++) {
-        int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
-        if (ns) NCK(g_nccl.Send(H.sendbuf + (size_t)H.exp_ptr[k] * 5, (size_t)ns * 5, ncclDouble, H.nbr_rank[k], comm, ctx->stream));
-        if (nr) NCK(g_nccl.Recv(dat_ptr(ctx, level, which) + (size_t)(no + H.imp_ptr[k]) * 5, (size_t)nr * 5, ncclDouble,
-                                H.nbr_rank[k], comm, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
+    if (!H.nbr_rank.empty()) {
+        int rc = pack_exports(ctx, level, which);
+        if (rc) return rc;
+        ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+        const int no = ctx->H[level].n_owned;
+        NCK(g_nccl.GroupStart());
+        for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+            int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
+            if (ns) NCK(g_nccl.Send(H.sendbuf + (size_t)H.exp_ptr[k] * 5, (size_t)ns * 5, ncclDouble, H.nbr_rank[k], comm, ctx->comm_stream));
+            if (nr) NCK(g_nccl.Recv(dat_ptr(ctx, level, which) + (size_t)(no + H.imp_ptr[k]) * 5, (size_t)nr * 5, ncclDouble,
+                                    H.nbr_rank[k], comm, ctx->comm_stream));
+        }
+        NCK(g_nccl.GroupEnd());
     }
-    NCK(g_nccl.GroupEnd());
+    CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
     return MGCFD_OK;
 }
 
-int exchange(mgcfd_ctx **R, int n, int level, int which)
+// mark "the producers of this exchange are queued" on every rank's main stream
+void mark_produced(mgcfd_ctx **R, int n)
+{
+    for (int r = 0; r < n; r++) {
+        cudaSetDevice(R[r]->device);
+        cudaEventRecord(R[r]->ev_prod, R[r]->stream);
+    }
+}
+
+// start the exchange of `which` on the communication streams (after mark_produced)
+int exchange_start(mgcfd_ctx **R, int n, int level, int which)
 {
     if (n == 1 && R[0]->nccl_comm) return exchange_nccl(R[0], level, which);
     if (n == 1) return MGCFD_OK;
     return exchange_group(R, n, level, which);
 }
+
+// main streams wait for the last started exchange
+void exchange_wait(mgcfd_ctx **R, int n)
+{
+    if (n == 1 && !R[0]->nccl_comm) return;
+    for (int r = 0; r < n; r++) {
+        cudaSetDevice(R[r]->device);
+        cudaStreamWaitEvent(R[r]->stream, R[r]->ev_ready, 0);
+    }
+}
+
+int exchange(mgcfd_ctx **R, int n, int level, int which)      // not overlapped: produce -> exchange -> wait
+{
+    mark_produced(R, n);
+    int rc = exchange_start(R, n, level, which);
+    if (rc) return rc;
+    exchange_wait(R, n);
+    return MGCFD_OK;
+}
+
+int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles);
 
 // the fused schedule over a set of ranks in lock step
 int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
@@ -286,10 +394,23 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
         }
         if (cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 4, c->stream) != cudaSuccess) return MGCFD_ERR_CUDA;
     }
-    int level = 0, dir = 0, i = 0, rc;
+    int rc;
     // halos of the start state (a caller may have set variables on the owned nodes only)
     for (int l = 0; l < nl; l++)
         if ((rc = exchange(R, n, l, DAT_VAR))) return rc;
+    // one process per GPU: the whole multi-stream schedule, NCCL calls included, replays as a CUDA graph
+    if (nccl) rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_ranks(R, n, k); });
+    else rc = enqueue_ranks(R, n, n_cycles);
+    if (rc) return rc;
+    return MGCFD_OK;
+}
+
+int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
+{
+    mgcfd_ctx *ctx = R[0];
+    const int nl = ctx->n_levels;
+    const bool nccl = n == 1 && ctx->nccl_comm;
+    int level = 0, dir = 0, i = 0, rc;
     while (i < n_cycles) {
         // ---- visit prologue: copy, dt, local min (euler3d.cpp:467-479)
         for (int r = 0; r < n; r++) {
@@ -312,7 +433,12 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
             LoopScope t(c, "compute_step_factor", level, no);
             if (nccl) {
                 ctx = c;
-                NCK(g_nccl.AllReduce(slot, slot, 1, ncclUint64, ncclMin, static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+                // every NCCL call of this rank goes through the communication stream, in one program order
+                CK(cudaEventRecord(c->ev_prod, c->stream));
+                CK(cudaStreamWaitEvent(c->comm_stream, c->ev_prod, 0));
+                NCK(g_nccl.AllReduce(slot, slot, 1, ncclUint64, ncclMin, static_cast<ncclComm_t>(c->nccl_comm), c->comm_stream));
+                CK(cudaEventRecord(c->ev_ready, c->comm_stream));
+                CK(cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
                 c->launches += k_step_factor_fused(c->stream, no, D.vol, slot, next, D.sf, &c->d_min_dt[level], c->d_flags);
             } else {
                 MinSlots ms;
@@ -326,32 +452,46 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
             if (level == 0) c->launches += k_fill(c->stream, 1, c->d_rms, 0.0);
         }
         for (int r = 0; r < n; r++) R[r]->D[level].visit_parity ^= 1;
-        // ---- three fused Runge-Kutta stages, halo exchange of the new variables after each (euler3d.cpp:492-531)
+        // ---- three fused Runge-Kutta stages (euler3d.cpp:492-531).  Per stage: chunks owning exported nodes first,
+        //      then the halo exchange of the new variables starts and the interior chunks run underneath it
         for (int rk = 0; rk < MGCFD_RK; rk++) {
-            for (int r = 0; r < n; r++) {
-                mgcfd_ctx *c = R[r];
-                cudaSetDevice(c->device);
-                LevelHost &L = c->H[level];
-                LevelDev &D = c->D[level];
-                RkStageArgs ra;
-                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
-                ra.d_rms = level == 0 ? c->d_rms : nullptr;
-                ra.d_bad = &c->d_flags[0];
-                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
-                ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = api_dev_consts(c);
-                FluxArgs a;
-                a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
-                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
-                {
-                    LoopScope t(c, "rk_stage", level, L.n_edges);
-                    c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
+            const bool last = rk == MGCFD_RK - 1;
+            for (int part = 0; part < 2; part++) {
+                for (int r = 0; r < n; r++) {
+                    mgcfd_ctx *c = R[r];
+                    cudaSetDevice(c->device);
+                    LevelHost &L = c->H[level];
+                    LevelDev &D = c->D[level];
+                    HaloLevel &Hd = c->halo[level];
+                    RkStageArgs ra;
+                    ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
+                    ra.d_rms = level == 0 ? c->d_rms : nullptr;
+                    ra.d_bad = &c->d_flags[0];
+                    ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
+                    ra.rk = rk; ra.last = last; ra.c = api_dev_consts(c);
+                    FluxArgs a;
+                    a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
+                    a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
+                    a.chunk_list = Hd.d_chunk_list + (part == 0 ? 0 : Hd.n_boundary_chunks);
+                    a.n_list = part == 0 ? Hd.n_boundary_chunks : Hd.n_chunks - Hd.n_boundary_chunks;
+                    {
+                        LoopScope t(c, "rk_stage", level, part == 0 ? 0 : L.n_edges);
+                        c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
+                    }
+                    if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
                 }
-                if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
-                std::swap(D.var, D.var_alt);
+                if (part == 0) {
+                    // exported values exist now: swap so that "var" names the new buffer, then start the exchange(s)
+                    for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
+                    mark_produced(R, n);
+                    if ((rc = exchange_start(R, n, level, DAT_VAR))) return rc;
+                    if (last && level >= 1 && (rc = exchange_start(R, n, level, DAT_RES))) return rc;   // prolong of level-1 reads res[level]
+                    for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
+                }
             }
-            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+            for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
+            exchange_wait(R, n);
         }
-        if (level >= 1 && (rc = exchange(R, n, level, DAT_RES))) return rc;      // prolong of level-1 reads res[level] parents
         if (nl <= 1) {
             i++;
         } else if (dir == 0) {
@@ -378,28 +518,17 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
             if (level == 0) { dir = 0; i++; }
         }
     }
-    // deferred checks (euler3d.cpp:480, :544): any rank's flag fails the run
-    int bad = 0, neg = 0;
-    for (int r = 0; r < n; r++) {
-        mgcfd_ctx *c = R[r];
-        cudaSetDevice(c->device);
-        if ((rc = api_check_launch(c, "mgcfd_run_cycles"))) { ctx->err = c->err; return rc; }
-        int *hp = reinterpret_cast<int *>(&c->h_pinned[6]);
-        if (cudaMemcpyAsync(hp, c->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-            cudaStreamSynchronize(c->stream) != cudaSuccess) {
-            ctx->err = std::string("run_ranks: ") + cudaGetErrorString(cudaGetLastError());
-            return MGCFD_ERR_CUDA;
-        }
-        bad += hp[0];
-        neg += hp[1];
-    }
-    ctx = R[0];
-    if (neg) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
-    if (bad > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
     return MGCFD_OK;
 }
 
 }  // namespace
+
+void mgcfd::cycle_drop_graphs(mgcfd_ctx *ctx)
+{
+    for (auto &kv : ctx->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+}
 
 extern "C" {
 

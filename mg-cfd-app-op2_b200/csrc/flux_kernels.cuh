@@ -418,8 +418,9 @@ __device__ __forceinline__ void stage_tile(double *raw, uint64_t *bar, int node0
 template <bool STREAM, bool OVERWRITE, bool FUSE>
 __global__ void __launch_bounds__(256)
 flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
-                  const int *__restrict__ halo_gid, const unsigned char *__restrict__ blob,
-                  const double *__restrict__ var, double *__restrict__ flux, RkStageArgs rk)
+                  const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
+                  const unsigned char *__restrict__ blob, const double *__restrict__ var, double *__restrict__ flux,
+                  RkStageArgs rk)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int NREC = STREAM ? 5 : NF;
@@ -432,7 +433,8 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     // FUSE: old_variables tile [max_own][5] and step factors [max_own], both 16-byte aligned bulk-copy targets
     double *told = raw + (((size_t)NREC * max_loc + 1) & ~(size_t)1);
     double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
-    const OwnerChunkDesc d = descs[blockIdx.x];
+    // chunk_list (multi-GPU): the launch covers a subset of the chunks, e.g. those that own exported nodes
+    const OwnerChunkDesc d = descs[chunk_list ? chunk_list[blockIdx.x] : blockIdx.x];
     const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
     const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
 
@@ -777,19 +779,21 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
     if (h.n_chunks == 0) return 0;
     size_t smem = owner_smem(h.max_loc, h.max_edges, h.max_blob, a.stream_kernel);
     RkStageArgs none{};
-#define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, p.halo_gid, p.blob, a.var, a.flux
+    const int grid = a.chunk_list ? a.n_list : h.n_chunks;
+    if (grid == 0) return 0;
+#define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, a.chunk_list, p.halo_gid, p.blob, a.var, a.flux
     if (a.stream_kernel)
-        flux_owner_kernel<true, false, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<true, false, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
     else if (a.rk) {
         RkStageArgs ra = *a.rk;
         ra.max_own = h.max_own;
         size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.max_blob, false, h.max_own);
-        flux_owner_kernel<false, true, true><<<h.n_chunks, 256, fsmem, s>>>(OWNER_ARGS, ra);
+        flux_owner_kernel<false, true, true><<<grid, 256, fsmem, s>>>(OWNER_ARGS, ra);
     }
     else if (a.overwrite)
-        flux_owner_kernel<false, true, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<false, true, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
     else
-        flux_owner_kernel<false, false, false><<<h.n_chunks, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<false, false, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
 #undef OWNER_ARGS
     return 1;
 }

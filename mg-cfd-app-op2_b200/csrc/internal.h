@@ -141,6 +141,7 @@ struct LevelDev {
     double *var_alt = nullptr;     // second variables buffer: the fused stage writes var_new here, then the two swap
     int *bnd_ptr = nullptr;        // [n_owned+1] boundary entry range per owned node (fused stage)
     int visit_parity = 0;          // which min_dt slot the next visit reduces into
+    int var_flip = 0;              // whether var / var_alt are currently swapped (CUDA-graph cache key)
     double *vol = nullptr, *sf = nullptr, *coords = nullptr;
     int *up_count = nullptr;       // p_up_scratch payload
     int *mg = nullptr;             // internal fine node -> internal coarse node (level+1)
@@ -165,6 +166,15 @@ struct HaloLevel {
     int *d_export_idx = nullptr;     // internal indices of exported owned nodes, concatenated per neighbour
     double *sendbuf = nullptr;       // [n_export][5]
     int n_export = 0;
+    int *d_chunk_list = nullptr;     // owner chunks that own exported nodes first (n_boundary_chunks), then the rest
+    int n_boundary_chunks = 0, n_chunks = 0;
+};
+
+struct GraphEntry {
+    struct LevelState { double *var, *var_alt; int visit_parity, var_flip; };
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0, halo_bytes = 0;   // per replay (one cycle)
+    std::vector<LevelState> after;            // host bookkeeping the cycle leaves behind
 };
 
 struct LoopTimer {
@@ -197,11 +207,13 @@ struct mgcfd_ctx {
     int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only
     std::map<std::string, mgcfd::LoopTimer> timers;
     std::vector<cudaEvent_t> event_pool;
+    std::map<unsigned, mgcfd::GraphEntry> graphs;   // captured one-cycle graphs by parity state
     // multi-GPU
     std::vector<mgcfd::HaloLevel> halo;
     int rank = 0, n_ranks = 1;
     void *nccl_comm = nullptr;
-    cudaEvent_t ev_pack = nullptr, ev_done = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_done = nullptr, ev_k1 = nullptr, ev_prod = nullptr, ev_ready = nullptr;
+    cudaStream_t comm_stream = nullptr;   // halo exchanges run here, overlapped with interior chunks on `stream`
     long long halo_bytes = 0;
 };
 
@@ -214,6 +226,7 @@ int api_ensure_flux_plan(mgcfd_ctx *ctx, int level);
 int api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel);
 void timers_collect(mgcfd_ctx *ctx);
 int cycle_run_single(mgcfd_ctx *ctx, int n_cycles);
+void cycle_drop_graphs(mgcfd_ctx *ctx);
 
 // per-call-site device timer (CUDA events on the context's stream)
 struct LoopScope {
@@ -308,6 +321,8 @@ struct FluxArgs {
     bool stream_kernel = false;     // unstructured_stream_kernel body instead of the flux body
     bool overwrite = false;         // owner variant: flux known to be zero -> plain store, no read
     const RkStageArgs *rk = nullptr; // owner variant: fuse the rest of the Runge-Kutta stage into the kernel
+    const int *chunk_list = nullptr; // owner variant: launch only these chunks (device array of n_list chunk ids)
+    int n_list = 0;
 };
 int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
 int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);

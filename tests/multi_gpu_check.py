@@ -20,6 +20,7 @@ def main():
     cycles = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = ge.load_package()
     mesh = pkg.meshgen.make_multigrid(name)
@@ -31,11 +32,12 @@ def main():
         uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     gpu.comm_init_nccl(uid.cpu().numpy().tobytes())
-    gpu.run_cycles(cycles)
+    gpu.run_cycles(cycles)           # pairs of cycles replay as a CUDA graph with the NCCL calls captured
+    gpu.run_cycles(2)
     ok = True
     if rank == 0:
         with pkg.MGCFD(mesh["levels"], device=local, exact_arith=True) as single:
-            single.run_cycles(cycles)
+            single.run_cycles(cycles + 2)
             refs = [single.fetch(l, "variables") for l in range(len(mesh["levels"]))]
     for l, lev in enumerate(mesh["levels"]):
         n = lev["node_coordinates"].shape[0]

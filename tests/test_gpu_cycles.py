@@ -146,3 +146,18 @@ def test_m6_full_size(pkg, meshgen, oracle_port, variant):
         gpu.run_cycles(2)
         ff = np.array(list(gpu.consts.ff_variable))
         check_levels(gpu, [a["var"] for a in run.levels], ff)
+
+
+@pytest.mark.parametrize("variant,fuse", [("owner", True), ("owner", False), ("colour", True)])
+def test_graph_replay_equals_direct_launches(pkg, meshgen, variant, fuse):
+    """pairs of cycles replay as a captured CUDA graph; odd leftovers and changing parity states are handled"""
+    mesh = meshgen.make_multigrid("small")
+    with pkg.MGCFD(mesh["levels"], flux_variant=variant, fuse=fuse, exact_arith=True) as a, \
+            pkg.MGCFD(mesh["levels"], flux_variant=variant, fuse=fuse, exact_arith=True, graphs=False) as b:
+        for n in (5, 2, 1, 4, 3):                 # 15 cycles in uneven pieces: both parity states get captured
+            a.run_cycles(n)
+            b.run_cycles(n)
+        assert a.kernel_launches() == b.kernel_launches()
+        for l in range(len(mesh["levels"])):
+            assert np.array_equal(a.fetch(l, "variables"), b.fetch(l, "variables"))
+            assert np.array_equal(a.fetch(l, "residuals"), b.fetch(l, "residuals"))
