@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh", default="m6")
-    ap.add_argument("--variant", default="owner", choices=["owner", "gather", "colour", "atomic"])
+    ap.add_argument("--variant", default="owner", choices=["owner", "emit", "gather", "colour", "atomic"])
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--cpu-cycles", type=int, default=2)
@@ -203,7 +203,7 @@ def main():
                 f": {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
                 f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
     config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
-              "arith": "exact" if args.exact else "fast", "fused_schedule": args.variant == "owner" and not args.no_fusion, "cuda_graphs": not args.no_graphs,
+              "arith": "exact" if args.exact else "fast", "fused_schedule": args.variant in ("owner", "emit") and not args.no_fusion, "cuda_graphs": not args.no_graphs,
               "l2": "no flush between steps: the V-cycle working set (~%d MB) exceeds the 126 MB L2"
                     % (sum(300 * s[0] + 32 * s[1] for s in sizes) // 2**20)}
     nthreads = os.cpu_count() or 1
@@ -238,7 +238,8 @@ def main():
     if world > 1:
         parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world)
         lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
-        gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant="owner", exact_arith=args.exact,
+        gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant=args.variant if args.variant == "emit" else "owner",
+                        exact_arith=args.exact,
                         owner_chunk_nodes=args.chunk, graphs=not args.no_graphs)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -290,7 +291,7 @@ def main():
     barrier()
     ms_timed = max_over_ranks(e2.elapsed_time(e3))
     clocks = sampler.stop() if sampler else None
-    fused = world > 1 or (args.variant == "owner" and not args.no_fusion)
+    fused = world > 1 or (args.variant in ("owner", "emit") and not args.no_fusion)
     flux_ms, flux_calls, flux_elems = gpu.timer("rk_stage" if fused else "compute_flux_edge")
     per_level = []
     for l in range(len(sizes)):
@@ -304,7 +305,7 @@ def main():
     # per-GPU roofline: this rank's launches move this rank's edges (owned + recomputed cut edges) and nodes
     flux_bytes = (rk_stage_bytes_per_cycle(local_sizes) if fused else flux_bytes_per_cycle(local_sizes)) * args.steps
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
-    kname = (f"flux_owner_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
+    kname = (f"flux_{args.variant if args.variant == 'emit' else 'owner'}_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
              if fused else f"compute_flux_edge_kernel[{args.variant}]")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")

@@ -54,7 +54,10 @@ enum {
     MGCFD_FLUX_GATHER = 3,     /* node gather over the same owner chunks: one thread per owned node evaluates its
                                   incident edges from its own side (interior edges twice), rows in sliced-ELL
                                   layout streamed coalesced, neighbour states gathered from shared memory */
-    MGCFD_FLUX_NVARIANTS = 4
+    MGCFD_FLUX_EMIT = 4,       /* owner chunks, one thread per owned node: every edge evaluated once by its lowest owned
+                                  endpoint, which keeps its own sum in registers; only the other owned end reads the
+                                  edge's flux vector from shared memory.  Fast arithmetic only (sums not in file order) */
+    MGCFD_FLUX_NVARIANTS = 5
 };
 
 typedef struct mgcfd_ctx mgcfd_ctx;

@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmgcfd_b200.so")
 
 NVAR, NDIM, RK = 5, 3, 3
-FLUX_ATOMIC, FLUX_COLOUR, FLUX_OWNER, FLUX_GATHER = 0, 1, 2, 3
-FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWNER, "gather": FLUX_GATHER}
+FLUX_ATOMIC, FLUX_COLOUR, FLUX_OWNER, FLUX_GATHER, FLUX_EMIT = 0, 1, 2, 3, 4
+FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWNER, "gather": FLUX_GATHER,
+                 "emit": FLUX_EMIT}
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NODEVICE", -4: "ERR_MIN_DT",
              -5: "ERR_BAD_VALS", -6: "ERR_PLAN"}

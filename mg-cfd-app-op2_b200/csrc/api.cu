@@ -216,7 +216,9 @@ static void free_level(LevelDev &d)
                     d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.perm, d.atomic.nodes, d.atomic.w,
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
                     d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.gather.desc, d.gather.halo_gid,
-                    d.gather.row_node, d.gather.row_deg, d.gather.ent, d.gather.w0, d.gather.w1, d.gather.w2, d.gather.g};
+                    d.gather.row_node, d.gather.row_deg, d.gather.ent, d.gather.w0, d.gather.w1, d.gather.w2, d.gather.g,
+                    d.emit.desc, d.emit.halo_gid, d.emit.row_node, d.emit.row_cnt, d.emit.ent, d.emit.w0, d.emit.w1, d.emit.w2,
+                    d.emit.g, d.emit.csr_words};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     d = LevelDev();
@@ -284,7 +286,7 @@ int mgcfd_decl_consts(mgcfd_ctx *ctx, const mgcfd_consts *c)
     REQUIRE(ctx && c, "null argument");
     ctx->consts = *c;
     ctx->have_consts = true;
-    for (auto &d : ctx->D) d.atomic.valid = d.colour.valid = d.owner.valid = d.gather.valid = false;   // g depends on smoothing
+    for (auto &d : ctx->D) d.atomic.valid = d.colour.valid = d.owner.valid = d.gather.valid = d.emit.valid = false;   // g depends on smoothing
     return MGCFD_OK;
 }
 
@@ -367,7 +369,7 @@ static int upload_bnd(mgcfd_ctx *ctx, int level)
         if (rc0) return rc0;
     }
     L.bnd_node_ptr = node_ptr;
-    D.owner.valid = false;                             // chunk descriptors carry a has-boundary flag
+    D.owner.valid = D.emit.valid = false;              // chunk descriptors carry a has-boundary flag
     int rc;
     if ((rc = dev_upload(ctx, &D.bu_node, bu_node))) return rc;
     if ((rc = dev_upload(ctx, &D.bu_ptr, bu_ptr))) return rc;
@@ -631,7 +633,7 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
         return MGCFD_ERR_PLAN;
     }
-    if (ctx->n_ranks > 1) {
+    if (ctx->n_ranks > 1 && !ctx->halo[level].d_chunk_list) {
         // chunks that own exported nodes run first so that the halo exchange overlaps the remaining (interior) chunks
         HaloLevel &Hd = ctx->halo[level];
         std::vector<char> exported(L.n_owned, 0);
@@ -767,9 +769,124 @@ static int ensure_gather(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
+// sliced-ELL layout of the edges each owned node emits + incidence lists of the non-emitter ends (emit variant)
+static int ensure_emit(mgcfd_ctx *ctx, int level)
+{
+    LevelHost &L = ctx->H[level];
+    LevelDev &D = ctx->D[level];
+    if (D.emit.valid) return MGCFD_OK;
+    if (ctx->opt.exact_arith) { ctx->err = "the emit variant is fast-arithmetic only (its sums are not in file order)"; return MGCFD_ERR_ARG; }
+    int rc0 = ensure_owner(ctx, level);          // chunks, halo lists, chunk launch order
+    if (rc0) return rc0;
+    OwnerPlanHost &O = L.owner;
+    std::vector<EmitChunkDesc> desc(O.n_chunks);
+    std::vector<uint16_t> row_node((size_t)O.n_chunks * 256, 0xffff), row_cnt((size_t)O.n_chunks * 256, 0);
+    std::vector<uint32_t> ent, csr_words;
+    std::vector<double> w0, w1, w2, g;
+    std::vector<int> order, emitter, slot_of_edge;
+    std::vector<std::vector<int>> emitted;
+    int max_ent = 0, max_csr = 0;
+    for (int k = 0; k < O.n_chunks; k++) {
+        EmitChunkDesc &d = desc[k];
+        d.node0 = O.node0[k];
+        d.n_own = O.node0[k + 1] - O.node0[k];
+        d.n_halo = O.halo_off[k + 1] - O.halo_off[k];
+        d.halo_off = O.halo_off[k];
+        d.ent_off = (long long)ent.size();
+        d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] > L.bnd_node_ptr[O.node0[k]] ? 1 : 0;
+        const int ne = O.n_edges[k];
+        const uint32_t *lab = &O.lab[O.edge_off[k]];
+        emitter.assign(ne, 0);
+        slot_of_edge.assign(ne, -1);
+        emitted.assign(d.n_own, std::vector<int>());
+        for (int e = 0; e < ne; e++) {
+            int la = lab[e] & 0xffff, lb = lab[e] >> 16;
+            int em = (la < d.n_own && lb < d.n_own) ? std::min(la, lb) : (la < d.n_own ? la : lb);
+            emitter[e] = em;
+            emitted[em].push_back(e);
+        }
+        order.resize(d.n_own);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return emitted[x].size() > emitted[y].size(); });
+        for (int s = 0; s < 8; s++) {
+            int lo = s * 32, hi = std::min(d.n_own, lo + 32), len = 0;
+            for (int t = lo; t < hi; t++) len = std::max(len, (int)emitted[order[t]].size());
+            d.slice_len[s] = (unsigned short)len;
+            size_t base = ent.size();
+            ent.resize(base + (size_t)len * 32, 0);
+            w0.resize(ent.size(), 0.0); w1.resize(ent.size(), 0.0); w2.resize(ent.size(), 0.0); g.resize(ent.size(), 0.0);
+            for (int t = lo; t < hi; t++) {
+                int node = order[t], cnt = (int)emitted[node].size();
+                row_node[(size_t)k * 256 + t] = (uint16_t)node;
+                row_cnt[(size_t)k * 256 + t] = (uint16_t)cnt;
+                for (int j = 0; j < len; j++) {
+                    size_t idx = base + (size_t)j * 32 + (t - lo);
+                    if (j >= cnt) { ent[idx] = (uint32_t)node; continue; }      // padding: neighbour = self, zero weights
+                    int e = emitted[node][j];
+                    int la = lab[e] & 0xffff, lb = lab[e] >> 16;
+                    bool is_b = node == lb;
+                    int other = is_b ? la : lb;
+                    double p[4];
+                    pack_weight(ctx, L, O.edge_file[O.edge_off[k] + e], p);
+                    double sgn = is_b ? -1.0 : 1.0;      // flipping an edge negates its weight vector; |w| is unchanged
+                    ent[idx] = (uint32_t)other | (other < d.n_own ? 0x10000u : 0u);
+                    w0[idx] = sgn * p[0]; w1[idx] = sgn * p[1]; w2[idx] = sgn * p[2]; g[idx] = p[3];
+                    slot_of_edge[e] = (int)(idx - (size_t)d.ent_off);
+                }
+            }
+        }
+        int n_ent = (int)(ent.size() - (size_t)d.ent_off);
+        if (n_ent > 65535) { ctx->err = "emit chunk has more than 65535 row slots"; return MGCFD_ERR_PLAN; }
+        max_ent = std::max(max_ent, n_ent);
+        // incidence lists of the non-emitter ends: rowptr2[n_own+1] | csr2, both u16, 4-byte aligned blocks
+        const uint16_t *rowptr = &O.rowptr[O.rowptr_off[k]];
+        const uint16_t *csr = O.csr.data() + O.csr_off[k];
+        std::vector<uint16_t> rp2(d.n_own + 1, 0), c2;
+        for (int m = 0; m < d.n_own; m++) {
+            rp2[m] = (uint16_t)c2.size();
+            for (int j = rowptr[m]; j < rowptr[m + 1]; j++) {
+                int e = csr[j] & 0x7fff;
+                if (emitter[e] != m) c2.push_back((uint16_t)slot_of_edge[e]);
+            }
+        }
+        rp2[d.n_own] = (uint16_t)c2.size();
+        if (rp2.size() & 1) rp2.push_back(0);
+        if (c2.size() & 1) c2.push_back(0);
+        d.rowptr_pad = (int)rp2.size();
+        d.csr_off = (int)csr_words.size();
+        d.csr_words = (int)((rp2.size() + c2.size()) / 2);
+        size_t w = csr_words.size();
+        csr_words.resize(w + d.csr_words);
+        memcpy(&csr_words[w], rp2.data(), rp2.size() * 2);
+        memcpy(reinterpret_cast<uint16_t *>(&csr_words[w]) + rp2.size(), c2.data(), c2.size() * 2);
+        max_csr = std::max(max_csr, d.csr_words);
+    }
+    if (flux_emit_smem_bytes(O.max_loc, max_ent, max_csr, O.max_own) > 227 * 1024) {
+        ctx->err = "emit chunk does not fit in shared memory";
+        return MGCFD_ERR_PLAN;
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &D.emit.desc, desc))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.halo_gid, O.halo_gid))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.row_node, row_node))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.row_cnt, row_cnt))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.ent, ent))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.w0, w0))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.w1, w1))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.w2, w2))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.g, g))) return rc;
+    if ((rc = dev_upload(ctx, &D.emit.csr_words, csr_words))) return rc;
+    D.emit.n_chunks = O.n_chunks; D.emit.max_loc = O.max_loc; D.emit.max_ent = max_ent; D.emit.max_csr = max_csr;
+    D.emit.max_own = O.max_own;
+    D.emit.valid = true;
+    cycle_drop_graphs(ctx);
+    return MGCFD_OK;
+}
+
 extern "C++" int mgcfd::api_ensure_flux_plan(mgcfd_ctx *ctx, int level)
 {
     switch (ctx->opt.flux_variant) {
+    case MGCFD_FLUX_EMIT: return ensure_emit(ctx, level);
     case MGCFD_FLUX_GATHER: return ensure_gather(ctx, level);
     case MGCFD_FLUX_ATOMIC: return ensure_atomic(ctx, level);
     case MGCFD_FLUX_COLOUR: return ensure_colour(ctx, level);
@@ -850,7 +967,7 @@ int mgcfd_loop_calculate_cell_volumes(mgcfd_ctx *ctx, int level)
         for (int i = 0; i < 3; i++) w[i] = (d[i] / dist) * area;
         for (int i = 0; i < 3; i++) w[i] /= dist;
     }
-    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = false;
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = ctx->D[level].emit.valid = false;
     return upload_volumes(ctx, level, vol);
 }
 
@@ -858,7 +975,7 @@ int mgcfd_loop_dampen_ewt_edges(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();
     for (double &w : ctx->H[level].ewt) w *= 1e-7;                               // misc.h:78-84
-    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = false;
+    ctx->D[level].atomic.valid = ctx->D[level].colour.valid = ctx->D[level].owner.valid = ctx->D[level].gather.valid = ctx->D[level].emit.valid = false;
     return MGCFD_OK;
 }
 
@@ -944,6 +1061,15 @@ extern "C++" int mgcfd::api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kern
     case MGCFD_FLUX_COLOUR: ctx->launches += flux_colour(ctx->stream, a, D.colour, L.colour, exact); break;
     case MGCFD_FLUX_OWNER: ctx->launches += flux_owner(ctx->stream, a, D.owner, L.owner, exact); break;
     case MGCFD_FLUX_GATHER: ctx->launches += flux_gather(ctx->stream, a, D.gather, L.owner.n_chunks, L.owner.max_loc, exact); break;
+    case MGCFD_FLUX_EMIT:
+        if (stream_kernel) {          // unstructured_stream_kernel has no emit form: the owner chunks run it
+            int rco = ensure_owner(ctx, level);
+            if (rco) return rco;
+            ctx->launches += flux_owner(ctx->stream, a, D.owner, L.owner, exact);
+        } else {
+            ctx->launches += flux_emit(ctx->stream, a, D.emit);
+        }
+        break;
     }
     if (!stream_kernel) D.flux_is_zero = false;
     return api_check_launch(ctx, "compute_flux_edge_kernel");
@@ -1121,7 +1247,7 @@ int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_
     std::string s(name);
     if (s == "edge_weights") {
         memcpy(L.ewt.data(), host_in, L.ewt.size() * sizeof(double));
-        D.atomic.valid = D.colour.valid = D.owner.valid = D.gather.valid = false;
+        D.atomic.valid = D.colour.valid = D.owner.valid = D.gather.valid = D.emit.valid = false;
         return MGCFD_OK;
     }
     if (s == "bnd_node_weights") {

@@ -118,7 +118,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
     const bool exact = ctx->opt.exact_arith != 0;
     const DevConsts dc = api_dev_consts(ctx);
     // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
-    const bool fused = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && !ctx->opt.no_fusion;
+    const bool fused = (ctx->opt.flux_variant == MGCFD_FLUX_OWNER || ctx->opt.flux_variant == MGCFD_FLUX_EMIT) && !ctx->opt.no_fusion;
     int level = 0, dir = 0, i = 0;
     while (i < n_cycles) {
         LevelHost &L = ctx->H[level];
@@ -155,7 +155,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                 a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
                 {
                     LoopScope t(ctx, "rk_stage", level, L.n_edges);
-                    ctx->launches += flux_owner(s, a, D.owner, L.owner, exact);
+                    ctx->launches += ctx->opt.flux_variant == MGCFD_FLUX_EMIT ? flux_emit(s, a, D.emit) : flux_owner(s, a, D.owner, L.owner, exact);
                 }
                 if (L.n_nodes > no)   // halo entries of the new buffer are refreshed by the exchange; keep them defined
                     CK(cudaMemcpyAsync(D.var_alt + (size_t)no * 5, D.var + (size_t)no * 5, (size_t)(L.n_nodes - no) * 40,
@@ -382,8 +382,8 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
     for (int r = 0; r < n; r++) {
         mgcfd_ctx *c = R[r];
         if (!c->planned || c->device < 0 || c->n_levels != nl) { ctx->err = "ranks are not planned alike"; return MGCFD_ERR_ARG; }
-        if (c->opt.flux_variant != MGCFD_FLUX_OWNER || c->opt.no_fusion) {
-            ctx->err = "multi-GPU runs use the fused owner schedule (flux_variant owner, no_fusion 0)";
+        if ((c->opt.flux_variant != MGCFD_FLUX_OWNER && c->opt.flux_variant != MGCFD_FLUX_EMIT) || c->opt.no_fusion) {
+            ctx->err = "multi-GPU runs use the fused schedule (flux_variant owner or emit, no_fusion 0)";
             return MGCFD_ERR_ARG;
         }
         cudaSetDevice(c->device);
@@ -476,7 +476,8 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                     a.n_list = part == 0 ? Hd.n_boundary_chunks : Hd.n_chunks - Hd.n_boundary_chunks;
                     {
                         LoopScope t(c, "rk_stage", level, part == 0 ? 0 : L.n_edges);
-                        c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
+                        c->launches += c->opt.flux_variant == MGCFD_FLUX_EMIT ? flux_emit(c->stream, a, D.emit)
+                                                                               : flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
                     }
                     if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
                 }

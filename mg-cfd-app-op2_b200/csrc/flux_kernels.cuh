@@ -410,6 +410,50 @@ __device__ __forceinline__ void stage_tile(double *raw, uint64_t *bar, int node0
     cp_async_wait_all();
 }
 
+// Last step of a chunk: the tile `raw` holds the owned nodes' flux sums (AoS).  Plain variant: one contiguous,
+// coalesced store to `flux`.  FUSE: time_stepping_kernels.h:66-86 applied on the spot (+ validation.h:27-44,102-115
+// after the last stage) with the prefetched old_variables / step_factor tiles.
+template <bool FUSE>
+__device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n_own, double *__restrict__ flux,
+                                             const RkStageArgs &rk, const double *told, const double *tsf,
+                                             uint32_t old_bulk, uint32_t sf_bulk)
+{
+    const int tid = threadIdx.x;
+    if (!FUSE) {
+        double *out = flux + (size_t)node0 * 5;
+        for (int f = tid; f < n_own * 5; f += blockDim.x) out[f] = raw[f];
+    } else {
+        const size_t g0 = (size_t)node0 * 5;
+        const double denom = (double)(MGCFD_RK + 1 - rk.rk);
+        double sq = 0.0;
+        int bad = 0;
+        const int old_n = (int)(old_bulk >> 3), sf_n = (int)(sf_bulk >> 3);    // an odd last chunk has one tail element
+        for (int f = tid; f < n_own * 5; f += blockDim.x) {
+            int node = f / 5;
+            double factor = (node < sf_n ? tsf[node] : rk.sf[node0 + node]) / denom;
+            double o = f < old_n ? told[f] : rk.old[g0 + f];
+            double vn = __dadd_rn(o, __dmul_rn(factor, raw[f]));
+            rk.var_out[g0 + f] = vn;
+            if (rk.last) {
+                double r = vn - o;
+                rk.res[g0 + f] = r;
+                sq += r * r;
+                bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
+            }
+        }
+        if (rk.last && rk.d_rms) {
+            for (int o = 16; o > 0; o >>= 1) {
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                bad += __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            if ((tid & 31) == 0) {
+                atomicAdd(rk.d_rms, sq);
+                if (bad) atomicAdd(rk.d_bad, bad);
+            }
+        }
+    }
+}
+
 // FUSE: the Runge-Kutta stage in one kernel -- compute_flux_edge + compute_bnd_node_flux + time_step (+ residual,
 // calc_rms, count_bad_vals after the last stage).  The owner of a node holds the node's complete edge-flux sum in
 // registers, so it adds the boundary entries and applies var_new = old + step_factor/(RK+1-rk) * flux on the spot;
@@ -546,41 +590,166 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
         for (int v = 0; v < 5; v++) raw[n * 5 + v] = acc[v];      // the state tile is dead: reuse it for the output
     }
     __syncthreads();
-    if (!FUSE) {
-        double *out = flux + (size_t)d.node0 * 5;
-        for (int f = tid; f < d.n_own * 5; f += blockDim.x) out[f] = raw[f];
-    } else {
-        // time_stepping_kernels.h:66-86 (+ validation.h:27-44,102-115 after the last stage), flat and coalesced
-        const size_t g0 = (size_t)d.node0 * 5;
-        const double denom = (double)(MGCFD_RK + 1 - rk.rk);
-        double sq = 0.0;
-        int bad = 0;
-        const int old_n = (int)(old_bulk >> 3), sf_n = (int)(sf_bulk >> 3);    // an odd last chunk has one tail element
-        for (int f = tid; f < d.n_own * 5; f += blockDim.x) {
-            int node = f / 5;
-            double factor = (node < sf_n ? tsf[node] : rk.sf[d.node0 + node]) / denom;
-            double o = f < old_n ? told[f] : rk.old[g0 + f];
-            double vn = __dadd_rn(o, __dmul_rn(factor, raw[f]));
-            rk.var_out[g0 + f] = vn;
-            if (rk.last) {
-                double r = vn - o;
-                rk.res[g0 + f] = r;
-                sq += r * r;
-                bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
-            }
+    finish_chunk<FUSE>(raw, d.node0, d.n_own, flux, rk, told, tsf, old_bulk, sf_bulk);
+}
+
+#ifndef MGCFD_EXACT
+// ------------------------------------------------------------------------------------------
+// variant 4: emit.  Same owner chunks, one thread per owned node.  Every edge of the chunk is evaluated ONCE, by the
+// thread of its lowest-numbered owned endpoint (its "emitter"), which keeps its own state and its own flux sum in
+// registers; only when the other endpoint is owned too, the edge's flux vector is parked in shared memory for that
+// node to subtract afterwards.  Compared with the owner kernel this halves the state reads (one neighbour per
+// edge instead of two endpoints), writes fewer flux vectors and reads each of them once instead of twice.  Emitted
+// edges are stored sliced-ELL (rows sorted by length, slices of 32 padded, column-major) with pre-signed weights, so
+// they stream from HBM fully coalesced, software-pipelined one row ahead.  Fast arithmetic only: sums are not in
+// file order.
+// shared: mbarrier | raw[max_loc][5] | der[3][max_loc] | Fs[5][max_ent] | csr (rowptr2, csr2) | told | tsf
+// ------------------------------------------------------------------------------------------
+template <bool OVERWRITE, bool FUSE>
+__global__ void __launch_bounds__(256, 4)
+flux_emit_kernel(int max_loc, int max_ent, int max_csr, const EmitChunkDesc *__restrict__ descs,
+                 const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
+                 const uint16_t *__restrict__ row_node, const uint16_t *__restrict__ row_cnt,
+                 const uint32_t *__restrict__ ent, const double *__restrict__ pw0, const double *__restrict__ pw1,
+                 const double *__restrict__ pw2, const double *__restrict__ pg, const uint32_t *__restrict__ csr_words,
+                 const double *__restrict__ var, double *__restrict__ flux, RkStageArgs rk)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+    double *raw = reinterpret_cast<double *>(smraw + 16);
+    double *der = raw + (size_t)max_loc * 5;
+    double *Fs = der + (size_t)max_loc * 3;
+    uint32_t *scsr = reinterpret_cast<uint32_t *>(Fs + (size_t)max_ent * 5);
+    double *told = reinterpret_cast<double *>(smraw + ((16 + ((size_t)max_loc * 8 + (size_t)max_ent * 5) * 8 + (size_t)max_csr * 4 + 15) & ~(size_t)15));
+    double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
+    const int chunk = chunk_list ? chunk_list[blockIdx.x] : blockIdx.x;
+    const EmitChunkDesc d = descs[chunk];
+    const int tid = threadIdx.x, lane = tid & 31, slice = tid >> 5;
+    const int nloc = d.n_own + d.n_halo;
+    const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, owned_bulk_bytes(d.n_own) + old_bulk + sf_bulk);
+        if (FUSE) {
+            if (old_bulk) bulk_g2s(told, rk.old + (size_t)d.node0 * 5, old_bulk, bar);
+            if (sf_bulk) bulk_g2s(tsf, rk.sf + d.node0, sf_bulk, bar);
         }
-        if (rk.last && rk.d_rms) {
-            for (int o = 16; o > 0; o >>= 1) {
-                sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                bad += __shfl_xor_sync(0xffffffffu, bad, o);
-            }
-            if ((tid & 31) == 0) {
-                atomicAdd(rk.d_rms, sq);
-                if (bad) atomicAdd(rk.d_bad, bad);
+    }
+    // first row of this thread's emitted edges: requested before anything else waits
+    const int me = row_node[(size_t)chunk * 256 + tid];               // local owned index or 0xffff
+    const int cnt = row_cnt[(size_t)chunk * 256 + tid];
+    int len = 0;
+    long long base = d.ent_off;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        int L = d.slice_len[s];
+        if (s < slice) base += (long long)L * 32;
+        if (s == slice) len = L;
+    }
+    uint32_t en_n = 0;
+    double x_n = 0.0, y_n = 0.0, z_n = 0.0, g_n = 0.0;
+    if (len > 0) {
+        long long idx = base + lane;
+        en_n = __ldg(ent + idx); x_n = __ldg(pw0 + idx); y_n = __ldg(pw1 + idx); z_n = __ldg(pw2 + idx); g_n = __ldg(pg + idx);
+    }
+    // incidence lists of the non-emitter ends (4-byte async copies), state tile (bulk + 8-byte async copies)
+    for (int i = tid; i < d.csr_words; i += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(scsr + i)), "l"(csr_words + d.csr_off + i) : "memory");
+    stage_tile(raw, bar, d.node0, d.n_own, d.n_halo, halo_gid + d.halo_off, var, tid, blockDim.x);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    for (int i = tid; i < nloc; i += blockDim.x) {
+        double u[5], r[8];
+#pragma unroll
+        for (int v = 0; v < 5; v++) u[v] = raw[i * 5 + v];
+        derive(u, r);
+        der[i] = r[5]; der[max_loc + i] = r[6]; der[2 * max_loc + i] = r[7];
+    }
+    __syncthreads();
+
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (!OVERWRITE && me != 0xffff) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] = flux[(size_t)(d.node0 + me) * 5 + v];
+    }
+    const int self = me != 0xffff ? me : 0;
+    double a[8];
+    load_state<8>(raw, der, max_loc, self, a);
+    const int slot0 = (int)(base - d.ent_off) + lane;                  // position of this lane's row j = 0 in the chunk
+    for (int j = 0; j < len; j++) {
+        const uint32_t en = en_n;
+        const double x = x_n, y = y_n, z = z_n, g = g_n;
+        if (j + 1 < len) {                                             // next row in flight while this one computes
+            long long idx = base + (long long)(j + 1) * 32 + lane;
+            en_n = __ldg(ent + idx); x_n = __ldg(pw0 + idx); y_n = __ldg(pw1 + idx); z_n = __ldg(pw2 + idx); g_n = __ldg(pg + idx);
+        }
+        double b[8], F[5];
+        load_state<8>(raw, der, max_loc, (int)(en & 0xffff), b);
+        edge_flux(a, b, x, y, z, g, F);                               // weights pre-signed: the emitter is end "a"
+        if (j < cnt) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] += F[v];
+            if (en & 0x10000u) {                                       // the other end is owned: it subtracts this vector
+                const int slot = slot0 + j * 32;
+#pragma unroll
+                for (int v = 0; v < 5; v++) Fs[v * max_ent + slot] = F[v];
             }
         }
     }
+    __syncthreads();
+    if (me != 0xffff) {
+        const uint16_t *rowptr2 = reinterpret_cast<const uint16_t *>(scsr);
+        const uint16_t *csr2 = rowptr2 + d.rowptr_pad;
+        for (int j = rowptr2[me]; j < rowptr2[me + 1]; j++) {
+            int slot = csr2[j];
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] -= Fs[v * max_ent + slot];
+        }
+        if (FUSE && d.has_bnd) {
+            int j0 = rk.bnd_ptr[d.node0 + me], j1 = rk.bnd_ptr[d.node0 + me + 1];
+            if (j1 > j0) {
+                double u[5];
+#pragma unroll
+                for (int v = 0; v < 5; v++) u[v] = raw[me * 5 + v];
+                bnd_apply(u, acc, j0, j1, rk.b_group, rk.b_wt, rk.c);
+            }
+        }
+    }
+    __syncthreads();                                                  // every read of the state tile is done
+    if (me != 0xffff) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) raw[me * 5 + v] = acc[v];
+    }
+    __syncthreads();
+    finish_chunk<FUSE>(raw, d.node0, d.n_own, flux, rk, told, tsf, old_bulk, sf_bulk);
 }
+
+inline size_t emit_smem(int max_loc, int max_ent, int max_csr, int max_own)
+{
+    return 16 + ((size_t)max_loc * 8 + (size_t)max_ent * 5) * 8 + (size_t)max_csr * 4 + 16 + ((size_t)max_own * 6 + 4) * 8;
+}
+
+inline int launch_emit(cudaStream_t s, const FluxArgs &a, const EmitPlanDev &p)
+{
+    const int grid = a.chunk_list ? a.n_list : p.n_chunks;
+    if (grid == 0) return 0;
+    size_t smem = emit_smem(p.max_loc, p.max_ent, p.max_csr, p.max_own);
+    RkStageArgs ra{};
+    if (a.rk) ra = *a.rk;
+    ra.max_own = p.max_own;
+#define EMIT_ARGS p.max_loc, p.max_ent, p.max_csr, p.desc, a.chunk_list, p.halo_gid, p.row_node, p.row_cnt, p.ent, p.w0, p.w1, p.w2, \
+                  p.g, p.csr_words, a.var, a.flux, ra
+    if (a.rk)
+        flux_emit_kernel<true, true><<<grid, 256, smem, s>>>(EMIT_ARGS);
+    else if (a.overwrite)
+        flux_emit_kernel<true, false><<<grid, 256, smem, s>>>(EMIT_ARGS);
+    else
+        flux_emit_kernel<false, false><<<grid, 256, smem, s>>>(EMIT_ARGS);
+#undef EMIT_ARGS
+    return 1;
+}
+#endif  // !MGCFD_EXACT
 
 // ------------------------------------------------------------------------------------------
 // variant 3: node gather ("pull").  Same owner chunks, but one thread per owned node walks the node's
@@ -814,6 +983,11 @@ inline std::string configure()
     OPT_IN((flux_gather_kernel<true, false>));
     OPT_IN((flux_gather_kernel<false, true>));
     OPT_IN((flux_gather_kernel<false, false>));
+#ifndef MGCFD_EXACT
+    OPT_IN((flux_emit_kernel<true, true>));
+    OPT_IN((flux_emit_kernel<true, false>));
+    OPT_IN((flux_emit_kernel<false, false>));
+#endif
 #undef OPT_IN
     return "";
 }

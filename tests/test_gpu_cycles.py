@@ -28,7 +28,7 @@ def check_levels(gpu, ref_vars, ff, exact=False):
         assert gpu.validate(l, ref) <= ref.shape[0] // 5000  # ... and its pass criterion (euler3d.cpp:700)
 
 
-@pytest.mark.parametrize("variant", ["owner", "gather", "colour", "atomic"])
+@pytest.mark.parametrize("variant", ["owner", "emit", "gather", "colour", "atomic"])
 @pytest.mark.parametrize("name,cycles", [("tiny", 3), ("small", 10)])
 def test_cycles_golden(pkg, meshgen, golden, variant, name, cycles):
     g = golden(f"{name}_cycles{cycles}.npz")
@@ -134,7 +134,7 @@ def test_errors_are_reported_not_thrown(pkg, meshgen):
         pkg.MGCFD(mesh["levels"], base_array_index=2)  # maps out of range for the wrong base index
 
 
-@pytest.mark.parametrize("variant", ["owner", "gather", "colour", "atomic"])
+@pytest.mark.parametrize("variant", ["owner", "emit", "gather", "colour", "atomic"])
 def test_m6_full_size(pkg, meshgen, oracle_port, variant):
     """BASELINE.json configs[0]/[1]: the M6-shaped 4-level deck at full size, 2 cycles against the live oracle."""
     mesh = meshgen.make_multigrid("m6")
