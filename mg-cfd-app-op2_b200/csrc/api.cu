@@ -609,6 +609,9 @@ static int build_owner_host(mgcfd_ctx *ctx, int level)
     int nb = ctx->opt.owner_chunk_nodes;
     // caps on local nodes and edges bound the shared-memory footprint (DESIGN.md "owner chunk sizing")
     int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
+    // tuning knobs for experiments (not part of the specified plan): override the local-node / edge caps
+    if (const char *e = getenv("MGCFD_OWNER_MAX_LOC")) max_loc = atoi(e);
+    if (const char *e = getenv("MGCFD_OWNER_MAX_EDGES")) max_edges = atoi(e);
     std::string err;
     if (!plan_owner(L, nb, max_loc, max_edges, err)) {
         ctx->err = err;

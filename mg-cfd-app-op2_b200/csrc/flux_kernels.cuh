@@ -459,8 +459,11 @@ __device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n
 // registers, so it adds the boundary entries and applies var_new = old + step_factor/(RK+1-rk) * flux on the spot;
 // the fluxes never travel to HBM (they are zero before and after every stage).  var_new goes to the
 // alternate variables buffer because neighbouring chunks still read this stage's input.
+#ifndef MGCFD_OWNER_MINB
+#define MGCFD_OWNER_MINB 3      // resident CTAs per SM the register allocation aims for (4 forces spills and measured slower)
+#endif
 template <bool STREAM, bool OVERWRITE, bool FUSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MGCFD_OWNER_MINB)
 flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
                   const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
                   const unsigned char *__restrict__ blob, const double *__restrict__ var, double *__restrict__ flux,
