@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel per op_par_loop call site")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every launch instead of replaying CUDA graphs")
+    ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"],
+                    help="N>1: direct peer stores over CUDA-IPC-mapped memory (default) or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -241,11 +243,19 @@ def main():
         gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant=args.variant if args.variant == "emit" else "owner",
                         exact_arith=args.exact,
                         owner_chunk_nodes=args.chunk, graphs=not args.no_graphs)
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        gpu.comm_init_nccl(bytes(uid.cpu().numpy().tobytes()))
+        if args.transport == "ipc":
+            mine = torch.frombuffer(bytearray(gpu.ipc_export()), dtype=torch.uint8).cuda()
+            blobs = [torch.zeros(4096, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(blobs, mine)
+            gpu.comm_init_ipc(b"".join(b.cpu().numpy().tobytes() for b in blobs))
+            dist.barrier()
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            gpu.comm_init_nccl(bytes(uid.cpu().numpy().tobytes()))
+        config["transport"] = args.transport
         local_sizes = [(lm.sizes(l)[0], lm.sizes(l)[1], lm.sizes(l)[2]) for l in range(len(sizes))]
     else:
         gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,

@@ -179,7 +179,7 @@ void mgcfd_local_mesh_free(mgcfd_local_mesh *m);
 
 /* ---- multi-GPU execution.  Halo exchange of `variables` after every Runge-Kutta stage / restrict / prolong and
  * of `residuals` after every visit (OP2: dirty-bit halo exchanges inside op_par_loop), min_dt all-reduce(MIN).
- * Two transports:
+ * Three transports:
  *   group  one process drives several contexts (one per GPU, or several on one GPU for tests): packed export
  *          buffers are pulled by the neighbour with peer copies, ordered by CUDA events;
  *   NCCL   one process per GPU (torchrun): grouped ncclSend/ncclRecv per neighbour + ncclAllReduce(min);
@@ -187,6 +187,16 @@ void mgcfd_local_mesh_free(mgcfd_local_mesh *m);
 int mgcfd_group_run_cycles(mgcfd_ctx **ranks, int n_ranks, int n_cycles);
 int mgcfd_nccl_unique_id(void *id_out_128);
 int mgcfd_comm_init_nccl(mgcfd_ctx *ctx, int n_ranks, int rank, const void *unique_id_128);
+/*   p2p    direct peer stores: the pack kernel writes the exported rows straight into the neighbours' halo ranges
+ *          (peer-mapped memory over NVLink), one warp publishes an epoch flag per neighbour and waits for theirs;
+ *          min_dt travels through per-rank mailboxes the same way.  No library call on the data path.
+ *          - ranks of one process: mgcfd_group_enable_p2p(ranks, n) then mgcfd_group_run_cycles;
+ *          - one process per GPU: every rank calls mgcfd_ipc_export (a 4096-byte blob holding a CUDA IPC handle and
+ *            the layout of its exchange arena), the launcher all-gathers the blobs, every rank calls
+ *            mgcfd_comm_init_ipc(all blobs in rank order), then mgcfd_run_cycles. */
+int mgcfd_group_enable_p2p(mgcfd_ctx **ranks, int n_ranks);
+int mgcfd_ipc_export(mgcfd_ctx *ctx, void *blob_out_4096);
+int mgcfd_comm_init_ipc(mgcfd_ctx *ctx, const void *blobs_n_ranks_x_4096);
 /* bytes this rank has sent in halo exchanges so far */
 long long mgcfd_halo_bytes_sent(const mgcfd_ctx *ctx);
 

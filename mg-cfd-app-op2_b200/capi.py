@@ -108,7 +108,7 @@ ABI_SYMBOLS = [
     "mgcfd_host_alloc", "mgcfd_host_free",
     "mgcfd_partition_rcb", "mgcfd_partition_coarse", "mgcfd_local_mesh_build", "mgcfd_local_mesh_level",
     "mgcfd_local_mesh_query", "mgcfd_local_mesh_free", "mgcfd_group_run_cycles", "mgcfd_nccl_unique_id",
-    "mgcfd_comm_init_nccl", "mgcfd_halo_bytes_sent",
+    "mgcfd_comm_init_nccl", "mgcfd_halo_bytes_sent", "mgcfd_group_enable_p2p", "mgcfd_ipc_export", "mgcfd_comm_init_ipc",
 ]
 
 _DAT_DIMS = {"variables": 5, "old_variables": 5, "residuals": 5, "fluxes": 5, "dummy_fluxes": 5,
@@ -245,6 +245,15 @@ class LocalMesh:
             pass
 
 
+def group_enable_p2p(ranks):
+    """switch a single-process group to the direct peer-store transport (flags instead of events + peer copies)"""
+    lib = load_library()
+    arr = (C.c_void_p * len(ranks))(*[r.ctx for r in ranks])
+    rc = lib.mgcfd_group_enable_p2p(arr, len(ranks))
+    if rc != 0:
+        raise MgcfdError(rc, lib.mgcfd_last_error(ranks[0].ctx).decode())
+
+
 def group_run_cycles(ranks, n_cycles):
     """V-cycles over several contexts driven by this process (one per GPU, or several on one GPU)."""
     lib = load_library()
@@ -302,6 +311,18 @@ class MGCFD:
         """unique_id: the 128 bytes mgcfd_nccl_unique_id() produced on rank 0"""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self.lib.mgcfd_comm_init_nccl(self.ctx, self.n_ranks, self.rank, buf))
+
+    def ipc_export(self):
+        """4096-byte blob (CUDA IPC handle + arena layout) for mgcfd_comm_init_ipc on the other ranks"""
+        buf = C.create_string_buffer(4096)
+        self._ck(self.lib.mgcfd_ipc_export(self.ctx, buf))
+        return buf.raw
+
+    def comm_init_ipc(self, blobs):
+        """blobs: the ipc_export() of every rank, concatenated in rank order"""
+        data = bytes(blobs)
+        assert len(data) == 4096 * self.n_ranks
+        self._ck(self.lib.mgcfd_comm_init_ipc(self.ctx, C.create_string_buffer(data, len(data))))
 
     def halo_bytes_sent(self):
         return int(self.lib.mgcfd_halo_bytes_sent(self.ctx))

@@ -212,6 +212,7 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
 
 static void free_level(LevelDev &d)
 {
+    if (d.in_arena) d.var = d.var_alt = d.res = nullptr;     // owned by the p2p arena
     void *ptrs[] = {d.var_alt, d.bnd_ptr, d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
                     d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.perm, d.atomic.nodes, d.atomic.w,
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
@@ -249,6 +250,10 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int r = 0; r < mgcfd::P2P_MAX_RANKS; r++)
+        if (ctx->p2p.ipc && ctx->p2p.peer_base[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->p2p.peer_base[r]);
+    if (ctx->p2p.arena_owner && ctx->p2p.arena) cudaFree(ctx->p2p.arena);
+    if (ctx->p2p.d_counters) cudaFree(ctx->p2p.d_counters);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -448,15 +453,54 @@ int mgcfd_plan(mgcfd_ctx *ctx)
     }
     if (ctx->device < 0) { ctx->planned = true; return MGCFD_OK; }
     CK(cudaSetDevice(ctx->device));
+    if (ctx->n_ranks > 1) {
+        // partitioned context: variables (both buffers) and residuals of every level, the exchange flags and the
+        // min_dt mailboxes live in one arena that peers can map and store into (p2p transport)
+        REQUIRE(ctx->n_levels <= P2P_MAX_LEVELS && ctx->n_ranks <= P2P_MAX_RANKS, "too many levels / ranks for the p2p arena");
+        P2PState &P = ctx->p2p;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        memset(&P.me, 0, sizeof(P.me));
+        P.me.n_levels = ctx->n_levels;
+        P.me.rank = ctx->rank;
+        for (int l = 0; l < ctx->n_levels; l++) {
+            size_t bytes = (size_t)std::max(ctx->H[l].n_nodes, 1) * 40;
+            P.me.off_var[0][l] = (long long)take(bytes);
+            P.me.off_var[1][l] = (long long)take(bytes);
+            P.me.off_res[l] = (long long)take(bytes);
+            P.me.n_owned[l] = ctx->H[l].n_owned;
+            for (int r = 0; r < P2P_MAX_RANKS; r++) { P.me.import_off[l][r] = -1; P.me.import_cnt[l][r] = 0; }
+            for (size_t k = 0; k < ctx->H[l].nbr_rank.size(); k++) {
+                int cnt = ctx->H[l].import_ptr[k + 1] - ctx->H[l].import_ptr[k];
+                if (cnt > 0) { P.me.import_off[l][ctx->H[l].nbr_rank[k]] = ctx->H[l].import_ptr[k]; P.me.import_cnt[l][ctx->H[l].nbr_rank[k]] = cnt; }
+            }
+        }
+        P.me.off_flags = (long long)take(sizeof(unsigned long long) * P2P_MAX_RANKS * 4);
+        P.arena_bytes = off;
+        CK(cudaMalloc((void **)&P.arena, P.arena_bytes));
+        CK(cudaMemsetAsync(P.arena, 0, P.arena_bytes, ctx->stream));
+        P.arena_owner = true;
+        int rcc = dev_alloc(ctx, &P.d_counters, (size_t)P2P_MAX_RANKS * 4);
+        if (rcc) return rcc;
+        for (int l = 0; l < ctx->n_levels; l++) {
+            LevelDev &D = ctx->D[l];
+            D.var = reinterpret_cast<double *>(P.arena + P.me.off_var[0][l]);
+            D.var_alt = reinterpret_cast<double *>(P.arena + P.me.off_var[1][l]);
+            D.res = reinterpret_cast<double *>(P.arena + P.me.off_res[l]);
+            D.in_arena = true;
+        }
+    }
     for (int l = 0; l < ctx->n_levels; l++) {
         LevelHost &L = ctx->H[l];
         LevelDev &D = ctx->D[l];
         const size_t n = L.n_nodes;
         int rc;
-        if ((rc = dev_alloc(ctx, &D.var, n * 5))) return rc;
-        if ((rc = dev_alloc(ctx, &D.var_alt, n * 5))) return rc;
+        if (!D.in_arena) {
+            if ((rc = dev_alloc(ctx, &D.var, n * 5))) return rc;
+            if ((rc = dev_alloc(ctx, &D.var_alt, n * 5))) return rc;
+            if ((rc = dev_alloc(ctx, &D.res, n * 5))) return rc;
+        }
         if ((rc = dev_alloc(ctx, &D.old, n * 5))) return rc;
-        if ((rc = dev_alloc(ctx, &D.res, n * 5))) return rc;
         if ((rc = dev_alloc(ctx, &D.flux, n * 5))) return rc;
         if ((rc = dev_alloc(ctx, &D.vol, n))) return rc;
         if ((rc = dev_alloc(ctx, &D.cbrt_vol, n))) return rc;

@@ -335,6 +335,80 @@ int exchange_nccl(mgcfd_ctx *ctx, int level, int which)
     return MGCFD_OK;
 }
 
+// direct peer stores: the pack kernel writes my exported rows straight into every neighbour's halo range, then one
+// warp publishes an epoch to each neighbour's flag word and waits for the neighbours' epochs
+int exchange_p2p(mgcfd_ctx *ctx, int level, int which)
+{
+    HaloLevel &H = ctx->halo[level];
+    P2PState &P = ctx->p2p;
+    CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
+    if (!H.nbr_rank.empty()) {
+        PushTable t;
+        memset(&t, 0, sizeof(t));
+        const int me = ctx->rank;
+        // which of the two variables buffers is "var" right now (identical on every rank: they swap in lock step)
+        const int buf = ctx->D[level].var == reinterpret_cast<double *>(P.arena + P.me.off_var[0][level]) ? 0 : 1;
+        unsigned long long *cnt = P.d_counters;
+        for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+            const int q = H.nbr_rank[k];
+            const int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
+            const P2PInfo &Q = P.peer[q];
+            if (ns) {
+                if (Q.import_cnt[level][me] != ns) { ctx->err = "halo lists of the ranks do not match"; return MGCFD_ERR_ARG; }
+                long long off = which == DAT_VAR ? Q.off_var[buf][level] : Q.off_res[level];
+                int d = t.n_dst++;
+                t.exp_ptr[d] = H.exp_ptr[k];
+                t.exp_ptr[d + 1] = H.exp_ptr[k + 1];
+                t.dst[d] = reinterpret_cast<double *>(P.peer_base[q] + off) + (size_t)(Q.n_owned[level] + Q.import_off[level][me]) * 5;
+                t.dst_flag[d] = reinterpret_cast<unsigned long long *>(P.peer_base[q] + Q.off_flags) + me;
+                t.sent[d] = cnt + q;
+            }
+            if (nr) {
+                int s = t.n_src++;
+                t.src_flag[s] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + q;
+                t.expected[s] = cnt + P2P_MAX_RANKS + q;
+            }
+        }
+        // export lists are grouped by neighbour in ascending order, and neighbours without exports have empty ranges:
+        // the destinations' row ranges are contiguous in the export list
+        ctx->launches += k_push_rows(ctx->comm_stream, H.n_export, H.d_export_idx, dat_ptr(ctx, level, which), t);
+        ctx->launches += k_signal_wait(ctx->comm_stream, t);
+        ctx->halo_bytes += (long long)H.n_export * 40;
+        int rc = api_check_launch(ctx, "p2p exchange");
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
+    return MGCFD_OK;
+}
+
+// all-reduce(MIN) through the peers' mailboxes (p2p transport); leaves ev_ready recorded on the communication stream
+int min_exchange_p2p(mgcfd_ctx *ctx, int level, const unsigned long long *slot, int parity)
+{
+    P2PState &P = ctx->p2p;
+    MinTable t;
+    memset(&t, 0, sizeof(t));
+    t.me = ctx->rank;
+    t.parity = parity;
+    unsigned long long *cnt = P.d_counters;
+    for (int q = 0; q < ctx->n_ranks; q++) {
+        if (q == ctx->rank) continue;
+        int d = t.n_peers++;
+        unsigned long long *qflags = reinterpret_cast<unsigned long long *>(P.peer_base[q] + P.peer[q].off_flags);
+        t.dst_box[d] = qflags + 2 * P2P_MAX_RANKS + 2 * ctx->rank + parity;
+        t.dst_flag[d] = qflags + P2P_MAX_RANKS + ctx->rank;
+        t.sent[d] = cnt + 2 * P2P_MAX_RANKS + q;
+        t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
+        t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
+    }
+    CK(cudaEventRecord(ctx->ev_prod, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
+    ctx->launches += k_min_exchange(ctx->comm_stream, slot, t);
+    CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready, 0));
+    (void)level;
+    return api_check_launch(ctx, "p2p min exchange");
+}
+
 // mark "the producers of this exchange are queued" on every rank's main stream
 void mark_produced(mgcfd_ctx **R, int n)
 {
@@ -347,6 +421,14 @@ void mark_produced(mgcfd_ctx **R, int n)
 // start the exchange of `which` on the communication streams (after mark_produced)
 int exchange_start(mgcfd_ctx **R, int n, int level, int which)
 {
+    if (R[0]->p2p.enabled) {
+        for (int r = 0; r < n; r++) {
+            cudaSetDevice(R[r]->device);
+            int rc = exchange_p2p(R[r], level, which);
+            if (rc) { R[0]->err = R[r]->err; return rc; }
+        }
+        return MGCFD_OK;
+    }
     if (n == 1 && R[0]->nccl_comm) return exchange_nccl(R[0], level, which);
     if (n == 1) return MGCFD_OK;
     return exchange_group(R, n, level, which);
@@ -355,7 +437,7 @@ int exchange_start(mgcfd_ctx **R, int n, int level, int which)
 // main streams wait for the last started exchange
 void exchange_wait(mgcfd_ctx **R, int n)
 {
-    if (n == 1 && !R[0]->nccl_comm) return;
+    if (n == 1 && !R[0]->nccl_comm && !R[0]->p2p.enabled) return;
     for (int r = 0; r < n; r++) {
         cudaSetDevice(R[r]->device);
         cudaStreamWaitEvent(R[r]->stream, R[r]->ev_ready, 0);
@@ -379,6 +461,7 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
     mgcfd_ctx *ctx = R[0];
     const int nl = ctx->n_levels;
     const bool nccl = n == 1 && ctx->nccl_comm;
+    const bool remote = n == 1 && (ctx->nccl_comm || ctx->p2p.ipc);      // one process per GPU
     for (int r = 0; r < n; r++) {
         mgcfd_ctx *c = R[r];
         if (!c->planned || c->device < 0 || c->n_levels != nl) { ctx->err = "ranks are not planned alike"; return MGCFD_ERR_ARG; }
@@ -399,7 +482,7 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
     for (int l = 0; l < nl; l++)
         if ((rc = exchange(R, n, l, DAT_VAR))) return rc;
     // one process per GPU: the whole multi-stream schedule, NCCL calls included, replays as a CUDA graph
-    if (nccl) rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_ranks(R, n, k); });
+    if (remote) rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_ranks(R, n, k); });
     else rc = enqueue_ranks(R, n, n_cycles);
     if (rc) return rc;
     return MGCFD_OK;
@@ -420,7 +503,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             unsigned long long *slot = &c->d_min_enc[2 * level + D.visit_parity];
             LoopScope t(c, "visit_begin", level, c->H[level].n_owned);
             c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot);
-            if (n > 1) cudaEventRecord(c->ev_k1, c->stream);
+            if (n > 1 && !c->p2p.enabled) cudaEventRecord(c->ev_k1, c->stream);
         }
         // ---- global minimum + step factor (euler3d.cpp:477-489)
         for (int r = 0; r < n; r++) {
@@ -431,7 +514,15 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             unsigned long long *next = &c->d_min_enc[2 * level + (D.visit_parity ^ 1)];
             const int no = c->H[level].n_owned;
             LoopScope t(c, "compute_step_factor", level, no);
-            if (nccl) {
+            if (c->p2p.enabled) {
+                // mailboxes: my minimum goes to every peer, theirs arrive in my arena; K2 reads my slot + the boxes
+                if ((rc = min_exchange_p2p(c, level, slot, D.visit_parity))) { ctx->err = c->err; return rc; }
+                MinSlots ms;
+                ms.n = 0;
+                const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(c->p2p.arena + c->p2p.me.off_flags) + 2 * P2P_MAX_RANKS;
+                for (int q = 0; q < c->n_ranks; q++) ms.p[ms.n++] = q == c->rank ? slot : boxes + 2 * q + D.visit_parity;
+                c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags);
+            } else if (nccl) {
                 ctx = c;
                 // every NCCL call of this rank goes through the communication stream, in one program order
                 CK(cudaEventRecord(c->ev_prod, c->stream));
@@ -540,8 +631,8 @@ int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
     if (ctx->device < 0) { ctx->err = "planning-only context (device -1): compute entry points need a CUDA device"; return MGCFD_ERR_NODEVICE; }
     REQUIRE(n_cycles >= 0, "negative cycle count");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->nccl_comm) return run_ranks(&ctx, 1, n_cycles);
-    REQUIRE(ctx->n_ranks == 1, "a partitioned context needs mgcfd_comm_init_nccl() or mgcfd_group_run_cycles()");
+    if (ctx->nccl_comm || ctx->p2p.ipc) return run_ranks(&ctx, 1, n_cycles);
+    REQUIRE(ctx->n_ranks == 1, "a partitioned context needs mgcfd_comm_init_nccl(), mgcfd_comm_init_ipc() or mgcfd_group_run_cycles()");
     return cycle_run_single(ctx, n_cycles);
 }
 
@@ -592,6 +683,67 @@ int mgcfd_comm_init_nccl(mgcfd_ctx *ctx, int n_ranks, int rank, const void *uniq
     ncclComm_t comm;
     NCK(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
     ctx->nccl_comm = comm;
+    return MGCFD_OK;
+}
+
+int mgcfd_group_enable_p2p(mgcfd_ctx **ranks, int n_ranks)
+{
+    if (!ranks || n_ranks < 2 || n_ranks > P2P_MAX_RANKS || !ranks[0]) return MGCFD_ERR_ARG;
+    mgcfd_ctx *ctx = ranks[0];
+    for (int r = 0; r < n_ranks; r++)
+        REQUIRE(ranks[r] && ranks[r]->planned && ranks[r]->rank == r && ranks[r]->n_ranks == n_ranks && ranks[r]->p2p.arena,
+                "ranks[r] must be the planned context of rank r of n_ranks");
+    for (int a = 0; a < n_ranks; a++) {
+        for (int b = 0; b < n_ranks; b++) {
+            ranks[a]->p2p.peer[b] = ranks[b]->p2p.me;
+            ranks[a]->p2p.peer_base[b] = ranks[b]->p2p.arena;
+            if (ranks[a]->device != ranks[b]->device) {
+                cudaSetDevice(ranks[a]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ranks[b]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                    return MGCFD_ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+        }
+        ranks[a]->p2p.enabled = true;
+        cycle_drop_graphs(ranks[a]);
+    }
+    return MGCFD_OK;
+}
+
+int mgcfd_ipc_export(mgcfd_ctx *ctx, void *blob_out_4096)
+{
+    if (!ctx) return MGCFD_ERR_ARG;
+    REQUIRE(blob_out_4096 && ctx->planned && ctx->p2p.arena, "mgcfd_ipc_export needs a planned, partitioned context");
+    static_assert(sizeof(P2PInfo) <= 4096 && sizeof(cudaIpcMemHandle_t) == 64, "blob layout");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->p2p.arena));
+    memcpy(ctx->p2p.me.ipc_handle, &h, 64);
+    memset(blob_out_4096, 0, 4096);
+    memcpy(blob_out_4096, &ctx->p2p.me, sizeof(P2PInfo));
+    return MGCFD_OK;
+}
+
+int mgcfd_comm_init_ipc(mgcfd_ctx *ctx, const void *blobs)
+{
+    if (!ctx) return MGCFD_ERR_ARG;
+    REQUIRE(blobs && ctx->planned && ctx->p2p.arena && ctx->n_ranks <= P2P_MAX_RANKS, "mgcfd_comm_init_ipc needs a planned, partitioned context");
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->n_ranks; r++) {
+        memcpy(&ctx->p2p.peer[r], static_cast<const unsigned char *>(blobs) + (size_t)r * 4096, sizeof(P2PInfo));
+        REQUIRE(ctx->p2p.peer[r].rank == r && ctx->p2p.peer[r].n_levels == ctx->n_levels, "blob r is not rank r's export");
+        if (r == ctx->rank) { ctx->p2p.peer_base[r] = ctx->p2p.arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ctx->p2p.peer[r].ipc_handle, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p.peer_base[r] = static_cast<unsigned char *>(p);
+    }
+    ctx->p2p.enabled = ctx->p2p.ipc = true;
+    cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }
 

@@ -157,6 +157,7 @@ struct EmitPlanDev {
 
 struct LevelDev {
     double *var = nullptr, *old = nullptr, *res = nullptr, *flux = nullptr, *dummy_flux = nullptr;
+    bool in_arena = false;         // var / var_alt / res live in the p2p arena (not freed individually)
     double *var_alt = nullptr;     // second variables buffer: the fused stage writes var_new here, then the two swap
     int *bnd_ptr = nullptr;        // [n_owned+1] boundary entry range per owned node (fused stage)
     int visit_parity = 0;          // which min_dt slot the next visit reduces into
@@ -197,6 +198,47 @@ struct GraphEntry {
     std::vector<LevelState> after;            // host bookkeeping the cycle leaves behind
 };
 
+// ---- direct peer-store halo exchange ("p2p" transport): every rank keeps variables (both buffers) and residuals of
+// all levels, its flag words and the min_dt mailboxes in ONE arena that its peers map (CUDA IPC between processes,
+// plain pointers inside one process) and write into.
+constexpr int P2P_MAX_RANKS = 16, P2P_MAX_LEVELS = 16;
+struct P2PInfo {                         // what a peer must know about a rank's arena (exchanged as an opaque blob)
+    unsigned char ipc_handle[64];
+    int n_levels, rank;
+    long long off_var[2][P2P_MAX_LEVELS], off_res[P2P_MAX_LEVELS];
+    long long off_flags;                 // u64 halo_flag[P2P_MAX_RANKS] | u64 min_flag[P2P_MAX_RANKS] | u64 min_box[P2P_MAX_RANKS][2]
+    int n_owned[P2P_MAX_LEVELS];
+    int import_off[P2P_MAX_LEVELS][P2P_MAX_RANKS];   // where rows from rank r land in the halo range (nodes), -1: none
+    int import_cnt[P2P_MAX_LEVELS][P2P_MAX_RANKS];
+};
+struct P2PState {
+    bool arena_owner = false, enabled = false, ipc = false;
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
+    P2PInfo me{};
+    P2PInfo peer[P2P_MAX_RANKS];
+    unsigned char *peer_base[P2P_MAX_RANKS] = {};
+    unsigned long long *d_counters = nullptr;   // sent_halo[16] | expected_halo[16] | sent_min[16] | expected_min[16]
+};
+
+struct PushTable {                       // kernel parameter of one halo push
+    int n_dst, n_src;
+    int exp_ptr[P2P_MAX_RANKS + 1];
+    double *dst[P2P_MAX_RANKS];                      // where my rows land in each destination's arena
+    unsigned long long *dst_flag[P2P_MAX_RANKS];     // the destination's halo_flag[my rank]
+    unsigned long long *sent[P2P_MAX_RANKS];         // my epoch counter towards that destination
+    const unsigned long long *src_flag[P2P_MAX_RANKS];   // my halo_flag[source rank]
+    unsigned long long *expected[P2P_MAX_RANKS];     // my epoch counter for that source
+};
+struct MinTable {
+    int n_peers, me, parity;
+    unsigned long long *dst_box[P2P_MAX_RANKS];      // peer's min_box[me][parity]
+    unsigned long long *dst_flag[P2P_MAX_RANKS];     // peer's min_flag[me]
+    unsigned long long *sent[P2P_MAX_RANKS];
+    const unsigned long long *src_flag[P2P_MAX_RANKS];
+    unsigned long long *expected[P2P_MAX_RANKS];
+};
+
 struct LoopTimer {
     double ms = 0.0;
     long long calls = 0, elements = 0;
@@ -235,6 +277,7 @@ struct mgcfd_ctx {
     cudaEvent_t ev_pack = nullptr, ev_done = nullptr, ev_k1 = nullptr, ev_prod = nullptr, ev_ready = nullptr;
     cudaStream_t comm_stream = nullptr;   // halo exchanges run here, overlapped with interior chunks on `stream`
     long long halo_bytes = 0;
+    mgcfd::P2PState p2p;
 };
 
 namespace mgcfd {
@@ -319,6 +362,10 @@ struct MinSlots { const unsigned long long *p[16]; int n; };
 int k_step_factor_group(cudaStream_t s, int n, const double *vol, MinSlots slots, unsigned long long *next_slot, double *sf,
                         double *d_min_out, int *d_flags);
 int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double *dst);
+// p2p transport: rows straight into the peers' halo ranges, then epoch flags; returns kernels launched
+int k_push_rows(cudaStream_t s, int n_rows, const int *idx, const double *src, const PushTable &t);
+int k_signal_wait(cudaStream_t s, const PushTable &t);
+int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t);
 
 // extra arguments of the fused Runge-Kutta stage (flux + boundary flux + time_step [+ residual, rms, bad values])
 struct RkStageArgs {

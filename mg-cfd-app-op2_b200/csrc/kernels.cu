@@ -195,6 +195,66 @@ __global__ void pack_rows_kernel(int n5, const int *__restrict__ idx, const doub
     if (i < n5) dst[i] = src[(size_t)idx[i / 5] * 5 + i % 5];
 }
 
+// ---- p2p transport ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// gather the exported rows and store them straight into each destination rank's halo range (peer-mapped pointers)
+__global__ void push_rows_kernel(int n5, const int *__restrict__ idx, const double *__restrict__ src, PushTable t)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n5) return;
+    int row = i / 5, c = i - row * 5, k = 0;
+    while (k + 1 < t.n_dst && row >= t.exp_ptr[k + 1]) k++;
+    t.dst[k][(size_t)(row - t.exp_ptr[k]) * 5 + c] = src[(size_t)idx[row] * 5 + c];
+}
+
+// one warp: tell every destination that my rows of this exchange have landed (epoch counters live on the device so
+// that the kernel can be replayed from a CUDA graph), then wait until every source has told me the same
+__global__ void signal_wait_kernel(PushTable t)
+{
+    const int lane = threadIdx.x;
+    if (lane < t.n_dst) {
+        unsigned long long e = *t.sent[lane] + 1;
+        *t.sent[lane] = e;
+        __threadfence_system();
+        st_release_sys(t.dst_flag[lane], e);
+    }
+    __syncwarp();
+    if (lane < t.n_src) {
+        unsigned long long e = *t.expected[lane] + 1;
+        *t.expected[lane] = e;
+        while (ld_acquire_sys(t.src_flag[lane]) < e) { }
+    }
+}
+
+// all-reduce(MIN) of min_dt by mailboxes: my encoded minimum goes into every peer's box, then the same flag handshake
+__global__ void min_exchange_kernel(const unsigned long long *my_slot, MinTable t)
+{
+    const int lane = threadIdx.x;
+    if (lane < t.n_peers) {
+        *t.dst_box[lane] = *my_slot;
+        unsigned long long e = *t.sent[lane] + 1;
+        *t.sent[lane] = e;
+        __threadfence_system();
+        st_release_sys(t.dst_flag[lane], e);
+    }
+    __syncwarp();
+    if (lane < t.n_peers) {
+        unsigned long long e = *t.expected[lane] + 1;
+        *t.expected[lane] = e;
+        while (ld_acquire_sys(t.src_flag[lane]) < e) { }
+    }
+}
+
 __global__ void reset_min_slots_kernel(int n, unsigned long long *slots)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,6 +494,23 @@ int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double
 {
     if (n == 0) return 0;
     pack_rows_kernel<<<blocks_for((long long)n * 5), TPB, 0, s>>>(n * 5, idx, src, dst);
+    return 1;
+}
+int k_push_rows(cudaStream_t s, int n_rows, const int *idx, const double *src, const PushTable &t)
+{
+    if (n_rows == 0) return 0;
+    push_rows_kernel<<<blocks_for((long long)n_rows * 5), TPB, 0, s>>>(n_rows * 5, idx, src, t);
+    return 1;
+}
+int k_signal_wait(cudaStream_t s, const PushTable &t)
+{
+    if (t.n_dst == 0 && t.n_src == 0) return 0;
+    signal_wait_kernel<<<1, 32, 0, s>>>(t);
+    return 1;
+}
+int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t)
+{
+    min_exchange_kernel<<<1, 32, 0, s>>>(my_slot, t);
     return 1;
 }
 int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots)

@@ -10,6 +10,9 @@ import sys
 import numpy as np
 import pytest
 
+# virtual-rank tests put up to 16 streams with spin-wait kernels on one GPU: give every stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)

@@ -18,6 +18,7 @@ import __graft_entry__ as ge  # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "medium"
     cycles = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    transport = sys.argv[3] if len(sys.argv) > 3 else "nccl"          # nccl | ipc
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     os.environ.setdefault("NCCL_DEBUG", "WARN")
@@ -27,11 +28,18 @@ def main():
     parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world)
     lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
     gpu = pkg.MGCFD(local_mesh=lm, device=local, exact_arith=True)
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, 0)
-    gpu.comm_init_nccl(uid.cpu().numpy().tobytes())
+    if transport == "ipc":
+        mine = torch.frombuffer(bytearray(gpu.ipc_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.zeros(4096, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        gpu.comm_init_ipc(b"".join(b.cpu().numpy().tobytes() for b in blobs))
+        dist.barrier()
+    else:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        gpu.comm_init_nccl(uid.cpu().numpy().tobytes())
     gpu.run_cycles(cycles)           # pairs of cycles replay as a CUDA graph with the NCCL calls captured
     gpu.run_cycles(2)
     ok = True
@@ -47,7 +55,7 @@ def main():
         dist.all_reduce(full)                       # every node is owned exactly once, the rest are zeros
         if rank == 0:
             same = np.array_equal(full.cpu().numpy(), refs[l])
-            print(f"level {l}: NCCL x{world} == single GPU bit for bit: {same}")
+            print(f"level {l}: {transport} x{world} == single GPU bit for bit: {same}")
             ok = ok and same
     halo = gpu.halo_bytes_sent()
     gpu.close()

@@ -37,7 +37,7 @@ def test_odd_sizes_and_tiny_decks(pkg, meshgen, oracle_port, dims, variant):
 
 
 def test_level_without_boundary_nodes_and_all_groups(pkg, meshgen, oracle_port):
-    mesh = meshgen.make_multigrid(("m6wing", [(7, 6, 5, 600), (4, 4, 3, 100)], 23))
+    mesh = meshgen.make_multigrid(("m6wing", [(7, 6, 5, 600), (4, 4, 3, 120)], 23))
     lv1 = mesh["levels"][1]
     for k in ("bnd_node-->node", "bnd_node-->group"):
         lv1[k] = lv1[k][:0].copy()
@@ -53,7 +53,7 @@ def test_level_without_boundary_nodes_and_all_groups(pkg, meshgen, oracle_port):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_level_without_edges_is_a_no_op_for_the_flux_loops(pkg, meshgen, variant):
-    mesh = meshgen.make_multigrid(("m6wing", [(4, 3, 3, 70)], 29))
+    mesh = meshgen.make_multigrid(("m6wing", [(4, 3, 3, None)], 29))
     lev = mesh["levels"][0]
     lev["edge-->node"] = lev["edge-->node"][:0].copy()
     lev["edge_weights"] = lev["edge_weights"][:0].copy()

@@ -15,11 +15,13 @@ def normwise(a, b):
     return np.abs(a - b).max(axis=0) / np.maximum(np.abs(b).max(axis=0), 1e-300)
 
 
-def run_decomposed(pkg, mesh, n_ranks, cycles, devices=None, **kw):
+def run_decomposed(pkg, mesh, n_ranks, cycles, devices=None, p2p=False, **kw):
     parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], n_ranks)
     lms = [pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, n_ranks) for r in range(n_ranks)]
     ranks = [pkg.MGCFD(local_mesh=lm, device=(devices[r] if devices else 0), **kw) for r, lm in enumerate(lms)]
     try:
+        if p2p and n_ranks > 1:
+            pkg.group_enable_p2p(ranks)
         pkg.group_run_cycles(ranks, cycles)
         out = []
         for l, lev in enumerate(mesh["levels"]):
@@ -36,10 +38,13 @@ def run_decomposed(pkg, mesh, n_ranks, cycles, devices=None, **kw):
             g.close()
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["events", "p2p"])
 @pytest.mark.parametrize("n_ranks", [2, 4, 8])
-def test_virtual_ranks_bit_identical_to_single(pkg, meshgen, golden, n_ranks):
+def test_virtual_ranks_bit_identical_to_single(pkg, meshgen, golden, n_ranks, p2p):
+    """p2p: the direct peer-store transport (pack kernel writes into the neighbours' halo ranges, epoch flags, min_dt
+    mailboxes) instead of events + peer copies"""
     mesh = meshgen.make_multigrid("small")
-    got, halo = run_decomposed(pkg, mesh, n_ranks, 10, exact_arith=True)
+    got, halo = run_decomposed(pkg, mesh, n_ranks, 10, exact_arith=True, p2p=p2p)
     g = golden("small_cycles10.npz")
     assert halo > 0
     for l in range(len(mesh["levels"])):
@@ -47,13 +52,14 @@ def test_virtual_ranks_bit_identical_to_single(pkg, meshgen, golden, n_ranks):
         assert np.array_equal(got[l], g[f"var_L{l}"]), (l, np.abs(got[l] - g[f"var_L{l}"]).max())
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["events", "p2p"])
 @pytest.mark.parametrize("n_ranks", [2, 3, 8])
-def test_virtual_ranks_fast_build(pkg, meshgen, n_ranks):
+def test_virtual_ranks_fast_build(pkg, meshgen, n_ranks, p2p):
     mesh = meshgen.make_multigrid("medium")
     with pkg.MGCFD(mesh["levels"]) as single:
         single.run_cycles(3)
         ref = [single.fetch(l, "variables") for l in range(len(mesh["levels"]))]
-    got, _ = run_decomposed(pkg, mesh, n_ranks, 3)
+    got, _ = run_decomposed(pkg, mesh, n_ranks, 3, p2p=p2p)
     for l in range(len(ref)):
         assert (normwise(got[l], ref[l]) <= 1e-13).all(), (l, normwise(got[l], ref[l]))
 
