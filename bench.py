@@ -171,13 +171,13 @@ def cpu_run(levels0_ordered, n_cycles, warmup, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh", default="m6")
     ap.add_argument("--variant", default="owner", choices=["owner", "emit", "gather", "colour", "atomic"])
     ap.add_argument("--exact", action="store_true")
-    ap.add_argument("--chunk", type=int, default=128)
+    ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--cpu-cycles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -105,7 +105,7 @@ typedef struct {
 typedef struct {
     int flux_variant;      /* MGCFD_FLUX_*; default MGCFD_FLUX_OWNER */
     int renumber;          /* 1 (default): Hilbert-curve locality renumbering of nodes; 0: keep file order */
-    int owner_chunk_nodes; /* owner/gather variants: max owned nodes per chunk (even, <= 256; default 128) */
+    int owner_chunk_nodes; /* owner/gather variants: max owned nodes per chunk (even, <= 256; default 64) */
     int colour_block_edges;/* colour variant: edges per block (default 256) */
     int exact_arith;       /* 1: reference operation order, IEEE div/sqrt, no FMA contraction in the flux kernels */
     int no_fusion;         /* 1: mgcfd_run_cycles launches one kernel per call site instead of the fused schedule

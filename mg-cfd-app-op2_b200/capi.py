@@ -267,7 +267,7 @@ class MGCFD:
     """One context = one GPU's share of the mesh.  Methods are the op_par_loop call sites of euler3d.cpp."""
 
     def __init__(self, levels=None, base_array_index=1, device=0, flux_variant="owner", renumber=True,
-                 exact_arith=False, owner_chunk_nodes=128, colour_block_edges=256, consts=None,
+                 exact_arith=False, owner_chunk_nodes=64, colour_block_edges=256, consts=None,
                  init=True, fuse=True, local_mesh=None, graphs=True):
         """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"]), or
         local_mesh: a LocalMesh (this rank's share of a partitioned deck)."""

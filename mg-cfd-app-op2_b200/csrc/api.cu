@@ -121,7 +121,7 @@ void mgcfd_default_options(mgcfd_options *opt)
     memset(opt, 0, sizeof(*opt));
     opt->flux_variant = MGCFD_FLUX_OWNER;
     opt->renumber = 1;
-    opt->owner_chunk_nodes = 128;
+    opt->owner_chunk_nodes = 64;
     opt->colour_block_edges = 256;
     opt->exact_arith = 0;
 }

@@ -6,6 +6,8 @@
 //   flux_fast.cu  default flags: per-node derived quantities (p, |v|+c, 1/rho) computed once
 //                 per staged node, one antisymmetric 5-vector per edge, FMA contraction.
 #pragma once
+#include <cstdlib>
+
 #include <cuda_runtime.h>
 
 #include "internal.h"
@@ -953,19 +955,25 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
     RkStageArgs none{};
     const int grid = a.chunk_list ? a.n_list : h.n_chunks;
     if (grid == 0) return 0;
+    // CTA size: 128 threads for chunks of up to 64 owned nodes (the default; more, smaller CTAs hide the staging
+    // latency better: 0.49 -> 0.53 of the HBM roofline on an 18.75M-node deck), 256 threads for larger chunks.
+    // MGCFD_OWNER_THREADS overrides for experiments (it must cover the largest chunk: one thread per owned node).
+    static const int env_threads = getenv("MGCFD_OWNER_THREADS") ? atoi(getenv("MGCFD_OWNER_THREADS")) : 0;
+    int threads = h.max_own <= 64 ? 128 : 256;
+    if ((env_threads == 64 || env_threads == 128 || env_threads == 256) && h.max_own <= env_threads) threads = env_threads;
 #define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, a.chunk_list, p.halo_gid, p.blob, a.var, a.flux
     if (a.stream_kernel)
-        flux_owner_kernel<true, false, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<true, false, false><<<grid, threads, smem, s>>>(OWNER_ARGS, none);
     else if (a.rk) {
         RkStageArgs ra = *a.rk;
         ra.max_own = h.max_own;
         size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.max_blob, false, h.max_own);
-        flux_owner_kernel<false, true, true><<<grid, 256, fsmem, s>>>(OWNER_ARGS, ra);
+        flux_owner_kernel<false, true, true><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
     }
     else if (a.overwrite)
-        flux_owner_kernel<false, true, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<false, true, false><<<grid, threads, smem, s>>>(OWNER_ARGS, none);
     else
-        flux_owner_kernel<false, false, false><<<grid, 256, smem, s>>>(OWNER_ARGS, none);
+        flux_owner_kernel<false, false, false><<<grid, threads, smem, s>>>(OWNER_ARGS, none);
 #undef OWNER_ARGS
     return 1;
 }
