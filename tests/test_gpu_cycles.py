@@ -161,3 +161,19 @@ def test_graph_replay_equals_direct_launches(pkg, meshgen, variant, fuse):
         for l in range(len(mesh["levels"])):
             assert np.array_equal(a.fetch(l, "variables"), b.fetch(l, "variables"))
             assert np.array_equal(a.fetch(l, "residuals"), b.fetch(l, "residuals"))
+
+
+def test_rotor37_1m_full_size(pkg, meshgen, orc_mod):
+    """BASELINE.json configs[2] at full size (1.0M / 512K / 250K / 125K nodes, 3.2M edges on level 0): one cycle
+    against the CPU oracle run with the same arithmetic flags the baseline uses."""
+    mesh = meshgen.make_multigrid("rotor37_1m")
+    lev0 = [meshgen.zero_based(l) for l in mesh["levels"]]
+    o = orc_mod.Oracle("port")
+    o.set_threads(1)
+    run = o.make_state(lev0)
+    run.init()
+    assert run.run(1)[0] == 0
+    with pkg.MGCFD(mesh["levels"]) as gpu:
+        gpu.run_cycles(1)
+        ff = np.array(list(gpu.consts.ff_variable))
+        check_levels(gpu, [a["var"] for a in run.levels], ff)
