@@ -218,8 +218,7 @@ static void free_level(LevelDev &d)
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
                     d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.gather.desc, d.gather.halo_gid,
                     d.gather.row_node, d.gather.row_deg, d.gather.ent, d.gather.w0, d.gather.w1, d.gather.w2, d.gather.g,
-                    d.emit.desc, d.emit.halo_gid, d.emit.row_node, d.emit.row_cnt, d.emit.ent, d.emit.w0, d.emit.w1, d.emit.w2,
-                    d.emit.g, d.emit.csr_words};
+                    d.emit.desc, d.emit.halo_gid, d.emit.row_node, d.emit.row_cnt, d.emit.blob};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     d = LevelDev();
@@ -816,7 +815,8 @@ static int ensure_gather(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
-// sliced-ELL layout of the edges each owned node emits + incidence lists of the non-emitter ends (emit variant)
+// emit variant: per chunk, the edges each owned node emits as two sliced-ELL half-rows per node + the incidence
+// lists of the non-emitter ends, packed into one blob per chunk
 static int ensure_emit(mgcfd_ctx *ctx, int level)
 {
     LevelHost &L = ctx->H[level];
@@ -826,20 +826,21 @@ static int ensure_emit(mgcfd_ctx *ctx, int level)
     int rc0 = ensure_owner(ctx, level);          // chunks, halo lists, chunk launch order
     if (rc0) return rc0;
     OwnerPlanHost &O = L.owner;
+    if (O.max_own > 128) { ctx->err = "emit variant needs owner_chunk_nodes <= 128 (two threads per owned node)"; return MGCFD_ERR_PLAN; }
     std::vector<EmitChunkDesc> desc(O.n_chunks);
     std::vector<uint16_t> row_node((size_t)O.n_chunks * 256, 0xffff), row_cnt((size_t)O.n_chunks * 256, 0);
-    std::vector<uint32_t> ent, csr_words;
+    std::vector<unsigned char> blob;
+    std::vector<uint32_t> ent;
     std::vector<double> w0, w1, w2, g;
     std::vector<int> order, emitter, slot_of_edge;
     std::vector<std::vector<int>> emitted;
-    int max_ent = 0, max_csr = 0;
+    int max_ent = 0, max_blob = 0;
     for (int k = 0; k < O.n_chunks; k++) {
         EmitChunkDesc &d = desc[k];
         d.node0 = O.node0[k];
         d.n_own = O.node0[k + 1] - O.node0[k];
         d.n_halo = O.halo_off[k + 1] - O.halo_off[k];
         d.halo_off = O.halo_off[k];
-        d.ent_off = (long long)ent.size();
         d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] > L.bnd_node_ptr[O.node0[k]] ? 1 : 0;
         const int ne = O.n_edges[k];
         const uint32_t *lab = &O.lab[O.edge_off[k]];
@@ -855,21 +856,26 @@ static int ensure_emit(mgcfd_ctx *ctx, int level)
         order.resize(d.n_own);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return emitted[x].size() > emitted[y].size(); });
+        ent.clear(); w0.clear(); w1.clear(); w2.clear(); g.clear();
+        const int n_threads = 2 * d.n_own;
         for (int s = 0; s < 8; s++) {
-            int lo = s * 32, hi = std::min(d.n_own, lo + 32), len = 0;
-            for (int t = lo; t < hi; t++) len = std::max(len, (int)emitted[order[t]].size());
+            int lo = s * 32, hi = std::min(n_threads, lo + 32), len = 0;
+            for (int t = lo; t < hi; t++) {
+                int cnt = (int)emitted[order[t / 2]].size();
+                len = std::max(len, (cnt + 1 - (t & 1)) / 2);
+            }
             d.slice_len[s] = (unsigned short)len;
             size_t base = ent.size();
             ent.resize(base + (size_t)len * 32, 0);
             w0.resize(ent.size(), 0.0); w1.resize(ent.size(), 0.0); w2.resize(ent.size(), 0.0); g.resize(ent.size(), 0.0);
             for (int t = lo; t < hi; t++) {
-                int node = order[t], cnt = (int)emitted[node].size();
+                int node = order[t / 2], half = t & 1, cnt = (int)emitted[node].size(), hcnt = (cnt + 1 - half) / 2;
                 row_node[(size_t)k * 256 + t] = (uint16_t)node;
-                row_cnt[(size_t)k * 256 + t] = (uint16_t)cnt;
-                for (int j = 0; j < len; j++) {
-                    size_t idx = base + (size_t)j * 32 + (t - lo);
-                    if (j >= cnt) { ent[idx] = (uint32_t)node; continue; }      // padding: neighbour = self, zero weights
-                    int e = emitted[node][j];
+                row_cnt[(size_t)k * 256 + t] = (uint16_t)hcnt;
+                for (int kk = 0; kk < len; kk++) {
+                    size_t idx = base + (size_t)kk * 32 + (t - lo);
+                    if (kk >= hcnt) { ent[idx] = (uint32_t)node; continue; }      // padding: neighbour = self, zero weights
+                    int e = emitted[node][2 * kk + half];
                     int la = lab[e] & 0xffff, lb = lab[e] >> 16;
                     bool is_b = node == lb;
                     int other = is_b ? la : lb;
@@ -878,14 +884,14 @@ static int ensure_emit(mgcfd_ctx *ctx, int level)
                     double sgn = is_b ? -1.0 : 1.0;      // flipping an edge negates its weight vector; |w| is unchanged
                     ent[idx] = (uint32_t)other | (other < d.n_own ? 0x10000u : 0u);
                     w0[idx] = sgn * p[0]; w1[idx] = sgn * p[1]; w2[idx] = sgn * p[2]; g[idx] = p[3];
-                    slot_of_edge[e] = (int)(idx - (size_t)d.ent_off);
+                    slot_of_edge[e] = (int)idx;
                 }
             }
         }
-        int n_ent = (int)(ent.size() - (size_t)d.ent_off);
-        if (n_ent > 65535) { ctx->err = "emit chunk has more than 65535 row slots"; return MGCFD_ERR_PLAN; }
-        max_ent = std::max(max_ent, n_ent);
-        // incidence lists of the non-emitter ends: rowptr2[n_own+1] | csr2, both u16, 4-byte aligned blocks
+        d.n_ent = (int)ent.size();
+        if (d.n_ent > 65535) { ctx->err = "emit chunk has more than 65535 row slots"; return MGCFD_ERR_PLAN; }
+        max_ent = std::max(max_ent, d.n_ent);
+        // incidence lists of the non-emitter ends: rowptr2[n_own+1] | csr2, both u16
         const uint16_t *rowptr = &O.rowptr[O.rowptr_off[k]];
         const uint16_t *csr = O.csr.data() + O.csr_off[k];
         std::vector<uint16_t> rp2(d.n_own + 1, 0), c2;
@@ -897,18 +903,24 @@ static int ensure_emit(mgcfd_ctx *ctx, int level)
             }
         }
         rp2[d.n_own] = (uint16_t)c2.size();
-        if (rp2.size() & 1) rp2.push_back(0);
-        if (c2.size() & 1) c2.push_back(0);
+        while (rp2.size() % 8) rp2.push_back(0);
+        while (c2.size() % 8) c2.push_back(0);
         d.rowptr_pad = (int)rp2.size();
-        d.csr_off = (int)csr_words.size();
-        d.csr_words = (int)((rp2.size() + c2.size()) / 2);
-        size_t w = csr_words.size();
-        csr_words.resize(w + d.csr_words);
-        memcpy(&csr_words[w], rp2.data(), rp2.size() * 2);
-        memcpy(reinterpret_cast<uint16_t *>(&csr_words[w]) + rp2.size(), c2.data(), c2.size() * 2);
-        max_csr = std::max(max_csr, d.csr_words);
+        d.blob_off = (long long)blob.size();
+        size_t bytes = (size_t)d.n_ent * 36 + (rp2.size() + c2.size()) * 2;
+        d.blob_bytes = (int)bytes;
+        max_blob = std::max(max_blob, d.blob_bytes);
+        blob.resize(blob.size() + bytes);
+        unsigned char *p = blob.data() + d.blob_off;
+        memcpy(p, w0.data(), (size_t)d.n_ent * 8); p += (size_t)d.n_ent * 8;
+        memcpy(p, w1.data(), (size_t)d.n_ent * 8); p += (size_t)d.n_ent * 8;
+        memcpy(p, w2.data(), (size_t)d.n_ent * 8); p += (size_t)d.n_ent * 8;
+        memcpy(p, g.data(), (size_t)d.n_ent * 8); p += (size_t)d.n_ent * 8;
+        memcpy(p, ent.data(), (size_t)d.n_ent * 4); p += (size_t)d.n_ent * 4;
+        memcpy(p, rp2.data(), rp2.size() * 2); p += rp2.size() * 2;
+        memcpy(p, c2.data(), c2.size() * 2);
     }
-    if (flux_emit_smem_bytes(O.max_loc, max_ent, max_csr, O.max_own) > 227 * 1024) {
+    if (flux_emit_smem_bytes(O.max_loc, max_ent, max_blob, O.max_own) > 227 * 1024) {
         ctx->err = "emit chunk does not fit in shared memory";
         return MGCFD_ERR_PLAN;
     }
@@ -917,13 +929,8 @@ static int ensure_emit(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.emit.halo_gid, O.halo_gid))) return rc;
     if ((rc = dev_upload(ctx, &D.emit.row_node, row_node))) return rc;
     if ((rc = dev_upload(ctx, &D.emit.row_cnt, row_cnt))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.ent, ent))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.w0, w0))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.w1, w1))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.w2, w2))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.g, g))) return rc;
-    if ((rc = dev_upload(ctx, &D.emit.csr_words, csr_words))) return rc;
-    D.emit.n_chunks = O.n_chunks; D.emit.max_loc = O.max_loc; D.emit.max_ent = max_ent; D.emit.max_csr = max_csr;
+    if ((rc = dev_upload(ctx, &D.emit.blob, blob))) return rc;
+    D.emit.n_chunks = O.n_chunks; D.emit.max_loc = O.max_loc; D.emit.max_ent = max_ent; D.emit.max_blob = max_blob;
     D.emit.max_own = O.max_own;
     D.emit.valid = true;
     cycle_drop_graphs(ctx);

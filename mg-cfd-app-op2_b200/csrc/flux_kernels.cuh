@@ -600,67 +600,58 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
 
 #ifndef MGCFD_EXACT
 // ------------------------------------------------------------------------------------------
-// variant 4: emit.  Same owner chunks, one thread per owned node.  Every edge of the chunk is evaluated ONCE, by the
-// thread of its lowest-numbered owned endpoint (its "emitter"), which keeps its own state and its own flux sum in
-// registers; only when the other endpoint is owned too, the edge's flux vector is parked in shared memory for that
-// node to subtract afterwards.  Compared with the owner kernel this halves the state reads (one neighbour per
-// edge instead of two endpoints), writes fewer flux vectors and reads each of them once instead of twice.  Emitted
-// edges are stored sliced-ELL (rows sorted by length, slices of 32 padded, column-major) with pre-signed weights, so
-// they stream from HBM fully coalesced, software-pipelined one row ahead.  Fast arithmetic only: sums are not in
-// file order.
-// shared: mbarrier | raw[max_loc][5] | der[3][max_loc] | Fs[5][max_ent] | csr (rowptr2, csr2) | told | tsf
+// variant 4: emit.  Same owner chunks, TWO threads per owned node.  Every edge of the chunk is evaluated ONCE, by
+// the thread pair of its lowest-numbered owned endpoint (its "emitter"), which keeps its own state and its own flux
+// sum in registers; only when the other endpoint is owned too is the edge's flux vector parked in shared memory
+// (in place of the edge's weights) for that node to subtract afterwards.  Compared with the owner kernel this
+// halves the state reads (one neighbour per edge instead of two endpoints), parks fewer flux vectors and reads each
+// of them once instead of twice.  A node's emitted edges are split between its two threads (even / odd entries);
+// the half-rows are stored sliced-ELL (sorted by length, slices of 32 threads padded, column-major) with pre-signed
+// weights inside the chunk's blob, which one bulk async copy brings into shared memory.  Fast arithmetic only:
+// sums are not in file order.
+// shared: mbarrier | blob (w0 w1 w2 g [n_ent] doubles, ent [n_ent] u32, rowptr2 | csr2 u16) | Fx[max_ent] |
+//         raw[max_loc][5] | der[3][max_loc] | told | tsf
 // ------------------------------------------------------------------------------------------
 template <bool OVERWRITE, bool FUSE>
-__global__ void __launch_bounds__(256, 4)
-flux_emit_kernel(int max_loc, int max_ent, int max_csr, const EmitChunkDesc *__restrict__ descs,
+__global__ void __launch_bounds__(256, 3)
+flux_emit_kernel(int max_loc, int max_ent, int max_blob, const EmitChunkDesc *__restrict__ descs,
                  const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
                  const uint16_t *__restrict__ row_node, const uint16_t *__restrict__ row_cnt,
-                 const uint32_t *__restrict__ ent, const double *__restrict__ pw0, const double *__restrict__ pw1,
-                 const double *__restrict__ pw2, const double *__restrict__ pg, const uint32_t *__restrict__ csr_words,
-                 const double *__restrict__ var, double *__restrict__ flux, RkStageArgs rk)
+                 const unsigned char *__restrict__ blob, const double *__restrict__ var, double *__restrict__ flux,
+                 RkStageArgs rk)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
-    double *raw = reinterpret_cast<double *>(smraw + 16);
+    unsigned char *sblob = smraw + 16;
+    double *Fx = reinterpret_cast<double *>(sblob + max_blob);
+    double *raw = Fx + max_ent;
     double *der = raw + (size_t)max_loc * 5;
-    double *Fs = der + (size_t)max_loc * 3;
-    uint32_t *scsr = reinterpret_cast<uint32_t *>(Fs + (size_t)max_ent * 5);
-    double *told = reinterpret_cast<double *>(smraw + ((16 + ((size_t)max_loc * 8 + (size_t)max_ent * 5) * 8 + (size_t)max_csr * 4 + 15) & ~(size_t)15));
+    double *told = raw + (((size_t)max_loc * 8 + 1) & ~(size_t)1);
     double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
     const int chunk = chunk_list ? chunk_list[blockIdx.x] : blockIdx.x;
     const EmitChunkDesc d = descs[chunk];
-    const int tid = threadIdx.x, lane = tid & 31, slice = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, slice = tid >> 5, half = tid & 1;
     const int nloc = d.n_own + d.n_halo;
     const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, owned_bulk_bytes(d.n_own) + old_bulk + sf_bulk);
+        mbar_expect_tx(bar, (uint32_t)d.blob_bytes + owned_bulk_bytes(d.n_own) + old_bulk + sf_bulk);
+        bulk_g2s(sblob, blob + d.blob_off, (uint32_t)d.blob_bytes, bar);
         if (FUSE) {
             if (old_bulk) bulk_g2s(told, rk.old + (size_t)d.node0 * 5, old_bulk, bar);
             if (sf_bulk) bulk_g2s(tsf, rk.sf + d.node0, sf_bulk, bar);
         }
     }
-    // first row of this thread's emitted edges: requested before anything else waits
     const int me = row_node[(size_t)chunk * 256 + tid];               // local owned index or 0xffff
-    const int cnt = row_cnt[(size_t)chunk * 256 + tid];
-    int len = 0;
-    long long base = d.ent_off;
+    const int cnt = row_cnt[(size_t)chunk * 256 + tid];               // entries of this thread's half-row
+    int len = 0, base = 0;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         int L = d.slice_len[s];
-        if (s < slice) base += (long long)L * 32;
+        if (s < slice) base += L * 32;
         if (s == slice) len = L;
     }
-    uint32_t en_n = 0;
-    double x_n = 0.0, y_n = 0.0, z_n = 0.0, g_n = 0.0;
-    if (len > 0) {
-        long long idx = base + lane;
-        en_n = __ldg(ent + idx); x_n = __ldg(pw0 + idx); y_n = __ldg(pw1 + idx); z_n = __ldg(pw2 + idx); g_n = __ldg(pg + idx);
-    }
-    // incidence lists of the non-emitter ends (4-byte async copies), state tile (bulk + 8-byte async copies)
-    for (int i = tid; i < d.csr_words; i += blockDim.x)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(scsr + i)), "l"(csr_words + d.csr_off + i) : "memory");
     stage_tile(raw, bar, d.node0, d.n_own, d.n_halo, halo_gid + d.halo_off, var, tid, blockDim.x);
     __syncthreads();
     mbar_wait(bar, 0);
@@ -673,56 +664,57 @@ flux_emit_kernel(int max_loc, int max_ent, int max_csr, const EmitChunkDesc *__r
     }
     __syncthreads();
 
+    double *w0 = reinterpret_cast<double *>(sblob);
+    double *w1 = w0 + d.n_ent, *w2 = w1 + d.n_ent, *gg = w2 + d.n_ent;
+    const uint32_t *ent = reinterpret_cast<const uint32_t *>(gg + d.n_ent);
+    const uint16_t *rowptr2 = reinterpret_cast<const uint16_t *>(ent + d.n_ent);
+    const uint16_t *csr2 = rowptr2 + d.rowptr_pad;
+
+    const bool valid = me != 0xffff;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    if (!OVERWRITE && me != 0xffff) {
+    if (!OVERWRITE && valid && half == 0) {
 #pragma unroll
         for (int v = 0; v < 5; v++) acc[v] = flux[(size_t)(d.node0 + me) * 5 + v];
     }
-    const int self = me != 0xffff ? me : 0;
+    const int self = valid ? me : 0;
     double a[8];
     load_state<8>(raw, der, max_loc, self, a);
-    const int slot0 = (int)(base - d.ent_off) + lane;                  // position of this lane's row j = 0 in the chunk
-    for (int j = 0; j < len; j++) {
-        const uint32_t en = en_n;
-        const double x = x_n, y = y_n, z = z_n, g = g_n;
-        if (j + 1 < len) {                                             // next row in flight while this one computes
-            long long idx = base + (long long)(j + 1) * 32 + lane;
-            en_n = __ldg(ent + idx); x_n = __ldg(pw0 + idx); y_n = __ldg(pw1 + idx); z_n = __ldg(pw2 + idx); g_n = __ldg(pg + idx);
-        }
+    for (int k = 0; k < len; k++) {
+        const int idx = base + k * 32 + lane;
+        const uint32_t en = ent[idx];
+        const double x = w0[idx], y = w1[idx], z = w2[idx], g = gg[idx];
         double b[8], F[5];
         load_state<8>(raw, der, max_loc, (int)(en & 0xffff), b);
         edge_flux(a, b, x, y, z, g, F);                               // weights pre-signed: the emitter is end "a"
-        if (j < cnt) {
+        if (k < cnt) {
 #pragma unroll
             for (int v = 0; v < 5; v++) acc[v] += F[v];
             if (en & 0x10000u) {                                       // the other end is owned: it subtracts this vector
-                const int slot = slot0 + j * 32;
-#pragma unroll
-                for (int v = 0; v < 5; v++) Fs[v * max_ent + slot] = F[v];
+                w0[idx] = F[0]; w1[idx] = F[1]; w2[idx] = F[2]; gg[idx] = F[3];      // slot idx is private to this thread
+                Fx[idx] = F[4];
             }
         }
     }
     __syncthreads();
-    if (me != 0xffff) {
-        const uint16_t *rowptr2 = reinterpret_cast<const uint16_t *>(scsr);
-        const uint16_t *csr2 = rowptr2 + d.rowptr_pad;
-        for (int j = rowptr2[me]; j < rowptr2[me + 1]; j++) {
-            int slot = csr2[j];
-#pragma unroll
-            for (int v = 0; v < 5; v++) acc[v] -= Fs[v * max_ent + slot];
+    if (valid) {
+        for (int j = rowptr2[me] + half; j < rowptr2[me + 1]; j += 2) {
+            const int slot = csr2[j];
+            acc[0] -= w0[slot]; acc[1] -= w1[slot]; acc[2] -= w2[slot]; acc[3] -= gg[slot]; acc[4] -= Fx[slot];
         }
-        if (FUSE && d.has_bnd) {
-            int j0 = rk.bnd_ptr[d.node0 + me], j1 = rk.bnd_ptr[d.node0 + me + 1];
-            if (j1 > j0) {
-                double u[5];
+    }
 #pragma unroll
-                for (int v = 0; v < 5; v++) u[v] = raw[me * 5 + v];
-                bnd_apply(u, acc, j0, j1, rk.b_group, rk.b_wt, rk.c);
-            }
+    for (int v = 0; v < 5; v++) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 1);       // the node's two half-rows
+    if (valid && half == 0 && FUSE && d.has_bnd) {
+        int j0 = rk.bnd_ptr[d.node0 + me], j1 = rk.bnd_ptr[d.node0 + me + 1];
+        if (j1 > j0) {
+            double u[5];
+#pragma unroll
+            for (int v = 0; v < 5; v++) u[v] = raw[me * 5 + v];
+            bnd_apply(u, acc, j0, j1, rk.b_group, rk.b_wt, rk.c);
         }
     }
     __syncthreads();                                                  // every read of the state tile is done
-    if (me != 0xffff) {
+    if (valid && half == 0) {
 #pragma unroll
         for (int v = 0; v < 5; v++) raw[me * 5 + v] = acc[v];
     }
@@ -730,27 +722,27 @@ flux_emit_kernel(int max_loc, int max_ent, int max_csr, const EmitChunkDesc *__r
     finish_chunk<FUSE>(raw, d.node0, d.n_own, flux, rk, told, tsf, old_bulk, sf_bulk);
 }
 
-inline size_t emit_smem(int max_loc, int max_ent, int max_csr, int max_own)
+inline size_t emit_smem(int max_loc, int max_ent, int max_blob, int max_own)
 {
-    return 16 + ((size_t)max_loc * 8 + (size_t)max_ent * 5) * 8 + (size_t)max_csr * 4 + 16 + ((size_t)max_own * 6 + 4) * 8;
+    return 16 + (size_t)max_blob + ((size_t)max_ent + (size_t)max_loc * 8 + (size_t)max_own * 6 + 4) * 8;
 }
 
 inline int launch_emit(cudaStream_t s, const FluxArgs &a, const EmitPlanDev &p)
 {
     const int grid = a.chunk_list ? a.n_list : p.n_chunks;
     if (grid == 0) return 0;
-    size_t smem = emit_smem(p.max_loc, p.max_ent, p.max_csr, p.max_own);
+    size_t smem = emit_smem(p.max_loc, p.max_ent, p.max_blob, p.max_own);
     RkStageArgs ra{};
     if (a.rk) ra = *a.rk;
     ra.max_own = p.max_own;
-#define EMIT_ARGS p.max_loc, p.max_ent, p.max_csr, p.desc, a.chunk_list, p.halo_gid, p.row_node, p.row_cnt, p.ent, p.w0, p.w1, p.w2, \
-                  p.g, p.csr_words, a.var, a.flux, ra
+    const int threads = p.max_own <= 64 ? 128 : 256;                  // two threads per owned node
+#define EMIT_ARGS p.max_loc, p.max_ent, p.max_blob, p.desc, a.chunk_list, p.halo_gid, p.row_node, p.row_cnt, p.blob, a.var, a.flux, ra
     if (a.rk)
-        flux_emit_kernel<true, true><<<grid, 256, smem, s>>>(EMIT_ARGS);
+        flux_emit_kernel<true, true><<<grid, threads, smem, s>>>(EMIT_ARGS);
     else if (a.overwrite)
-        flux_emit_kernel<true, false><<<grid, 256, smem, s>>>(EMIT_ARGS);
+        flux_emit_kernel<true, false><<<grid, threads, smem, s>>>(EMIT_ARGS);
     else
-        flux_emit_kernel<false, false><<<grid, 256, smem, s>>>(EMIT_ARGS);
+        flux_emit_kernel<false, false><<<grid, threads, smem, s>>>(EMIT_ARGS);
 #undef EMIT_ARGS
     return 1;
 }

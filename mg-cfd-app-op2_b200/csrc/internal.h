@@ -138,20 +138,18 @@ struct GatherPlanDev {
 
 struct EmitChunkDesc {
     int node0, n_own, n_halo, halo_off;
-    long long ent_off;              // first entry of the chunk in the sliced-ELL planes (multiple of 32)
-    unsigned short slice_len[8];
-    int csr_off, csr_words;         // chunk's (rowptr2 | csr2) block in 4-byte words
+    long long blob_off;             // chunk blob: w0 w1 w2 g [n_ent] doubles | ent [n_ent] u32 | rowptr2 | csr2 (u16)
+    int blob_bytes, n_ent;          // n_ent: padded sliced-ELL slots (multiple of 32)
+    unsigned short slice_len[8];    // padded half-row length of each 32-thread slice
     int rowptr_pad, has_bnd;        // u16 entries before csr2 starts
 };
 
 struct EmitPlanDev {
     EmitChunkDesc *desc = nullptr;
     int *halo_gid = nullptr;
-    uint16_t *row_node = nullptr, *row_cnt = nullptr;   // [n_chunks*256] thread slot -> local owned node / emitted edges
-    uint32_t *ent = nullptr;                             // neighbour local id | (neighbour is owned) << 16
-    double *w0 = nullptr, *w1 = nullptr, *w2 = nullptr, *g = nullptr;
-    uint32_t *csr_words = nullptr;                       // per chunk: rowptr2[n_own+1] u16 (padded) | csr2 u16 (padded)
-    int n_chunks = 0, max_loc = 0, max_ent = 0, max_csr = 0, max_own = 0;
+    uint16_t *row_node = nullptr, *row_cnt = nullptr;   // [n_chunks*256] thread slot -> local owned node / half-row length
+    unsigned char *blob = nullptr;
+    int n_chunks = 0, max_loc = 0, max_ent = 0, max_blob = 0, max_own = 0;
     bool valid = false;
 };
 
@@ -398,7 +396,7 @@ int flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n
 int fast_flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc);
 size_t flux_gather_smem_bytes(int max_loc, bool exact);
 int flux_emit(cudaStream_t s, const FluxArgs &a, const EmitPlanDev &p);      // fast arithmetic only
-size_t flux_emit_smem_bytes(int max_loc, int max_ent, int max_csr, int max_own);
+size_t flux_emit_smem_bytes(int max_loc, int max_ent, int max_blob, int max_own);
 // one-time kernel attribute setup (dynamic shared memory opt-in); returns "" or an error text
 std::string flux_configure();
 // the fast-math translation unit (flux_fast.cu)
