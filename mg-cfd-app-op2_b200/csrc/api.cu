@@ -373,6 +373,8 @@ static int upload_bnd(mgcfd_ctx *ctx, int level)
         if (rc0) return rc0;
     }
     L.bnd_node_ptr = node_ptr;
+    L.bnd_group_sorted = group;
+    L.bnd_wt_sorted = wt;
     D.owner.valid = D.emit.valid = false;              // chunk descriptors carry a has-boundary flag
     int rc;
     if ((rc = dev_upload(ctx, &D.bu_node, bu_node))) return rc;
@@ -663,6 +665,95 @@ static int build_owner_host(mgcfd_ctx *ctx, int level)
     return MGCFD_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Bank-aware slotting of a chunk's edges (device packing only; the plan's index sets are untouched).
+// The edge phase reads the two endpoint states of 16 consecutive edge slots per shared-memory wavefront and the node
+// phase reads the flux vectors of the incidences 16 consecutive threads are at; both are 8-byte accesses, so a
+// wavefront is conflict-free when its 16 addresses fall into 16 different 8-byte banks (or coincide).  With the AoS
+// state tile and the SoA flux planes the bank is (local node mod 16) resp. (edge slot mod 16).  Two greedy passes:
+//   1. groups of 16 edges whose `a` ends and whose `b` ends are pairwise different mod 16 (or the same node), scanning
+//      a bounded window of the remaining edges in first-touch order;
+//   2. inside each group (any lane order costs the edge phase the same) the lanes are assigned so that the incidences
+//      a half-warp of node threads reads together sit in different banks.
+// `split` = threads per owned node in the node phase (1: thread n reads incidence `it` of node n; 2: threads 2n, 2n+1
+// read incidences 2*it, 2*it+1).  On the M6-shaped deck this takes the state gathers from 1.98 to 1.08 wavefronts per
+// half-warp and the flux-vector gathers from 2.08 to 1.24 (ideal 1).  slot[i] = new position of plan edge i.
+// ---------------------------------------------------------------------------------------
+static void bank_aware_slots(int ne, const uint32_t *lab, int n_own, const uint16_t *rowptr, const uint16_t *csr, int split,
+                             std::vector<int> &slot)
+{
+    slot.assign(ne, 0);
+    std::vector<int> order;
+    order.reserve(ne);
+    std::vector<char> used(ne, 0);
+    const int WINDOW = 160;
+    int start = 0;
+    while ((int)order.size() < ne) {
+        int bank_a[16], bank_b[16], cnt = 0;
+        std::fill(bank_a, bank_a + 16, -1);
+        std::fill(bank_b, bank_b + 16, -1);
+        const size_t g0 = order.size();
+        for (int e = start, seen = 0; e < ne && cnt < 16 && seen < WINDOW; e++) {
+            if (used[e]) continue;
+            seen++;
+            const int a = (int)(lab[e] & 0xffff), b = (int)(lab[e] >> 16);
+            if ((bank_a[a & 15] == -1 || bank_a[a & 15] == a) && (bank_b[b & 15] == -1 || bank_b[b & 15] == b)) {
+                bank_a[a & 15] = a; bank_b[b & 15] = b;
+                used[e] = 1; order.push_back(e); cnt++;
+            }
+        }
+        for (int e = start; e < ne && cnt < 16; e++)           // not enough compatible edges: fill up in order
+            if (!used[e]) { used[e] = 1; order.push_back(e); cnt++; }
+        (void)g0;
+        while (start < ne && used[start]) start++;
+    }
+    // node-phase access sets: set id per (half-warp of node threads, iteration)
+    std::vector<int> set_of[2];                                 // per edge: the (at most two) access sets it belongs to
+    set_of[0].assign(ne, -1); set_of[1].assign(ne, -1);
+    int n_sets = 0;
+    const int nodes_per_hw = 16 / split;
+    for (int n0 = 0; n0 < n_own; n0 += nodes_per_hw) {
+        int max_it = 0;
+        for (int n = n0; n < std::min(n_own, n0 + nodes_per_hw); n++)
+            max_it = std::max(max_it, (rowptr[n + 1] - rowptr[n] + split - 1) / split);
+        for (int n = n0; n < std::min(n_own, n0 + nodes_per_hw); n++)
+            for (int j = rowptr[n]; j < rowptr[n + 1]; j++) {
+                const int e = csr[j] & 0x7fff, sid = n_sets + (j - rowptr[n]) / split;
+                (set_of[0][e] == -1 ? set_of[0][e] : set_of[1][e]) = sid;
+            }
+        n_sets += max_it;
+    }
+    std::vector<unsigned char> set_bank((size_t)std::max(n_sets, 1) * 16, 0);     // edges already placed per (set, bank)
+    auto pressure = [&](int e) {
+        int p = 0;
+        for (int k = 0; k < 2; k++)
+            if (set_of[k][e] >= 0)
+                for (int b = 0; b < 16; b++) p += set_bank[(size_t)set_of[k][e] * 16 + b];
+        return p;
+    };
+    std::vector<int> grp;
+    for (int g0 = 0; g0 < ne; g0 += 16) {
+        const int r = std::min(16, ne - g0);
+        grp.assign(order.begin() + g0, order.begin() + g0 + r);
+        std::stable_sort(grp.begin(), grp.end(), [&](int x, int y) { return pressure(x) > pressure(y); });   // most constrained first
+        bool taken[16] = {false};
+        for (int e : grp) {
+            int best = -1, best_cost = 1 << 30;
+            for (int b = 0; b < r; b++) {
+                if (taken[b]) continue;
+                int c = 0;
+                for (int k = 0; k < 2; k++)
+                    if (set_of[k][e] >= 0) c += set_bank[(size_t)set_of[k][e] * 16 + b];
+                if (c < best_cost) { best_cost = c; best = b; }
+            }
+            taken[best] = true;
+            slot[e] = g0 + best;
+            for (int k = 0; k < 2; k++)
+                if (set_of[k][e] >= 0) set_bank[(size_t)set_of[k][e] * 16 + best]++;
+        }
+    }
+}
+
 static int ensure_owner(mgcfd_ctx *ctx, int level)
 {
     LevelHost &L = ctx->H[level];
@@ -675,7 +766,18 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         ctx->err = "owner variant needs owner_chunk_nodes <= 256";
         return MGCFD_ERR_PLAN;
     }
-    if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
+    // device packing: the plan's blob, then the boundary entries of the chunk's owned nodes (they are a contiguous
+    // range of the entries sorted by internal node)
+    auto pad16 = [](long long b) { return (b + 15) & ~15ll; };
+    O.dev_blob_off.assign(O.n_chunks + 1, 0);
+    O.dev_max_blob = 0;
+    for (int k = 0; k < O.n_chunks; k++) {
+        long long nb = L.bnd_node_ptr[O.node0[k + 1]] - L.bnd_node_ptr[O.node0[k]];
+        long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + (nb ? pad16(nb * (24 + 2 + 2)) : 0);
+        O.dev_blob_off[k + 1] = O.dev_blob_off[k] + bytes;
+        O.dev_max_blob = std::max(O.dev_max_blob, (int)bytes);
+    }
+    if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.dev_max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
         return MGCFD_ERR_PLAN;
     }
@@ -696,8 +798,16 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         int rcl = dev_upload(ctx, &Hd.d_chunk_list, first);
         if (rcl) return rcl;
     }
+    // edge slots inside a chunk are chosen against shared-memory bank conflicts (MGCFD_OWNER_SLOTTING=0: plan order);
+    // the fused stage's node phase uses two threads per owned node in the fast build (CTAs have 128 threads for up to
+    // 64 owned nodes, 256 beyond), one in the exact build
+    const char *slot_s = getenv("MGCFD_OWNER_SLOTTING"), *split_s = getenv("MGCFD_OWNER_SLOT_SPLIT");
+    const bool slotting = !(slot_s && atoi(slot_s) == 0);
+    int node_split = (!ctx->opt.exact_arith && O.max_own <= 128) ? 2 : 1;
+    if (split_s && (atoi(split_s) == 1 || atoi(split_s) == 2)) node_split = atoi(split_s);
+    std::vector<int> slot;
     std::vector<OwnerChunkDesc> desc(O.n_chunks);
-    std::vector<unsigned char> blob((size_t)O.blob_off[O.n_chunks], 0);
+    std::vector<unsigned char> blob((size_t)O.dev_blob_off[O.n_chunks], 0);
     for (int k = 0; k < O.n_chunks; k++) {
         OwnerChunkDesc &d = desc[k];
         d.node0 = O.node0[k];
@@ -707,23 +817,47 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         d.n_edges = O.n_edges[k];
         d.e_pad = (d.n_edges + 3) & ~3;
         d.n_inc = O.n_inc[k];
-        d.blob_off = O.blob_off[k];
-        d.blob_bytes = (int)(O.blob_off[k + 1] - O.blob_off[k]);
-        d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] > L.bnd_node_ptr[O.node0[k]] ? 1 : 0;
-        d.pad_ = 0;
+        d.blob_off = O.dev_blob_off[k];
+        d.blob_bytes = (int)(O.dev_blob_off[k + 1] - O.dev_blob_off[k]);
+        const int b_first = L.bnd_node_ptr[O.node0[k]];
+        d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] - b_first;
+        d.bnd_off = (int)(O.blob_off[k + 1] - O.blob_off[k]);
         unsigned char *base = blob.data() + d.blob_off;
+        if (d.has_bnd) {
+            double *bw = reinterpret_cast<double *>(base + d.bnd_off);
+            uint16_t *bnode = reinterpret_cast<uint16_t *>(bw + (size_t)d.has_bnd * 3);
+            int16_t *bgrp = reinterpret_cast<int16_t *>(bnode + d.has_bnd);
+            int i = 0;
+            for (int v = O.node0[k]; v < O.node0[k + 1]; v++)
+                for (int j = L.bnd_node_ptr[v]; j < L.bnd_node_ptr[v + 1]; j++, i++) {
+                    for (int c = 0; c < 3; c++) bw[(size_t)i * 3 + c] = L.bnd_wt_sorted[(size_t)j * 3 + c];
+                    bnode[i] = (uint16_t)(v - O.node0[k]);
+                    bgrp[i] = (int16_t)std::max(-32768, std::min(32767, L.bnd_group_sorted[j]));   // only <=2 / 3..7 matter
+                }
+        }
         double *w0 = reinterpret_cast<double *>(base), *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *g = w2 + d.e_pad;
         uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);
         uint16_t *rowptr = reinterpret_cast<uint16_t *>(lab + d.e_pad);
         uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
+        if (slotting)
+            bank_aware_slots(d.n_edges, &O.lab[O.edge_off[k]], d.n_own, &O.rowptr[O.rowptr_off[k]], O.csr.data() + O.csr_off[k],
+                             node_split, slot);
+        else {
+            slot.resize(d.n_edges);
+            std::iota(slot.begin(), slot.end(), 0);
+        }
         for (int i = 0; i < d.n_edges; i++) {
             double p[4];
             pack_weight(ctx, L, O.edge_file[O.edge_off[k] + i], p);
-            w0[i] = p[0]; w1[i] = p[1]; w2[i] = p[2]; g[i] = p[3];
-            lab[i] = O.lab[O.edge_off[k] + i];
+            const int t = slot[i];
+            w0[t] = p[0]; w1[t] = p[1]; w2[t] = p[2]; g[t] = p[3];
+            lab[t] = O.lab[O.edge_off[k] + i];
         }
         memcpy(rowptr, &O.rowptr[O.rowptr_off[k]], sizeof(uint16_t) * (d.n_own + 1));
-        memcpy(csr, &O.csr[O.csr_off[k]], sizeof(uint16_t) * d.n_inc);
+        for (int j = 0; j < d.n_inc; j++) {
+            const uint16_t c = O.csr[O.csr_off[k] + j];
+            csr[j] = (uint16_t)(slot[c & 0x7fff] | (c & 0x8000));
+        }
     }
     int rc;
     if ((rc = dev_upload(ctx, &D.owner.desc, desc))) return rc;
@@ -1386,6 +1520,18 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
         if (s == "owner_halo_gid") return emit(O.halo_gid, out, cap);
         if (s == "owner_edge_off") return emit(O.edge_off, out, cap);
         if (s == "owner_edge_file") return emit(O.edge_file, out, cap);
+        if (s == "owner_lab") return emit(std::vector<int>(O.lab.begin(), O.lab.end()), out, cap);
+        if (s == "owner_slots_split1" || s == "owner_slots_split2") {
+            // device packing: slot of every plan edge inside its chunk (bank_aware_slots), concatenated like owner_edge_file
+            std::vector<int> all, slot;
+            all.reserve(O.edge_file.size());
+            for (int k = 0; k < O.n_chunks; k++) {
+                bank_aware_slots(O.n_edges[k], &O.lab[O.edge_off[k]], O.node0[k + 1] - O.node0[k], &O.rowptr[O.rowptr_off[k]],
+                                 O.csr.data() + O.csr_off[k], s.back() == '2' ? 2 : 1, slot);
+                all.insert(all.end(), slot.begin(), slot.end());
+            }
+            return emit(all, out, cap);
+        }
         if (s == "owner_stats") return emit(std::vector<int>{O.n_chunks, O.max_loc, O.max_edges, O.max_own, O.max_inc,
                                                              (int)std::min<long long>(O.total_edges, 0x7fffffff)}, out, cap);
     }

@@ -7,6 +7,8 @@
 //                 per staged node, one antisymmetric 5-vector per edge, FMA contraction.
 #pragma once
 #include <cstdlib>
+#include <map>
+#include <tuple>
 
 #include <cuda_runtime.h>
 
@@ -125,8 +127,9 @@ __device__ __forceinline__ void load5(const double *__restrict__ p, double u[5])
 // applies the node's boundary entries [j0, j1) (ascending file order) to fl[5].  Shared by the stand-alone
 // boundary kernel and the fused Runge-Kutta stage.
 // ------------------------------------------------------------------------------------------
+template <typename GroupT>
 __device__ __forceinline__ void bnd_apply(const double u[5], double fl[5], int j0, int j1,
-                                          const int *__restrict__ b_group, const double *__restrict__ b_wt,
+                                          const GroupT *__restrict__ b_group, const double *__restrict__ b_wt,
                                           const DevConsts &c)
 {
     double rho = u[0], m[3] = {u[1], u[2], u[3]}, E = u[4];
@@ -456,6 +459,126 @@ __device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Node phase shared by the owner kernels (after the edge phase has parked every edge's flux vector in shared
+// memory): owned nodes sum their incident edges in ascending file order -- the fast build splits a node's incidences
+// between 2 or 4 threads when the CTA has them --, add the chunk's boundary entries (they travel in the blob, sorted by
+// owned node), and finish from registers: plain store of the flux sums, or FUSE: time_stepping_kernels.h:66-86
+// (+ validation.h:27-44,102-115 after the last stage) with the prefetched old_variables / step_factor tiles, bit for
+// bit the arithmetic of time_step_kernel.  No shared-memory staging of the result and no barrier after it.
+// ------------------------------------------------------------------------------------------
+template <bool OVERWRITE, bool FUSE>
+__device__ __forceinline__ void node_phase(int tid, int nthreads, const OwnerChunkDesc &d, const unsigned char *sblob,
+                                           const double *raw, const double *w0, const double *w1, const double *w2,
+                                           const double *gg, const double *Fx, const uint16_t *rowptr, const uint16_t *csr,
+                                           int max_edges, const double *told, const double *tsf, double *__restrict__ flux,
+                                           const RkStageArgs &rk)
+{
+#ifdef MGCFD_EXACT
+    const int lg_split = 0;
+#else
+    const int lg_split = 4 * rk.max_own <= nthreads ? 2 : (2 * rk.max_own <= nthreads ? 1 : 0);
+#endif
+    const int step = 1 << lg_split;                 // threads per owned node
+    const int n = tid >> lg_split, part = tid & (step - 1);
+    const bool active = n < d.n_own;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (active) {
+        if (!OVERWRITE && part == 0) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] = flux[(size_t)(d.node0 + n) * 5 + v];
+        }
+        // the flux vector an incidence contributes (end b of an edge receives the negated / the fb vector)
+        auto fetch = [&](uint16_t c, double f[5]) {
+            const int e = c & 0x7fff;
+#ifdef MGCFD_EXACT
+            if (c & 0x8000) {
+#pragma unroll
+                for (int v = 0; v < 5; v++) f[v] = Fx[(1 + v) * max_edges + e];
+            } else {
+                f[0] = w0[e]; f[1] = w1[e]; f[2] = w2[e]; f[3] = gg[e]; f[4] = Fx[e];
+            }
+#else
+            const int sgn = (c & 0x8000) ? (int)0x80000000 : 0;
+            f[0] = flip_sign(w0[e], sgn); f[1] = flip_sign(w1[e], sgn); f[2] = flip_sign(w2[e], sgn);
+            f[3] = flip_sign(gg[e], sgn); f[4] = flip_sign(Fx[e], sgn);
+#endif
+        };
+        const int j1 = rowptr[n + 1];
+        for (int jj = rowptr[n] + part; jj < j1; jj += step) {
+            double f[5];
+            fetch(csr[jj], f);
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[v] += f[v];
+        }
+    }
+#ifndef MGCFD_EXACT
+    if (lg_split >= 1) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 1);      // every thread of a node
+    }                                                                                       // ends up with the sum
+    if (lg_split == 2) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 2);
+    }
+#endif
+    double sq = 0.0;
+    int bad = 0;
+    if (active) {
+        if (FUSE && d.has_bnd) {
+            // find this node's range of the chunk's boundary entries
+            const double *bw = reinterpret_cast<const double *>(sblob + d.bnd_off);
+            const uint16_t *bnode = reinterpret_cast<const uint16_t *>(bw + (size_t)d.has_bnd * 3);
+            const int16_t *bgrp = reinterpret_cast<const int16_t *>(bnode + d.has_bnd);
+            int b0 = d.has_bnd, b1 = 0;
+            for (int i = 0; i < d.has_bnd; i++)
+                if (bnode[i] == n) { b0 = min(b0, i); b1 = i + 1; }
+            if (b1 > b0) {
+                double u[5];
+#pragma unroll
+                for (int v = 0; v < 5; v++) u[v] = raw[n * 5 + v];
+                bnd_apply(u, acc, b0, b1, bgrp, bw, rk.c);                 // a split node's threads all do the same
+            }
+        }
+        const size_t g0 = (size_t)d.node0 * 5;
+        // component v is finished by the node's thread v mod (threads per node)
+        if (!FUSE) {
+            double *out = flux + g0 + n * 5;
+#pragma unroll
+            for (int v = 0; v < 5; v++)
+                if ((v & (step - 1)) == part) out[v] = acc[v];
+        } else {
+            const int old_n = (int)(owned_bulk_bytes(d.n_own) >> 3), sf_n = (int)((((uint32_t)d.n_own * 8u) & ~15u) >> 3);
+            const double factor = (n < sf_n ? tsf[n] : rk.sf[d.node0 + n]) / (double)(MGCFD_RK + 1 - rk.rk);
+            auto update = [&](int v, double fl) {
+                const int f = n * 5 + v;
+                const double o = f < old_n ? told[f] : rk.old[g0 + f];
+                const double vn = __dadd_rn(o, __dmul_rn(factor, fl));
+                rk.var_out[g0 + f] = vn;
+                if (rk.last) {
+                    const double r = vn - o;
+                    rk.res[g0 + f] = r;
+                    sq += r * r;
+                    bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
+                }
+            };
+#pragma unroll
+            for (int v = 0; v < 5; v++)
+                if ((v & (step - 1)) == part) update(v, acc[v]);
+        }
+    }
+    if (FUSE && rk.last && rk.d_rms) {
+        for (int o = 16; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(rk.d_rms, sq);
+            if (bad) atomicAdd(rk.d_bad, bad);
+        }
+    }
+}
+
 // FUSE: the Runge-Kutta stage in one kernel -- compute_flux_edge + compute_bnd_node_flux + time_step (+ residual,
 // calc_rms, count_bad_vals after the last stage).  The owner of a node holds the node's complete edge-flux sum in
 // registers, so it adds the boundary entries and applies var_new = old + step_factor/(RK+1-rk) * flux on the spot;
@@ -464,7 +587,7 @@ __device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n
 #ifndef MGCFD_OWNER_MINB
 #define MGCFD_OWNER_MINB 3      // resident CTAs per SM the register allocation aims for (4 forces spills and measured slower)
 #endif
-template <bool STREAM, bool OVERWRITE, bool FUSE>
+template <bool STREAM, bool OVERWRITE, bool FUSE, bool REGEPI = false>
 __global__ void __launch_bounds__(256, MGCFD_OWNER_MINB)
 flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
                   const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
@@ -549,6 +672,12 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     }
     __syncthreads();
 
+    // 5. (REGEPI) node sums, boundary entries and the update straight from registers: see node_phase
+    if constexpr (REGEPI) {
+        node_phase<OVERWRITE, FUSE>(tid, (int)blockDim.x, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf,
+                                    flux, rk);
+        return;
+    }
     // 5. one thread per owned node (chunks never own more than blockDim nodes) sums its incident edges in ascending
     //    file order; the sums go to HBM through shared memory so that the store is one contiguous, coalesced run
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -596,6 +725,269 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     }
     __syncthreads();
     finish_chunk<FUSE>(raw, d.node0, d.n_own, flux, rk, told, tsf, old_bulk, sf_bulk);
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 2p: the owner kernel as a persistent, double-buffered pipeline.  The grid is sized to the number of CTAs
+// that are resident at once; CTA b works through chunks b, b+G, b+2G, ... of the launch.  While chunk j is being
+// computed out of stage j&1, everything chunk j+1 needs is already on its way into the other stage:
+//   * blob and owned conserved variables: bulk async copies (TMA 1-D) issued by one thread at the top of iteration j;
+//   * halo node states: 8-byte cp.async requests issued by all threads at the top of iteration j from halo ids that
+//     were loaded into registers one iteration earlier (so neither the id list nor the gather waits on HBM);
+//   * both complete on the stage's mbarrier (expect_tx for the bulk copies, cp.async.mbarrier.arrive.noinc for every
+//     thread's gather requests; phase parity (j>>1)&1), so a stage is consumed after ONE wait and no CTA barrier;
+//   * chunk descriptors: a 4-entry ring in shared memory, loaded three chunks ahead through registers.
+// Only the prologue (first chunk of a CTA) sees memory latency.  Per chunk there are two CTA barriers:
+//   D. one thread per edge turns the edge's weights in place into its flux vector            -> barrier
+//   E. owned nodes sum their incident edges (ascending file order; the fast build splits a node between two
+//      threads), add the boundary entries, apply the Runge-Kutta update and store to HBM straight from registers;
+//      a warp that is done waits for the next stage and computes the next chunk's derived quantities (p, |v|+c,
+//      1/rho per staged node) in the shadow of the warps still summing                        -> barrier
+// The update operands (old_variables, step_factors; FUSE) are single-buffered: they are requested at the top of their
+// own chunk and only read by phase E.
+// shared: bar[3] | desc ring [4] | stage 0 | stage 1 | told [max_own][5] | tsf [max_own] | Fx [NFL-4][max_edges] |
+//         der [3][max_loc] (fast build);   stage = blob [max_blob] | raw [max_loc][5]
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+constexpr int PIPE_HG = 8;          // halo ids a thread keeps in registers (covers 5*n_halo <= 8*blockDim)
+constexpr int PIPE_HEAD = 32 + 4 * (int)sizeof(OwnerChunkDesc);   // 3 mbarriers + descriptor ring
+static_assert(sizeof(OwnerChunkDesc) == 48, "descriptor ring moves three 16-byte pieces per chunk");
+
+struct PipeLayout {
+    size_t raw_d, told_d, tsf_d, stage_bytes, total;
+};
+__host__ __device__ inline PipeLayout pipe_layout(int max_loc, int max_edges, int max_blob, int max_own, bool fuse, int nrec, int nfl,
+                                                  int stages)
+{
+    PipeLayout l;
+    l.raw_d = ((size_t)max_loc * 5 + 1) & ~(size_t)1;
+    l.told_d = fuse ? (((size_t)max_own * 5 + 1) & ~(size_t)1) : 0;
+    l.tsf_d = fuse ? (((size_t)max_own + 1) & ~(size_t)1) : 0;
+    l.stage_bytes = (size_t)max_blob + 8 * l.raw_d;
+    l.total = PIPE_HEAD + (size_t)stages * l.stage_bytes + 8 * (l.told_d + l.tsf_d + (size_t)(nfl - 4) * max_edges + (size_t)(nrec - 5) * max_loc);
+    return l;
+}
+
+template <int THREADS, int MINB, int STAGES, bool OVERWRITE, bool FUSE>
+__global__ void __launch_bounds__(THREADS, MINB)
+flux_owner_pipe_kernel(int max_loc, int max_edges, int max_blob, int n_list, const OwnerChunkDesc *__restrict__ descs,
+                       const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
+                       const unsigned char *__restrict__ blob, const double *__restrict__ var, double *__restrict__ flux,
+                       RkStageArgs rk)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int NREC = NF, NFL = NFLUX;
+    constexpr bool DB = STAGES == 2;       // double-buffered stages; otherwise one stage, the next chunk is prefetched into L2
+    const PipeLayout lay = pipe_layout(max_loc, max_edges, max_blob, rk.max_own, FUSE, NREC, NFL, STAGES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+    unsigned char *dring = smraw + 32;
+    unsigned char *stage0 = smraw + PIPE_HEAD;
+    double *told = reinterpret_cast<double *>(stage0 + (size_t)STAGES * lay.stage_bytes);
+    double *tsf = told + lay.told_d;
+    double *Fx = tsf + lay.tsf_d;
+    double *der = Fx + (size_t)(NFL - 4) * max_edges;
+    constexpr int nthreads = THREADS;
+    const int tid = threadIdx.x, G = gridDim.x;
+    const int first = blockIdx.x;
+
+    auto stage_raw = [&](int st) { return reinterpret_cast<double *>(stage0 + (size_t)st * lay.stage_bytes + max_blob); };
+    // bulk copies of chunk `c` into stage `st` (one thread)
+    auto issue_bulk = [&](const OwnerChunkDesc &c, int st) {
+        const uint32_t own_bulk = owned_bulk_bytes(c.n_own);
+        fence_proxy_async();          // earlier generic-proxy accesses to this stage are ordered before the async writes
+        mbar_expect_tx(bar + st, (uint32_t)c.blob_bytes + own_bulk);
+        bulk_g2s(stage0 + (size_t)st * lay.stage_bytes, blob + c.blob_off, (uint32_t)c.blob_bytes, bar + st);
+        if (own_bulk) bulk_g2s(stage_raw(st), var + (size_t)c.node0 * 5, own_bulk, bar + st);
+    };
+    // old_variables / step_factor tiles of chunk `c` (one thread)
+    auto issue_update_operands = [&](const OwnerChunkDesc &c) {
+        const uint32_t old_b = owned_bulk_bytes(c.n_own), sf_b = ((uint32_t)c.n_own * 8u) & ~15u;
+        fence_proxy_async();
+        mbar_expect_tx(bar + 2, old_b + sf_b);
+        if (old_b) bulk_g2s(told, rk.old + (size_t)c.node0 * 5, old_b, bar + 2);
+        if (sf_b) bulk_g2s(tsf, rk.sf + c.node0, sf_b, bar + 2);
+    };
+    // halo ids of chunk `c`, element-consecutive mapping: this thread's k-th element is f = k*nthreads + tid
+    auto load_hg = [&](const OwnerChunkDesc &c, int hg[PIPE_HG]) {
+        const int nh5 = c.n_halo * 5;
+#pragma unroll
+        for (int k = 0; k < PIPE_HG; k++) {
+            int f = k * nthreads + tid;
+            hg[k] = f < nh5 ? __ldg(halo_gid + c.halo_off + f / 5) : -1;
+        }
+    };
+    // halo gather of chunk `c` into stage `st`: every thread issues its requests and lets the stage's mbarrier count them
+    auto issue_gather = [&](const OwnerChunkDesc &c, int st, const int hg[PIPE_HG]) {
+        double *sraw = stage_raw(st);
+        double *hraw = sraw + (size_t)c.n_own * 5;
+        const int nh5 = c.n_halo * 5;
+#pragma unroll
+        for (int k = 0; k < PIPE_HG; k++) {
+            int f = k * nthreads + tid;
+            if (hg[k] >= 0) cp_async8(hraw + f, var + (size_t)hg[k] * 5 + (f % 5));
+        }
+        for (int f = PIPE_HG * nthreads + tid; f < nh5; f += nthreads)      // chunks with very long halo lists
+            cp_async8(hraw + f, var + (size_t)__ldg(halo_gid + c.halo_off + f / 5) * 5 + (f % 5));
+        cp_async_arrive_noinc(bar + st);
+        // an odd owned run (last chunk of a level only): its last 8 bytes are not part of the bulk copy
+        if (tid == 32 && (c.n_own & 1)) sraw[c.n_own * 5 - 1] = __ldg(var + (size_t)(c.node0 + c.n_own) * 5 - 1);
+    };
+    // derived quantities once per staged node of chunk `c` (stage `st` must be complete)
+    auto derive_stage = [&](const OwnerChunkDesc &c, int st) {
+#ifndef MGCFD_EXACT
+        const double *sraw = stage_raw(st);
+        const int nloc = c.n_own + c.n_halo;
+        for (int i = tid; i < nloc; i += nthreads) {
+            double u[5], r[8];
+#pragma unroll
+            for (int v = 0; v < 5; v++) u[v] = sraw[i * 5 + v];
+            derive(u, r);
+            der[i] = r[5]; der[max_loc + i] = r[6]; der[2 * max_loc + i] = r[7];
+        }
+#endif
+    };
+    auto chunk_id = [&](int pos) { return chunk_list ? __ldg(chunk_list + pos) : pos; };
+    auto ring = [&](int j) { return reinterpret_cast<OwnerChunkDesc *>(dring + (size_t)(j & 3) * sizeof(OwnerChunkDesc)); };
+    auto desc_piece = [&](int cid) { return __ldg(reinterpret_cast<const uint4 *>(descs + cid) + tid); };     // tid < 3
+
+    // ---- prologue: descriptors of the first three chunks, mbarriers, first chunk's stage and derived quantities
+    int cid_ahead = 0;                 // threads 0..2: id of the chunk four positions ahead, loaded one iteration early
+    if (tid < 3) {
+        for (int j = 0; j < 3; j++) {
+            int pos = first + j * G;
+            if (pos < n_list) reinterpret_cast<uint4 *>(ring(j))[tid] = desc_piece(chunk_id(pos));
+        }
+        int pos3 = first + 3 * G;
+        cid_ahead = pos3 < n_list ? chunk_id(pos3) : 0;
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1 + THREADS);
+        mbar_init(bar + 1, 1 + THREADS);
+        mbar_init(bar + 2, 1);
+    }
+    __syncthreads();
+    int hg[PIPE_HG];
+    if (DB) {
+        const OwnerChunkDesc c0 = *ring(0);
+        if (tid == 0) issue_bulk(c0, 0);
+        load_hg(c0, hg);
+        issue_gather(c0, 0, hg);
+        if (first + G < n_list) load_hg(*ring(1), hg);
+        mbar_wait(bar, 0);
+        __syncthreads();              // the hand-copied tail element of an odd owned run
+        derive_stage(c0, 0);
+        __syncthreads();
+    } else {
+        load_hg(*ring(0), hg);
+    }
+
+    for (int j = 0, pos = first; pos < n_list; j++, pos += G) {
+        const int st = DB ? (j & 1) : 0;
+        const OwnerChunkDesc d = *ring(j);
+        const bool has_next = pos + G < n_list;
+        if (FUSE && tid == 0) issue_update_operands(d);
+        if (DB) {
+            // ---- top: everything the next chunk needs is requested now
+            if (has_next) {
+                const OwnerChunkDesc dn = *ring(j + 1);
+                if (tid == 0) issue_bulk(dn, st ^ 1);
+                issue_gather(dn, st ^ 1, hg);
+            }
+        } else {
+            // ---- top: this chunk's stage is requested (its halo ids are in registers, its lines were prefetched into
+            //      L2 during the previous chunk), then the next chunk's contiguous inputs are prefetched into L2
+            if (tid == 0) issue_bulk(d, 0);
+            issue_gather(d, 0, hg);
+            if (has_next) {
+                const OwnerChunkDesc dn = *ring(j + 1);
+                load_hg(dn, hg);                                      // consumed by the L2 prefetch in phase E and the next gather
+                if (tid == 0) {
+                    const uint32_t own_b = owned_bulk_bytes(dn.n_own), sf_b = ((uint32_t)dn.n_own * 8u) & ~15u;
+                    bulk_prefetch_l2(blob + dn.blob_off, (uint32_t)dn.blob_bytes);
+                    if (own_b) bulk_prefetch_l2(var + (size_t)dn.node0 * 5, own_b);
+                    if (FUSE && own_b) bulk_prefetch_l2(rk.old + (size_t)dn.node0 * 5, own_b);
+                    if (FUSE && sf_b) bulk_prefetch_l2(rk.sf + dn.node0, sf_b);
+                }
+            }
+            mbar_wait(bar, (uint32_t)j & 1u);
+            __syncthreads();          // the hand-copied tail element of an odd owned run
+            derive_stage(d, 0);
+            __syncthreads();
+        }
+
+        unsigned char *sblob = stage0 + (size_t)st * lay.stage_bytes;
+        const double *raw = stage_raw(st);
+        double *w0 = reinterpret_cast<double *>(sblob);
+        double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
+        const uint32_t *lab = reinterpret_cast<const uint32_t *>(gg + d.e_pad);
+        const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + d.e_pad);
+        const uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
+
+        // ---- D. one thread per edge: the edge's weights are replaced in place by its flux vector
+        auto one_edge = [&](int e) {
+            uint32_t l = lab[e];
+            int la = l & 0xffff, lb = l >> 16;
+            double x = w0[e], y = w1[e], z = w2[e], g = gg[e];
+            double a[NREC], b[NREC];
+            load_state<NREC>(raw, der, max_loc, la, a);
+            load_state<NREC>(raw, der, max_loc, lb, b);
+            double fa[5];
+#ifdef MGCFD_EXACT
+            double fb[5];
+            edge_flux(a, b, x, y, z, g, fa, fb);
+#pragma unroll
+            for (int v = 0; v < 5; v++) Fx[(1 + v) * max_edges + e] = fb[v];
+#else
+            edge_flux(a, b, x, y, z, g, fa);
+#endif
+            w0[e] = fa[0]; w1[e] = fa[1]; w2[e] = fa[2]; gg[e] = fa[3];
+            Fx[e] = fa[4];
+        };
+        for (int e = tid; e < d.n_edges; e += nthreads) one_edge(e);
+        __syncthreads();
+
+        // requests whose results are needed one iteration from now: halo ids of the chunk after next, descriptor of
+        // the chunk three ahead (issued here so that the registers are not live across the edge phase)
+        if (DB && pos + 2 * G < n_list) load_hg(*ring(j + 2), hg);
+        uint4 dreg = make_uint4(0, 0, 0, 0);
+        const bool ring_fill = pos + 3 * G < n_list;
+        if (tid < 3) {
+            if (ring_fill) dreg = desc_piece(cid_ahead);              // stored into the ring at the end of the iteration
+            int pos4 = pos + 4 * G;
+            cid_ahead = pos4 < n_list ? chunk_id(pos4) : 0;
+        }
+
+        // ---- E. owned nodes: incident-edge sums in ascending file order (the fast build splits a node's incidences
+        //         between two threads when the CTA has them), boundary entries, Runge-Kutta update, store
+        if (FUSE) mbar_wait(bar + 2, (uint32_t)j & 1u);               // old_variables / step_factor tiles
+        node_phase<OVERWRITE, FUSE>(tid, nthreads, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+        // ---- next chunk's derived quantities, in the shadow of the warps still in E
+        if (DB) {
+            if (has_next) {
+                mbar_wait(bar + (st ^ 1), (uint32_t)((j + 1) >> 1) & 1u);
+                derive_stage(*ring(j + 1), st ^ 1);
+            }
+        } else if (has_next) {
+            // the next chunk's halo rows into L2 (first and last element of a row cover the sectors it touches)
+#pragma unroll
+            for (int k = 0; k < PIPE_HG; k++) {
+                const int c5 = (k * nthreads + tid) % 5;
+                if (hg[k] >= 0 && (c5 == 0 || c5 == 4)) prefetch_l2(var + (size_t)hg[k] * 5 + c5);
+            }
+        }
+        if (tid < 3 && ring_fill) reinterpret_cast<uint4 *>(ring(j + 3))[tid] = dreg;
+        __syncthreads();              // this stage, the operand tiles and Fx are free; der and the ring are published
+    }
 }
 
 #ifndef MGCFD_EXACT
@@ -940,27 +1332,90 @@ inline int launch_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev 
     return 1;
 }
 
+// persistent pipelined owner kernel: grid = resident CTAs (balanced over the waves the launch needs).
+// Returns -1 when the two stages do not fit in shared memory (the caller falls back to one CTA per chunk).
+inline int launch_owner_pipe(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, int threads, int stages)
+{
+    const int n_list = a.chunk_list ? a.n_list : h.n_chunks;
+    const bool fuse = a.rk != nullptr;
+    const PipeLayout lay = pipe_layout(h.max_loc, h.max_edges, h.dev_max_blob, h.max_own, fuse, NF, NFLUX, stages);
+    if (lay.total > 227 * 1024) return -1;
+    RkStageArgs ra{};
+    if (a.rk) ra = *a.rk;
+    ra.max_own = h.max_own;
+    const int which = fuse ? 0 : (a.overwrite ? 1 : 2);
+    static std::map<std::tuple<int, int, int, size_t, int>, int> slots_cache;   // (device, kernel, threads, smem, cap) -> resident CTAs
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const char *cap_s = getenv("MGCFD_OWNER_PIPE_CTAS");      // experiments: cap on resident CTAs per SM
+    const int env_occ = cap_s ? atoi(cap_s) : 0;
+#define PIPE_ROW(T, B, S) {(const void *)flux_owner_pipe_kernel<T, B, S, true, true>, (const void *)flux_owner_pipe_kernel<T, B, S, true, false>, \
+                           (const void *)flux_owner_pipe_kernel<T, B, S, false, false>}
+    // rows: two stages with 128 threads x 4 CTAs/SM and 256 threads x 2; one stage with 128 x 6 and 256 x 3
+    static const void *const kernels[4][3] = {PIPE_ROW(128, 4, 2), PIPE_ROW(256, 2, 2), PIPE_ROW(128, 6, 1), PIPE_ROW(256, 3, 1)};
+#undef PIPE_ROW
+    if ((threads != 128 && threads != 256) || (stages != 1 && stages != 2)) return -1;
+    const int row = (stages == 2 ? 0 : 2) + (threads == 128 ? 0 : 1);
+    const void *kernel = kernels[row][which];
+    auto key = std::make_tuple(dev, which, row, lay.total, env_occ);
+    auto it = slots_cache.find(key);
+    if (it == slots_cache.end()) {
+        int occ = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, lay.total);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (env_occ > 0 && env_occ < occ) occ = env_occ;
+        if (occ < 1 || sms < 1) return -1;
+        it = slots_cache.emplace(key, occ * sms).first;
+    }
+    const int slots = it->second;
+    const int waves = (n_list + slots - 1) / slots;
+    const int grid = (n_list + waves - 1) / waves;
+    int max_loc = h.max_loc, max_edges = h.max_edges, max_blob = h.dev_max_blob, n = n_list;
+    const OwnerChunkDesc *desc = p.desc;
+    const int *list = a.chunk_list, *hgid = p.halo_gid;
+    const unsigned char *blob = p.blob;
+    const double *var = a.var;
+    double *flux = a.flux;
+    void *args[] = {&max_loc, &max_edges, &max_blob, &n, &desc, &list, &hgid, &blob, &var, &flux, &ra};
+    if (cudaLaunchKernel(kernel, dim3(grid), dim3(threads), args, lay.total, s) != cudaSuccess) return -1;
+    return 1;
+}
+
 inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h)
 {
     if (h.n_chunks == 0) return 0;
-    size_t smem = owner_smem(h.max_loc, h.max_edges, h.max_blob, a.stream_kernel);
+    size_t smem = owner_smem(h.max_loc, h.max_edges, h.dev_max_blob, a.stream_kernel);
     RkStageArgs none{};
     const int grid = a.chunk_list ? a.n_list : h.n_chunks;
     if (grid == 0) return 0;
     // CTA size: 128 threads for chunks of up to 64 owned nodes (the default; more, smaller CTAs hide the staging
     // latency better: 0.49 -> 0.53 of the HBM roofline on an 18.75M-node deck), 256 threads for larger chunks.
     // MGCFD_OWNER_THREADS overrides for experiments (it must cover the largest chunk: one thread per owned node).
-    static const int env_threads = getenv("MGCFD_OWNER_THREADS") ? atoi(getenv("MGCFD_OWNER_THREADS")) : 0;
+    const char *thr_s = getenv("MGCFD_OWNER_THREADS");
+    const int env_threads = thr_s ? atoi(thr_s) : 0;
     int threads = h.max_own <= 64 ? 128 : 256;
     if ((env_threads == 64 || env_threads == 128 || env_threads == 256) && h.max_own <= env_threads) threads = env_threads;
-#define OWNER_ARGS h.max_loc, h.max_edges, h.max_blob, p.desc, a.chunk_list, p.halo_gid, p.blob, a.var, a.flux
+    // MGCFD_OWNER_PIPE: 0 = one CTA per chunk (flux_owner_kernel); 1 = persistent CTAs, one shared-memory stage, next
+    // chunk prefetched into L2; 2 = persistent CTAs, two shared-memory stages
+    const char *pipe_s = getenv("MGCFD_OWNER_PIPE");
+    const int pipe = pipe_s ? atoi(pipe_s) : MGCFD_OWNER_PIPE_DEFAULT;
+    if (pipe > 0 && !a.stream_kernel && threads >= 128) {
+        int rc = launch_owner_pipe(s, a, p, h, threads, pipe >= 2 ? 2 : 1);
+        if (rc >= 0) return rc;
+    }
+#define OWNER_ARGS h.max_loc, h.max_edges, h.dev_max_blob, p.desc, a.chunk_list, p.halo_gid, p.blob, a.var, a.flux
     if (a.stream_kernel)
         flux_owner_kernel<true, false, false><<<grid, threads, smem, s>>>(OWNER_ARGS, none);
     else if (a.rk) {
         RkStageArgs ra = *a.rk;
         ra.max_own = h.max_own;
-        size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.max_blob, false, h.max_own);
-        flux_owner_kernel<false, true, true><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
+        size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.dev_max_blob, false, h.max_own);
+        // MGCFD_OWNER_EPILOGUE=0: node sums staged through shared memory and a separate coalesced update pass
+        const char *epi_s = getenv("MGCFD_OWNER_EPILOGUE");
+        if (epi_s && atoi(epi_s) == 0)
+            flux_owner_kernel<false, true, true, false><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
+        else
+            flux_owner_kernel<false, true, true, true><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
     }
     else if (a.overwrite)
         flux_owner_kernel<false, true, false><<<grid, threads, smem, s>>>(OWNER_ARGS, none);
@@ -982,7 +1437,17 @@ inline std::string configure()
     OPT_IN((flux_owner_kernel<true, false, false>));
     OPT_IN((flux_owner_kernel<false, true, false>));
     OPT_IN((flux_owner_kernel<false, false, false>));
-    OPT_IN((flux_owner_kernel<false, true, true>));
+    OPT_IN((flux_owner_kernel<false, true, true, false>));
+    OPT_IN((flux_owner_kernel<false, true, true, true>));
+#define OPT_IN_PIPE(T, B, S)                                    \
+    OPT_IN((flux_owner_pipe_kernel<T, B, S, true, true>));     \
+    OPT_IN((flux_owner_pipe_kernel<T, B, S, true, false>));    \
+    OPT_IN((flux_owner_pipe_kernel<T, B, S, false, false>));
+    OPT_IN_PIPE(128, 4, 2)
+    OPT_IN_PIPE(256, 2, 2)
+    OPT_IN_PIPE(128, 6, 1)
+    OPT_IN_PIPE(256, 3, 1)
+#undef OPT_IN_PIPE
     OPT_IN((flux_gather_kernel<true, false>));
     OPT_IN((flux_gather_kernel<false, true>));
     OPT_IN((flux_gather_kernel<false, false>));

@@ -12,6 +12,12 @@
 
 namespace mgcfd {
 
+// default owner-kernel mode (MGCFD_OWNER_PIPE overrides): 0 one CTA per chunk, 1 persistent CTAs with one
+// shared-memory stage and L2 prefetch of the next chunk, 2 persistent CTAs with two shared-memory stages
+#ifndef MGCFD_OWNER_PIPE_DEFAULT
+#define MGCFD_OWNER_PIPE_DEFAULT 0
+#endif
+
 constexpr int NVAR = MGCFD_NVAR;
 constexpr int NDIM = MGCFD_NDIM;
 
@@ -58,6 +64,9 @@ struct OwnerPlanHost {
     std::vector<int> csr_off;         // [n_chunks+1]
     int max_loc = 0, max_edges = 0, max_own = 0, max_inc = 0, max_blob = 0;
     long long total_edges = 0;
+    // device packing (ensure_owner): the plan's blob followed by the chunk's boundary entries
+    std::vector<long long> dev_blob_off;   // [n_chunks+1]
+    int dev_max_blob = 0;
 };
 
 struct LevelHost {
@@ -66,6 +75,8 @@ struct LevelHost {
     std::vector<int> e2n, b2n, bgroup, mg;    // 0-based, file order (mg empty on the coarsest)
     std::vector<int> new_of_old, old_of_new;  // node renumbering
     std::vector<int> bnd_node_ptr;            // [n_owned+1] boundary entries per owned internal node
+    std::vector<int> bnd_group_sorted;        // boundary entries sorted by (internal node, file index): group ...
+    std::vector<double> bnd_wt_sorted;        // ... and weights [3]
     std::vector<int> global_node;             // partition: file index in the undecomposed mesh (else empty)
     std::vector<int> nbr_rank, export_ptr, export_idx, import_ptr;   // partition: halo lists in local file numbering
     SortedEdges sorted;
@@ -109,13 +120,14 @@ struct OwnerChunkDesc {         // one per chunk, read by the kernel
     int node0, n_own, n_halo, halo_off;
     int n_edges, e_pad, n_inc, blob_bytes;
     long long blob_off;
-    int has_bnd, pad_;           // some owned node has boundary entries (fused stage)
+    int has_bnd, bnd_off;        // boundary entries of the owned nodes (count) and where they sit in the blob:
+                                 // bw [has_bnd][3] double | local node [has_bnd] u16 | group [has_bnd] i16
 };
 
 struct OwnerPlanDev {
     OwnerChunkDesc *desc = nullptr;
     int *halo_gid = nullptr;
-    unsigned char *blob = nullptr;   // per chunk: w0[e_pad] w1 w2 g (double) | lab[e_pad] (u32) | rowptr | csr (u16)
+    unsigned char *blob = nullptr;   // per chunk: w0[e_pad] w1 w2 g (double) | lab[e_pad] (u32) | rowptr | csr (u16) | boundary entries
     long long blob_bytes = 0;
     bool valid = false;
 };
