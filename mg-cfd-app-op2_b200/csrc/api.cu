@@ -773,7 +773,8 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     O.dev_max_blob = 0;
     for (int k = 0; k < O.n_chunks; k++) {
         long long nb = L.bnd_node_ptr[O.node0[k + 1]] - L.bnd_node_ptr[O.node0[k]];
-        long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + (nb ? pad16(nb * (24 + 2 + 2)) : 0);
+        const long long n_own = O.node0[k + 1] - O.node0[k];
+        long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + (nb ? pad16(nb * (24 + 2) + ((n_own + 2) & ~1ll) * 2) : 0);
         O.dev_blob_off[k + 1] = O.dev_blob_off[k] + bytes;
         O.dev_max_blob = std::max(O.dev_max_blob, (int)bytes);
     }
@@ -825,15 +826,17 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         unsigned char *base = blob.data() + d.blob_off;
         if (d.has_bnd) {
             double *bw = reinterpret_cast<double *>(base + d.bnd_off);
-            uint16_t *bnode = reinterpret_cast<uint16_t *>(bw + (size_t)d.has_bnd * 3);
-            int16_t *bgrp = reinterpret_cast<int16_t *>(bnode + d.has_bnd);
+            uint16_t *bptr = reinterpret_cast<uint16_t *>(bw + (size_t)d.has_bnd * 3);       // [n_own+1] entry ranges
+            int16_t *bgrp = reinterpret_cast<int16_t *>(bptr + (((d.n_own + 1) + 1) & ~1));
             int i = 0;
-            for (int v = O.node0[k]; v < O.node0[k + 1]; v++)
+            for (int v = O.node0[k]; v < O.node0[k + 1]; v++) {
+                bptr[v - O.node0[k]] = (uint16_t)i;
                 for (int j = L.bnd_node_ptr[v]; j < L.bnd_node_ptr[v + 1]; j++, i++) {
                     for (int c = 0; c < 3; c++) bw[(size_t)i * 3 + c] = L.bnd_wt_sorted[(size_t)j * 3 + c];
-                    bnode[i] = (uint16_t)(v - O.node0[k]);
                     bgrp[i] = (int16_t)std::max(-32768, std::min(32767, L.bnd_group_sorted[j]));   // only <=2 / 3..7 matter
                 }
+            }
+            bptr[d.n_own] = (uint16_t)i;
         }
         double *w0 = reinterpret_cast<double *>(base), *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *g = w2 + d.e_pad;
         uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);

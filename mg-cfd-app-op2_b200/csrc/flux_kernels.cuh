@@ -467,19 +467,14 @@ __device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n
 // (+ validation.h:27-44,102-115 after the last stage) with the prefetched old_variables / step_factor tiles, bit for
 // bit the arithmetic of time_step_kernel.  No shared-memory staging of the result and no barrier after it.
 // ------------------------------------------------------------------------------------------
-template <bool OVERWRITE, bool FUSE>
-__device__ __forceinline__ void node_phase(int tid, int nthreads, const OwnerChunkDesc &d, const unsigned char *sblob,
+template <bool OVERWRITE, bool FUSE, int LG_SPLIT>
+__device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, const unsigned char *sblob,
                                            const double *raw, const double *w0, const double *w1, const double *w2,
                                            const double *gg, const double *Fx, const uint16_t *rowptr, const uint16_t *csr,
                                            int max_edges, const double *told, const double *tsf, double *__restrict__ flux,
                                            const RkStageArgs &rk)
 {
-#ifdef MGCFD_EXACT
-    const int lg_split = 0;
-#else
-    const int lg_split = 4 * rk.max_own <= nthreads ? 2 : (2 * rk.max_own <= nthreads ? 1 : 0);
-#endif
-    const int step = 1 << lg_split;                 // threads per owned node
+    constexpr int lg_split = LG_SPLIT, step = 1 << LG_SPLIT;      // threads per owned node (fast build: 1, 2 or 4)
     const int n = tid >> lg_split, part = tid & (step - 1);
     const bool active = n < d.n_own;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -526,13 +521,11 @@ __device__ __forceinline__ void node_phase(int tid, int nthreads, const OwnerChu
     int bad = 0;
     if (active) {
         if (FUSE && d.has_bnd) {
-            // find this node's range of the chunk's boundary entries
+            // this node's range of the chunk's boundary entries
             const double *bw = reinterpret_cast<const double *>(sblob + d.bnd_off);
-            const uint16_t *bnode = reinterpret_cast<const uint16_t *>(bw + (size_t)d.has_bnd * 3);
-            const int16_t *bgrp = reinterpret_cast<const int16_t *>(bnode + d.has_bnd);
-            int b0 = d.has_bnd, b1 = 0;
-            for (int i = 0; i < d.has_bnd; i++)
-                if (bnode[i] == n) { b0 = min(b0, i); b1 = i + 1; }
+            const uint16_t *bptr = reinterpret_cast<const uint16_t *>(bw + (size_t)d.has_bnd * 3);
+            const int16_t *bgrp = reinterpret_cast<const int16_t *>(bptr + (((d.n_own + 1) + 1) & ~1));
+            const int b0 = bptr[n], b1 = bptr[n + 1];
             if (b1 > b0) {
                 double u[5];
 #pragma unroll
@@ -674,8 +667,14 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
 
     // 5. (REGEPI) node sums, boundary entries and the update straight from registers: see node_phase
     if constexpr (REGEPI) {
-        node_phase<OVERWRITE, FUSE>(tid, (int)blockDim.x, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf,
-                                    flux, rk);
+#ifdef MGCFD_EXACT
+        node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+#else
+        if (2 * rk.max_own <= (int)blockDim.x)
+            node_phase<OVERWRITE, FUSE, 1>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+        else
+            node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+#endif
         return;
     }
     // 5. one thread per owned node (chunks never own more than blockDim nodes) sums its incident edges in ascending
@@ -970,7 +969,16 @@ flux_owner_pipe_kernel(int max_loc, int max_edges, int max_blob, int n_list, con
         // ---- E. owned nodes: incident-edge sums in ascending file order (the fast build splits a node's incidences
         //         between two threads when the CTA has them), boundary entries, Runge-Kutta update, store
         if (FUSE) mbar_wait(bar + 2, (uint32_t)j & 1u);               // old_variables / step_factor tiles
-        node_phase<OVERWRITE, FUSE>(tid, nthreads, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+#ifdef MGCFD_EXACT
+        node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+#else
+        if (4 * rk.max_own <= nthreads)
+            node_phase<OVERWRITE, FUSE, 2>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+        else if (2 * rk.max_own <= nthreads)
+            node_phase<OVERWRITE, FUSE, 1>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+        else
+            node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+#endif
         // ---- next chunk's derived quantities, in the shadow of the warps still in E
         if (DB) {
             if (has_next) {

@@ -121,7 +121,8 @@ struct OwnerChunkDesc {         // one per chunk, read by the kernel
     int n_edges, e_pad, n_inc, blob_bytes;
     long long blob_off;
     int has_bnd, bnd_off;        // boundary entries of the owned nodes (count) and where they sit in the blob:
-                                 // bw [has_bnd][3] double | local node [has_bnd] u16 | group [has_bnd] i16
+                                 // bw [has_bnd][3] double | entry range per owned node [n_own+1] u16 (padded to even) |
+                                 // group [has_bnd] i16
 };
 
 struct OwnerPlanDev {
