@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <map>
 #include <tuple>
+#include <type_traits>
 
 #include <cuda_runtime.h>
 
@@ -534,30 +535,50 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
             }
         }
         const size_t g0 = (size_t)d.node0 * 5;
-        // component v is finished by the node's thread v mod (threads per node)
+        // The node's thread `part` finishes components part, part+step, ...: at most NK of them, picked out of acc with
+        // static indices (all threads of a warp then run the same NK update bodies).
+        constexpr int NK = (5 + step - 1) / step;
+        double mine[NK];
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            mine[k] = acc[k * step];
+#pragma unroll
+            for (int q = 1; q < step; q++)
+                if (k * step + q < 5 && part == q) mine[k] = acc[k * step + q];
+        }
         if (!FUSE) {
             double *out = flux + g0 + n * 5;
 #pragma unroll
-            for (int v = 0; v < 5; v++)
-                if ((v & (step - 1)) == part) out[v] = acc[v];
+            for (int k = 0; k < NK; k++)
+                if (part + k * step < 5) out[part + k * step] = mine[k];
         } else {
-            const int old_n = (int)(owned_bulk_bytes(d.n_own) >> 3), sf_n = (int)((((uint32_t)d.n_own * 8u) & ~15u) >> 3);
-            const double factor = (n < sf_n ? tsf[n] : rk.sf[d.node0 + n]) / (double)(MGCFD_RK + 1 - rk.rk);
-            auto update = [&](int v, double fl) {
-                const int f = n * 5 + v;
-                const double o = f < old_n ? told[f] : rk.old[g0 + f];
-                const double vn = __dadd_rn(o, __dmul_rn(factor, fl));
-                rk.var_out[g0 + f] = vn;
-                if (rk.last) {
-                    const double r = vn - o;
-                    rk.res[g0 + f] = r;
-                    sq += r * r;
-                    bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
+            // An odd owned run (the last chunk of a level only) has one old_variables element and one step factor
+            // outside the bulk-copied tiles; the test is uniform, so that every other chunk runs without it.
+            auto finish = [&](auto tail_c) {
+                constexpr bool TAIL = decltype(tail_c)::value;
+                const int old_n = (int)(owned_bulk_bytes(d.n_own) >> 3), sf_n = (int)((((uint32_t)d.n_own * 8u) & ~15u) >> 3);
+                const double factor = ((!TAIL || n < sf_n) ? tsf[n] : rk.sf[d.node0 + n]) / (double)(MGCFD_RK + 1 - rk.rk);
+#pragma unroll
+                for (int k = 0; k < NK; k++) {
+                    const int v = part + k * step;
+                    if (v < 5) {
+                        const int f = n * 5 + v;
+                        const double o = (!TAIL || f < old_n) ? told[f] : rk.old[g0 + f];
+                        const double vn = __dadd_rn(o, __dmul_rn(factor, mine[k]));
+                        rk.var_out[g0 + f] = vn;
+                        if (rk.last) {
+                            const double r = vn - o;
+                            rk.res[g0 + f] = r;
+                            sq += r * r;
+                            bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
+                        }
+                    }
                 }
             };
-#pragma unroll
-            for (int v = 0; v < 5; v++)
-                if ((v & (step - 1)) == part) update(v, acc[v]);
+            if (d.n_own & 1)
+                finish(std::true_type{});
+            else
+                finish(std::false_type{});
         }
     }
     if (FUSE && rk.last && rk.d_rms) {
