@@ -1,12 +1,15 @@
 // euler3d_b200.cpp -- native host driver: the reference's euler3d.cpp main() restated over the C-ABI of
 // libmgcfd_b200 (include/mgcfd_b200.h).  Same command line (config.h:107-127), same input deck (io.h:28-205), same
 // initialisation and V-cycle schedule (euler3d.cpp:413-441, 458-641), same -v validation (euler3d.cpp:658-718) and
-// output naming (euler3d.cpp:720-779).  Level files are MGCFDBIN containers holding the reference's HDF5 dataset
-// names (see meshgen.py); a build with libhdf5 would only swap read_level().
+// output naming (euler3d.cpp:720-779).  Level and solution files are HDF5 files with the reference's dataset names
+// (read and written by h5lite.hpp, a from-scratch implementation of the HDF5 subset OP2's op_decl_*_hdf5 /
+// op_fetch_data_hdf5_file use -- the image has no libhdf5) or MGCFDBIN containers holding the same datasets (see
+// meshgen.py); the format is detected per file.  Outputs are .h5 when the deck is HDF5 or --hdf5 is given.
 //
 //   euler3d_b200 -i input.dat [-d dir] [-o prefix] [-g cycles] [-v] [-b] [-I n] [-m partitioner] [-r method]
 //                [--renumber] [--output-variables] [--output-fluxes] [--output-step-factors]
 //                [--gpus N] [--same-device] [--variant owner|gather|colour|atomic] [--exact] [--loopwise]
+//                [--hdf5] [--check-deck]
 #include <getopt.h>
 #include <sys/time.h>
 
@@ -22,6 +25,7 @@
 #include <string>
 #include <vector>
 
+#include "h5lite.hpp"
 #include "mgcfd_b200.h"
 
 namespace {
@@ -35,8 +39,32 @@ struct Dataset {
 };
 typedef std::map<std::string, Dataset> Container;
 
+// an HDF5 level / solution file: every numeric dataset, floating-point ones as float64 and integer ones as int32
+bool read_hdf5(const std::string &path, Container &out, std::string &err)
+{
+    try {
+        h5lite::File f(path);
+        for (const std::string &name : f.names()) {
+            const h5lite::DatasetInfo &info = f.info(name);
+            if (info.type.cls != 0 && info.type.cls != 1) continue;
+            Dataset d;
+            d.dtype = info.type.cls == 1 ? 0 : 1;
+            d.dims = info.dims;
+            d.bytes.resize(info.count() * (d.dtype == 0 ? 8 : 4));
+            if (d.dtype == 0) f.read_f64(name, reinterpret_cast<double *>(d.bytes.data()));
+            else f.read_i32(name, reinterpret_cast<int32_t *>(d.bytes.data()));
+            out[name] = std::move(d);
+        }
+        return true;
+    } catch (const std::exception &e) {
+        err = e.what();
+        return false;
+    }
+}
+
 bool read_container(const std::string &path, Container &out, std::string &err)
 {
+    if (h5lite::File::is_hdf5(path)) return read_hdf5(path, out, err);
     std::ifstream f(path, std::ios::binary);
     if (!f) { err = "cannot open " + path; return false; }
     char magic[8];
@@ -45,7 +73,7 @@ bool read_container(const std::string &path, Container &out, std::string &err)
     f.read(reinterpret_cast<char *>(&version), 4);
     f.read(reinterpret_cast<char *>(&n), 4);
     if (!f || memcmp(magic, "MGCFDBIN", 8) != 0) {
-        err = path + ": not an MGCFDBIN container (HDF5 level files need a libhdf5 build; none exists in this image)";
+        err = path + ": neither an HDF5 file nor an MGCFDBIN container";
         return false;
     }
     for (uint32_t i = 0; i < n; i++) {
@@ -70,8 +98,22 @@ bool read_container(const std::string &path, Container &out, std::string &err)
     return true;
 }
 
-bool write_container(const std::string &path, const std::string &name, const double *data, uint64_t rows, uint64_t cols)
+bool g_hdf5_output = false;       // outputs as .h5 (op_fetch_data_hdf5_file, euler3d.cpp:740-770) instead of .mgb
+
+bool write_container(std::string path, const std::string &name, const double *data, uint64_t rows, uint64_t cols)
 {
+    if (g_hdf5_output) {
+        if (path.size() > 4 && path.compare(path.size() - 4, 4, ".mgb") == 0) path.replace(path.size() - 4, 4, ".h5");
+        try {
+            h5lite::Writer w(path);
+            w.add(name, h5lite::DType::F64, cols > 1 ? std::vector<uint64_t>{rows, cols} : std::vector<uint64_t>{rows}, data);
+            w.close();
+            return true;
+        } catch (const std::exception &e) {
+            fprintf(stderr, "%s\n", e.what());
+            return false;
+        }
+    }
     std::ofstream f(path, std::ios::binary);
     if (!f) return false;
     uint32_t version = 1, n = 1, len = (uint32_t)name.size(), dtype = 0, ndim = cols > 1 ? 2 : 1;
@@ -162,6 +204,7 @@ struct Config {                               // config.h:64-103, defaults :129-
     std::string input_file, input_dir, prefix, variant = "owner";
     int cycles = 25, flow_interval = 0, gpus = 1;
     bool validate = false, mem_bound = false, renumber = true, exact = false, loopwise = false, same_device = false;
+    bool hdf5 = false, check_deck = false;
     int out_vars = 0, out_fluxes = 0, out_sf = 0;
 };
 
@@ -190,7 +233,8 @@ int main(int argc, char **argv)
         {"output-fluxes", no_argument, &conf.out_fluxes, 1}, {"output-step-factors", no_argument, &conf.out_sf, 1},
         {"output-flow-interval", required_argument, nullptr, 'I'}, {"gpus", required_argument, nullptr, 1001},
         {"variant", required_argument, nullptr, 1002}, {"exact", no_argument, nullptr, 1003},
-        {"loopwise", no_argument, nullptr, 1004}, {"same-device", no_argument, nullptr, 1005}, {nullptr, 0, nullptr, 0}};
+        {"loopwise", no_argument, nullptr, 1004}, {"same-device", no_argument, nullptr, 1005},
+        {"hdf5", no_argument, nullptr, 1006}, {"check-deck", no_argument, nullptr, 1007}, {nullptr, 0, nullptr, 0}};
     int opt;
     while ((opt = getopt_long(argc, argv, "hc:li:d:p:o:g:m:r:vbI:", long_opts, nullptr)) != -1) {
         switch (opt) {
@@ -209,12 +253,14 @@ int main(int argc, char **argv)
         case 1003: conf.exact = true; break;
         case 1004: conf.loopwise = true; break;
         case 1005: conf.same_device = true; break;       // all ranks of --gpus N on device 0 (tests on a one-GPU box)
+        case 1006: conf.hdf5 = true; break;              // write outputs as HDF5 even for an MGCFDBIN deck
+        case 1007: conf.check_deck = true; break;        // load the deck, print what was read, exit (no GPU needed)
         case 0: break;
         case 'h':
         default:
             printf("usage: %s -i input.dat [-d dir] [-o prefix] [-g cycles] [-v] [-b] [-I n] [--output-variables] "
                    "[--output-fluxes] [--output-step-factors] [--gpus N] [--variant owner|gather|colour|atomic] "
-                   "[--exact] [--loopwise]\n", argv[0]);
+                   "[--exact] [--loopwise] [--hdf5] [--check-deck]\n", argv[0]);
             return opt == 'h' ? 0 : 1;
         }
     }
@@ -251,12 +297,30 @@ int main(int argc, char **argv)
             h.node_to_mg_node = c["node-->mg_node"].i32();
         }
     }
+    g_hdf5_output = conf.hdf5 || h5lite::File::is_hdf5(dir + deck.files[0]);
+    if (conf.check_deck) {
+        // what the loader got out of every level file: sizes and order-sensitive checksums
+        for (int i = 0; i < levels; i++) {
+            printf("level %d: format=%s nodes=%d edges=%d bnd_nodes=%d\n", i,
+                   h5lite::File::is_hdf5(dir + deck.files[i]) ? "hdf5" : "mgcfdbin", lv[i].n_nodes, lv[i].n_edges, lv[i].n_bnd_nodes);
+            for (auto &kv : files[i]) {
+                const Dataset &d = kv.second;
+                long double sum = 0;
+                const size_t n = d.bytes.size() / (d.dtype == 0 ? 8 : 4);
+                for (size_t k = 0; k < n; k++) sum += (long double)(k % 97 + 1) * (d.dtype == 0 ? (long double)d.f64()[k] : (long double)d.i32()[k]);
+                printf("  %-20s %s rank=%zu checksum=%.12Le\n", kv.first.c_str(), d.dtype == 0 ? "f64" : "i32", d.dims.size(), sum);
+            }
+        }
+        return 0;
+    }
     // -v: solution.variables.L<l>.cycles=<g> with dataset p_variables_result_L<l> (euler3d.cpp:314-335)
     std::vector<Container> solution(levels);
     std::vector<const double *> variables_correct(levels, nullptr);
     if (conf.validate)
         for (int i = 0; i < levels; i++) {
-            std::string p = dir + "solution.variables.L" + std::to_string(i) + ".cycles=" + std::to_string(conf.cycles) + ".mgb";
+            std::string stem = dir + "solution.variables.L" + std::to_string(i) + ".cycles=" + std::to_string(conf.cycles);
+            std::string p = stem + ".h5";                    // the reference's name (euler3d.cpp:320); else the container
+            if (access(p.c_str(), R_OK) != 0) p = stem + ".mgb";
             std::string name = "p_variables_result_L" + std::to_string(i);
             if (read_container(p, solution[i], err) && solution[i].count(name)) variables_correct[i] = solution[i][name].f64();
             else printf("Cannot find level %d solution file: %s\n", i, p.c_str());

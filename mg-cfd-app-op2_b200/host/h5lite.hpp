@@ -1,0 +1,863 @@
+// h5lite.hpp -- a from-scratch reader / writer for the subset of the HDF5 file format that MG-CFD decks use
+// (level files and solution files: euler3d.cpp:248-327, 556-571, 736-771 go through OP2's op_decl_*_hdf5 /
+// op_fetch_data_hdf5_file, i.e. plain datasets in the root group).  No libhdf5 exists in the image, so this follows the
+// published "HDF5 File Format Specification Version 3.0" directly:
+//   read : superblock v0/v1 (symbol-table root) and v2/v3 (root object header); object headers v1 (with continuation
+//          blocks) and v2 ("OHDR"/"OCHK"); old-style groups (symbol table message -> v1 B-tree "TREE" -> "SNOD" nodes ->
+//          local heap "HEAP") and new-style groups with compact link storage (Link messages); nested groups; dataspace
+//          v1/v2; datatypes fixed-point / floating-point (any width 1-8 bytes, either byte order) and strings
+//          (attributes); data layout v3 contiguous / compact / chunked (v1 chunk B-tree) and the v1/v2 layout message;
+//          filter pipeline v1/v2 with deflate, shuffle and fletcher32; attributes v1-v3 (numeric scalars/arrays, strings);
+//   write: superblock v0, old-style root group, object headers v1, contiguous little-endian int32 / int64 / float32 /
+//          float64 datasets with OP2's "size" / "dim" / "type" attributes -- what h5py or the HDF5 C library write with
+//          default settings for such a file.
+// Not supported (reported as errors, never silently misread): dense link storage (fractal heaps), v4 layouts with the
+// new chunk indices, variable-length / compound / reference types as dataset element types, external storage, szip.
+// Parity note: there is no libhdf5 / h5py / sample .h5 file in the build image, so interoperability with real HDF5 is
+// unpinned; the implementation is cross-checked against an independent pure-Python restatement of the same
+// specification (oracle/h5_oracle.py, tests/test_h5lite.py) in both directions.
+#pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace h5lite {
+
+struct Error : std::runtime_error {
+    explicit Error(const std::string &m) : std::runtime_error(m) {}
+};
+
+constexpr uint64_t UNDEF = ~0ull;
+
+struct TypeInfo {
+    int cls = -1;              // 0 fixed-point, 1 floating-point, 3 string, other: unsupported as element type
+    uint32_t size = 0;         // bytes per element
+    bool big_endian = false, is_signed = false;
+    bool is_ieee = false;      // floating point with the IEEE 754 field layout for its size
+};
+
+struct Attribute {
+    TypeInfo type;
+    std::vector<uint64_t> dims;          // empty: scalar
+    std::vector<unsigned char> raw;      // element bytes as stored
+    std::string as_string() const
+    {
+        std::string s(raw.begin(), raw.end());
+        size_t z = s.find('\0');
+        return z == std::string::npos ? s : s.substr(0, z);
+    }
+    long long as_int(size_t i = 0) const;
+    double as_double(size_t i = 0) const;
+};
+
+struct Filter {
+    int id = 0;
+    std::vector<uint32_t> client;
+};
+
+struct DatasetInfo {
+    std::string name;
+    std::vector<uint64_t> dims;
+    TypeInfo type;
+    int layout = -1;                     // 0 compact, 1 contiguous, 2 chunked
+    uint64_t address = UNDEF, size = 0;  // contiguous: data address / bytes; chunked: B-tree address
+    std::vector<unsigned char> compact;
+    std::vector<uint32_t> chunk;         // chunked: chunk dimensions (rank values)
+    std::vector<Filter> filters;
+    std::map<std::string, Attribute> attrs;
+    uint64_t count() const
+    {
+        uint64_t n = 1;
+        for (uint64_t d : dims) n *= d;
+        return n;
+    }
+};
+
+namespace detail {
+
+inline uint64_t le(const unsigned char *p, int n)
+{
+    uint64_t v = 0;
+    for (int i = n - 1; i >= 0; i--) v = (v << 8) | p[i];
+    return v;
+}
+
+// element conversion: any fixed / IEEE float of 1-8 bytes, either byte order -> long long / double
+inline long long load_int(const unsigned char *p, const TypeInfo &t)
+{
+    unsigned char b[8] = {0};
+    for (uint32_t i = 0; i < t.size && i < 8; i++) b[i] = t.big_endian ? p[t.size - 1 - i] : p[i];
+    uint64_t v = le(b, 8);
+    if (t.is_signed && t.size < 8 && (v >> (8 * t.size - 1)) & 1) v |= ~0ull << (8 * t.size);
+    return (long long)v;
+}
+inline double load_float(const unsigned char *p, const TypeInfo &t)
+{
+    unsigned char b[8] = {0};
+    for (uint32_t i = 0; i < t.size && i < 8; i++) b[i] = t.big_endian ? p[t.size - 1 - i] : p[i];
+    if (t.size == 8) { double d; memcpy(&d, b, 8); return d; }
+    if (t.size == 4) { float f; memcpy(&f, b, 4); return (double)f; }
+    throw Error("floating-point elements of " + std::to_string(t.size) + " bytes are not supported");
+}
+
+}  // namespace detail
+
+inline long long Attribute::as_int(size_t i) const
+{
+    if (type.cls == 0) return detail::load_int(raw.data() + i * type.size, type);
+    if (type.cls == 1) return (long long)detail::load_float(raw.data() + i * type.size, type);
+    throw Error("attribute is not numeric");
+}
+inline double Attribute::as_double(size_t i) const
+{
+    if (type.cls == 1) return detail::load_float(raw.data() + i * type.size, type);
+    if (type.cls == 0) return (double)detail::load_int(raw.data() + i * type.size, type);
+    throw Error("attribute is not numeric");
+}
+
+// ------------------------------------------------------------------------------------------ reader
+class File {
+public:
+    explicit File(const std::string &path) : path_(path)
+    {
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) throw Error("cannot open " + path);
+        struct stat st;
+        if (fstat(fd_, &st) != 0) { ::close(fd_); throw Error("cannot stat " + path); }
+        file_size_ = (uint64_t)st.st_size;
+        try {
+            parse_superblock();
+            walk_group(root_header_, "", 0);
+        } catch (...) {
+            ::close(fd_);
+            throw;
+        }
+    }
+    ~File() { if (fd_ >= 0) ::close(fd_); }
+    File(const File &) = delete;
+    File &operator=(const File &) = delete;
+
+    static bool is_hdf5(const std::string &path)
+    {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        unsigned char sig[8] = {0};
+        bool ok = false;
+        for (uint64_t off = 0; !ok && off < (1ull << 24); off = off ? off * 2 : 512) {     // 0, 512, 1024, ...
+            if (fseek(f, (long)off, SEEK_SET) != 0 || fread(sig, 1, 8, f) != 8) break;
+            ok = memcmp(sig, "\x89HDF\r\n\x1a\n", 8) == 0;
+        }
+        fclose(f);
+        return ok;
+    }
+
+    const std::vector<std::string> &names() const { return order_; }
+    bool has(const std::string &name) const { return sets_.count(name) != 0; }
+    const DatasetInfo &info(const std::string &name) const
+    {
+        auto it = sets_.find(name);
+        if (it == sets_.end()) throw Error(path_ + ": no dataset '" + name + "'");
+        return it->second;
+    }
+    int superblock_version() const { return sb_version_; }
+
+    // the dataset's elements as stored (row-major, file byte order)
+    std::vector<unsigned char> read_raw(const std::string &name) const
+    {
+        const DatasetInfo &d = info(name);
+        if (d.type.cls != 0 && d.type.cls != 1 && d.type.cls != 3) throw Error(name + ": unsupported element type class " + std::to_string(d.type.cls));
+        const uint64_t bytes = d.count() * d.type.size;
+        std::vector<unsigned char> out(bytes, 0);
+        if (bytes == 0) return out;
+        if (d.layout == 0) {
+            if (d.compact.size() < bytes) throw Error(name + ": compact data shorter than the dataspace");
+            memcpy(out.data(), d.compact.data(), bytes);
+        } else if (d.layout == 1) {
+            if (d.address != UNDEF) {                // undefined address: storage never allocated -> fill value (zeros)
+                if (d.size < bytes) throw Error(name + ": contiguous storage shorter than the dataspace");
+                read_at(base_ + d.address, out.data(), bytes);
+            }
+        } else if (d.layout == 2) {
+            if (d.address != UNDEF) read_chunks(d, d.address, out);
+        } else {
+            throw Error(name + ": unknown data layout");
+        }
+        return out;
+    }
+    void read_f64(const std::string &name, double *out) const
+    {
+        const DatasetInfo &d = info(name);
+        std::vector<unsigned char> raw = read_raw(name);
+        const uint64_t n = d.count();
+        if (d.type.cls == 1 && d.type.size == 8 && !d.type.big_endian) { memcpy(out, raw.data(), n * 8); return; }
+        for (uint64_t i = 0; i < n; i++)
+            out[i] = d.type.cls == 1 ? detail::load_float(raw.data() + i * d.type.size, d.type)
+                                     : (double)detail::load_int(raw.data() + i * d.type.size, d.type);
+    }
+    void read_i32(const std::string &name, int32_t *out) const
+    {
+        const DatasetInfo &d = info(name);
+        if (d.type.cls != 0) throw Error(name + ": not an integer dataset");
+        std::vector<unsigned char> raw = read_raw(name);
+        const uint64_t n = d.count();
+        if (d.type.size == 4 && !d.type.big_endian) { memcpy(out, raw.data(), n * 4); return; }
+        for (uint64_t i = 0; i < n; i++) {
+            long long v = detail::load_int(raw.data() + i * d.type.size, d.type);
+            if (v < INT32_MIN || v > INT32_MAX) throw Error(name + ": value does not fit in 32 bits");
+            out[i] = (int32_t)v;
+        }
+    }
+
+private:
+    struct Message {
+        int type = 0, flags = 0;
+        std::vector<unsigned char> data;
+    };
+
+    void read_at(uint64_t off, void *dst, uint64_t n) const
+    {
+        if (off > file_size_ || n > file_size_ - off) throw Error(path_ + ": read beyond the end of the file (truncated or corrupt)");
+        unsigned char *p = static_cast<unsigned char *>(dst);
+        while (n) {
+            ssize_t r = pread(fd_, p, n, (off_t)off);
+            if (r <= 0) throw Error(path_ + ": read error");
+            p += r; off += (uint64_t)r; n -= (uint64_t)r;
+        }
+    }
+    std::vector<unsigned char> bytes_at(uint64_t off, uint64_t n) const
+    {
+        std::vector<unsigned char> v(n);
+        read_at(off, v.data(), n);
+        return v;
+    }
+    uint64_t offs(const unsigned char *p) const { return detail::le(p, so_) == (so_ == 8 ? UNDEF : ((1ull << (8 * so_)) - 1)) ? UNDEF : detail::le(p, so_); }
+    uint64_t lens(const unsigned char *p) const { return detail::le(p, sl_); }
+
+    void parse_superblock()
+    {
+        uint64_t off = 0;
+        unsigned char sig[8];
+        bool found = false;
+        for (; off + 8 <= file_size_; off = off ? off * 2 : 512) {
+            read_at(off, sig, 8);
+            if (memcmp(sig, "\x89HDF\r\n\x1a\n", 8) == 0) { found = true; break; }
+        }
+        if (!found) throw Error(path_ + ": not an HDF5 file (no superblock signature)");
+        std::vector<unsigned char> b = bytes_at(off + 8, std::min<uint64_t>(128, file_size_ - off - 8));
+        sb_version_ = b[0];
+        if (sb_version_ == 0 || sb_version_ == 1) {
+            so_ = b[5]; sl_ = b[6];
+            if ((so_ != 4 && so_ != 8) || (sl_ != 4 && sl_ != 8)) throw Error(path_ + ": unsupported offset / length sizes");
+            size_t p = 16 + (sb_version_ == 1 ? 4 : 0);     // after K values, consistency flags [, indexed storage K + reserved]
+            base_ = offs(&b[p]); p += so_;
+            p += so_;                                       // free-space info
+            p += so_;                                       // end of file
+            p += so_;                                       // driver info
+            // root group symbol table entry: link name offset, object header address, cache type, reserved, scratch
+            root_header_ = offs(&b[p + so_]);
+        } else if (sb_version_ == 2 || sb_version_ == 3) {
+            so_ = b[1]; sl_ = b[2];
+            if ((so_ != 4 && so_ != 8) || (sl_ != 4 && sl_ != 8)) throw Error(path_ + ": unsupported offset / length sizes");
+            size_t p = 4;
+            base_ = offs(&b[p]); p += so_;
+            p += so_;                                       // superblock extension
+            p += so_;                                       // end of file
+            root_header_ = offs(&b[p]);
+        } else {
+            throw Error(path_ + ": unsupported superblock version " + std::to_string(sb_version_));
+        }
+        // With a user block the base address is the absolute address of the superblock (every other address is
+        // relative to it); writers that leave the field 0 there are tolerated.
+        if (base_ == UNDEF || (base_ == 0 && off > 0)) base_ = off;
+        if (root_header_ == UNDEF) throw Error(path_ + ": no root group");
+    }
+
+    std::vector<Message> object_header(uint64_t addr) const
+    {
+        std::vector<Message> msgs;
+        unsigned char head[16];
+        read_at(base_ + addr, head, 16);
+        if (memcmp(head, "OHDR", 4) == 0) {
+            // ---- version 2
+            if (head[4] != 2) throw Error(path_ + ": unsupported object header version");
+            const int flags = head[5];
+            uint64_t p = base_ + addr + 6;
+            if (flags & 0x20) p += 16;                       // access, modification, change, birth times
+            if (flags & 0x10) p += 4;                        // max compact / min dense attributes
+            const int szlen = 1 << (flags & 3);
+            unsigned char sz[8] = {0};
+            read_at(p, sz, szlen);
+            p += szlen;
+            std::vector<std::pair<uint64_t, uint64_t>> blocks{{p, detail::le(sz, szlen)}};
+            const bool order = flags & 0x04;
+            for (size_t bi = 0; bi < blocks.size(); bi++) {
+                std::vector<unsigned char> blk = bytes_at(blocks[bi].first, blocks[bi].second);
+                size_t q = 0;
+                while (q + 4 + (order ? 2 : 0) <= blk.size()) {
+                    Message m;
+                    m.type = blk[q];
+                    size_t sz2 = detail::le(&blk[q + 1], 2);
+                    m.flags = blk[q + 3];
+                    q += 4 + (order ? 2 : 0);
+                    if (q + sz2 > blk.size()) break;         // gap before the checksum
+                    m.data.assign(blk.begin() + q, blk.begin() + q + sz2);
+                    q += sz2;
+                    if (m.type == 0x10) {
+                        uint64_t caddr = offs(m.data.data()), clen = lens(m.data.data() + so_);
+                        unsigned char csig[4];
+                        read_at(base_ + caddr, csig, 4);
+                        if (memcmp(csig, "OCHK", 4) != 0) throw Error(path_ + ": bad continuation block");
+                        blocks.push_back({base_ + caddr + 4, clen - 8});     // without signature and checksum
+                    } else if (m.type != 0) {
+                        msgs.push_back(std::move(m));
+                    }
+                }
+            }
+            return msgs;
+        }
+        // ---- version 1
+        if (head[0] != 1) throw Error(path_ + ": unsupported object header version " + std::to_string(head[0]));
+        const int n_msgs = (int)detail::le(&head[2], 2);
+        const uint64_t hsize = detail::le(&head[8], 4);
+        std::vector<std::pair<uint64_t, uint64_t>> blocks{{base_ + addr + 16, hsize}};
+        int seen = 0;
+        for (size_t bi = 0; bi < blocks.size() && seen < n_msgs; bi++) {
+            std::vector<unsigned char> blk = bytes_at(blocks[bi].first, blocks[bi].second);
+            size_t q = 0;
+            while (q + 8 <= blk.size() && seen < n_msgs) {
+                Message m;
+                m.type = (int)detail::le(&blk[q], 2);
+                size_t sz2 = detail::le(&blk[q + 2], 2);
+                m.flags = blk[q + 4];
+                q += 8;
+                if (q + sz2 > blk.size()) throw Error(path_ + ": object header message overruns its block");
+                m.data.assign(blk.begin() + q, blk.begin() + q + sz2);
+                q += sz2;
+                seen++;
+                if (m.type == 0x10) blocks.push_back({base_ + offs(m.data.data()), lens(m.data.data() + so_)});
+                else if (m.type != 0) msgs.push_back(std::move(m));
+            }
+        }
+        return msgs;
+    }
+
+    std::string heap_string(uint64_t heap_addr, uint64_t offset) const
+    {
+        unsigned char h[8 + 3 * 8];
+        read_at(base_ + heap_addr, h, 8 + sl_ * 2 + so_);
+        if (memcmp(h, "HEAP", 4) != 0) throw Error(path_ + ": bad local heap");
+        const uint64_t seg_size = lens(&h[8]), seg = offs(&h[8 + 2 * sl_]);
+        if (offset >= seg_size) throw Error(path_ + ": heap offset out of range");
+        std::vector<unsigned char> s = bytes_at(base_ + seg + offset, std::min<uint64_t>(seg_size - offset, 1024));
+        return std::string(reinterpret_cast<const char *>(s.data()), strnlen(reinterpret_cast<const char *>(s.data()), s.size()));
+    }
+
+    void walk_btree_group(uint64_t node, uint64_t heap, std::vector<std::pair<std::string, uint64_t>> &out, int depth) const
+    {
+        if (depth > 32) throw Error(path_ + ": group B-tree too deep");
+        unsigned char h[8 + 16];
+        read_at(base_ + node, h, 8 + 2 * so_);
+        if (memcmp(h, "SNOD", 4) == 0) {
+            const int n = (int)detail::le(&h[6], 2);
+            const size_t esz = 2 * so_ + 8 + 16;
+            std::vector<unsigned char> e = bytes_at(base_ + node + 8, (uint64_t)n * esz);
+            for (int i = 0; i < n; i++) {
+                const unsigned char *p = &e[i * esz];
+                out.push_back({heap_string(heap, offs(p)), offs(p + so_)});
+            }
+            return;
+        }
+        if (memcmp(h, "TREE", 4) != 0 || h[4] != 0) throw Error(path_ + ": bad group B-tree node");
+        const int used = (int)detail::le(&h[6], 2);
+        std::vector<unsigned char> body = bytes_at(base_ + node + 8 + 2 * so_, (uint64_t)used * (sl_ + so_) + sl_);
+        for (int i = 0; i < used; i++) walk_btree_group(offs(&body[i * (sl_ + so_) + sl_]), heap, out, depth + 1);
+    }
+
+    TypeInfo parse_type(const unsigned char *p, size_t n) const
+    {
+        if (n < 8) throw Error(path_ + ": short datatype message");
+        TypeInfo t;
+        t.cls = p[0] & 0x0f;
+        t.size = (uint32_t)detail::le(p + 4, 4);
+        if (t.cls == 0) {
+            t.big_endian = p[1] & 1;
+            t.is_signed = p[1] & 8;
+        } else if (t.cls == 1) {
+            t.big_endian = p[1] & 1;
+            if (p[1] & 0x40) throw Error(path_ + ": VAX byte order is not supported");
+            if (n >= 20) {
+                const int eloc = p[12], esz = p[13], mloc = p[14], msz = p[15];
+                const uint32_t bias = (uint32_t)detail::le(p + 16, 4);
+                t.is_ieee = (t.size == 8 && eloc == 52 && esz == 11 && mloc == 0 && msz == 52 && bias == 1023) ||
+                            (t.size == 4 && eloc == 23 && esz == 8 && mloc == 0 && msz == 23 && bias == 127);
+            }
+            if (!t.is_ieee) throw Error(path_ + ": non-IEEE floating-point type");
+        }
+        return t;
+    }
+    static std::vector<uint64_t> parse_space(const unsigned char *p, size_t n, uint64_t sl)
+    {
+        std::vector<uint64_t> dims;
+        if (n < 4) return dims;
+        const int version = p[0], rank = p[1];
+        size_t q = version == 1 ? 8 : 4;
+        if (version != 1 && version != 2) throw Error("unsupported dataspace version");
+        for (int i = 0; i < rank; i++) dims.push_back(detail::le(p + q + i * sl, (int)sl));
+        return dims;
+    }
+
+    void walk_group(uint64_t header, const std::string &prefix, int depth)
+    {
+        if (depth > 16) throw Error(path_ + ": groups nested too deeply");
+        std::vector<Message> msgs = object_header(header);
+        std::vector<std::pair<std::string, uint64_t>> children;
+        for (const Message &m : msgs) {
+            if (m.type == 0x11) {                             // symbol table: B-tree + local heap
+                walk_btree_group(offs(m.data.data()), offs(m.data.data() + so_), children, 0);
+            } else if (m.type == 0x06) {                      // link message (compact new-style group)
+                const unsigned char *p = m.data.data();
+                const int flags = p[1];
+                size_t q = 2;
+                int ltype = 0;
+                if (flags & 0x08) ltype = p[q++];
+                if (flags & 0x04) q += 8;
+                if (flags & 0x10) q++;
+                const int nlen = 1 << (flags & 3);
+                const uint64_t len = detail::le(p + q, nlen);
+                q += nlen;
+                std::string name(reinterpret_cast<const char *>(p + q), len);
+                q += len;
+                if (ltype == 0) children.push_back({name, offs(p + q)});     // hard links only
+            } else if (m.type == 0x02) {                      // link info: dense storage?
+                const unsigned char *p = m.data.data();
+                size_t q = 2 + ((p[1] & 1) ? 8 : 0);
+                if (offs(p + q) != UNDEF) throw Error(path_ + ": group '" + prefix + "' uses dense link storage (fractal heap), which h5lite does not read");
+            }
+        }
+        for (auto &c : children) {
+            std::vector<Message> cm = object_header(c.second);
+            bool is_dataset = false, is_group = false;
+            for (const Message &m : cm) {
+                if (m.type == 0x08) is_dataset = true;
+                if (m.type == 0x11 || m.type == 0x02 || m.type == 0x06) is_group = true;
+            }
+            const std::string full = prefix.empty() ? c.first : prefix + "/" + c.first;
+            if (is_dataset) add_dataset(full, cm);
+            else if (is_group) walk_group(c.second, full, depth + 1);
+        }
+    }
+
+    void add_dataset(const std::string &name, const std::vector<Message> &msgs)
+    {
+        DatasetInfo d;
+        d.name = name;
+        for (const Message &m : msgs) {
+            const unsigned char *p = m.data.data();
+            const size_t n = m.data.size();
+            if (m.type == 0x01) d.dims = parse_space(p, n, sl_);
+            else if (m.type == 0x03) d.type = parse_type(p, n);
+            else if (m.type == 0x08) {
+                const int version = p[0];
+                if (version == 3) {
+                    d.layout = p[1];
+                    if (d.layout == 0) {
+                        size_t sz = detail::le(p + 2, 2);
+                        d.compact.assign(p + 4, p + 4 + sz);
+                    } else if (d.layout == 1) {
+                        d.address = offs(p + 2);
+                        d.size = lens(p + 2 + so_);
+                    } else if (d.layout == 2) {
+                        const int dim = p[2];
+                        d.address = offs(p + 3);
+                        for (int i = 0; i + 1 < dim; i++) d.chunk.push_back((uint32_t)detail::le(p + 3 + so_ + 4 * i, 4));
+                    }
+                } else if (version == 1 || version == 2) {
+                    const int dim = p[1];
+                    d.layout = p[2];
+                    size_t q = 8;
+                    if (d.layout != 0) { d.address = offs(p + q); q += so_; }
+                    std::vector<uint32_t> sizes;
+                    for (int i = 0; i < dim; i++) sizes.push_back((uint32_t)detail::le(p + q + 4 * i, 4));
+                    q += 4 * dim;
+                    if (d.layout == 2) { sizes.pop_back(); d.chunk = sizes; }      // last entry: element size
+                    else if (d.layout == 1) d.size = UNDEF;                          // extent = dataspace x element size
+                    else { size_t sz = detail::le(p + q, 4); d.compact.assign(p + q + 4, p + q + 4 + sz); }
+                } else {
+                    throw Error(name + ": data layout message version " + std::to_string(version) + " is not supported");
+                }
+            } else if (m.type == 0x0b) {
+                const int version = p[0], nf = p[1];
+                size_t q = version == 1 ? 8 : 2;
+                for (int i = 0; i < nf; i++) {
+                    Filter f;
+                    f.id = (int)detail::le(p + q, 2);
+                    size_t name_len = 0;
+                    if (version == 1 || f.id >= 256) { name_len = detail::le(p + q + 2, 2); q += 4; } else q += 2;
+                    q += 2;                                  // flags
+                    const int nc = (int)detail::le(p + q, 2);
+                    q += 2;
+                    q += version == 1 ? ((name_len + 7) & ~size_t(7)) : name_len;
+                    for (int k = 0; k < nc; k++) f.client.push_back((uint32_t)detail::le(p + q + 4 * k, 4));
+                    q += 4 * nc;
+                    if (version == 1 && (nc & 1)) q += 4;
+                    d.filters.push_back(f);
+                }
+            } else if (m.type == 0x0c) {
+                parse_attribute(p, n, d.attrs);
+            }
+        }
+        if (d.layout < 0) throw Error(name + ": dataset without a layout message");
+        sets_[name] = d;
+        order_.push_back(name);
+    }
+
+    void parse_attribute(const unsigned char *p, size_t n, std::map<std::string, Attribute> &out) const
+    {
+        const int version = p[0];
+        if (version < 1 || version > 3) return;
+        const size_t name_sz = detail::le(p + 2, 2), type_sz = detail::le(p + 4, 2), space_sz = detail::le(p + 6, 2);
+        size_t q = version == 3 ? 9 : 8;
+        auto pad = [&](size_t x) { return version == 1 ? ((x + 7) & ~size_t(7)) : x; };
+        if (q + pad(name_sz) + pad(type_sz) + pad(space_sz) > n) return;
+        std::string name(reinterpret_cast<const char *>(p + q), strnlen(reinterpret_cast<const char *>(p + q), name_sz));
+        q += pad(name_sz);
+        Attribute a;
+        try {
+            a.type = parse_type(p + q, type_sz);
+        } catch (const Error &) {
+            return;                                          // attribute of a type h5lite does not decode: skipped
+        }
+        q += pad(type_sz);
+        a.dims = parse_space(p + q, space_sz, sl_);
+        q += pad(space_sz);
+        uint64_t cnt = 1;
+        for (uint64_t d : a.dims) cnt *= d;
+        if (a.type.cls != 0 && a.type.cls != 1 && a.type.cls != 3) return;
+        if (q + cnt * a.type.size > n) return;
+        a.raw.assign(p + q, p + q + cnt * a.type.size);
+        out[name] = a;
+    }
+
+    void read_chunks(const DatasetInfo &d, uint64_t node, std::vector<unsigned char> &out) const
+    {
+        const int rank = (int)d.dims.size();
+        unsigned char h[8 + 16];
+        read_at(base_ + node, h, 8 + 2 * so_);
+        if (memcmp(h, "TREE", 4) != 0 || h[4] != 1) throw Error(d.name + ": bad chunk B-tree node");
+        const int level = h[5], used = (int)detail::le(&h[6], 2);
+        const size_t key = 8 + 8 * (rank + 1);
+        std::vector<unsigned char> body = bytes_at(base_ + node + 8 + 2 * so_, (uint64_t)used * (key + so_) + key);
+        for (int i = 0; i < used; i++) {
+            const unsigned char *k = &body[i * (key + so_)];
+            const uint64_t child = offs(k + key);
+            if (level > 0) { read_chunks(d, child, out); continue; }
+            const uint32_t csize = (uint32_t)detail::le(k, 4), mask = (uint32_t)detail::le(k + 4, 4);
+            std::vector<uint64_t> off(rank);
+            for (int r = 0; r < rank; r++) off[r] = detail::le(k + 8 + 8 * r, 8);
+            std::vector<unsigned char> buf = bytes_at(base_ + child, csize);
+            for (int f = (int)d.filters.size() - 1; f >= 0; f--) {
+                if (mask & (1u << f)) continue;
+                buf = unfilter(d, d.filters[f], buf);
+            }
+            uint64_t celems = 1;
+            for (uint32_t c : d.chunk) celems *= c;
+            if (buf.size() < celems * d.type.size) throw Error(d.name + ": chunk shorter than its dimensions");
+            scatter_chunk(d, off, buf, out);
+        }
+    }
+    std::vector<unsigned char> unfilter(const DatasetInfo &d, const Filter &f, const std::vector<unsigned char> &in) const
+    {
+        if (f.id == 1) {                                      // deflate
+            uint64_t celems = 1;
+            for (uint32_t c : d.chunk) celems *= c;
+            std::vector<unsigned char> out(celems * d.type.size + 64);
+            for (;;) {
+                uLongf len = (uLongf)out.size();
+                int rc = uncompress(out.data(), &len, in.data(), (uLong)in.size());
+                if (rc == Z_OK) { out.resize(len); return out; }
+                if (rc != Z_BUF_ERROR || out.size() > (1ull << 32)) throw Error(d.name + ": corrupt deflate stream");
+                out.resize(out.size() * 2);
+            }
+        }
+        if (f.id == 2) {                                      // shuffle: byte planes -> elements
+            const size_t es = f.client.empty() ? d.type.size : f.client[0], n = es ? in.size() / es : 0;
+            std::vector<unsigned char> out(in.size());
+            for (size_t b = 0; b < es; b++)
+                for (size_t i = 0; i < n; i++) out[i * es + b] = in[b * n + i];
+            for (size_t i = n * es; i < in.size(); i++) out[i] = in[i];
+            return out;
+        }
+        if (f.id == 3) return std::vector<unsigned char>(in.begin(), in.end() - std::min<size_t>(4, in.size()));   // fletcher32 trailer
+        throw Error(d.name + ": filter " + std::to_string(f.id) + " is not supported");
+    }
+    void scatter_chunk(const DatasetInfo &d, const std::vector<uint64_t> &off, const std::vector<unsigned char> &buf,
+                       std::vector<unsigned char> &out) const
+    {
+        const int rank = (int)d.dims.size();
+        const size_t es = d.type.size;
+        if (rank == 0) { memcpy(out.data(), buf.data(), es); return; }
+        // rows of the innermost dimension are contiguous in both the chunk and the dataset
+        std::vector<uint64_t> idx(rank, 0);
+        const uint64_t inner = d.chunk[rank - 1];
+        for (;;) {
+            bool inside = true;
+            uint64_t dst = 0, src = 0;
+            for (int r = 0; r < rank; r++) {
+                uint64_t g = off[r] + idx[r];
+                if (r < rank - 1 && g >= d.dims[r]) inside = false;
+                dst = dst * d.dims[r] + (r < rank - 1 ? g : off[r]);
+                src = src * d.chunk[r] + idx[r];
+            }
+            if (inside && off[rank - 1] < d.dims[rank - 1]) {
+                uint64_t len = std::min<uint64_t>(inner, d.dims[rank - 1] - off[rank - 1]);
+                memcpy(out.data() + dst * es, buf.data() + src * es, len * es);
+            }
+            int r = rank - 2;
+            for (; r >= 0; r--) {
+                if (++idx[r] < d.chunk[r]) break;
+                idx[r] = 0;
+            }
+            if (r < 0) break;
+        }
+    }
+
+    std::string path_;
+    int fd_ = -1, sb_version_ = 0, so_ = 8, sl_ = 8;
+    uint64_t file_size_ = 0, base_ = 0, root_header_ = UNDEF;
+    std::map<std::string, DatasetInfo> sets_;
+    std::vector<std::string> order_;
+};
+
+// ------------------------------------------------------------------------------------------ writer
+enum class DType { I32, I64, F32, F64 };
+
+class Writer {
+public:
+    explicit Writer(const std::string &path) : path_(path) {}
+    // data is borrowed until close(); op2_attrs adds OP2's "size" / "dim" / "type" attributes (op_decl_*_hdf5 conventions)
+    void add(const std::string &name, DType t, const std::vector<uint64_t> &dims, const void *data, bool op2_attrs = true)
+    {
+        if (name.empty() || name.find('/') != std::string::npos) throw Error("h5lite::Writer: dataset names are plain root-group names");
+        for (const Item &i : items_)
+            if (i.name == name) throw Error("h5lite::Writer: duplicate dataset " + name);
+        items_.push_back({name, t, dims, data, op2_attrs, 0, 0});
+    }
+    void close()
+    {
+        std::sort(items_.begin(), items_.end(), [](const Item &a, const Item &b) { return a.name < b.name; });
+        if (items_.size() > 256) throw Error("h5lite::Writer: more than 256 datasets");
+        // ---- local heap: the empty string at offset 0, then the names, each padded to 8 bytes
+        std::vector<unsigned char> heap(8, 0);
+        std::vector<uint64_t> name_off;
+        for (const Item &i : items_) {
+            name_off.push_back(heap.size());
+            heap.insert(heap.end(), i.name.begin(), i.name.end());
+            heap.push_back(0);
+            while (heap.size() % 8) heap.push_back(0);
+        }
+        // ---- layout of the metadata
+        const int LEAF_K = 4, INTERNAL_K = 16;
+        const size_t per_snod = 2 * LEAF_K, n_snod = std::max<size_t>(1, (items_.size() + per_snod - 1) / per_snod);
+        uint64_t pos = 96;                                   // superblock v0
+        const uint64_t root_hdr = pos; pos += 16 + 8 + 16;   // prefix + symbol table message
+        const uint64_t heap_hdr = pos; pos += 32;
+        const uint64_t heap_seg = pos; pos += heap.size();
+        const uint64_t btree = pos; pos += 24 + (2 * INTERNAL_K + 1) * 8 + 2 * INTERNAL_K * 8;
+        const uint64_t snod0 = pos; pos += n_snod * (8 + per_snod * 40);
+        std::vector<std::vector<unsigned char>> headers;
+        for (Item &i : items_) {
+            headers.push_back(dataset_header(i, 0));         // sized with a dummy data address
+            i.header = pos;
+            pos += headers.back().size();
+        }
+        for (Item &i : items_) {
+            pos = (pos + 7) & ~7ull;
+            i.data_addr = pos;
+            pos += bytes_of(i);
+        }
+        const uint64_t eof = pos;
+        for (size_t k = 0; k < items_.size(); k++) headers[k] = dataset_header(items_[k], items_[k].data_addr);
+
+        FILE *f = fopen(path_.c_str(), "wb");
+        if (!f) throw Error("cannot create " + path_);
+        std::vector<unsigned char> m;
+        // ---- superblock, version 0
+        put(m, "\x89HDF\r\n\x1a\n", 8);
+        put8(m, 0); put8(m, 0); put8(m, 0); put8(m, 0); put8(m, 0);     // versions: superblock, free space, root entry, reserved, shared header
+        put8(m, 8); put8(m, 8); put8(m, 0);                             // sizes of offsets and lengths, reserved
+        put16(m, LEAF_K); put16(m, INTERNAL_K);
+        put32(m, 0);                                                    // file consistency flags
+        put64(m, 0); put64(m, UNDEF); put64(m, eof); put64(m, UNDEF);   // base, free-space info, end of file, driver info
+        put64(m, 0); put64(m, root_hdr); put32(m, 1); put32(m, 0); put64(m, btree); put64(m, heap_hdr);   // root symbol table entry
+        // ---- root group object header: one symbol table message
+        put8(m, 1); put8(m, 0); put16(m, 1); put32(m, 1); put32(m, 24); put32(m, 0);
+        put16(m, 0x11); put16(m, 16); put8(m, 0); put8(m, 0); put16(m, 0);
+        put64(m, btree); put64(m, heap_hdr);
+        // ---- local heap
+        put(m, "HEAP", 4); put8(m, 0); put8(m, 0); put16(m, 0);
+        put64(m, heap.size()); put64(m, 1 /* H5HL_FREE_NULL: no free block */); put64(m, heap_seg);
+        m.insert(m.end(), heap.begin(), heap.end());
+        // ---- group B-tree: one leaf-level node pointing at the symbol nodes
+        put(m, "TREE", 4); put8(m, 0); put8(m, 0); put16(m, (int)n_snod);
+        put64(m, UNDEF); put64(m, UNDEF);
+        size_t written = 0;
+        put64(m, 0);                                                    // key 0: the empty string
+        for (size_t s = 0; s < n_snod; s++) {
+            put64(m, snod0 + s * (8 + per_snod * 40));
+            size_t last = std::min(items_.size(), (s + 1) * per_snod);
+            put64(m, items_.empty() ? 0 : name_off[last - 1]);          // key s+1: largest name in child s
+            written++;
+        }
+        for (size_t s = written; s < 2 * (size_t)INTERNAL_K; s++) { put64(m, 0); put64(m, 0); }
+        // ---- symbol nodes
+        for (size_t s = 0; s < n_snod; s++) {
+            size_t lo = s * per_snod, hi = std::min(items_.size(), lo + per_snod);
+            put(m, "SNOD", 4); put8(m, 1); put8(m, 0); put16(m, (int)(hi - lo));
+            for (size_t k = lo; k < hi; k++) {
+                put64(m, name_off[k]); put64(m, items_[k].header); put32(m, 0); put32(m, 0); put64(m, 0); put64(m, 0);
+            }
+            for (size_t k = hi; k < lo + per_snod; k++)
+                for (int z = 0; z < 5; z++) put64(m, 0);
+        }
+        for (auto &h : headers) m.insert(m.end(), h.begin(), h.end());
+        bool ok = fwrite(m.data(), 1, m.size(), f) == m.size();
+        uint64_t at = m.size();
+        static const unsigned char zeros[8] = {0};
+        for (const Item &i : items_) {
+            ok = ok && fwrite(zeros, 1, i.data_addr - at, f) == i.data_addr - at;
+            uint64_t nb = bytes_of(i);
+            ok = ok && (nb == 0 || fwrite(i.data, 1, nb, f) == nb);
+            at = i.data_addr + nb;
+        }
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw Error("write error on " + path_);
+        items_.clear();
+    }
+
+private:
+    struct Item {
+        std::string name;
+        DType t;
+        std::vector<uint64_t> dims;
+        const void *data;
+        bool op2_attrs;
+        uint64_t header, data_addr;
+    };
+    static size_t elem(DType t) { return (t == DType::I32 || t == DType::F32) ? 4 : 8; }
+    static uint64_t bytes_of(const Item &i)
+    {
+        uint64_t n = elem(i.t);
+        for (uint64_t d : i.dims) n *= d;
+        return n;
+    }
+    static void put(std::vector<unsigned char> &m, const char *p, size_t n) { m.insert(m.end(), p, p + n); }
+    static void put8(std::vector<unsigned char> &m, int v) { m.push_back((unsigned char)v); }
+    static void put16(std::vector<unsigned char> &m, int v) { for (int i = 0; i < 2; i++) m.push_back((unsigned char)(v >> (8 * i))); }
+    static void put32(std::vector<unsigned char> &m, uint32_t v) { for (int i = 0; i < 4; i++) m.push_back((unsigned char)(v >> (8 * i))); }
+    static void put64(std::vector<unsigned char> &m, uint64_t v) { for (int i = 0; i < 8; i++) m.push_back((unsigned char)(v >> (8 * i))); }
+    static void pad8(std::vector<unsigned char> &m) { while (m.size() % 8) m.push_back(0); }
+
+    static std::vector<unsigned char> type_msg(DType t)
+    {
+        std::vector<unsigned char> m;
+        if (t == DType::I32 || t == DType::I64) {
+            put8(m, 0x10); put8(m, 0x08); put8(m, 0); put8(m, 0);                   // version 1 | class 0; little-endian, signed
+            put32(m, (uint32_t)elem(t));
+            put16(m, 0); put16(m, (int)(8 * elem(t)));                              // bit offset, precision
+        } else {
+            const bool dbl = t == DType::F64;
+            put8(m, 0x11); put8(m, 0x20); put8(m, dbl ? 63 : 31); put8(m, 0);       // version 1 | class 1; LE, implied-msb mantissa, sign bit
+            put32(m, dbl ? 8 : 4);
+            put16(m, 0); put16(m, dbl ? 64 : 32);
+            put8(m, dbl ? 52 : 23); put8(m, dbl ? 11 : 8); put8(m, 0); put8(m, dbl ? 52 : 23);
+            put32(m, dbl ? 1023 : 127);
+        }
+        return m;
+    }
+    static std::vector<unsigned char> space_msg(const std::vector<uint64_t> &dims)
+    {
+        std::vector<unsigned char> m;
+        put8(m, 1); put8(m, (int)dims.size()); put8(m, 0); put8(m, 0); put32(m, 0);
+        for (uint64_t d : dims) put64(m, d);
+        return m;
+    }
+    static void message(std::vector<unsigned char> &h, int type, std::vector<unsigned char> data, int &count)
+    {
+        pad8(data);
+        put16(h, type); put16(h, (int)data.size()); put8(h, 0); put8(h, 0); put16(h, 0);
+        h.insert(h.end(), data.begin(), data.end());
+        count++;
+    }
+    static std::vector<unsigned char> attribute(const std::string &name, std::vector<unsigned char> type,
+                                                std::vector<unsigned char> space, std::vector<unsigned char> value)
+    {
+        std::vector<unsigned char> a, nm(name.begin(), name.end());
+        nm.push_back(0);
+        put8(a, 1); put8(a, 0); put16(a, (int)nm.size()); put16(a, (int)type.size()); put16(a, (int)space.size());
+        pad8(nm); pad8(type); pad8(space);
+        a.insert(a.end(), nm.begin(), nm.end());
+        a.insert(a.end(), type.begin(), type.end());
+        a.insert(a.end(), space.begin(), space.end());
+        a.insert(a.end(), value.begin(), value.end());
+        return a;
+    }
+    static std::vector<unsigned char> int_attr(const std::string &name, int32_t v)
+    {
+        std::vector<unsigned char> val;
+        put32(val, (uint32_t)v);
+        return attribute(name, type_msg(DType::I32), space_msg({1}), val);
+    }
+    static std::vector<unsigned char> str_attr(const std::string &name, const std::string &s)
+    {
+        std::vector<unsigned char> t, val(s.begin(), s.end());
+        val.push_back(0);
+        put8(t, 0x13); put8(t, 0x00); put8(t, 0); put8(t, 0);       // version 1 | class 3; null-terminated ASCII
+        put32(t, (uint32_t)val.size());
+        return attribute(name, t, space_msg({}), val);              // scalar dataspace, as H5LTset_attribute_string
+    }
+    static std::vector<unsigned char> dataset_header(const Item &i, uint64_t data_addr)
+    {
+        std::vector<unsigned char> body;
+        int count = 0;
+        message(body, 0x01, space_msg(i.dims), count);
+        message(body, 0x03, type_msg(i.t), count);
+        {
+            std::vector<unsigned char> fill;
+            put8(fill, 2); put8(fill, 2); put8(fill, 2); put8(fill, 0);             // v2: allocate late, write if set, no value
+            message(body, 0x05, fill, count);
+        }
+        {
+            std::vector<unsigned char> lay;
+            put8(lay, 3); put8(lay, 1);                                             // v3, contiguous
+            put64(lay, bytes_of(i) ? data_addr : UNDEF); put64(lay, bytes_of(i));
+            message(body, 0x08, lay, count);
+        }
+        if (i.op2_attrs) {
+            const char *tname = i.t == DType::I32 ? "int" : i.t == DType::I64 ? "long" : i.t == DType::F32 ? "float" : "double";
+            uint64_t dim = 1;
+            for (size_t k = 1; k < i.dims.size(); k++) dim *= i.dims[k];
+            message(body, 0x0c, int_attr("size", (int32_t)(i.dims.empty() ? 1 : i.dims[0])), count);
+            message(body, 0x0c, int_attr("dim", (int32_t)dim), count);
+            message(body, 0x0c, str_attr("type", tname), count);
+        }
+        std::vector<unsigned char> h;
+        put8(h, 1); put8(h, 0); put16(h, count); put32(h, 1); put32(h, (uint32_t)body.size()); put32(h, 0);
+        h.insert(h.end(), body.begin(), body.end());
+        return h;
+    }
+
+    std::string path_;
+    std::vector<Item> items_;
+};
+
+}  // namespace h5lite

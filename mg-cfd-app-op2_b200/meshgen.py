@@ -257,13 +257,83 @@ def read_container(path):
     return out
 
 
-def write_deck(directory, mesh, stem="mesh"):
-    """input.dat (io.h:28-205 format) + one level file per multigrid level"""
+# ---- HDF5 level / solution files through the library's own from-scratch HDF5 subset (include/mgcfd_h5.h; the image
+# has no libhdf5 / h5py).  Datasets carry OP2's "size" / "dim" / "type" attributes (op_decl_*_hdf5 conventions).
+_H5 = None
+
+
+def _h5lib():
+    global _H5
+    if _H5 is None:
+        import ctypes as C
+        lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmgcfd_h5.so"))
+        lib.mgcfd_h5_open.restype = C.c_void_p
+        lib.mgcfd_h5_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        lib.mgcfd_h5_close.argtypes = [C.c_void_p]
+        lib.mgcfd_h5_count.argtypes = [C.c_void_p]
+        lib.mgcfd_h5_name.restype = C.c_char_p
+        lib.mgcfd_h5_name.argtypes = [C.c_void_p, C.c_int]
+        lib.mgcfd_h5_info.argtypes = [C.c_void_p, C.c_char_p] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_ulonglong)]
+        lib.mgcfd_h5_read_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
+        lib.mgcfd_h5_read_i32.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
+        lib.mgcfd_h5_create.restype = C.c_void_p
+        lib.mgcfd_h5_create.argtypes = [C.c_char_p]
+        lib.mgcfd_h5_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_void_p]
+        lib.mgcfd_h5_finish.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _H5 = lib
+    return _H5
+
+
+def write_h5(path, datasets):
+    import ctypes as C
+    lib = _h5lib()
+    w = lib.mgcfd_h5_create(path.encode())
+    keep = []
+    for name, arr in datasets.items():
+        a = np.ascontiguousarray(arr)
+        if a.dtype not in (np.float64, np.int32):
+            raise TypeError(f"{name}: only float64 / int32 datasets exist in MG-CFD decks")
+        keep.append(a)
+        dims = (C.c_ulonglong * 8)(*a.shape)
+        if lib.mgcfd_h5_add(w, name.encode(), 3 if a.dtype == np.float64 else 0, a.ndim, dims, a.ctypes.data) != 0:
+            raise ValueError(f"{path}: cannot add dataset {name}")
+    err = C.create_string_buffer(512)
+    if lib.mgcfd_h5_finish(w, err, 512) != 0:
+        raise OSError(err.value.decode())
+
+
+def read_h5(path):
+    import ctypes as C
+    lib = _h5lib()
+    err = C.create_string_buffer(512)
+    r = lib.mgcfd_h5_open(path.encode(), err, 512)
+    if not r:
+        raise ValueError(err.value.decode())
+    out = {}
+    try:
+        for i in range(lib.mgcfd_h5_count(r)):
+            name = lib.mgcfd_h5_name(r, i)
+            cls, es, sg, lay, rank = (C.c_int() for _ in range(5))
+            dims = (C.c_ulonglong * 8)()
+            lib.mgcfd_h5_info(r, name, cls, es, sg, lay, rank, dims)
+            shape = tuple(dims[k] for k in range(rank.value))
+            a = np.empty(shape, dtype=np.float64 if cls.value == 1 else np.int32)
+            read = lib.mgcfd_h5_read_f64 if cls.value == 1 else lib.mgcfd_h5_read_i32
+            if read(r, name, a.ctypes.data, err, 512) != 0:
+                raise ValueError(err.value.decode())
+            out[name.decode()] = a
+    finally:
+        lib.mgcfd_h5_close(r)
+    return out
+
+
+def write_deck(directory, mesh, stem="mesh", fmt="mgb"):
+    """input.dat (io.h:28-205 format) + one level file per multigrid level (fmt "mgb": container, "h5": HDF5)"""
     os.makedirs(directory, exist_ok=True)
     names = []
     for l, lev in enumerate(mesh["levels"]):
-        names.append(f"{stem}.L{l}.mgb")
-        write_container(os.path.join(directory, names[-1]), lev)
+        names.append(f"{stem}.L{l}.{fmt}")
+        (write_h5 if fmt == "h5" else write_container)(os.path.join(directory, names[-1]), lev)
     with open(os.path.join(directory, "input.dat"), "w") as f:
         f.write("# synthetic MG-CFD deck (meshgen.py)\n")
         f.write(f"size = {mesh['levels'][0]['node_coordinates'].shape[0]}\n")
@@ -276,8 +346,8 @@ def write_deck(directory, mesh, stem="mesh"):
     return os.path.join(directory, "input.dat")
 
 
-def write_solution(directory, level, cycles, variables, prefix="solution."):
+def write_solution(directory, level, cycles, variables, prefix="solution.", fmt="mgb"):
     """solution.variables.L<l>.cycles=<g> with dataset p_variables_result_L<l> (euler3d.cpp:315-327, 765-771)"""
-    path = os.path.join(directory, f"{prefix}variables.L{level}.cycles={cycles}.mgb")
-    write_container(path, {f"p_variables_result_L{level}": np.ascontiguousarray(variables, dtype=np.float64)})
+    path = os.path.join(directory, f"{prefix}variables.L{level}.cycles={cycles}.{fmt}")
+    (write_h5 if fmt == "h5" else write_container)(path, {f"p_variables_result_L{level}": np.ascontiguousarray(variables, dtype=np.float64)})
     return path

@@ -51,3 +51,21 @@ def test_driver_argument_errors(tmp_path):
     assert p.returncode == 1 and "input_file not set" in p.stdout
     p = subprocess.run([EXE, "-i", "missing.dat", "-d", str(tmp_path)], capture_output=True, text=True)
     assert p.returncode == 1 and "Could not open input file" in p.stderr
+
+
+def test_driver_hdf5_deck_end_to_end(tmp_path, meshgen, golden):
+    """the reference's own file formats end to end: HDF5 level files in, -v against solution.variables.L<l>.cycles=<g>.h5
+    (euler3d.cpp:314-335), --output-variables written as HDF5 (op_fetch_data_hdf5_file, euler3d.cpp:740-770)"""
+    mesh = meshgen.make_multigrid("small")
+    meshgen.write_deck(str(tmp_path), mesh, fmt="h5")
+    g = golden("small_cycles10.npz")
+    for l in range(len(mesh["levels"])):
+        meshgen.write_solution(str(tmp_path), l, 10, g[f"var_L{l}"], fmt="h5")
+    out = os.path.join(str(tmp_path), "out.")
+    cmd = [EXE, "-i", "input.dat", "-d", str(tmp_path), "-g", "10", "-v", "--output-variables", "-o", out, "--exact"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Validation passed" in p.stdout
+    for l in range(len(mesh["levels"])):
+        got = meshgen.read_h5(f"{out}variables.L{l}.cycles=10.h5")[f"p_variables_result_L{l}"]
+        assert np.array_equal(got, g[f"var_L{l}"])
