@@ -163,6 +163,12 @@ int mgcfd_loop_down(mgcfd_ctx *ctx, int level);                                 
 typedef struct mgcfd_local_mesh mgcfd_local_mesh;
 /* recursive coordinate bisection of level-0 nodes (the reference offers "INERTIAL"/"GEOM" methods, :373-375) */
 int mgcfd_partition_rcb(int n_nodes, const double *node_coordinates, int n_parts, int *part_out);
+/* op_partition's library / method selection (euler3d.cpp:340-375, config.h:203-240) on level 0: method "geom" /
+ * "inertial" = mgcfd_partition_rcb; "kway" / "parmetis" / "ptscotch" / "geomkway" = recursive graph bisection refined by
+ * Fiduccia-Mattheyses passes (smaller edge cut than the coordinate split); "block" = contiguous index ranges;
+ * "random" = equal shares of a hashed node order.  Deterministic; MGCFD_ERR_ARG for an unknown method. */
+int mgcfd_partition_graph(int n_nodes, const double *node_coordinates, int n_edges, const int *edge_to_node,
+                          int base_array_index, int n_parts, const char *method, int *part_out);
 /* coarse node -> owner of its lowest-numbered child; childless -> owner of the nearest edge neighbour with children */
 int mgcfd_partition_coarse(int n_fine, const int *fine_part, const int *fine_to_coarse, int base_array_index, int n_coarse,
                            int n_coarse_edges, const int *coarse_edge_to_node, const double *coarse_coordinates,

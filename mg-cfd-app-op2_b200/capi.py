@@ -105,7 +105,7 @@ ABI_SYMBOLS = [
     "mgcfd_run_cycles", "mgcfd_fetch_dat", "mgcfd_set_dat", "mgcfd_sync", "mgcfd_validate_level",
     "mgcfd_plan_query", "mgcfd_timers_enable", "mgcfd_timers_reset", "mgcfd_timers_get",
     "mgcfd_kernel_launches", "mgcfd_set_flux_variant", "mgcfd_stream", "mgcfd_device_ptr",
-    "mgcfd_host_alloc", "mgcfd_host_free",
+    "mgcfd_host_alloc", "mgcfd_host_free", "mgcfd_partition_graph",
     "mgcfd_partition_rcb", "mgcfd_partition_coarse", "mgcfd_local_mesh_build", "mgcfd_local_mesh_level",
     "mgcfd_local_mesh_query", "mgcfd_local_mesh_free", "mgcfd_group_run_cycles", "mgcfd_nccl_unique_id",
     "mgcfd_comm_init_nccl", "mgcfd_halo_bytes_sent", "mgcfd_group_enable_p2p", "mgcfd_ipc_export", "mgcfd_comm_init_ipc",
@@ -178,15 +178,20 @@ def _level_struct(lev, keep):
     return h
 
 
-def partition_levels(levels, base_array_index, n_ranks):
-    """Owner rank of every node of every level (op_partition, euler3d.cpp:340-375): recursive coordinate bisection
-    on level 0, coarse nodes follow their lowest-numbered child."""
+def partition_levels(levels, base_array_index, n_ranks, method="geom"):
+    """Owner rank of every node of every level (op_partition, euler3d.cpp:340-375): level 0 by `method` ("geom":
+    recursive coordinate bisection, "kway": recursive graph bisection with FM refinement, "block", "random"), coarse
+    nodes follow their lowest-numbered child."""
     lib = load_library()
     parts = []
     for l, lev in enumerate(levels):
         coords = _as(lev["node_coordinates"], np.float64)
         part = np.empty(coords.shape[0], dtype=np.int32)
-        if l == 0:
+        if l == 0 and method != "geom":
+            e2n = _as(lev["edge-->node"], np.int32)
+            rc = lib.mgcfd_partition_graph(coords.shape[0], coords.ctypes.data_as(_dp), e2n.shape[0], e2n.ctypes.data_as(_ip),
+                                           int(base_array_index), int(n_ranks), method.encode(), part.ctypes.data_as(_ip))
+        elif l == 0:
             rc = lib.mgcfd_partition_rcb(coords.shape[0], coords.ctypes.data_as(_dp), int(n_ranks), part.ctypes.data_as(_ip))
         else:
             fine = levels[l - 1]

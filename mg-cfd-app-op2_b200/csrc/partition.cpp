@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 
+#include <set>
+#include <string>
+
 #include "mgcfd_b200.h"
 
 namespace {
@@ -58,6 +61,113 @@ void rcb(std::vector<int> &ids, int lo, int hi, int p0, int p1, const double *xy
     rcb(ids, lo + n_left, hi, p0 + left_parts, p1, xyz, part);
 }
 
+// ---------------------------------------------------------------------------------------
+// "kway": recursive graph bisection.  Every split starts from the coordinate bisection above and is refined by
+// Fiduccia-Mattheyses passes on the edges inside the subset (the role ParMETIS / PT-Scotch k-way play behind OP2's
+// op_partition(..., "KWAY", ...), euler3d.cpp:340-375).  Fully specified so that oracle/plan_oracle.py can restate it:
+//   * the left side must keep  n_left - tol <= size <= n_left + tol,  tol = max(1, |S| / 200);
+//   * gain(v) = edges of v to the other side - edges of v to its own side (inside S);
+//   * a pass moves, one at a time, the unlocked node of highest gain among those whose move keeps the balance (ties:
+//     lowest node id), locks it and updates its neighbours' gains; the pass stops
+//     after 64 moves without a new best cumulative gain or when no move is allowed, and is rolled back to the best
+//     prefix (first occurrence of the maximum);
+//   * passes repeat while the best prefix gains something, at most 8 times.
+// ---------------------------------------------------------------------------------------
+struct Graph {
+    std::vector<int> ptr, adj;
+};
+
+void fm_refine(const std::vector<int> &S, const Graph &g, std::vector<int> &stamp, int tag, std::vector<char> &side, int n_left)
+{
+    const int n = (int)S.size(), tol = std::max(1, n / 200);
+    static thread_local std::vector<int> gain;
+    static thread_local std::vector<char> locked;
+    if (gain.size() < stamp.size()) { gain.assign(stamp.size(), 0); locked.assign(stamp.size(), 0); }
+    int c0 = 0;
+    for (int v : S) c0 += side[v] == 0;
+    for (int pass = 0; pass < 8; pass++) {
+        std::set<std::pair<int, int>> heap[2];           // (-gain, id): begin() = highest gain, lowest id
+        for (int v : S) {
+            int gsum = 0;
+            for (int j = g.ptr[v]; j < g.ptr[v + 1]; j++) {
+                int u = g.adj[j];
+                if (stamp[u] != tag) continue;
+                gsum += side[u] != side[v] ? 1 : -1;
+            }
+            gain[v] = gsum;
+            locked[v] = 0;
+            heap[(int)side[v]].insert({-gsum, v});
+        }
+        std::vector<int> moves;
+        int cur = 0, best = 0, best_len = 0, c0_run = c0;
+        while ((int)moves.size() < n) {
+            // a move from side 0 shrinks side 0, a move from side 1 grows it
+            bool ok0 = !heap[0].empty() && c0_run - 1 >= n_left - tol, ok1 = !heap[1].empty() && c0_run + 1 <= n_left + tol;
+            if (!ok0 && !ok1) break;
+            int from = ok0 ? 0 : 1;
+            if (ok0 && ok1) from = *heap[1].begin() < *heap[0].begin() ? 1 : 0;     // higher gain, then lower id
+            auto top = *heap[from].begin();
+            heap[from].erase(heap[from].begin());
+            const int v = top.second;
+            locked[v] = 1;
+            cur += gain[v];
+            side[v] = (char)(1 - from);
+            c0_run += from == 0 ? -1 : 1;
+            for (int j = g.ptr[v]; j < g.ptr[v + 1]; j++) {
+                int u = g.adj[j];
+                if (stamp[u] != tag || locked[u]) continue;
+                heap[(int)side[u]].erase({-gain[u], u});
+                gain[u] += side[u] == from ? 2 : -2;     // u was on v's old side: the edge is cut now; else it is healed
+                heap[(int)side[u]].insert({-gain[u], u});
+            }
+            moves.push_back(v);
+            if (cur > best) { best = cur; best_len = (int)moves.size(); }
+            if ((int)moves.size() - best_len >= 64) break;
+        }
+        for (int i = (int)moves.size() - 1; i >= best_len; i--) side[moves[i]] = (char)(1 - side[moves[i]]);
+        c0 = 0;
+        for (int v : S) c0 += side[v] == 0;
+        if (best <= 0) break;
+    }
+}
+
+void graph_bisect(std::vector<int> &S, int p0, int p1, const double *xyz, const Graph &g, std::vector<int> &stamp, int &tag,
+                  std::vector<char> &side, int *part)
+{
+    if (p1 - p0 == 1) {
+        for (int v : S) part[v] = p0;
+        return;
+    }
+    const int n = (int)S.size();
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++)
+        for (int d = 0; d < 3; d++) {
+            double v = xyz[(size_t)S[i] * 3 + d];
+            if (i == 0 || v < mn[d]) mn[d] = v;
+            if (i == 0 || v > mx[d]) mx[d] = v;
+        }
+    int axis = 0;
+    for (int d = 1; d < 3; d++)
+        if (mx[d] - mn[d] > mx[axis] - mn[axis]) axis = d;
+    std::sort(S.begin(), S.end(), [&](int a, int b) {
+        double va = xyz[(size_t)a * 3 + axis], vb = xyz[(size_t)b * 3 + axis];
+        return va < vb || (va == vb && a < b);
+    });
+    const int left_parts = (p1 - p0) / 2;
+    const int n_left = (int)((long long)n * left_parts / (p1 - p0));
+    const int my_tag = ++tag;
+    for (int i = 0; i < n; i++) { side[S[i]] = i < n_left ? 0 : 1; stamp[S[i]] = my_tag; }
+    fm_refine(S, g, stamp, my_tag, side, n_left);
+    std::vector<int> L, R;
+    for (int v : S) (side[v] == 0 ? L : R).push_back(v);
+    std::sort(L.begin(), L.end());
+    std::sort(R.begin(), R.end());
+    S.clear();
+    S.shrink_to_fit();
+    graph_bisect(L, p0, p0 + left_parts, xyz, g, stamp, tag, side, part);
+    graph_bisect(R, p0 + left_parts, p1, xyz, g, stamp, tag, side, part);
+}
+
 }  // namespace
 
 struct mgcfd_local_mesh {
@@ -73,6 +183,56 @@ int mgcfd_partition_rcb(int n_nodes, const double *node_coordinates, int n_parts
     std::vector<int> ids(n_nodes);
     std::iota(ids.begin(), ids.end(), 0);
     rcb(ids, 0, n_nodes, 0, n_parts, node_coordinates, part_out);
+    return MGCFD_OK;
+}
+
+// op_partition's library / method selection (euler3d.cpp:340-375, config.h:203-240): "geom" (also "inertial") =
+// recursive coordinate bisection; "kway" (also "parmetis", "ptscotch", "geomkway") = recursive graph bisection with
+// Fiduccia-Mattheyses refinement; "block" = contiguous index ranges; "random" = equal shares of a hashed order.
+int mgcfd_partition_graph(int n_nodes, const double *node_coordinates, int n_edges, const int *edge_to_node, int base,
+                          int n_parts, const char *method, int *part_out)
+{
+    if (n_nodes < 0 || n_parts < 1 || !part_out || !method) return MGCFD_ERR_ARG;
+    std::string m(method);
+    for (char &c : m) c = (char)tolower(c);
+    if (m == "geom" || m == "inertial") return mgcfd_partition_rcb(n_nodes, node_coordinates, n_parts, part_out);
+    if (m == "block") {
+        for (int i = 0; i < n_nodes; i++) part_out[i] = (int)((long long)i * n_parts / std::max(n_nodes, 1));
+        return MGCFD_OK;
+    }
+    if (m == "random") {
+        std::vector<std::pair<uint64_t, int>> key(n_nodes);
+        for (int i = 0; i < n_nodes; i++) {
+            uint64_t z = (uint64_t)i + 0x9e3779b97f4a7c15ull;       // splitmix64
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            key[i] = {z ^ (z >> 31), i};
+        }
+        std::sort(key.begin(), key.end());
+        for (int r = 0; r < n_nodes; r++) part_out[key[r].second] = (int)((long long)r * n_parts / n_nodes);
+        return MGCFD_OK;
+    }
+    if (m != "kway" && m != "parmetis" && m != "ptscotch" && m != "geomkway") return MGCFD_ERR_ARG;
+    if ((n_nodes > 0 && !node_coordinates) || (n_edges > 0 && !edge_to_node)) return MGCFD_ERR_ARG;
+    Graph g;
+    g.ptr.assign(n_nodes + 1, 0);
+    for (int e = 0; e < n_edges; e++) {
+        int a = edge_to_node[2 * (size_t)e] - base, b = edge_to_node[2 * (size_t)e + 1] - base;
+        if (a < 0 || a >= n_nodes || b < 0 || b >= n_nodes) return MGCFD_ERR_ARG;
+        g.ptr[a + 1]++; g.ptr[b + 1]++;
+    }
+    for (int i = 0; i < n_nodes; i++) g.ptr[i + 1] += g.ptr[i];
+    g.adj.resize(2 * (size_t)n_edges);
+    std::vector<int> fill(g.ptr.begin(), g.ptr.end() - 1);
+    for (int e = 0; e < n_edges; e++) {
+        int a = edge_to_node[2 * (size_t)e] - base, b = edge_to_node[2 * (size_t)e + 1] - base;
+        g.adj[fill[a]++] = b; g.adj[fill[b]++] = a;
+    }
+    std::vector<int> S(n_nodes), stamp(n_nodes, 0);
+    std::iota(S.begin(), S.end(), 0);
+    std::vector<char> side(n_nodes, 0);
+    int tag = 0;
+    graph_bisect(S, 0, n_parts, node_coordinates, g, stamp, tag, side, part_out);
     return MGCFD_OK;
 }
 

@@ -205,6 +205,7 @@ struct Config {                               // config.h:64-103, defaults :129-
     int cycles = 25, flow_interval = 0, gpus = 1;
     bool validate = false, mem_bound = false, renumber = true, exact = false, loopwise = false, same_device = false;
     bool hdf5 = false, check_deck = false;
+    std::string partitioner, partitioner_method;   // -m / -r (config.h:203-240)
     int out_vars = 0, out_fluxes = 0, out_sf = 0;
 };
 
@@ -246,7 +247,9 @@ int main(int argc, char **argv)
         case 'b': conf.mem_bound = true; break;
         case 'I': conf.flow_interval = atoi(optarg); break;
         case 'n': conf.renumber = true; break;
-        case 'm': case 'r': case 'c': case 'p': break;       // OP2 partitioner / PAPI selections: accepted, not used
+        case 'm': conf.partitioner = optarg; break;          // block | random | parmetis | ptscotch | inertial
+        case 'r': conf.partitioner_method = optarg; break;   // geom | kway | geomkway
+        case 'c': case 'p': break;                           // config file / PAPI selections: accepted, not used
         case 'l': fprintf(stderr, "legacy mode (renumbered dataset names) is not supported\n"); return 1;
         case 1001: conf.gpus = atoi(optarg); break;
         case 1002: conf.variant = optarg; break;
@@ -344,9 +347,15 @@ int main(int argc, char **argv)
     if (P > 1) {
         printf("-----------------------------------------------------\nPartitioning ...\n");
         std::vector<const int *> pp(levels);
+        // op_partition(lib, method, ...) at euler3d.cpp:340-375: the method wins when given (geom | kway | geomkway),
+        // else the library name decides (parmetis / ptscotch are k-way partitioners, inertial is geometric)
+        std::string method = !conf.partitioner_method.empty() ? conf.partitioner_method
+                             : (!conf.partitioner.empty() ? conf.partitioner : std::string("geom"));
+        printf("partitioner: %s\n", method.c_str());
         for (int l = 0; l < levels; l++) {
             part[l].resize(lv[l].n_nodes);
-            int rc = l == 0 ? mgcfd_partition_rcb(lv[0].n_nodes, lv[0].node_coordinates, P, part[0].data())
+            int rc = l == 0 ? mgcfd_partition_graph(lv[0].n_nodes, lv[0].node_coordinates, lv[0].n_edges, lv[0].edge_to_node,
+                                                    deck.base, P, method.c_str(), part[0].data())
                             : mgcfd_partition_coarse(lv[l - 1].n_nodes, part[l - 1].data(), lv[l - 1].node_to_mg_node, deck.base,
                                                      lv[l].n_nodes, lv[l].n_edges, lv[l].edge_to_node, lv[l].node_coordinates,
                                                      part[l].data());

@@ -204,6 +204,99 @@ def rcb(coords, n_parts):
     return part
 
 
+def kway(coords, e2n0, n_parts):
+    """recursive graph bisection (partition.cpp "kway"): coordinate split of the subset, then Fiduccia-Mattheyses
+    passes on the edges inside it -- left side kept within max(1, |S|//200) of its share; a pass moves the unlocked node
+    of highest gain whose move keeps the balance (ties: lowest id), stops after 64 moves without a new best cumulative
+    gain, rolls back to the first best prefix; at most 8 passes, while a pass gains something"""
+    import heapq
+    n = coords.shape[0]
+    adj = [[] for _ in range(n)]
+    for a, b in np.asarray(e2n0).tolist():
+        adj[a].append(b)
+        adj[b].append(a)
+    part = np.empty(n, dtype=np.int32)
+
+    def refine(S, side, n_left):
+        inside = set(S)
+        tol = max(1, len(S) // 200)
+        c0 = sum(1 for v in S if side[v] == 0)
+        for _ in range(8):
+            gain, locked = {}, set()
+            heaps = ([], [])
+            for v in S:
+                g = 0
+                for u in adj[v]:
+                    if u in inside:
+                        g += 1 if side[u] != side[v] else -1
+                gain[v] = g
+                heapq.heappush(heaps[side[v]], (-g, v))
+
+            def top(s):
+                h = heaps[s]
+                while h and (h[0][1] in locked or -h[0][0] != gain[h[0][1]]):
+                    heapq.heappop(h)
+                return h[0] if h else None
+
+            moves, cur, best, best_len, run = [], 0, 0, 0, c0
+            while len(moves) < len(S):
+                t0, t1 = top(0), top(1)
+                ok0 = t0 is not None and run - 1 >= n_left - tol
+                ok1 = t1 is not None and run + 1 <= n_left + tol
+                if not ok0 and not ok1:
+                    break
+                frm = 0 if ok0 else 1
+                if ok0 and ok1:
+                    frm = 1 if t1 < t0 else 0
+                _, v = heapq.heappop(heaps[frm])
+                locked.add(v)
+                cur += gain[v]
+                side[v] = 1 - frm
+                run += -1 if frm == 0 else 1
+                for u in adj[v]:
+                    if u in inside and u not in locked:
+                        gain[u] += 2 if side[u] == frm else -2
+                        heapq.heappush(heaps[side[u]], (-gain[u], u))
+                moves.append(v)
+                if cur > best:
+                    best, best_len = cur, len(moves)
+                if len(moves) - best_len >= 64:
+                    break
+            for v in moves[best_len:]:
+                side[v] = 1 - side[v]
+            c0 = sum(1 for v in S if side[v] == 0)
+            if best <= 0:
+                break
+
+    def rec(ids, p0, p1):
+        if p1 - p0 == 1:
+            part[ids] = p0
+            return
+        c = coords[ids]
+        ext = c.max(axis=0) - c.min(axis=0) if ids.size else np.zeros(3)
+        axis = 0
+        for d in (1, 2):
+            if ext[d] > ext[axis]:
+                axis = d
+        order = ids[np.lexsort((ids, c[:, axis]))] if ids.size else ids
+        left_parts = (p1 - p0) // 2
+        n_left = (order.size * left_parts) // (p1 - p0)
+        side = {int(v): (0 if i < n_left else 1) for i, v in enumerate(order.tolist())}
+        refine(order.tolist(), side, n_left)
+        left = np.array(sorted(v for v in side if side[v] == 0), dtype=np.int64)
+        right = np.array(sorted(v for v in side if side[v] == 1), dtype=np.int64)
+        rec(left, p0, p0 + left_parts)
+        rec(right, p0 + left_parts, p1)
+
+    rec(np.arange(n, dtype=np.int64), 0, n_parts)
+    return part
+
+
+def edge_cut(part, e2n0):
+    e = np.asarray(e2n0)
+    return int((part[e[:, 0]] != part[e[:, 1]]).sum())
+
+
 def coarse_part(fine_part, fine_to_coarse0, n_coarse, coarse_e2n0, coarse_coords):
     part = np.full(n_coarse, -1, dtype=np.int32)
     parents, first = np.unique(fine_to_coarse0, return_index=True)     # first occurrence = lowest-numbered child
@@ -233,8 +326,11 @@ def coarse_part(fine_part, fine_to_coarse0, n_coarse, coarse_e2n0, coarse_coords
     return part
 
 
-def partition_levels(levels0, n_ranks):
-    parts = [rcb(np.asarray(levels0[0]["node_coordinates"]), n_ranks)]
+def partition_levels(levels0, n_ranks, method="geom"):
+    if method == "kway":
+        parts = [kway(np.asarray(levels0[0]["node_coordinates"]), levels0[0]["edge-->node"], n_ranks)]
+    else:
+        parts = [rcb(np.asarray(levels0[0]["node_coordinates"]), n_ranks)]
     for l in range(1, len(levels0)):
         parts.append(coarse_part(parts[l - 1], levels0[l - 1]["node-->mg_node"].reshape(-1),
                                  levels0[l]["node_coordinates"].shape[0], levels0[l]["edge-->node"],

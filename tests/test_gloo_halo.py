@@ -34,7 +34,7 @@ def _exchange(lm, l, arr, n_owned, rank):
         arr[n_owned + ip[k]:n_owned + ip[k + 1]] = recv.numpy()
 
 
-def _worker(rank, world, port, name, cycles, out_dir):
+def _worker(rank, world, port, name, cycles, out_dir, method="geom"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
@@ -43,7 +43,7 @@ def _worker(rank, world, port, name, cycles, out_dir):
     import orc
     pkg = ge.load_package()
     mesh = pkg.meshgen.make_multigrid(name)
-    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world)
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world, method=method)
     lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
     o = orc.Oracle("port")
     nl = len(mesh["levels"])
@@ -115,11 +115,13 @@ def _worker(rank, world, port, name, cycles, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,cycles", [("tiny", 3), ("small", 2)])
-def test_two_rank_decomposed_run_equals_undecomposed(tmp_path, name, cycles, meshgen, oracle_port):
-    world = 2
-    port = 29600 + (os.getpid() % 300)
-    mp.spawn(_worker, args=(world, port, name, cycles, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("name,cycles,world,method", [("tiny", 3, 2, "geom"), ("small", 2, 2, "geom"), ("small", 2, 3, "kway"),
+                                                      ("tiny", 2, 5, "random")])
+def test_decomposed_run_equals_undecomposed(tmp_path, name, cycles, world, method, meshgen, oracle_port):
+    """2 ranks with the geometric partition, 3 ranks with the k-way graph partition, 5 ranks with the random one (every
+    rank neighbours every other, halo lists at their worst): all bit-identical to the undecomposed run"""
+    port = 29600 + (os.getpid() % 300) + 7 * world
+    mp.spawn(_worker, args=(world, port, name, cycles, str(tmp_path), method), nprocs=world, join=True)
     lev0 = [meshgen.zero_based(l) for l in meshgen.make_multigrid(name)["levels"]]
     ref = oracle_port.make_state(lev0)
     ref.init()

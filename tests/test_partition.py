@@ -75,3 +75,54 @@ def test_single_rank_partition_is_the_whole_mesh(pkg, meshgen):
         assert lm.sizes(l) == (n, lev["edge-->node"].shape[0], lev["bnd_node-->node"].shape[0], n)
         assert np.array_equal(lm.query(l, "global_node"), np.arange(n))
         assert lm.query(l, "neighbour_rank").size == 0
+
+
+@pytest.mark.parametrize("name,n_ranks", [("tiny", 2), ("small", 2), ("small", 8), ("small", 5), ("small", 7), ("medium", 5)])
+def test_kway_partition_bit_exact_and_better_than_geometric(pkg, meshgen, plan_oracle, name, n_ranks):
+    """op_partition's k-way method (euler3d.cpp:340-375): recursive graph bisection with Fiduccia-Mattheyses refinement.
+    Bit for bit against the restatement, balanced, and never a larger edge cut than the coordinate bisection it starts
+    from: equal where the median falls between two grid planes of these structured-like decks (2, 8 ranks), 30-35 %
+    smaller where a grid plane has to be shared (5, 7 ranks: the coordinate split scatters the shared plane)."""
+    mesh = meshgen.make_multigrid(name)
+    lev0 = mesh0(meshgen, name)
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], n_ranks, method="kway")
+    ref_parts = plan_oracle.partition_levels(lev0, n_ranks, method="kway")
+    for a, b in zip(parts, ref_parts):
+        assert np.array_equal(a, b)
+    geom = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], n_ranks)
+    n = lev0[0]["node_coordinates"].shape[0]
+    sizes = np.bincount(parts[0], minlength=n_ranks)
+    assert sizes.min() > 0 and sizes.max() <= 1.03 * n / n_ranks + 2      # 0.5 % slack per bisection level
+    cut_kway, cut_geom = plan_oracle.edge_cut(parts[0], lev0[0]["edge-->node"]), plan_oracle.edge_cut(geom[0], lev0[0]["edge-->node"])
+    assert cut_kway <= cut_geom
+    if n_ranks in (5, 7):
+        assert cut_kway < 0.8 * cut_geom
+    # the rank meshes built from a k-way partition satisfy the same invariants
+    for r in range(n_ranks):
+        lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, n_ranks)
+        ref = plan_oracle.local_mesh(lev0, ref_parts, r)
+        for l in range(len(lev0)):
+            assert np.array_equal(lm.query(l, "global_node"), ref[l]["global_node"])
+            assert np.array_equal(lm.query(l, "global_edge"), ref[l]["global_edge"])
+
+
+@pytest.mark.parametrize("method", ["block", "random", "inertial", "parmetis", "ptscotch", "geomkway"])
+def test_partition_method_names(pkg, meshgen, method):
+    """every library / method name of config.h:203-240 is accepted; each gives a balanced, complete partition"""
+    mesh = meshgen.make_multigrid("small")
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 4, method=method)
+    n = mesh["levels"][0]["node_coordinates"].shape[0]
+    sizes = np.bincount(parts[0], minlength=4)
+    assert sizes.sum() == n and sizes.min() >= 0.95 * n / 4 - 2
+    if method == "inertial":
+        assert np.array_equal(parts[0], pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 4)[0])
+    if method in ("parmetis", "ptscotch", "geomkway"):
+        assert np.array_equal(parts[0], pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 4, method="kway")[0])
+    if method == "block":
+        assert (np.diff(parts[0]) >= 0).all()
+
+
+def test_partition_unknown_method_is_an_error(pkg, meshgen):
+    mesh = meshgen.make_multigrid("tiny")
+    with pytest.raises(pkg.capi.MgcfdError):
+        pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 2, method="metis5")
