@@ -200,6 +200,41 @@ double wall()
     return t.tv_sec + 1e-6 * t.tv_usec;
 }
 
+// io.h:296-417: the CSV files the reference's run-scripts aggregate (aggregate-output-data.py).  Rows are appended;
+// the header is written when the file is new or empty.  <prefix>P=<rank>.PerfData.csv and <prefix>P=<rank>.FileIoTimes.csv
+std::string perf_path(const std::string &prefix, int rank, const char *what)
+{
+    std::string p = prefix;
+    if (p.length() > 1 && p[p.size() - 1] != '/' && p[p.size() - 1] != '.') p += ".";
+    return p + "P=" + std::to_string(rank) + "." + what + ".csv";
+}
+bool csv_needs_header(const std::string &path)
+{
+    std::ifstream f(path);
+    return !f || f.peek() == std::ifstream::traits_type::eof();
+}
+void dump_perf_data(const std::string &prefix, int rank, const std::string &partitioner, const std::vector<double> &flux_seconds,
+                    const std::vector<long long> &flux_iters)
+{
+    const std::string path = perf_path(prefix, rank, "PerfData");
+    const bool header = csv_needs_header(path);
+    std::ofstream out(path, std::ios_base::app);
+    if (header) out << "rank,partitioner,kernel,level,computeTime,syncTime,iters" << std::endl;
+    for (size_t l = 0; l < flux_iters.size(); l++)
+        out << rank << ',' << partitioner << ",compute_flux_edge_kernel," << l << ',' << flux_seconds[l] << ',' << 0.0 << ','
+            << flux_iters[l] << std::endl;
+}
+void dump_file_io_perf_data(const std::string &prefix, int rank, const std::string &partitioner, int write_interval, int n_writes,
+                            double io_seconds, double walltime)
+{
+    const std::string path = perf_path(prefix, rank, "FileIoTimes");
+    const bool header = csv_needs_header(path);
+    std::ofstream out(path, std::ios_base::app);
+    if (header) out << "rank,partitioner,level,writeInterval,numberOfWrites,fileIoTime,wallTime" << std::endl;
+    out << rank << ',' << partitioner << ',' << 0 << ',' << write_interval << ',' << n_writes << ',' << io_seconds << ',' << walltime
+        << std::endl;      // base level only, as the reference
+}
+
 struct Config {                               // config.h:64-103, defaults :129-165
     std::string input_file, input_dir, prefix, variant = "owner";
     int cycles = 25, flow_interval = 0, gpus = 1;
@@ -208,6 +243,12 @@ struct Config {                               // config.h:64-103, defaults :129-
     std::string partitioner, partitioner_method;   // -m / -r (config.h:203-240)
     int out_vars = 0, out_fluxes = 0, out_sf = 0;
 };
+
+// op_partition's method when given (geom | kway | geomkway), else the library name, else the default
+std::string partitioner_name(const Config &conf)
+{
+    return !conf.partitioner_method.empty() ? conf.partitioner_method : (!conf.partitioner.empty() ? conf.partitioner : std::string("geom"));
+}
 
 #define CHECK(call)                                                                                  \
     do {                                                                                             \
@@ -314,6 +355,11 @@ int main(int argc, char **argv)
                 printf("  %-20s %s rank=%zu checksum=%.12Le\n", kv.first.c_str(), d.dtype == 0 ? "f64" : "i32", d.dims.size(), sum);
             }
         }
+        if (!conf.prefix.empty()) {
+            // the perf CSVs of a run that did nothing (the writers run without a GPU)
+            dump_perf_data(conf.prefix, 0, partitioner_name(conf), std::vector<double>(levels, 0.0), std::vector<long long>(levels, 0));
+            dump_file_io_perf_data(conf.prefix, 0, partitioner_name(conf), conf.flow_interval, 0, 0.0, 0.0);
+        }
         return 0;
     }
     // -v: solution.variables.L<l>.cycles=<g> with dataset p_variables_result_L<l> (euler3d.cpp:314-335)
@@ -349,8 +395,7 @@ int main(int argc, char **argv)
         std::vector<const int *> pp(levels);
         // op_partition(lib, method, ...) at euler3d.cpp:340-375: the method wins when given (geom | kway | geomkway),
         // else the library name decides (parmetis / ptscotch are k-way partitioners, inertial is geometric)
-        std::string method = !conf.partitioner_method.empty() ? conf.partitioner_method
-                             : (!conf.partitioner.empty() ? conf.partitioner : std::string("geom"));
+        std::string method = partitioner_name(conf);
         printf("partitioner: %s\n", method.c_str());
         for (int l = 0; l < levels; l++) {
             part[l].resize(lv[l].n_nodes);
@@ -391,7 +436,8 @@ int main(int argc, char **argv)
     ctx = R[0];
 
     printf("-----------------------------------------------------\nCompute beginning\n");
-    double t1 = wall();
+    double t1 = wall(), file_io_seconds = 0.0;
+    int n_file_io_writes = 0;
     if (P > 1 || !conf.loopwise) {
         // device-driven schedule (host checks of :480 and :544 deferred to the end of the run)
         if (conf.flow_interval > 0 || conf.mem_bound) printf("note: -I / -b need --loopwise on one GPU; ignored\n");
@@ -430,8 +476,11 @@ int main(int argc, char **argv)
             if (conf.flow_interval > 0 && ((i + 1) % conf.flow_interval) == 0 && level == 0) {      // :552-571
                 std::vector<double> v((size_t)lv[0].n_nodes * 5);
                 CHECK(mgcfd_fetch_dat(ctx, 0, "variables", v.data()));
+                const double w0 = wall();
                 write_container(conf.prefix + "variables.L0.cycle=" + std::to_string(i + 1) + ".mgb", "p_variables", v.data(),
                                 lv[0].n_nodes, 5);
+                file_io_seconds += wall() - w0;
+                n_file_io_writes++;
             }
             if (levels <= 1) {
                 i++;
@@ -449,8 +498,9 @@ int main(int argc, char **argv)
         }
     }
     for (int r = 0; r < P; r++) mgcfd_sync(R[r]);
+    const double walltime = wall() - t1;
     printf("\nCompute complete\n");
-    printf("Max total runtime = %f\n", wall() - t1);
+    printf("Max total runtime = %f\n", walltime);
 
     // assemble file-order results (ranks return [owned | halo] in their local order)
     std::vector<std::vector<double>> vars(levels);
@@ -504,6 +554,8 @@ int main(int argc, char **argv)
     }
     if (conf.out_vars || conf.out_fluxes || conf.out_sf) {                                    // :720-779
         printf("-----------------------------------------------------\nWriting out data...\n");
+        const double w0 = wall();
+        n_file_io_writes += levels * (conf.out_vars + conf.out_fluxes + conf.out_sf);
         for (int l = 0; l < levels; l++) {
             std::string suffix = ".L" + std::to_string(l) + ".cycles=" + std::to_string(conf.cycles) + ".mgb";
             std::vector<double> buf;
@@ -511,6 +563,24 @@ int main(int argc, char **argv)
             if (conf.out_fluxes) { CHECK(fetch_all("fluxes", l, 5, buf)); write_container(conf.prefix + "fluxes" + suffix, "p_fluxes_result_L" + std::to_string(l), buf.data(), lv[l].n_nodes, 5); }
             if (conf.out_vars) { CHECK(fetch_all("variables", l, 5, buf)); write_container(conf.prefix + "variables" + suffix, "p_variables_result_L" + std::to_string(l), buf.data(), lv[l].n_nodes, 5); }
         }
+        file_io_seconds += wall() - w0;
+    }
+    // io.h:296-417 / euler3d.cpp:780-819: per-rank flux-kernel rows and the base-level file I/O row (next to the other
+    // outputs; with no -o prefix they go into the input directory instead of the working directory)
+    {
+        const std::string csv_prefix = conf.prefix.empty() ? dir : conf.prefix;
+        std::vector<int> visits(levels, 0);                       // level visits of one V-cycle (euler3d.cpp:573-640)
+        if (levels == 1) visits[0] = 1;
+        else for (int l = 0; l < levels; l++) visits[l] = (l == 0 || l == levels - 1) ? 1 : 2;
+        for (int r = 0; r < P; r++) {
+            std::vector<long long> iters(levels);
+            for (int l = 0; l < levels; l++) {
+                const int n_edges = P == 1 ? lv[l].n_edges : mgcfd_local_mesh_level(LM[r], l)->n_edges;
+                iters[l] = (long long)n_edges * MGCFD_RK * visits[l] * conf.cycles;
+            }
+            dump_perf_data(csv_prefix, r, partitioner_name(conf), std::vector<double>(levels, 0.0), iters);
+        }
+        dump_file_io_perf_data(csv_prefix, 0, partitioner_name(conf), conf.flow_interval, n_file_io_writes, file_io_seconds, walltime);
     }
     printf("-----------------------------------------------------\nWinding down\n");
     for (int r = 0; r < P; r++) {

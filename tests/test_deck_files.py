@@ -62,3 +62,21 @@ def test_native_driver_loads_hdf5_and_container_decks_alike(tmp_path, meshgen):
         assert ("format=hdf5" in p.stdout) == (fmt != "mgb")
     assert "nodes=378 edges=1000" in outs["mgb"] and "checksum=" in outs["mgb"]
     assert outs["mgb"] == outs["h5"] == outs["h5-chunked"]
+
+
+def test_perf_csv_files_have_the_reference_layout(tmp_path, meshgen):
+    """<prefix>P=<rank>.PerfData.csv and <prefix>P=<rank>.FileIoTimes.csv (io.h:296-417), the files the reference's
+    aggregate-output-data.py collects: header once, rows appended on every run; written here by --check-deck (no GPU)"""
+    mesh = meshgen.make_multigrid("tiny")
+    meshgen.write_deck(str(tmp_path), mesh)
+    prefix = str(tmp_path / "out")
+    for _ in range(2):
+        p = subprocess.run([EXE, "-i", "input.dat", "-d", str(tmp_path), "-o", prefix, "-r", "kway", "--check-deck"],
+                           capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stdout + p.stderr
+    perf = open(prefix + ".P=0.PerfData.csv").read().splitlines()
+    assert perf[0] == "rank,partitioner,kernel,level,computeTime,syncTime,iters"
+    assert len(perf) == 1 + 2 * 3 and perf[1].startswith("0,kway,compute_flux_edge_kernel,0,") and perf[3].split(",")[3] == "2"
+    io = open(prefix + ".P=0.FileIoTimes.csv").read().splitlines()
+    assert io[0] == "rank,partitioner,level,writeInterval,numberOfWrites,fileIoTime,wallTime"
+    assert len(io) == 3 and io[1].split(",")[:5] == ["0", "kway", "0", "0", "0"]
