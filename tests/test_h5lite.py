@@ -272,3 +272,22 @@ def test_h5_library_exports_every_declared_symbol():
     assert len(declared) >= 14
     for sym in declared:
         assert hasattr(lib, sym), sym
+
+
+def test_written_messages_use_the_standard_encodings(h5, tmp_path):
+    """known-answer bytes: the datatype messages libhdf5 writes for native little-endian double and int (as seen in any
+    h5dump -H / hexdump of a file written on x86-64), the version-1 dataspace and the version-3 contiguous layout"""
+    a = np.arange(6.0).reshape(2, 3)
+    b = np.arange(4, dtype=np.int32)
+    path = str(tmp_path / "kat.h5")
+    c_write(h5, path, {"a": a, "b": b})
+    blob = open(path, "rb").read()
+    f64 = bytes.fromhex("11203f00" "08000000" "0000" "4000" "340b0034" "ff030000")     # IEEE double, LE: sign 63, exp 52/11, mantissa 0/52, bias 1023
+    i32 = bytes.fromhex("10080000" "04000000" "0000" "2000")                            # fixed-point, LE, signed, 32 bits
+    assert blob.count(f64) == 1 and blob.count(i32) >= 1
+    space = bytes.fromhex("01020000" "00000000") + (2).to_bytes(8, "little") + (3).to_bytes(8, "little")
+    assert space in blob
+    at = blob.index(a.tobytes())
+    assert at % 8 == 0
+    layout = bytes([3, 1]) + at.to_bytes(8, "little") + (48).to_bytes(8, "little")
+    assert layout in blob
