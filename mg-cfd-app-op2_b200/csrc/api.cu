@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "internal.h"
 
@@ -754,6 +755,33 @@ static void bank_aware_slots(int ne, const uint32_t *lab, int n_own, const uint1
     }
 }
 
+// slots of the chunks [k0, k1), concatenated like OwnerPlanHost::edge_file (index: edge_off[k] - edge_off[k0] + i);
+// chunks are independent, so the greedy passes run on up to 16 host threads (identity slots when slotting is off)
+static void slots_for_chunks(const OwnerPlanHost &O, int k0, int k1, int split, bool slotting, std::vector<int> &buf)
+{
+    buf.resize((size_t)(O.edge_off[k1] - O.edge_off[k0]));
+    auto work = [&](int a, int b) {
+        std::vector<int> slot;
+        for (int k = a; k < b; k++) {
+            int *dst = buf.data() + (O.edge_off[k] - O.edge_off[k0]);
+            if (slotting) {
+                bank_aware_slots(O.n_edges[k], &O.lab[O.edge_off[k]], O.node0[k + 1] - O.node0[k], &O.rowptr[O.rowptr_off[k]],
+                                 O.csr.data() + O.csr_off[k], split, slot);
+                std::copy(slot.begin(), slot.end(), dst);
+            } else {
+                std::iota(dst, dst + O.n_edges[k], 0);
+            }
+        }
+    };
+    const int n = k1 - k0;
+    int nt = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    nt = std::max(1, std::min(nt, n / 64));                  // small plans: not worth a thread
+    if (nt == 1) { work(k0, k1); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++) pool.emplace_back(work, k0 + (int)((long long)n * t / nt), k0 + (int)((long long)n * (t + 1) / nt));
+    for (std::thread &t : pool) t.join();
+}
+
 static int ensure_owner(mgcfd_ctx *ctx, int level)
 {
     LevelHost &L = ctx->H[level];
@@ -806,10 +834,13 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     const bool slotting = !(slot_s && atoi(slot_s) == 0);
     int node_split = (!ctx->opt.exact_arith && O.max_own <= 128) ? 2 : 1;
     if (split_s && (atoi(split_s) == 1 || atoi(split_s) == 2)) node_split = atoi(split_s);
-    std::vector<int> slot;
+    std::vector<int> slots;                  // of one batch of chunks
+    const int BATCH = 8192;
     std::vector<OwnerChunkDesc> desc(O.n_chunks);
     std::vector<unsigned char> blob((size_t)O.dev_blob_off[O.n_chunks], 0);
     for (int k = 0; k < O.n_chunks; k++) {
+        if (k % BATCH == 0) slots_for_chunks(O, k, std::min(O.n_chunks, k + BATCH), node_split, slotting, slots);
+        const int *slot = slots.data() + (O.edge_off[k] - O.edge_off[k - k % BATCH]);
         OwnerChunkDesc &d = desc[k];
         d.node0 = O.node0[k];
         d.n_own = O.node0[k + 1] - O.node0[k];
@@ -842,13 +873,6 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         uint32_t *lab = reinterpret_cast<uint32_t *>(g + d.e_pad);
         uint16_t *rowptr = reinterpret_cast<uint16_t *>(lab + d.e_pad);
         uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
-        if (slotting)
-            bank_aware_slots(d.n_edges, &O.lab[O.edge_off[k]], d.n_own, &O.rowptr[O.rowptr_off[k]], O.csr.data() + O.csr_off[k],
-                             node_split, slot);
-        else {
-            slot.resize(d.n_edges);
-            std::iota(slot.begin(), slot.end(), 0);
-        }
         for (int i = 0; i < d.n_edges; i++) {
             double p[4];
             pack_weight(ctx, L, O.edge_file[O.edge_off[k] + i], p);
@@ -1526,13 +1550,8 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
         if (s == "owner_lab") return emit(std::vector<int>(O.lab.begin(), O.lab.end()), out, cap);
         if (s == "owner_slots_split1" || s == "owner_slots_split2") {
             // device packing: slot of every plan edge inside its chunk (bank_aware_slots), concatenated like owner_edge_file
-            std::vector<int> all, slot;
-            all.reserve(O.edge_file.size());
-            for (int k = 0; k < O.n_chunks; k++) {
-                bank_aware_slots(O.n_edges[k], &O.lab[O.edge_off[k]], O.node0[k + 1] - O.node0[k], &O.rowptr[O.rowptr_off[k]],
-                                 O.csr.data() + O.csr_off[k], s.back() == '2' ? 2 : 1, slot);
-                all.insert(all.end(), slot.begin(), slot.end());
-            }
+            std::vector<int> all;
+            slots_for_chunks(O, 0, O.n_chunks, s.back() == '2' ? 2 : 1, true, all);
             return emit(all, out, cap);
         }
         if (s == "owner_stats") return emit(std::vector<int>{O.n_chunks, O.max_loc, O.max_edges, O.max_own, O.max_inc,
