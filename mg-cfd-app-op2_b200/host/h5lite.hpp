@@ -177,6 +177,8 @@ public:
         const DatasetInfo &d = info(name);
         if (d.type.cls != 0 && d.type.cls != 1 && d.type.cls != 3) throw Error(name + ": unsupported element type class " + std::to_string(d.type.cls));
         const uint64_t bytes = d.count() * d.type.size;
+        // deflate cannot expand by more than ~1032:1, the other layouts not at all: a larger extent is a corrupt header
+        if (bytes / 1100 > file_size_) throw Error(name + ": extent larger than the file can hold (corrupt dataspace?)");
         std::vector<unsigned char> out(bytes, 0);
         if (bytes == 0) return out;
         if (d.layout == 0) {
@@ -412,6 +414,7 @@ private:
         const int version = p[0], rank = p[1];
         size_t q = version == 1 ? 8 : 4;
         if (version != 1 && version != 2) throw Error("unsupported dataspace version");
+        if (n < q + (size_t)rank * sl) throw Error("truncated dataspace message");
         for (int i = 0; i < rank; i++) dims.push_back(detail::le(p + q + i * sl, (int)sl));
         return dims;
     }
@@ -423,6 +426,7 @@ private:
         std::vector<std::pair<std::string, uint64_t>> children;
         for (const Message &m : msgs) {
             if (m.type == 0x11) {                             // symbol table: B-tree + local heap
+                if (m.data.size() < 2 * (size_t)so_) throw Error(path_ + ": truncated symbol table message");
                 walk_btree_group(offs(m.data.data()), offs(m.data.data() + so_), children, 0);
             } else if (m.type == 0x06) {                      // link message (compact new-style group)
                 const unsigned char *p = m.data.data();
@@ -433,8 +437,10 @@ private:
                 if (flags & 0x04) q += 8;
                 if (flags & 0x10) q++;
                 const int nlen = 1 << (flags & 3);
+                if (m.data.size() < q + nlen) throw Error(path_ + ": truncated link message");
                 const uint64_t len = detail::le(p + q, nlen);
                 q += nlen;
+                if (m.data.size() < q + len + (ltype == 0 ? so_ : 0)) throw Error(path_ + ": truncated link message");
                 std::string name(reinterpret_cast<const char *>(p + q), len);
                 q += len;
                 if (ltype == 0) children.push_back({name, offs(p + q)});     // hard links only
@@ -464,27 +470,36 @@ private:
         for (const Message &m : msgs) {
             const unsigned char *p = m.data.data();
             const size_t n = m.data.size();
+            auto need = [&](size_t k) { if (n < k) throw Error(name + ": truncated object header message (type " + std::to_string(m.type) + ")"); };
             if (m.type == 0x01) d.dims = parse_space(p, n, sl_);
             else if (m.type == 0x03) d.type = parse_type(p, n);
             else if (m.type == 0x08) {
+                need(2);
                 const int version = p[0];
                 if (version == 3) {
                     d.layout = p[1];
                     if (d.layout == 0) {
+                        need(4);
                         size_t sz = detail::le(p + 2, 2);
+                        need(4 + sz);
                         d.compact.assign(p + 4, p + 4 + sz);
                     } else if (d.layout == 1) {
+                        need(2 + so_ + sl_);
                         d.address = offs(p + 2);
                         d.size = lens(p + 2 + so_);
                     } else if (d.layout == 2) {
+                        need(3);
                         const int dim = p[2];
+                        need(3 + so_ + 4 * (size_t)dim);
                         d.address = offs(p + 3);
                         for (int i = 0; i + 1 < dim; i++) d.chunk.push_back((uint32_t)detail::le(p + 3 + so_ + 4 * i, 4));
                     }
                 } else if (version == 1 || version == 2) {
+                    need(8);
                     const int dim = p[1];
                     d.layout = p[2];
                     size_t q = 8;
+                    need(8 + so_ + 4 * (size_t)dim + 4);
                     if (d.layout != 0) { d.address = offs(p + q); q += so_; }
                     std::vector<uint32_t> sizes;
                     for (int i = 0; i < dim; i++) sizes.push_back((uint32_t)detail::le(p + q + 4 * i, 4));
@@ -496,9 +511,11 @@ private:
                     throw Error(name + ": data layout message version " + std::to_string(version) + " is not supported");
                 }
             } else if (m.type == 0x0b) {
+                need(2);
                 const int version = p[0], nf = p[1];
                 size_t q = version == 1 ? 8 : 2;
                 for (int i = 0; i < nf; i++) {
+                    need(q + 8);
                     Filter f;
                     f.id = (int)detail::le(p + q, 2);
                     size_t name_len = 0;
@@ -507,6 +524,7 @@ private:
                     const int nc = (int)detail::le(p + q, 2);
                     q += 2;
                     q += version == 1 ? ((name_len + 7) & ~size_t(7)) : name_len;
+                    need(q + 4 * (size_t)nc);
                     for (int k = 0; k < nc; k++) f.client.push_back((uint32_t)detail::le(p + q + 4 * k, 4));
                     q += 4 * nc;
                     if (version == 1 && (nc & 1)) q += 4;
@@ -580,14 +598,11 @@ private:
         if (f.id == 1) {                                      // deflate
             uint64_t celems = 1;
             for (uint32_t c : d.chunk) celems *= c;
-            std::vector<unsigned char> out(celems * d.type.size + 64);
-            for (;;) {
-                uLongf len = (uLongf)out.size();
-                int rc = uncompress(out.data(), &len, in.data(), (uLong)in.size());
-                if (rc == Z_OK) { out.resize(len); return out; }
-                if (rc != Z_BUF_ERROR || out.size() > (1ull << 32)) throw Error(d.name + ": corrupt deflate stream");
-                out.resize(out.size() * 2);
-            }
+            std::vector<unsigned char> out(celems * d.type.size + 64);     // a chunk inflates to its nominal size (+ trailers)
+            uLongf len = (uLongf)out.size();
+            if (uncompress(out.data(), &len, in.data(), (uLong)in.size()) != Z_OK) throw Error(d.name + ": corrupt deflate stream");
+            out.resize(len);
+            return out;
         }
         if (f.id == 2) {                                      // shuffle: byte planes -> elements
             const size_t es = f.client.empty() ? d.type.size : f.client[0], n = es ? in.size() / es : 0;

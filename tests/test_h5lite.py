@@ -291,3 +291,40 @@ def test_written_messages_use_the_standard_encodings(h5, tmp_path):
     assert at % 8 == 0
     layout = bytes([3, 1]) + at.to_bytes(8, "little") + (48).to_bytes(8, "little")
     assert layout in blob
+
+
+def test_corrupted_files_never_crash_the_reader(h5, tmp_path):
+    """fuzz: single-byte corruptions and truncations of valid files either still open or fail with an error text"""
+    rng = np.random.default_rng(9)
+    data = {"a": rng.standard_normal((6, 3)), "b": rng.integers(0, 9, (5, 2)).astype(np.int32)}
+    err = C.create_string_buffer(512)
+    for variant in (dict(), dict(superblock=2, layout="chunked", filters=("shuffle", "deflate"))):
+        good = tmp_path / "good.h5"
+        h5_oracle.write_h5(str(good), data, **variant)
+        blob = good.read_bytes()
+        bad = tmp_path / "bad.h5"
+        for trial in range(150):
+            b = bytearray(blob)
+            if trial % 3 == 0:
+                b = b[:int(rng.integers(8, len(b)))]
+            else:
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(8, len(b)))] = int(rng.integers(0, 256))
+            bad.write_bytes(bytes(b))
+            r = h5.mgcfd_h5_open(str(bad).encode(), err, 512)
+            if not r:
+                assert err.value                                     # an error text, not a crash
+                continue
+            for i in range(h5.mgcfd_h5_count(r)):
+                name = h5.mgcfd_h5_name(r, i)
+                dims = (C.c_ulonglong * 8)()
+                cls, es, sg, lay, rank = (C.c_int() for _ in range(5))
+                h5.mgcfd_h5_info(r, name, cls, es, sg, lay, rank, dims)
+                n = 1
+                for k in range(rank.value):
+                    n *= dims[k]
+                if n > 10**6 or cls.value not in (0, 1):
+                    continue                                         # a corrupted extent: do not allocate for it
+                out = np.empty(max(n, 1), dtype=np.float64)
+                h5.mgcfd_h5_read_f64(r, name, out.ctypes.data, err, 512)
+            h5.mgcfd_h5_close(r)
