@@ -183,6 +183,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel per op_par_loop call site")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every launch instead of replaying CUDA graphs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = the deck grows with N along x (default, the driver's scaling run); strong = the --mesh deck "
+                         "itself is partitioned over the N GPUs (BASELINE configs[3])")
+    ap.add_argument("--partitioner", default="geom", help="N>1: geom | kway | block | random (op_partition methods)")
     ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"],
                     help="N>1: direct peer stores over CUDA-IPC-mapped memory (default) or NCCL send/recv")
     args = ap.parse_args()
@@ -192,7 +196,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = ge.load_package()
-    if world > 1:
+    if world > 1 and args.scaling == "weak":
         # weak scaling: the deck grows with the GPU count along x, so every rank's share stays about one --mesh deck
         mesh_name, dims, seed0 = pkg.meshgen.CONFIGS[args.mesh]
         dims = [(nx * world, ny, nz, None if ne is None else ne * world) for nx, ny, nz, ne in dims]
@@ -201,7 +205,9 @@ def main():
         mesh = pkg.meshgen.make_multigrid(args.mesh)
     levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
     sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
-    workload = (f"{args.mesh}{' x%d along x (weak scaling, recursive-bisection partition, 1 rank per GPU)' % world if world > 1 else ''}"
+    how = (" x%d along x (weak scaling" % world if args.scaling == "weak" else " partitioned over %d GPUs (strong scaling" % world) + \
+        f", {args.partitioner} partition, 1 rank per GPU)"
+    workload = (f"{args.mesh}{how if world > 1 else ''}"
                 f": {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
                 f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
     config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
@@ -238,7 +244,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if world > 1:
-        parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world)
+        parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world, method=args.partitioner)
         lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
         gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant=args.variant if args.variant == "emit" else "owner",
                         exact_arith=args.exact,
@@ -377,7 +383,7 @@ def main():
         config["halo_bytes_sent_rank0"] = halo_bytes
         line = {"metric": "mg_cycle_flux_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "mg_cycles_per_s": args.steps / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         emit(line)
