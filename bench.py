@@ -196,17 +196,27 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = ge.load_package()
-    if world > 1 and args.scaling == "weak":
-        # weak scaling: the deck grows with the GPU count along x, so every rank's share stays about one --mesh deck
-        mesh_name, dims, seed0 = pkg.meshgen.CONFIGS[args.mesh]
-        dims = [(nx * world, ny, nz, None if ne is None else ne * world) for nx, ny, nz, ne in dims]
-        mesh = pkg.meshgen.make_multigrid((mesh_name, dims, seed0))
+    slab = args.mesh in pkg.meshgen.SLAB_CONFIGS          # single-level decks that every rank generates for itself
+    if slab and world > 1:
+        # BASELINE configs[4]: the deck (150M nodes for rotor37_150m) is never materialised on one host; the job is a
+        # fixed deck cut into x-slabs, i.e. strong scaling
+        mesh, levels0 = None, None
+        sizes = [pkg.meshgen.slab_sizes(args.mesh)]
+        args.scaling = "strong"
     else:
-        mesh = pkg.meshgen.make_multigrid(args.mesh)
-    levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
-    sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
+        if slab:
+            mesh = pkg.meshgen.make_slab_global(args.mesh)
+        elif world > 1 and args.scaling == "weak":
+            # weak scaling: the deck grows with the GPU count along x, so every rank's share stays about one --mesh deck
+            mesh_name, dims, seed0 = pkg.meshgen.CONFIGS[args.mesh]
+            dims = [(nx * world, ny, nz, None if ne is None else ne * world) for nx, ny, nz, ne in dims]
+            mesh = pkg.meshgen.make_multigrid((mesh_name, dims, seed0))
+        else:
+            mesh = pkg.meshgen.make_multigrid(args.mesh)
+        levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
+        sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
     how = (" x%d along x (weak scaling" % world if args.scaling == "weak" else " partitioned over %d GPUs (strong scaling" % world) + \
-        f", {args.partitioner} partition, 1 rank per GPU)"
+        (", x-slabs generated per rank" if slab else f", {args.partitioner} partition") + ", 1 rank per GPU)"
     workload = (f"{args.mesh}{how if world > 1 else ''}"
                 f": {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
                 f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
@@ -220,6 +230,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if levels0 is None:
+            # a deck that is only ever generated per rank: the CPU arm runs rank 0's slab (owned + halo nodes, the edges
+            # and boundary entries of its owned nodes) as a stand-alone deck -- a bounded sample of the workload
+            d = pkg.meshgen.make_slab_rank(args.mesh, 0, world)
+            levels0 = [{k: d[k] for k in ("node_coordinates", "edge-->node", "edge_weights", "bnd_node-->node", "bnd_node-->group",
+                                          "bnd_node_weights")}]
+            config["cpu_sample"] = f"x-slab of rank 0 of {world} ({d['node_coordinates'].shape[0]} nodes, {d['edge-->node'].shape[0]} edges)"
         perms, orders = hilbert_orders(levels0)
         ordered = reorder_for_cpu(levels0, perms, orders)
         r = cpu_run(ordered, args.steps, args.warmup, nthreads)
@@ -244,8 +261,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if world > 1:
-        parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world, method=args.partitioner)
-        lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
+        if slab:
+            lm = pkg.RankMesh(pkg.meshgen.make_slab_rank(args.mesh, rank, world))      # this rank's x-slab + halo planes only
+        else:
+            parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], world, method=args.partitioner)
+            lm = pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, rank, world)
         gpu = pkg.MGCFD(local_mesh=lm, device=local_rank, flux_variant=args.variant if args.variant == "emit" else "owner",
                         exact_arith=args.exact,
                         owner_chunk_nodes=args.chunk, graphs=not args.no_graphs)

@@ -6,5 +6,5 @@ level-file layout), host/ (native euler3d driver).  Nothing here imports oracle/
 """
 from . import meshgen  # noqa: F401
 from . import capi  # noqa: F401
-from .capi import (MGCFD, MgcfdError, PinnedArray, LocalMesh, load_library, farfield_consts,  # noqa: F401
+from .capi import (MGCFD, MgcfdError, PinnedArray, LocalMesh, RankMesh, load_library, farfield_consts,  # noqa: F401
                    partition_levels, group_run_cycles, group_enable_p2p, nccl_unique_id)

@@ -250,6 +250,54 @@ class LocalMesh:
             pass
 
 
+class RankMesh:
+    """One rank's share of a single-level deck given directly as arrays (meshgen.make_slab_rank): the same interface as
+    LocalMesh, without ever building the undecomposed deck -- BASELINE.json configs[4] generates the 150M-node deck
+    per partition."""
+
+    def __init__(self, d):
+        self.n_levels, self.rank, self.n_ranks = 1, int(d["rank"]), int(d["n_ranks"])
+        self._keep = {
+            "coords": _as(d["node_coordinates"], np.float64), "e2n": _as(d["edge-->node"], np.int32),
+            "ewt": _as(d["edge_weights"], np.float64), "b2n": _as(d["bnd_node-->node"], np.int32),
+            "bgr": _as(d["bnd_node-->group"], np.int32), "bwt": _as(d["bnd_node_weights"], np.float64),
+            "gn": _as(d["global_node"], np.int32), "nbr": _as(d["neighbour_rank"], np.int32),
+            "ep": _as(d["export_ptr"], np.int32), "ei": _as(d["export_idx"], np.int32), "ip": _as(d["import_ptr"], np.int32),
+        }
+        k = self._keep
+        h = LevelHost()
+        h.n_nodes, h.n_edges, h.n_bnd_nodes, h.n_owned_nodes = k["coords"].shape[0], k["e2n"].shape[0], k["b2n"].shape[0], int(d["n_owned"])
+        h.node_coordinates = k["coords"].ctypes.data_as(_dp)
+        h.edge_to_node = k["e2n"].ctypes.data_as(_ip)
+        h.edge_weights = k["ewt"].ctypes.data_as(_dp)
+        h.bnd_node_to_node = k["b2n"].ctypes.data_as(_ip)
+        h.bnd_node_to_group = k["bgr"].ctypes.data_as(_ip)
+        h.bnd_node_weights = k["bwt"].ctypes.data_as(_dp)
+        h.node_to_mg_node = _ip()
+        h.global_node_id = k["gn"].ctypes.data_as(_ip)
+        h.n_neighbours = k["nbr"].shape[0]
+        h.neighbour_rank = k["nbr"].ctypes.data_as(_ip)
+        h.export_ptr = k["ep"].ctypes.data_as(_ip)
+        h.export_idx = k["ei"].ctypes.data_as(_ip)
+        h.import_ptr = k["ip"].ctypes.data_as(_ip)
+        self._h = h
+
+    def level(self, l):
+        assert l == 0
+        return C.pointer(self._h)
+
+    def sizes(self, l):
+        v = self._h
+        return v.n_nodes, v.n_edges, v.n_bnd_nodes, v.n_owned_nodes
+
+    def query(self, l, what):
+        return {"global_node": self._keep["gn"], "neighbour_rank": self._keep["nbr"], "export_ptr": self._keep["ep"],
+                "export_idx": self._keep["ei"], "import_ptr": self._keep["ip"], "edge_to_node": self._keep["e2n"].ravel()}[what]
+
+    def free(self):
+        pass
+
+
 def group_enable_p2p(ranks):
     """switch a single-process group to the direct peer-store transport (flags instead of events + peer copies)"""
     lib = load_library()

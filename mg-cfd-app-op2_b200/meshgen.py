@@ -351,3 +351,211 @@ def write_solution(directory, level, cycles, variables, prefix="solution.", fmt=
     path = os.path.join(directory, f"{prefix}variables.L{level}.cycles={cycles}.{fmt}")
     (write_h5 if fmt == "h5" else write_container)(path, {f"p_variables_result_L{level}": np.ascontiguousarray(variables, dtype=np.float64)})
     return path
+
+
+# ---------------------------------------------------------------------------------------------------
+# Slab decks generated PER RANK (BASELINE.json configs[4]: the 600x500x500 single-level deck on 8 GPUs is never
+# materialised on one host).  Every random quantity is a hash of the GLOBAL node / edge / boundary-entry
+# index, so a rank can generate its x-slab (+ one halo plane on either side) alone and gets exactly the arrays
+# mgcfd_local_mesh_build would cut out of the whole deck (tests/test_meshgen.py compares the two).
+#   nodes     natural order, id = (i*ny + j)*nz + k, perturbed grid coordinates
+#   edges     axis edges only; global order: x-edges (id = i*P + jk, P = ny*nz), then y-edges, then z-edges; hashed orientation
+#   boundary  six faces in the order xmin, xmax, ymin, ymax, zmin, zmax, each ascending in node id
+#   ownership x-plane i belongs to rank r with  r*nx//R <= i < (r+1)*nx//R
+# ---------------------------------------------------------------------------------------------------
+SLAB_CONFIGS = {
+    "rotor37_150m": ("rotor37", (600, 500, 500), 100),       # BASELINE.json configs[4]
+    "slab_test": ("rotor37", (12, 5, 4), 5),
+}
+
+
+def _hash_u01(ids, stream, seed):
+    """uniform [0,1) per index: splitmix64 of (index, stream, seed)"""
+    with np.errstate(over="ignore"):
+        z = (np.asarray(ids).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(stream) * np.uint64(0xD1B54A32D192ED03) +
+             np.uint64(seed) * np.uint64(0x8CB92BA72F3D8DD7))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def _slab_geometry(nx, ny, nz, extent):
+    ext = extent if extent is not None else (1.0, 0.6, 0.5)
+    h = np.array([ext[0] / max(nx - 1, 1), ext[1] / max(ny - 1, 1), ext[2] / max(nz - 1, 1)])
+    return h, float(h.mean())
+
+
+def _slab_coords(gid, nx, ny, nz, seed, h):
+    i, j, k = np.unravel_index(gid, (nx, ny, nz))
+    c = np.stack([i * h[0], j * h[1], k * h[2]], axis=1).astype(np.float64)
+    for d in range(3):
+        c[:, d] += (_hash_u01(gid, 10 + d, seed) - 0.5) * 0.4 * h[d]
+    return c
+
+
+def _slab_edges(nx, ny, nz, i_lo, i_hi):
+    """global ids, endpoints (global node ids) and axis of the axis edges whose lower x-plane index lies in the given
+    ranges: x-edges with i in [i_lo[0], i_hi[0]), y- and z-edges of planes [i_lo[1], i_hi[1])"""
+    P = ny * nz
+    Ex, Ey = (nx - 1) * P, nx * (ny - 1) * nz
+    out = []
+    # x
+    i = np.arange(max(i_lo[0], 0), min(i_hi[0], nx - 1), dtype=np.int64)
+    a = (i[:, None] * P + np.arange(P, dtype=np.int64)[None, :]).ravel()
+    out.append((a, a, a + P, 0))
+    # y
+    i = np.arange(i_lo[1], i_hi[1], dtype=np.int64)
+    jj, kk = np.meshgrid(np.arange(ny - 1, dtype=np.int64), np.arange(nz, dtype=np.int64), indexing="ij")
+    eid = Ex + (i[:, None] * (ny - 1) * nz + (jj * nz + kk).ravel()[None, :]).ravel()
+    a = (i[:, None] * P + (jj * nz + kk).ravel()[None, :]).ravel()
+    out.append((eid, a, a + nz, 1))
+    # z
+    jj, kk = np.meshgrid(np.arange(ny, dtype=np.int64), np.arange(nz - 1, dtype=np.int64), indexing="ij")
+    eid = Ex + Ey + (i[:, None] * ny * (nz - 1) + (jj * (nz - 1) + kk).ravel()[None, :]).ravel()
+    a = (i[:, None] * P + (jj * nz + kk).ravel()[None, :]).ravel()
+    out.append((eid, a, a + 1, 2))
+    eid = np.concatenate([o[0] for o in out])
+    ea = np.concatenate([o[1] for o in out])
+    eb = np.concatenate([o[2] for o in out])
+    axis = np.concatenate([np.full(o[0].size, o[3], dtype=np.int64) for o in out])
+    return eid, ea, eb, axis
+
+
+def _slab_edge_data(eid, ea, eb, axis, seed, hm):
+    flip = _hash_u01(eid, 1, seed) < 0.5
+    a, b = np.where(flip, eb, ea), np.where(flip, ea, eb)
+    w = np.zeros((eid.size, 3))
+    w[np.arange(eid.size), axis] = hm * hm * (0.9 + 0.2 * _hash_u01(eid, 2, seed))
+    return a, b, w
+
+
+def _slab_boundary(nx, ny, nz, x0, x1, seed, h):
+    """boundary entries of the nodes in planes [x0, x1): (global entry index, global node id, group, weight)"""
+    P = ny * nz
+    i = np.arange(x0, x1, dtype=np.int64)
+    faces = []
+    jk = np.arange(P, dtype=np.int64)
+    if x0 == 0:
+        faces.append((jk, jk, "xmin", (-1, 0, 0), h[1] * h[2]))
+    if x1 == nx:
+        faces.append((P + jk, (nx - 1) * P + jk, "xmax", (1, 0, 0), h[1] * h[2]))
+    k = np.arange(nz, dtype=np.int64)
+    j = np.arange(ny, dtype=np.int64)
+    base = 2 * P
+    faces.append((base + (i[:, None] * nz + k[None, :]).ravel(), (i[:, None] * P + k[None, :]).ravel(), "ymin", (0, -1, 0), h[0] * h[2]))
+    base += nx * nz
+    faces.append((base + (i[:, None] * nz + k[None, :]).ravel(), (i[:, None] * P + (ny - 1) * nz + k[None, :]).ravel(), "ymax", (0, 1, 0), h[0] * h[2]))
+    base += nx * nz
+    faces.append((base + (i[:, None] * ny + j[None, :]).ravel(), (i[:, None] * P + j[None, :] * nz).ravel(), "zmin", (0, 0, -1), h[0] * h[1]))
+    base += nx * ny
+    faces.append((base + (i[:, None] * ny + j[None, :]).ravel(), (i[:, None] * P + j[None, :] * nz + nz - 1).ravel(), "zmax", (0, 0, 1), h[0] * h[1]))
+    bid = np.concatenate([f[0] for f in faces])
+    bn = np.concatenate([f[1] for f in faces])
+    bg = np.concatenate([np.full(f[0].size, FACE_GROUPS[f[2]], dtype=np.int32) for f in faces])
+    bw = np.concatenate([np.outer(f[4] * (0.9 + 0.2 * _hash_u01(f[0], 3, seed)), np.array(f[3], dtype=float)) for f in faces])
+    return bid, bn, bg, bw
+
+
+def slab_sizes(config):
+    """(nodes, edges, boundary entries) of the whole deck, without generating it"""
+    _, (nx, ny, nz), _ = SLAB_CONFIGS[config] if isinstance(config, str) else config
+    return nx * ny * nz, (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1), 2 * (ny * nz + nx * nz + nx * ny)
+
+
+def slab_owner_planes(nx, rank, n_ranks):
+    return rank * nx // n_ranks, (rank + 1) * nx // n_ranks
+
+
+def make_slab_global(config, base=1, extent=None):
+    """the whole single-level deck (small sizes: tests, one GPU), same dict layout as make_multigrid"""
+    mesh_name, (nx, ny, nz), seed = SLAB_CONFIGS[config] if isinstance(config, str) else config
+    h, hm = _slab_geometry(nx, ny, nz, extent)
+    n = nx * ny * nz
+    coords = _slab_coords(np.arange(n, dtype=np.int64), nx, ny, nz, seed, h)
+    eid, ea, eb, axis = _slab_edges(nx, ny, nz, (0, 0), (nx - 1, nx))
+    a, b, w = _slab_edge_data(eid, ea, eb, axis, seed, hm)
+    bid, bn, bg, bw = _slab_boundary(nx, ny, nz, 0, nx, seed, h)
+    assert np.array_equal(eid, np.arange(eid.size)) and np.array_equal(bid, np.arange(bid.size))
+    level = {
+        "node_coordinates": coords,
+        "edge-->node": np.ascontiguousarray(np.stack([a, b], axis=1) + base, dtype=np.int32),
+        "edge_weights": w,
+        "bnd_node-->node": np.ascontiguousarray(bn[:, None] + base, dtype=np.int32),
+        "bnd_node-->group": np.ascontiguousarray(bg[:, None], dtype=np.int32),
+        "bnd_node_weights": bw,
+    }
+    return {"mesh_name": mesh_name, "base_array_index": base, "levels": [level], "dims": [(nx, ny, nz)]}
+
+
+def make_slab_rank(config, rank, n_ranks, extent=None):
+    """this rank's share of the deck, generated without the rest: the arrays of mgcfd_level_host for a partition
+    (local 0-based maps, [owned | lower halo plane | upper halo plane] nodes, edges with an owned endpoint in ascending
+    global edge index, boundary entries of owned nodes, neighbour / export / import lists)"""
+    mesh_name, (nx, ny, nz), seed = SLAB_CONFIGS[config] if isinstance(config, str) else config
+    h, hm = _slab_geometry(nx, ny, nz, extent)
+    P = ny * nz
+    x0, x1 = slab_owner_planes(nx, rank, n_ranks)
+    assert x1 > x0, "more ranks than x-planes"
+    owned = np.arange(x0 * P, x1 * P, dtype=np.int64)
+    lower = np.arange((x0 - 1) * P, x0 * P, dtype=np.int64) if x0 > 0 else np.zeros(0, np.int64)
+    upper = np.arange(x1 * P, (x1 + 1) * P, dtype=np.int64) if x1 < nx else np.zeros(0, np.int64)
+    gnode = np.concatenate([owned, lower, upper])
+    n_owned = owned.size
+
+    def local_of(g):
+        loc = g - x0 * P                                        # owned
+        loc = np.where(g < x0 * P, n_owned + (g - (x0 - 1) * P), loc)
+        loc = np.where(g >= x1 * P, n_owned + lower.size + (g - x1 * P), loc)
+        return loc
+
+    eid, ea, eb, axis = _slab_edges(nx, ny, nz, (x0 - 1, x0), (x1, x1))
+    a, b, w = _slab_edge_data(eid, ea, eb, axis, seed, hm)
+    bid, bn, bg, bw = _slab_boundary(nx, ny, nz, x0, x1, seed, h)
+    order = np.argsort(bid, kind="stable")                      # ascending global entry index (faces interleave per rank)
+    bid, bn, bg, bw = bid[order], bn[order], bg[order], bw[order]
+    nbr, exp_idx, exp_ptr, imp_ptr = [], [], [0], [0]
+    if x0 > 0:
+        nbr.append(rank - 1 if n_ranks > 1 else 0)
+        exp_idx.append(np.arange(0, P, dtype=np.int64))                        # my first plane, the neighbour's upper halo
+        exp_ptr.append(exp_ptr[-1] + P)
+        imp_ptr.append(imp_ptr[-1] + lower.size)
+    if x1 < nx:
+        nbr.append(rank + 1)
+        exp_idx.append(np.arange(n_owned - P, n_owned, dtype=np.int64))        # my last plane, the neighbour's lower halo
+        exp_ptr.append(exp_ptr[-1] + P)
+        imp_ptr.append(imp_ptr[-1] + upper.size)
+    # ranks need not be adjacent in rank number when a rank owns no plane in between; planes are contiguous here
+    if nbr:
+        nbr[0] = _owner_of_plane(nx, n_ranks, x0 - 1) if x0 > 0 else nbr[0]
+        if x1 < nx:
+            nbr[-1] = _owner_of_plane(nx, n_ranks, x1)
+    return {
+        "mesh_name": mesh_name, "rank": rank, "n_ranks": n_ranks, "n_owned": n_owned,
+        "node_coordinates": _slab_coords(gnode, nx, ny, nz, seed, h),
+        "edge-->node": np.ascontiguousarray(np.stack([local_of(a), local_of(b)], axis=1), dtype=np.int32),
+        "edge_weights": w,
+        "bnd_node-->node": np.ascontiguousarray(local_of(bn)[:, None], dtype=np.int32),
+        "bnd_node-->group": np.ascontiguousarray(bg[:, None], dtype=np.int32),
+        "bnd_node_weights": bw,
+        "global_node": gnode.astype(np.int32), "global_edge": eid.astype(np.int64), "global_bnd": bid.astype(np.int64),
+        "neighbour_rank": np.array(nbr, dtype=np.int32), "export_ptr": np.array(exp_ptr, dtype=np.int32),
+        "export_idx": (np.concatenate(exp_idx) if exp_idx else np.zeros(0, np.int64)).astype(np.int32),
+        "import_ptr": np.array(imp_ptr, dtype=np.int32),
+    }
+
+
+def _owner_of_plane(nx, n_ranks, i):
+    r = (i * n_ranks) // nx
+    while slab_owner_planes(nx, r, n_ranks)[1] <= i:
+        r += 1
+    while slab_owner_planes(nx, r, n_ranks)[0] > i:
+        r -= 1
+    return r
+
+
+def slab_part(config, n_ranks):
+    """owner rank of every node of the whole deck (for tests against mgcfd_local_mesh_build)"""
+    _, (nx, ny, nz), _ = SLAB_CONFIGS[config] if isinstance(config, str) else config
+    plane_owner = np.array([_owner_of_plane(nx, n_ranks, i) for i in range(nx)], dtype=np.int32)
+    return np.repeat(plane_owner, ny * nz)

@@ -30,6 +30,20 @@ def test_reference_arm_line():
     assert d["gpu_launches"] == 0 and d["value"] > 0
 
 
+def test_reference_arm_on_a_per_rank_deck(monkeypatch):
+    """a deck that only exists per rank (BASELINE configs[4]): under torchrun rank 0 times its own slab as the bounded
+    sample, the other ranks print nothing"""
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--mesh", "slab_test", "--gpus", "2")
+    assert d["impl"] == "reference" and d["value"] > 0 and "x-slab of rank 0 of 2" in d["config"]["cpu_sample"]
+    assert "generated per rank" in d["config"]["workload"] and d["scaling"] == "strong"
+    monkeypatch.setenv("RANK", "1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--mesh", "slab_test", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
 @pytest.mark.gpu
 def test_b200_arm_line():
     d = run_bench("--steps", "4", "--warmup", "3", "--mesh", "medium", "--cpu-cycles", "1")

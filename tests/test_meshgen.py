@@ -32,3 +32,42 @@ def test_layout_and_determinism(meshgen):
     assert mg.min() >= 0 and mg.max() < cn
     assert np.setdiff1d(np.arange(cn), mg).size > 0                           # childless coarse nodes exist (Q8)
     assert not np.array_equal(np.sort(e[:, 0]), e[:, 0])                      # file order is shuffled
+
+
+import pytest
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 4, 5])
+def test_slab_deck_generated_per_rank_equals_the_partitioned_whole(pkg, meshgen, n_ranks):
+    """BASELINE.json configs[4] ("generated per-partition, never materialised on one host"): a rank's
+    slab generated alone is exactly what mgcfd_local_mesh_build cuts out of the whole deck -- nodes, edges, weights,
+    boundary entries, halo / export / import lists, bit for bit (12 x-planes over 2..5 ranks, divisible or not)"""
+    mesh = meshgen.make_slab_global("slab_test")
+    assert tuple(mesh["levels"][0][k].shape[0] for k in ("node_coordinates", "edge-->node", "bnd_node-->node")) == meshgen.slab_sizes("slab_test")
+    part = meshgen.slab_part("slab_test", n_ranks)
+    owned_total = 0
+    for r in range(n_ranks):
+        lm = pkg.LocalMesh(mesh["levels"], 1, [part], r, n_ranks)
+        d = meshgen.make_slab_rank("slab_test", r, n_ranks)
+        rm = pkg.RankMesh(d)
+        assert lm.sizes(0) == rm.sizes(0)
+        for what in ("global_node", "neighbour_rank", "export_ptr", "export_idx", "import_ptr", "edge_to_node"):
+            assert np.array_equal(lm.query(0, what), rm.query(0, what)), (r, what)
+        assert np.array_equal(lm.query(0, "global_edge"), d["global_edge"]) and np.array_equal(lm.query(0, "global_bnd"), d["global_bnd"])
+        v = lm.level(0).contents
+        for ptr, n, ref in ((v.node_coordinates, v.n_nodes * 3, d["node_coordinates"]), (v.edge_weights, v.n_edges * 3, d["edge_weights"]),
+                            (v.bnd_node_weights, v.n_bnd_nodes * 3, d["bnd_node_weights"]),
+                            (v.bnd_node_to_group, v.n_bnd_nodes, d["bnd_node-->group"]), (v.bnd_node_to_node, v.n_bnd_nodes, d["bnd_node-->node"])):
+            assert np.array_equal(np.ctypeslib.as_array(ptr, shape=(n,)), ref.ravel())
+        owned_total += d["n_owned"]
+    assert owned_total == meshgen.slab_sizes("slab_test")[0]
+
+
+def test_slab_deck_shape_of_the_150m_config(meshgen):
+    n, e, b = meshgen.slab_sizes("rotor37_150m")
+    assert n == 150_000_000 and e == 449_150_000 and b == 2 * (500 * 500 + 600 * 500 * 2)      # SURVEY.md 8d config 5: "~449 M axis edges"
+    x = [meshgen.slab_owner_planes(600, r, 8) for r in range(8)]
+    assert x[0] == (0, 75) and x[7] == (525, 600) and all(hi - lo == 75 for lo, hi in x)
+    # the hashed quantities are reproducible and well spread
+    u = meshgen._hash_u01(np.arange(100000), 2, 100)
+    assert 0.49 < u.mean() < 0.51 and u.min() >= 0 and u.max() < 1 and np.array_equal(u, meshgen._hash_u01(np.arange(100000), 2, 100))
