@@ -18,3 +18,26 @@ def test_lean_kernel_matches_golden(pkg, meshgen, golden, monkeypatch):
             got, ref = gpu.fetch(l, "variables"), g[f"var_L{l}"]
             assert (np.abs(got - ref).max(axis=0) <= 1e-10 * np.abs(ref).max(axis=0)).all()
             assert gpu.validate(l, ref) == 0
+
+
+def test_per_rank_slab_decks_run_like_the_whole_deck(pkg, meshgen):
+    """round-2 preparation: contexts built from meshgen.make_slab_rank / RankMesh (BASELINE configs[4] path) driven as
+    virtual ranks reproduce the undecomposed run bit for bit in the exact build"""
+    mesh = meshgen.make_slab_global("slab_test")
+    with pkg.MGCFD(mesh["levels"], exact_arith=True) as single:
+        single.run_cycles(3)
+        ref = single.fetch(0, "variables")
+    for n_ranks in (2, 3):
+        rms = [pkg.RankMesh(meshgen.make_slab_rank("slab_test", r, n_ranks)) for r in range(n_ranks)]
+        ranks = [pkg.MGCFD(local_mesh=rm, device=0, exact_arith=True) for rm in rms]
+        try:
+            pkg.group_run_cycles(ranks, 3)
+            full = np.full_like(ref, np.nan)
+            for r, g in enumerate(ranks):
+                gn = rms[r].query(0, "global_node")
+                no = g.n_owned[0]
+                full[gn[:no]] = g.fetch(0, "variables")[:no]
+            assert np.array_equal(full, ref)
+        finally:
+            for g in ranks:
+                g.close()
