@@ -782,6 +782,24 @@ static void slots_for_chunks(const OwnerPlanHost &O, int k0, int k1, int split, 
     for (std::thread &t : pool) t.join();
 }
 
+// slots of one chunk at a time, computed a batch of chunks ahead (bounded host memory on 100M-node decks)
+struct SlotBatches {
+    const OwnerPlanHost &O;
+    int split;
+    bool slotting;
+    int batch;
+    std::vector<int> buf;
+    int k0 = -1;
+    const int *of(int k)
+    {
+        if (k0 < 0 || k < k0 || k >= k0 + batch) {
+            k0 = k - k % batch;
+            slots_for_chunks(O, k0, std::min(O.n_chunks, k0 + batch), split, slotting, buf);
+        }
+        return buf.data() + (O.edge_off[k] - O.edge_off[k0]);
+    }
+};
+
 static int ensure_owner(mgcfd_ctx *ctx, int level)
 {
     LevelHost &L = ctx->H[level];
@@ -834,13 +852,11 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     const bool slotting = !(slot_s && atoi(slot_s) == 0);
     int node_split = (!ctx->opt.exact_arith && O.max_own <= 128) ? 2 : 1;
     if (split_s && (atoi(split_s) == 1 || atoi(split_s) == 2)) node_split = atoi(split_s);
-    std::vector<int> slots;                  // of one batch of chunks
-    const int BATCH = 8192;
+    SlotBatches slot_batches{O, node_split, slotting, 8192, {}, -1};
     std::vector<OwnerChunkDesc> desc(O.n_chunks);
     std::vector<unsigned char> blob((size_t)O.dev_blob_off[O.n_chunks], 0);
     for (int k = 0; k < O.n_chunks; k++) {
-        if (k % BATCH == 0) slots_for_chunks(O, k, std::min(O.n_chunks, k + BATCH), node_split, slotting, slots);
-        const int *slot = slots.data() + (O.edge_off[k] - O.edge_off[k - k % BATCH]);
+        const int *slot = slot_batches.of(k);
         OwnerChunkDesc &d = desc[k];
         d.node0 = O.node0[k];
         d.n_own = O.node0[k + 1] - O.node0[k];
@@ -1564,6 +1580,16 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
         if (s == "owner_edge_off") return emit(O.edge_off, out, cap);
         if (s == "owner_edge_file") return emit(O.edge_file, out, cap);
         if (s == "owner_lab") return emit(std::vector<int>(O.lab.begin(), O.lab.end()), out, cap);
+        if (s == "owner_slots_split2_batch7") {
+            // the same slots through the batched accessor ensure_owner packs with (a small batch, for tests)
+            SlotBatches sb{O, 2, true, 7, {}, -1};
+            std::vector<int> all;
+            for (int k = 0; k < O.n_chunks; k++) {
+                const int *p = sb.of(k);
+                all.insert(all.end(), p, p + O.n_edges[k]);
+            }
+            return emit(all, out, cap);
+        }
         if (s == "owner_slots_split1" || s == "owner_slots_split2") {
             // device packing: slot of every plan edge inside its chunk (bank_aware_slots), concatenated like owner_edge_file
             std::vector<int> all;

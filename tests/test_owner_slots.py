@@ -43,3 +43,11 @@ def test_slots_are_deterministic(pkg, meshgen):
     mesh = meshgen.make_multigrid("small")
     with pkg.MGCFD(mesh["levels"], device=-1, init=False) as a, pkg.MGCFD(mesh["levels"], device=-1, init=False) as b:
         assert np.array_equal(a.plan_query(0, "owner_slots_split2"), b.plan_query(0, "owner_slots_split2"))
+
+
+def test_batched_slot_accessor_equals_the_whole_plan(pkg, meshgen):
+    """device packing asks for the slots chunk by chunk, computed a batch of chunks ahead: same answer for any batch size"""
+    mesh = meshgen.make_multigrid("small")
+    with pkg.MGCFD(mesh["levels"], device=-1, init=False) as g:
+        for l in range(len(mesh["levels"])):
+            assert np.array_equal(g.plan_query(l, "owner_slots_split2_batch7"), g.plan_query(l, "owner_slots_split2"))
