@@ -654,7 +654,7 @@ static int build_owner_host(mgcfd_ctx *ctx, int level)
     if (L.have_owner) return MGCFD_OK;
     int nb = ctx->opt.owner_chunk_nodes;
     // caps on local nodes and edges bound the shared-memory footprint (DESIGN.md "owner chunk sizing")
-    int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
+    int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 6;      // 6 edges per owned node: coarse levels (4-4.6 edges/node) fill their chunks
     // tuning knobs for experiments (not part of the specified plan): override the local-node / edge caps
     if (const char *e = getenv("MGCFD_OWNER_MAX_LOC")) max_loc = atoi(e);
     if (const char *e = getenv("MGCFD_OWNER_MAX_EDGES")) max_edges = atoi(e);
