@@ -217,7 +217,7 @@ static void free_level(LevelDev &d)
     void *ptrs[] = {d.var_alt, d.bnd_ptr, d.var, d.old, d.res, d.flux, d.dummy_flux, d.vol, d.sf, d.coords, d.up_count, d.mg, d.child_ptr,
                     d.child_idx, d.bu_node, d.bu_ptr, d.b_group, d.b_wt, d.cbrt_vol, d.perm, d.atomic.nodes, d.atomic.w,
                     d.colour.blk_edge0, d.colour.blk_node0, d.colour.blk_ncol, d.colour.node_gid, d.colour.lab,
-                    d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.gather.desc, d.gather.halo_gid,
+                    d.colour.ecol, d.colour.w, d.owner.desc, d.owner.halo_gid, d.owner.blob, d.owner.xtab, d.gather.desc, d.gather.halo_gid,
                     d.gather.row_node, d.gather.row_deg, d.gather.ent, d.gather.w0, d.gather.w1, d.gather.w2, d.gather.g,
                     d.emit.desc, d.emit.halo_gid, d.emit.row_node, d.emit.row_cnt, d.emit.blob};
     for (void *p : ptrs)
@@ -654,7 +654,7 @@ static int build_owner_host(mgcfd_ctx *ctx, int level)
     if (L.have_owner) return MGCFD_OK;
     int nb = ctx->opt.owner_chunk_nodes;
     // caps on local nodes and edges bound the shared-memory footprint (DESIGN.md "owner chunk sizing")
-    int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 5;
+    int max_loc = nb + (nb * 3) / 2 + 64, max_edges = nb * 6;      // 6 edges per owned node: coarse levels (4-4.6 edges/node) fill their chunks
     // tuning knobs for experiments (not part of the specified plan): override the local-node / edge caps
     if (const char *e = getenv("MGCFD_OWNER_MAX_LOC")) max_loc = atoi(e);
     if (const char *e = getenv("MGCFD_OWNER_MAX_EDGES")) max_edges = atoi(e);
@@ -903,6 +903,22 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         }
     }
     int rc;
+    if (const char *lean_s = getenv("MGCFD_OWNER_LEAN"); lean_s && atoi(lean_s) == 1) {
+        // lean kernel: descriptor and halo ids of a chunk in one fixed-stride record
+        int hs = 0;
+        for (int k = 0; k < O.n_chunks; k++) hs = std::max(hs, O.halo_off[k + 1] - O.halo_off[k]);
+        hs = (hs + 3) & ~3;
+        const int xs = 12 + hs;
+        std::vector<int> xtab((size_t)O.n_chunks * xs, -1);
+        static_assert(sizeof(OwnerChunkDesc) == 48, "record head = descriptor");
+        for (int k = 0; k < O.n_chunks; k++) {
+            memcpy(&xtab[(size_t)k * xs], &desc[k], sizeof(OwnerChunkDesc));
+            std::copy(O.halo_gid.begin() + O.halo_off[k], O.halo_gid.begin() + O.halo_off[k + 1], xtab.begin() + (size_t)k * xs + 12);
+        }
+        if (D.owner.xtab) { cudaFree(D.owner.xtab); D.owner.xtab = nullptr; }
+        if ((rc = dev_upload(ctx, &D.owner.xtab, xtab))) return rc;
+        D.owner.xs = xs; D.owner.hs = hs;
+    }
     if ((rc = dev_upload(ctx, &D.owner.desc, desc))) return rc;
     if ((rc = dev_upload(ctx, &D.owner.halo_gid, O.halo_gid))) return rc;
     if ((rc = dev_upload(ctx, &D.owner.blob, blob))) return rc;

@@ -468,7 +468,7 @@ __device__ __forceinline__ void finish_chunk(const double *raw, int node0, int n
 // (+ validation.h:27-44,102-115 after the last stage) with the prefetched old_variables / step_factor tiles, bit for
 // bit the arithmetic of time_step_kernel.  No shared-memory staging of the result and no barrier after it.
 // ------------------------------------------------------------------------------------------
-template <bool OVERWRITE, bool FUSE, int LG_SPLIT>
+template <bool OVERWRITE, bool FUSE, int LG_SPLIT, bool LEAN = false>
 __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, const unsigned char *sblob,
                                            const double *raw, const double *w0, const double *w1, const double *w2,
                                            const double *gg, const double *Fx, const uint16_t *rowptr, const uint16_t *csr,
@@ -500,15 +500,40 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
             f[3] = flip_sign(gg[e], sgn); f[4] = flip_sign(Fx[e], sgn);
 #endif
         };
-        const int j1 = rowptr[n + 1];
-        for (int jj = rowptr[n] + part; jj < j1; jj += step) {
-            double f[5];
-            fetch(csr[jj], f);
+        if (!LEAN) {
+            const int j1 = rowptr[n + 1];
+            for (int jj = rowptr[n] + part; jj < j1; jj += step) {
+                double f[5];
+                fetch(csr[jj], f);
 #pragma unroll
-            for (int v = 0; v < 5; v++) acc[v] += f[v];
+                for (int v = 0; v < 5; v++) acc[v] += f[v];
+            }
         }
     }
 #ifndef MGCFD_EXACT
+    if (LEAN) {
+        // lean sum loop (fast build): a warp-uniform trip count (no divergent-loop bookkeeping), the sign of an
+        // incidence applied by fma(+-1, F, acc) (exactly acc +- F), plane addresses by adds from one shifted index
+        const int j0 = active ? rowptr[n] + part : 0, j1 = active ? rowptr[n + 1] : 0;
+        const int mine = j1 > j0 ? (j1 - j0 + step - 1) >> lg_split : 0;
+        const int trips = __reduce_max_sync(0xffffffffu, mine);
+        const uint32_t pad8 = (uint32_t)(w1 - w0) * 8u;
+        const char *b0 = reinterpret_cast<const char *>(w0), *bx = reinterpret_cast<const char *>(Fx);
+        for (int it = 0, jj = j0; it < trips; it++, jj += step) {
+            const bool valid = jj < j1;
+            const uint32_t c = csr[valid ? jj : 0];
+            const uint32_t e8 = (c & 0x7fffu) << 3;
+            const double sg = (c & 0x8000u) ? -1.0 : 1.0;
+            const char *a0 = b0 + e8;
+            const double f0 = *reinterpret_cast<const double *>(a0), f1 = *reinterpret_cast<const double *>(a0 + pad8),
+                         f2 = *reinterpret_cast<const double *>(a0 + 2 * pad8), f3 = *reinterpret_cast<const double *>(a0 + 3 * pad8),
+                         f4 = *reinterpret_cast<const double *>(bx + e8);
+            if (valid) {
+                acc[0] = fma(sg, f0, acc[0]); acc[1] = fma(sg, f1, acc[1]); acc[2] = fma(sg, f2, acc[2]);
+                acc[3] = fma(sg, f3, acc[3]); acc[4] = fma(sg, f4, acc[4]);
+            }
+        }
+    }
     if (lg_split >= 1) {
 #pragma unroll
         for (int v = 0; v < 5; v++) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 1);      // every thread of a node
@@ -746,6 +771,92 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     __syncthreads();
     finish_chunk<FUSE>(raw, d.node0, d.n_own, flux, rk, told, tsf, old_bulk, sf_bulk);
 }
+
+// ------------------------------------------------------------------------------------------
+// variant 2l ("lean", MGCFD_OWNER_LEAN=1; fast build, fused stage, chunks of up to 64 owned nodes, 128 threads): the
+// one-CTA-per-chunk kernel with the two instruction-heavy phases of profiles/README.md section 5 rewritten --
+//   staging: the chunk's descriptor and halo ids sit in ONE fixed-stride record (xtab[chunk][12 + hs]), so the ids are
+//            requested together with the descriptor (two dependent L2 latencies instead of three); halo rows are copied by
+//            groups of 8 lanes (lane = component 0..4 of the row: no divisions, one id load per row);
+//   node phase: node_phase<..., LEAN> (warp-uniform trip count, fma sign, additive plane addresses).
+// Everything else is flux_owner_kernel<false, true, true, true>.
+// ------------------------------------------------------------------------------------------
+#ifndef MGCFD_EXACT
+constexpr int LEAN_ROWS = 8;            // halo rows per 8-lane group requested with the descriptor: 16 groups x 8 = 128
+                                        // halo nodes; longer lists finish in a loop once the descriptor is known
+__global__ void __launch_bounds__(128, 6)
+flux_owner_lean_kernel(int max_loc, int max_edges, int max_blob, const int *__restrict__ xtab, int xs, int hs,
+                       const int *__restrict__ chunk_list, const unsigned char *__restrict__ blob,
+                       const double *__restrict__ var, RkStageArgs rk)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+    unsigned char *sblob = smraw + 16;
+    double *Fx = reinterpret_cast<double *>(sblob + max_blob);
+    double *raw = Fx + (size_t)(NFLUX - 4) * max_edges;
+    double *der = raw + (size_t)max_loc * 5;
+    double *told = raw + (((size_t)NF * max_loc + 1) & ~(size_t)1);
+    double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
+    const int tid = threadIdx.x, grp = tid >> 3, comp = tid & 7;
+    const int chunk = chunk_list ? chunk_list[blockIdx.x] : blockIdx.x;
+    const int *rec = xtab + (size_t)chunk * xs;
+    // halo ids of this thread's rows and the descriptor: independent loads, one round trip
+    int hgv[LEAN_ROWS];
+#pragma unroll
+    for (int k = 0; k < LEAN_ROWS; k++) {
+        const int row = grp + 16 * k;
+        hgv[k] = row < hs ? __ldg(rec + 12 + row) : -1;
+    }
+    const OwnerChunkDesc d = *reinterpret_cast<const OwnerChunkDesc *>(rec);
+    const int nloc = d.n_own + d.n_halo;
+    const uint32_t old_bulk = owned_bulk_bytes(d.n_own), sf_bulk = ((uint32_t)d.n_own * 8u) & ~15u;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)d.blob_bytes + owned_bulk_bytes(d.n_own) + old_bulk + sf_bulk);
+        bulk_g2s(sblob, blob + d.blob_off, (uint32_t)d.blob_bytes, bar);
+        if (owned_bulk_bytes(d.n_own)) bulk_g2s(raw, var + (size_t)d.node0 * 5, owned_bulk_bytes(d.n_own), bar);
+        if (old_bulk) bulk_g2s(told, rk.old + (size_t)d.node0 * 5, old_bulk, bar);
+        if (sf_bulk) bulk_g2s(tsf, rk.sf + d.node0, sf_bulk, bar);
+    }
+    if (tid == 32 && (d.n_own & 1)) raw[d.n_own * 5 - 1] = __ldg(var + (size_t)(d.node0 + d.n_own) * 5 - 1);
+    {
+        double *hraw = raw + (size_t)d.n_own * 5;
+#pragma unroll
+        for (int k = 0; k < LEAN_ROWS; k++)
+            if (hgv[k] >= 0 && comp < 5) cp_async8(hraw + (grp + 16 * k) * 5 + comp, var + (size_t)hgv[k] * 5 + comp);
+        for (int row = grp + 16 * LEAN_ROWS; row < d.n_halo; row += 16)
+            if (comp < 5) cp_async8(hraw + row * 5 + comp, var + (size_t)__ldg(rec + 12 + row) * 5 + comp);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    mbar_wait(bar, 0);
+    for (int i = tid; i < nloc; i += 128) {
+        double u[5], r[8];
+#pragma unroll
+        for (int v = 0; v < 5; v++) u[v] = raw[i * 5 + v];
+        derive(u, r);
+        der[i] = r[5]; der[max_loc + i] = r[6]; der[2 * max_loc + i] = r[7];
+    }
+    __syncthreads();
+    double *w0 = reinterpret_cast<double *>(sblob);
+    double *w1 = w0 + d.e_pad, *w2 = w1 + d.e_pad, *gg = w2 + d.e_pad;
+    const uint32_t *lab = reinterpret_cast<const uint32_t *>(gg + d.e_pad);
+    const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + d.e_pad);
+    const uint16_t *csr = rowptr + (((d.n_own + 1) + 7) & ~7);
+    for (int e = tid; e < d.n_edges; e += 128) {
+        uint32_t l = lab[e];
+        double x = w0[e], y = w1[e], z = w2[e], g = gg[e];
+        double a[NF], b[NF], fa[5];
+        load_state<NF>(raw, der, max_loc, (int)(l & 0xffff), a);
+        load_state<NF>(raw, der, max_loc, (int)(l >> 16), b);
+        edge_flux(a, b, x, y, z, g, fa);
+        w0[e] = fa[0]; w1[e] = fa[1]; w2[e] = fa[2]; gg[e] = fa[3];
+        Fx[e] = fa[4];
+    }
+    __syncthreads();
+    node_phase<true, true, 1, true>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, nullptr, rk);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // variant 2p: the owner kernel as a persistent, double-buffered pipeline.  The grid is sized to the number of CTAs
@@ -1439,6 +1550,15 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
         RkStageArgs ra = *a.rk;
         ra.max_own = h.max_own;
         size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.dev_max_blob, false, h.max_own);
+#ifndef MGCFD_EXACT
+        // MGCFD_OWNER_LEAN=1: the lean kernel (needs the fixed-stride descriptor + halo-id table of ensure_owner)
+        const char *lean_s = getenv("MGCFD_OWNER_LEAN");
+        if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64) {
+            flux_owner_lean_kernel<<<grid, 128, fsmem, s>>>(h.max_loc, h.max_edges, h.dev_max_blob, p.xtab, p.xs, p.hs, a.chunk_list,
+                                                            p.blob, a.var, ra);
+            return 1;
+        }
+#endif
         // MGCFD_OWNER_EPILOGUE=0: node sums staged through shared memory and a separate coalesced update pass
         const char *epi_s = getenv("MGCFD_OWNER_EPILOGUE");
         if (epi_s && atoi(epi_s) == 0)
@@ -1468,6 +1588,9 @@ inline std::string configure()
     OPT_IN((flux_owner_kernel<false, false, false>));
     OPT_IN((flux_owner_kernel<false, true, true, false>));
     OPT_IN((flux_owner_kernel<false, true, true, true>));
+#ifndef MGCFD_EXACT
+    OPT_IN(flux_owner_lean_kernel);
+#endif
 #define OPT_IN_PIPE(T, B, S)                                    \
     OPT_IN((flux_owner_pipe_kernel<T, B, S, true, true>));     \
     OPT_IN((flux_owner_pipe_kernel<T, B, S, true, false>));    \

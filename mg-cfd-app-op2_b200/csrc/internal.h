@@ -130,6 +130,8 @@ struct OwnerPlanDev {
     int *halo_gid = nullptr;
     unsigned char *blob = nullptr;   // per chunk: w0[e_pad] w1 w2 g (double) | lab[e_pad] (u32) | rowptr | csr (u16) | boundary entries
     long long blob_bytes = 0;
+    int *xtab = nullptr;             // lean kernel: per chunk [descriptor (12 ints) | halo ids, -1 padded (hs)] at stride xs
+    int xs = 0, hs = 0;
     bool valid = false;
 };
 

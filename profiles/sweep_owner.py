@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (helpers only; bench redirects fd 1 to stderr, emit() writes to the real stdout)
 import __graft_entry__ as ge  # noqa: E402
 
-KNOBS = {"pipe": "MGCFD_OWNER_PIPE", "thr": "MGCFD_OWNER_THREADS", "ctas": "MGCFD_OWNER_PIPE_CTAS", "minb": "MGCFD_OWNER_PIPE_MINB", "slot": "MGCFD_OWNER_SLOTTING", "epi": "MGCFD_OWNER_EPILOGUE", "split": "MGCFD_OWNER_SLOT_SPLIT",
+KNOBS = {"pipe": "MGCFD_OWNER_PIPE", "thr": "MGCFD_OWNER_THREADS", "ctas": "MGCFD_OWNER_PIPE_CTAS", "minb": "MGCFD_OWNER_PIPE_MINB", "slot": "MGCFD_OWNER_SLOTTING", "lean": "MGCFD_OWNER_LEAN", "epi": "MGCFD_OWNER_EPILOGUE", "split": "MGCFD_OWNER_SLOT_SPLIT",
          "maxloc": "MGCFD_OWNER_MAX_LOC", "maxedges": "MGCFD_OWNER_MAX_EDGES"}
 
 

@@ -66,7 +66,7 @@ def test_owner_chunks_bit_exact(pkg, meshgen, plan_oracle, name, chunk):
             starts = gpu.plan_query(l, "owner_chunk_start")
             hoff, hgid = gpu.plan_query(l, "owner_halo_off"), gpu.plan_query(l, "owner_halo_gid")
             eoff, efile = gpu.plan_query(l, "owner_edge_off"), gpu.plan_query(l, "owner_edge_file")
-            max_loc, max_edges = chunk + (chunk * 3) // 2 + 64, chunk * 5
+            max_loc, max_edges = chunk + (chunk * 3) // 2 + 64, chunk * 6
             rs, rh, re = plan_oracle.owner_chunks(lev["edge-->node"], perm, perm.size, chunk, max_loc, max_edges)
             assert list(starts) == rs
             for k in range(len(rs) - 1):
