@@ -3,8 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mesh m6] [--variant owner]
 
-One "step" is one multigrid V-cycle (euler3d.cpp:458-641) over the synthetic deck.  At N=1 the deck is
-BASELINE.json configs[1] (Onera-M6-shaped, 4 levels).  Prints ONE JSON line (rank 0).
+One "step" is one multigrid V-cycle (euler3d.cpp:458-641) over the synthetic deck.  At EVERY N the deck is
+BASELINE.json configs[3]: the Rotor37-shaped 8M-node 4-level deck, partitioned over the N GPUs (strong scaling;
+it fits one GPU, so N=1 is the same job undecomposed).  The N=1 line also carries the Onera-M6-shaped cycle
+(configs[1]) as the sub-record "m6".  Prints ONE JSON line (rank 0).
 
   value        flux-edge edge updates per second of whole-cycle time, deck resident in HBM, CUDA-event timed
   e2e          same metric through the C-ABI with HOST buffers: per step the flow state of every level is
@@ -13,6 +15,10 @@ BASELINE.json configs[1] (Onera-M6-shaped, 4 levels).  Prints ONE JSON line (ran
                the CUDA-event time of the flux launches inside the timed region, against the measured HBM peak
   cpu_baseline the reference's own elemental kernels (oracle/_ref, OpenMP block-coloured, all host threads)
                on a bounded sample of the same deck
+  parity       after the timed regions the variables are re-initialised (euler3d.cpp:414-417), ONE cycle runs on the
+               GPU(s) and every level's owned-node state is compared with the CPU oracle's after one cycle
+               (<= 1e-10 relative to the variable's largest magnitude, north_star's tolerance; -v criterion of
+               validation.h:46-100 counted beside it).  A mismatch makes the run fail (exit code 3).
 
 `--impl reference` times that CPU implementation as the whole job instead (the reference has no GPU code in
 its tree; its OP2 build cannot be produced offline).
@@ -143,8 +149,29 @@ def hilbert_orders(levels0):
     return perms, orders
 
 
-def cpu_run(levels0_ordered, n_cycles, warmup, threads):
-    """oracle/_ref (the reference's own headers) if present, else the port; OpenMP block-coloured."""
+def cpu_info():
+    """CPU model string, physical cores and hardware threads of this host."""
+    model, phys = None, set()
+    pid = cid = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and model is None:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("physical id"):
+                pid = line.split(":", 1)[1].strip()
+            elif line.startswith("core id"):
+                cid = line.split(":", 1)[1].strip()
+            elif not line.strip():
+                if pid is not None or cid is not None:
+                    phys.add((pid, cid))
+                pid = cid = None
+    except OSError:
+        pass
+    return {"cpu_model": model, "physical_cores": len(phys) or None, "hardware_threads": os.cpu_count()}
+
+
+def pick_oracle():
+    """oracle/_ref (the reference's own headers compiled in place) if present, else the plain-C port"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     flags = open("/proc/cpuinfo").read()
@@ -154,38 +181,131 @@ def cpu_run(levels0_ordered, n_cycles, warmup, threads):
             continue
         if orc.available(kind):
             break
-    o = orc.Oracle(kind)
+    return orc.Oracle(kind), kind, label
+
+
+def cpu_run(levels0_ordered, n_cycles, warmup, threads, keep_first_cycle=False):
+    """The CPU implementation of the path, OpenMP block-coloured on `threads` host threads: init, `warmup` cycles,
+    then `n_cycles` timed cycles.  keep_first_cycle: also return every level's variables after the FIRST cycle from
+    the initial state (the parity reference; needs warmup >= 1)."""
+    o, kind, label = pick_oracle()
     used = o.set_threads(threads)
     run = o.make_state(levels0_ordered)
     run.init()
+    first = None
+    if keep_first_cycle:
+        assert warmup >= 1
+        rc, _ = run.run(1)
+        if rc != 0:
+            raise RuntimeError(f"CPU oracle failed rc={rc}")
+        first = [lv["var"].copy() for lv in run.levels]
+        warmup -= 1
     if warmup:
         run.run(warmup)
-    rc, st = run.run(n_cycles)
-    if rc != 0:
-        raise RuntimeError(f"CPU baseline failed rc={rc}")
-    return {"edges_per_s": st.flux_edges / st.wall_total, "cycles_per_s": n_cycles / st.wall_total,
-            "flux_kernel_edges_per_s": st.flux_edges / st.wall_flux_edge, "wall_s": st.wall_total,
-            "kind": label, "lib": kind, "cores": used}
+    out = {"kind": label, "lib": kind, "cores": used, "first_cycle": first}
+    if n_cycles > 0:
+        rc, st = run.run(n_cycles)
+        if rc != 0:
+            raise RuntimeError(f"CPU baseline failed rc={rc}")
+        out.update({"edges_per_s": st.flux_edges / st.wall_total, "cycles_per_s": n_cycles / st.wall_total,
+                    "flux_kernel_edges_per_s": st.flux_edges / st.wall_flux_edge, "wall_s": st.wall_total})
+    return out
+
+
+def log(msg):
+    sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
+def describe(mesh_name, sizes, world, scaling, slab, partitioner):
+    how = ""
+    if world > 1:
+        how = (" x%d along x (weak scaling" % world if scaling == "weak" else " partitioned over %d GPUs (strong scaling" % world) + \
+            (", x-slabs generated per rank" if slab else f", {partitioner} partition") + ", 1 rank per GPU)"
+    return (f"{mesh_name}{how}: {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
+            f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
+
+
+def time_cycles(gpu, stream, steps, barrier, max_over_ranks):
+    """K cycles exactly as a user runs them (CUDA-graph replay), CUDA events on the library's stream; ms for all K"""
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    gpu.run_cycles(steps)
+    e1.record(stream)
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1))
+
+
+def stage_timing(gpu, stream, steps, n_levels, fused, barrier, max_over_ranks):
+    """the same K cycles with every flux-edge / fused-stage launch bracketed by CUDA events (library timers, mode 2)"""
+    import torch
+    name = "rk_stage" if fused else "compute_flux_edge"
+    gpu.timers_enable(2)
+    gpu.timers_reset()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    gpu.run_cycles(steps)
+    e3.record(stream)
+    barrier()
+    ms_timed = max_over_ranks(e2.elapsed_time(e3))
+    flux_ms, flux_calls, flux_elems = gpu.timer(name)
+    per_level, per_level_ms = [], []
+    for l in range(n_levels):
+        ms_l, calls_l, _ = gpu.timer(name, l)
+        per_level.append(round(1e3 * ms_l / max(calls_l, 1), 2))
+        per_level_ms.append(ms_l)
+    gpu.timers_enable(0)
+    return {"ms_timed": ms_timed, "flux_ms": flux_ms, "calls": flux_calls, "elems": flux_elems, "per_level_us": per_level,
+            "per_level_ms": per_level_ms}
+
+
+def m6_subrecord(pkg, device, steps, warmup, peak):
+    """BASELINE configs[1]: the Onera-M6-shaped 4-level cycle on one GPU, reported inside the N=1 line"""
+    import torch
+    mesh = pkg.meshgen.make_multigrid("m6")
+    sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in mesh["levels"]]
+    gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=device)
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", device))
+    sync = torch.cuda.synchronize
+    gpu.run_cycles(warmup + warmup % 2)
+    ms = time_cycles(gpu, stream, steps, sync, lambda x: x)
+    st = stage_timing(gpu, stream, steps, len(sizes), True, sync, lambda x: x)
+    launches0 = gpu.kernel_launches()
+    gpu.run_cycles(1)
+    launches = gpu.kernel_launches() - launches0
+    gpu.close()
+    nbytes = rk_stage_bytes_per_cycle(sizes) * steps
+    return {"workload": describe("m6", sizes, 1, "strong", False, "geom"), "steps": steps, "ms_per_step": ms / steps,
+            "mg_cycles_per_s": steps / (ms * 1e-3), "edges_per_s": flux_edges_per_cycle(sizes) * steps / (ms * 1e-3),
+            "launches_per_cycle": launches,
+            "stage_frac_launch_timed": nbytes / (st["flux_ms"] * 1e-3) / 1e9 / peak,
+            "stage_per_level_us": st["per_level_us"],
+            "note": "levels are L2-sized (300K..81K nodes): the roofline fraction of the line is quoted on the 8M-node deck"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mesh", default="m6")
+    ap.add_argument("--mesh", default="rotor37_8m", help="deck (default: BASELINE configs[3], the Rotor37-shaped 8M-node 4-level deck)")
     ap.add_argument("--variant", default="owner", choices=["owner", "emit", "gather", "colour", "atomic"])
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--cpu-cycles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-m6", action="store_true", help="N=1: skip the Onera-M6 sub-record (BASELINE configs[1])")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel per op_par_loop call site")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every launch instead of replaying CUDA graphs")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = the deck grows with N along x (default, the driver's scaling run); strong = the --mesh deck "
-                         "itself is partitioned over the N GPUs (BASELINE configs[3])")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong = the --mesh deck itself is partitioned over the N GPUs (default, BASELINE configs[3]); "
+                         "weak = the deck grows with N along x")
     ap.add_argument("--partitioner", default="geom", help="N>1: geom | kway | block | random (op_partition methods)")
     ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"],
                     help="N>1: direct peer stores over CUDA-IPC-mapped memory (default) or NCCL send/recv")
@@ -195,7 +315,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return                                        # the CPU arm is rank 0's job alone
     pkg = ge.load_package()
+    t_start = time.time()
     slab = args.mesh in pkg.meshgen.SLAB_CONFIGS          # single-level decks that every rank generates for itself
     if slab and world > 1:
         # BASELINE configs[4]: the deck (150M nodes for rotor37_150m) is never materialised on one host; the job is a
@@ -215,37 +338,39 @@ def main():
             mesh = pkg.meshgen.make_multigrid(args.mesh)
         levels0 = [pkg.meshgen.zero_based(l) for l in mesh["levels"]]
         sizes = [(l["node_coordinates"].shape[0], l["edge-->node"].shape[0], l["bnd_node-->node"].shape[0]) for l in levels0]
-    how = (" x%d along x (weak scaling" % world if args.scaling == "weak" else " partitioned over %d GPUs (strong scaling" % world) + \
-        (", x-slabs generated per rank" if slab else f", {args.partitioner} partition") + ", 1 rank per GPU)"
-    workload = (f"{args.mesh}{how if world > 1 else ''}"
-                f": {len(sizes)}-level synthetic deck, nodes {[s[0] for s in sizes]}, edges {[s[1] for s in sizes]}; "
-                f"step = 1 multigrid V-cycle (visits {visits_per_cycle(len(sizes))}, RK=3)")
-    config = {"workload": workload, "mesh": args.mesh, "levels": len(sizes), "flux_variant": args.variant,
-              "arith": "exact" if args.exact else "fast", "fused_schedule": args.variant in ("owner", "emit") and not args.no_fusion, "cuda_graphs": not args.no_graphs,
-              "l2": "no flush between steps: the V-cycle working set (~%d MB) exceeds the 126 MB L2"
+    if rank == 0:
+        log(f"deck {args.mesh} ready after {time.time() - t_start:.1f} s")
+    # `config` is the same object in both arms (the driver compares them); run-specific facts go into `run_info`
+    config = {"workload": describe(args.mesh, sizes, world, args.scaling, slab, args.partitioner), "mesh": args.mesh,
+              "levels": len(sizes), "scaling": args.scaling,
+              "l2": "no flush between steps: one V-cycle streams ~%d MB, far beyond the 126 MB L2"
                     % (sum(300 * s[0] + 32 * s[1] for s in sizes) // 2**20)}
     nthreads = os.cpu_count() or 1
+    cinfo = cpu_info()
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
-        if rank != 0:
-            return
         if levels0 is None:
             # a deck that is only ever generated per rank: the CPU arm runs rank 0's slab (owned + halo nodes, the edges
             # and boundary entries of its owned nodes) as a stand-alone deck -- a bounded sample of the workload
             d = pkg.meshgen.make_slab_rank(args.mesh, 0, world)
             levels0 = [{k: d[k] for k in ("node_coordinates", "edge-->node", "edge_weights", "bnd_node-->node", "bnd_node-->group",
                                           "bnd_node_weights")}]
-            config["cpu_sample"] = f"x-slab of rank 0 of {world} ({d['node_coordinates'].shape[0]} nodes, {d['edge-->node'].shape[0]} edges)"
+            sample_what = f"x-slab of rank 0 of {world} ({d['node_coordinates'].shape[0]} nodes, {d['edge-->node'].shape[0]} edges)"
+        else:
+            sample_what = "the same deck"
         perms, orders = hilbert_orders(levels0)
         ordered = reorder_for_cpu(levels0, perms, orders)
+        log(f"locality ordering done after {time.time() - t_start:.1f} s")
         r = cpu_run(ordered, args.steps, args.warmup, nthreads)
-        sample = f"{args.steps} full V-cycles of the same deck (locality-renumbered), OpenMP block-coloured, {r['lib']}"
+        sample = (f"{args.steps} full V-cycles of {sample_what} (locality-renumbered like the GPU run), OpenMP block-coloured, "
+                  f"{r['lib']}, {r['cores']} threads")
         line = {"impl": "reference", "metric": "mg_cycle_flux_edges_per_s", "value": r["edges_per_s"], "unit": "edges/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["wall_s"] / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "mg_cycles_per_s": r["cycles_per_s"],
-                "cpu_baseline": {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+                "cpu_baseline": dict({"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+                                      "sample": sample}, **cinfo),
                 "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -260,6 +385,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    run_info = {"flux_variant": args.variant, "arith": "exact" if args.exact else "fast",
+                "fused_schedule": world > 1 or (args.variant in ("owner", "emit") and not args.no_fusion),
+                "cuda_graphs": not args.no_graphs}
+    lm = None
     if world > 1:
         if slab:
             lm = pkg.RankMesh(pkg.meshgen.make_slab_rank(args.mesh, rank, world))      # this rank's x-slab + halo planes only
@@ -281,7 +410,7 @@ def main():
                 uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             gpu.comm_init_nccl(bytes(uid.cpu().numpy().tobytes()))
-        config["transport"] = args.transport
+        run_info["transport"] = args.transport
         local_sizes = [(lm.sizes(l)[0], lm.sizes(l)[1], lm.sizes(l)[2]) for l in range(len(sizes))]
     else:
         gpu = pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=local_rank,
@@ -289,6 +418,8 @@ def main():
                         fuse=not args.no_fusion, graphs=not args.no_graphs)
         local_sizes = sizes
     stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
+    if rank == 0:
+        log(f"context planned after {time.time() - t_start:.1f} s")
 
     def barrier():
         torch.cuda.synchronize()
@@ -305,35 +436,18 @@ def main():
 
     # warm-up (also builds the flux plans and captures the one-cycle CUDA graphs)
     gpu.run_cycles(args.warmup + (args.warmup % 2))      # an even count leaves both one-cycle graphs captured
+    if rank == 0:
+        log(f"warm-up done after {time.time() - t_start:.1f} s")
     launches0 = gpu.kernel_launches()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- timed region 1: K cycles exactly as a user runs them (graph replay), CUDA events on the library's stream
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    gpu.run_cycles(args.steps)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = time_cycles(gpu, stream, args.steps, barrier, max_over_ranks)
     launches = gpu.kernel_launches() - launches0
     # ---- timed region 2: the same K cycles launch by launch, every flux-edge / fused-stage launch event-timed
-    gpu.timers_enable(2)
-    gpu.timers_reset()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    gpu.run_cycles(args.steps)
-    e3.record(stream)
-    barrier()
-    ms_timed = max_over_ranks(e2.elapsed_time(e3))
+    fused = run_info["fused_schedule"]
+    st = stage_timing(gpu, stream, args.steps, len(sizes), fused, barrier, max_over_ranks)
     clocks = sampler.stop() if sampler else None
-    fused = world > 1 or (args.variant in ("owner", "emit") and not args.no_fusion)
-    flux_ms, flux_calls, flux_elems = gpu.timer("rk_stage" if fused else "compute_flux_edge")
-    per_level = []
-    for l in range(len(sizes)):
-        ms_l, calls_l, _ = gpu.timer("rk_stage" if fused else "compute_flux_edge", l)
-        per_level.append(round(1e3 * ms_l / max(calls_l, 1), 2))
-    gpu.timers_enable(0)
+    flux_ms, flux_calls, flux_elems, ms_timed = st["flux_ms"], st["calls"], st["elems"], st["ms_timed"]
 
     edges_step = flux_edges_per_cycle(sizes)          # edges of the whole (undecomposed) deck, cut edges counted once
     value = edges_step * args.steps / (ms * 1e-3)
@@ -341,26 +455,39 @@ def main():
     # per-GPU roofline: this rank's launches move this rank's edges (owned + recomputed cut edges) and nodes
     flux_bytes = (rk_stage_bytes_per_cycle(local_sizes) if fused else flux_bytes_per_cycle(local_sizes)) * args.steps
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
-    kname = (f"flux_{args.variant if args.variant == 'emit' else 'owner'}_kernel<FUSE> = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
+    kname = ("rk_stage2_kernel (exact build: flux_owner_kernel<FUSE>) = compute_flux_edge + compute_bnd_node_flux + time_step (+ residual) in one launch"
              if fused else f"compute_flux_edge_kernel[{args.variant}]")
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if fused and world == 1 and args.mesh == "m6" and os.path.exists(tpath):
+    # level-0 launches alone, both accountings: the fused stage's own bytes (32E + 288N, +120N after the last stage) and the
+    # flux-edge loop's (32E + 120N) over the SAME launch time -- the latter is north_star's ">= 60 % on the flux-edge loop"
+    # read as strictly as possible (the launch also does time_step / residual, whose bytes are then not credited)
+    E0, N0 = local_sizes[0][1], local_sizes[0][0]
+    l0_calls = RK * args.steps
+    l0_us = 1e3 * st["per_level_ms"][0] / max(l0_calls, 1)
+    frac_fused_l0 = ((32 * E0 + 288 * N0 + 40 * N0) if fused else (32 * E0 + 120 * N0)) / (l0_us * 1e-6) / 1e9 / peak
+    frac_flux_only_l0 = (32 * E0 + 120 * N0) / (l0_us * 1e-6) / 1e9 / peak
+    traffic, traffic_note = None, "no ncu --set full capture of this deck committed yet"
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if fused and world == 1 and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f)["dram_bytes_per_launch"]      # ncu --set full capture of the level-0 launch
+            tj = json.load(f)
+        if tj.get("mesh") == args.mesh:
+            traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("note", "")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch (profiles/r01_traffic.json)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "algorithmic_bytes": ("per stage 32E+120N (flux-edge) + 168N (time_step), + 120N (residual) after the last stage"
                                       if fused else "32E+120N per launch"),
-                "algorithmic_bytes_per_launch_L0": (32 * local_sizes[0][1] + 288 * local_sizes[0][0]) if fused else (32 * local_sizes[0][1] + 120 * local_sizes[0][0]),
+                "algorithmic_bytes_per_launch_L0": (32 * E0 + 288 * N0) if fused else (32 * E0 + 120 * N0),
+                "frac_fused_L0": frac_fused_l0, "frac_flux_only_L0": frac_flux_only_l0, "avg_launch_us_L0": l0_us,
                 "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
                 "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms_timed,
                 "ms_per_step_with_launch_timers": ms_timed / args.steps,
-                "per_level_avg_launch_us": per_level,
-                "note": "achieved = algorithmic bytes of all timed launches / their summed CUDA-event time; M6 levels are "
-                        "L2-resident sized, see config.l2"}
+                "other_kernels_ms_per_step": (ms_timed - flux_ms) / args.steps,
+                "per_level_avg_launch_us": st["per_level_us"],
+                "note": "achieved = algorithmic bytes of all timed stage launches / their summed CUDA-event time (every level of the "
+                        "deck exceeds the 126 MB L2); frac_*_L0 = the level-0 launches alone under both accountings"}
+    if rank == 0:
+        log(f"timed regions done after {time.time() - t_start:.1f} s: {ms / args.steps:.3f} ms/cycle, stage frac {achieved / peak:.3f}")
 
     # end-to-end through the C-ABI with host buffers
     e2e = None
@@ -382,33 +509,108 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         for p_ in pinned:
             p_.free()
-        nbytes = sum(s[0] * 40 for s in local_sizes) * world
+        nbytes = sum(s[0] * 40 for s in local_sizes)
+        if world > 1:
+            t = torch.tensor([float(nbytes)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            nbytes = int(t.item())
         e2e = {"value": edges_step * n_e2e / dt, "unit": "edges/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
                "what": "per step: mgcfd_set_dat(variables) for every level from page-locked host arrays, mgcfd_run_cycles(1), "
                        "mgcfd_fetch_dat(variables) for every level back into them; wall clock around the loop"}
+        if rank == 0:
+            log(f"e2e done after {time.time() - t_start:.1f} s: {1e3 * dt / n_e2e:.2f} ms/step")
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        perms = [gpu.plan_query(l, "node_perm") for l in range(len(sizes))]
-        orders = [gpu.plan_query(l, "edge_order") for l in range(len(sizes))]
-        r = cpu_run(reorder_for_cpu(levels0, perms, orders), args.cpu_cycles, 1, nthreads)
-        cpu = {"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
-               "sample": f"{args.cpu_cycles} full V-cycles (+1 warm-up) of the same deck with the GPU run's node/edge ordering, "
-                         f"{r['lib']}, OpenMP block-coloured; flux kernel alone {r['flux_kernel_edges_per_s']:.3e} edges/s",
-               "mg_cycles_per_s": r["cycles_per_s"]}
+    # ---- CPU arm beside it (rank 0, N=1) and the parity reference (rank 0, every N): the oracle's state after ONE cycle
+    cpu, ref_first = None, None
+    want_parity = not args.no_parity and levels0 is not None
+    if rank == 0 and (want_parity or (world == 1 and not args.no_cpu)):
+        if world == 1:
+            perms = [gpu.plan_query(l, "node_perm") for l in range(len(sizes))]
+            orders = [gpu.plan_query(l, "edge_order") for l in range(len(sizes))]
+            deck = reorder_for_cpu(levels0, perms, orders)
+        else:
+            perms, deck = None, levels0                      # file order: slower on the CPU, only one cycle is needed
+        n_cpu = 0 if (world > 1 or args.no_cpu) else args.cpu_cycles
+        r = cpu_run(deck, n_cpu, 1, nthreads, keep_first_cycle=True)
+        ref_first = r["first_cycle"] if perms is None else [r["first_cycle"][l][perms[l].astype(np.int64)] for l in range(len(sizes))]
+        if n_cpu:
+            cpu = dict({"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+                        "sample": f"{n_cpu} full V-cycles (+1 warm-up) of the same deck with the GPU run's node/edge ordering, "
+                                  f"{r['lib']}, OpenMP block-coloured; flux kernel alone {r['flux_kernel_edges_per_s']:.3e} edges/s",
+                        "mg_cycles_per_s": r["cycles_per_s"]}, **cinfo)
+        log(f"CPU oracle done after {time.time() - t_start:.1f} s")
+
+    # ---- parity of the benchmarked configuration: re-initialise the variables, ONE cycle, compare with the oracle
+    parity = {"checked": False, "why": "disabled (--no-parity)" if args.no_parity else "deck generated per rank: no single-host oracle run"}
+    failed = False
+    if want_parity:
+        gpu.reinit_variables()
+        gpu.run_cycles(1)
+        max_rel, n_bad, vcount, bitwise = 0.0, 0, 0, True
+        for l in range(len(sizes)):
+            n_glob = sizes[l][0]
+            if world > 1:
+                # owned rows of this rank at their global (file) positions; the sum over ranks is the whole level
+                got_local = gpu.fetch(l, "variables")
+                gids = torch.from_numpy(lm.query(l, "global_node").astype(np.int64)[:gpu.n_owned[l]]).cuda()
+                full = torch.zeros((n_glob, 5), dtype=torch.float64, device="cuda")
+                full[gids] = torch.from_numpy(got_local[:gpu.n_owned[l]]).cuda()
+                dist.all_reduce(full)
+                got = full.cpu().numpy() if rank == 0 else None
+                del full
+                # -v criterion (validation.h:46-100) on this rank's owned nodes against the oracle's rows
+                ref_t = torch.zeros((n_glob, 5), dtype=torch.float64, device="cuda")
+                if rank == 0:
+                    ref_t.copy_(torch.from_numpy(ref_first[l]))
+                dist.broadcast(ref_t, 0)
+                master = ref_t[torch.from_numpy(lm.query(l, "global_node").astype(np.int64)).cuda()].cpu().numpy()
+                del ref_t
+                c = torch.tensor([float(gpu.validate(l, master))], dtype=torch.float64, device="cuda")
+                dist.all_reduce(c)
+                vcount += int(c.item())
+            else:
+                got = gpu.fetch(l, "variables")
+                vcount += gpu.validate(l, ref_first[l])
+            if rank == 0:
+                ref = ref_first[l]
+                scale = np.abs(ref).max(axis=0).clip(1e-300)
+                err = np.abs(got - ref).max(axis=0) / scale
+                max_rel = max(max_rel, float(err.max()))
+                n_bad += int((~np.isfinite(got)).sum())
+                bitwise = bitwise and bool(np.array_equal(got, ref))
+        if rank == 0:
+            ok = max_rel <= 1e-10 and n_bad == 0 and vcount == 0
+            parity = {"checked": True, "cycles": 1, "levels": len(sizes), "max_rel_err": max_rel, "tolerance": 1e-10,
+                      "bit_identical": bitwise, "validate_count": vcount, "non_finite": n_bad, "ok": ok,
+                      "oracle": r["lib"],
+                      "what": "variables re-initialised (euler3d.cpp:414-417), 1 V-cycle on the benchmarked configuration, every level's "
+                              "owned-node state vs the CPU oracle after 1 cycle; max over variables of |diff| / max|ref|; "
+                              "validate_count = nodes failing the -v criterion of validation.h:46-100"}
+            failed = not ok
+            log(f"parity: max_rel_err {max_rel:.3e}, validate_count {vcount}, ok={ok}")
+
     halo_bytes = gpu.halo_bytes_sent()
     gpu.close()
+    m6 = None
+    if rank == 0 and world == 1 and not args.no_m6 and args.mesh != "m6":
+        m6 = m6_subrecord(pkg, local_rank, 100, 4, peak)
+        log(f"m6 sub-record done after {time.time() - t_start:.1f} s: {m6['ms_per_step']:.4f} ms/cycle")
     if rank == 0:
-        config["halo_bytes_sent_rank0"] = halo_bytes
+        run_info["halo_bytes_sent_rank0"] = halo_bytes
         line = {"metric": "mg_cycle_flux_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config, "mg_cycles_per_s": args.steps / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "run_info": run_info, "mg_cycles_per_s": args.steps / (ms * 1e-3), "roofline": roofline,
+                "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "m6": m6, "gpu_launches": launches, "clocks": clocks}
         emit(line)
     if world > 1:
+        fl = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        failed = fl.item() > 0
         dist.destroy_process_group()
+    if failed:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

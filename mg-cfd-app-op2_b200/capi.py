@@ -414,6 +414,11 @@ class MGCFD:
             self._ck(L.mgcfd_loop_dampen_ewt_edges(self.ctx, l))
             self._ck(L.mgcfd_loop_dampen_ewt_bnd(self.ctx, l))
 
+    def reinit_variables(self):
+        """initialize_variables_kernel on every level again (euler3d.cpp:414-417): the flow state a fresh run starts from"""
+        for l in range(self.n_levels):
+            self._ck(self.lib.mgcfd_loop_initialize_variables(self.ctx, l))
+
     # ---- call sites of the cycle loop
     def copy_double(self, l): self._ck(self.lib.mgcfd_loop_copy_double(self.ctx, l))
     def calculate_dt(self, l): self._ck(self.lib.mgcfd_loop_calculate_dt(self.ctx, l))

@@ -817,12 +817,14 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     auto pad16 = [](long long b) { return (b + 15) & ~15ll; };
     O.dev_blob_off.assign(O.n_chunks + 1, 0);
     O.dev_max_blob = 0;
+    O.dev_max_tail = 0;
     for (int k = 0; k < O.n_chunks; k++) {
         long long nb = L.bnd_node_ptr[O.node0[k + 1]] - L.bnd_node_ptr[O.node0[k]];
         const long long n_own = O.node0[k + 1] - O.node0[k];
         long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + (nb ? pad16(nb * (24 + 2) + ((n_own + 2) & ~1ll) * 2) : 0);
         O.dev_blob_off[k + 1] = O.dev_blob_off[k] + bytes;
         O.dev_max_blob = std::max(O.dev_max_blob, (int)bytes);
+        O.dev_max_tail = std::max(O.dev_max_tail, (int)(O.blob_off[k + 1] - O.blob_off[k]) - 32 * ((O.n_edges[k] + 3) & ~3));
     }
     if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.dev_max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
@@ -903,8 +905,8 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         }
     }
     int rc;
-    if (const char *lean_s = getenv("MGCFD_OWNER_LEAN"); lean_s && atoi(lean_s) == 1) {
-        // lean kernel: descriptor and halo ids of a chunk in one fixed-stride record
+    if (O.max_own <= 64) {
+        // stage2 / lean kernels: descriptor and halo ids of a chunk in one fixed-stride record
         int hs = 0;
         for (int k = 0; k < O.n_chunks; k++) hs = std::max(hs, O.halo_off[k + 1] - O.halo_off[k]);
         hs = (hs + 3) & ~3;

@@ -1278,6 +1278,7 @@ inline int launch_emit(cudaStream_t s, const FluxArgs &a, const EmitPlanDev &p)
 #undef EMIT_ARGS
     return 1;
 }
+#include "stage_kernel.cuh"
 #endif  // !MGCFD_EXACT
 
 // ------------------------------------------------------------------------------------------
@@ -1551,6 +1552,9 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
         ra.max_own = h.max_own;
         size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.dev_max_blob, false, h.max_own);
 #ifndef MGCFD_EXACT
+        // default: the second-generation stage kernel (stage_kernel.cuh); MGCFD_STAGE2=0 or a plan outside its
+        // compiled limits falls through to flux_owner_kernel<FUSE>
+        if (threads == 128 && launch_stage2(s, a, p, h, grid)) return 1;
         // MGCFD_OWNER_LEAN=1: the lean kernel (needs the fixed-stride descriptor + halo-id table of ensure_owner)
         const char *lean_s = getenv("MGCFD_OWNER_LEAN");
         if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64) {
@@ -1590,6 +1594,12 @@ inline std::string configure()
     OPT_IN((flux_owner_kernel<false, true, true, true>));
 #ifndef MGCFD_EXACT
     OPT_IN(flux_owner_lean_kernel);
+    OPT_IN((rk_stage2_kernel<336, 240, true, 6>));
+    OPT_IN((rk_stage2_kernel<336, 240, false, 6>));
+    OPT_IN((rk_stage2_kernel<336, 240, false, 7>));
+    OPT_IN((rk_stage2_kernel<384, 240, true, 6>));
+    OPT_IN((rk_stage2_kernel<384, 240, false, 6>));
+    OPT_IN((rk_stage2_kernel<384, 240, false, 7>));
 #endif
 #define OPT_IN_PIPE(T, B, S)                                    \
     OPT_IN((flux_owner_pipe_kernel<T, B, S, true, true>));     \

@@ -67,6 +67,7 @@ struct OwnerPlanHost {
     // device packing (ensure_owner): the plan's blob followed by the chunk's boundary entries
     std::vector<long long> dev_blob_off;   // [n_chunks+1]
     int dev_max_blob = 0;
+    int dev_max_tail = 0;                  // largest blob minus its four weight planes (stage2 kernel's runtime-sized part)
 };
 
 struct LevelHost {
@@ -391,6 +392,7 @@ struct RkStageArgs {
     const double *b_wt;
     int rk, last;
     int max_own, pad_;           // filled by the launcher: tile sizes of the prefetched update operands
+    double inv_denom;            // filled by the launcher: 1 / (RK + 1 - rk) (stage2 kernel)
     DevConsts c;
 };
 

@@ -26,6 +26,7 @@ def test_reference_arm_line():
     assert d["metric"] == "mg_cycle_flux_edges_per_s" and d["unit"] == "edges/s" and d["higher_is_better"] is True
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["cpu_model"] and d["cpu_baseline"]["hardware_threads"] >= 1 and d["scaling"] == "strong"
     assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["value"] > 0
 
@@ -36,7 +37,7 @@ def test_reference_arm_on_a_per_rank_deck(monkeypatch):
     monkeypatch.setenv("WORLD_SIZE", "2")
     monkeypatch.setenv("RANK", "0")
     d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--mesh", "slab_test", "--gpus", "2")
-    assert d["impl"] == "reference" and d["value"] > 0 and "x-slab of rank 0 of 2" in d["config"]["cpu_sample"]
+    assert d["impl"] == "reference" and d["value"] > 0 and "x-slab of rank 0 of 2" in d["cpu_baseline"]["sample"]
     assert "generated per rank" in d["config"]["workload"] and d["scaling"] == "strong"
     monkeypatch.setenv("RANK", "1")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--mesh", "slab_test", "--gpus", "2"],
@@ -54,3 +55,17 @@ def test_b200_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
     assert d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["value"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert d["scaling"] == "strong" and {"frac_fused_L0", "frac_flux_only_L0"} <= set(r)
+    # the line checks itself against the CPU oracle (one cycle from the initial state) and carries the M6 cycle
+    p = d["parity"]
+    assert p["checked"] and p["ok"] and p["max_rel_err"] <= 1e-10 and p["validate_count"] == 0
+    assert d["m6"]["ms_per_step"] > 0 and "m6" in d["m6"]["workload"]
+
+
+def test_defaults_are_baseline_configs3():
+    """the driver's plain `bench.py --gpus N` must run BASELINE configs[3] (rotor37_8m, strong scaling) at every N"""
+    import importlib
+    sys.path.insert(0, ROOT)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'ap.add_argument("--mesh", default="rotor37_8m"' in src
+    assert 'ap.add_argument("--scaling", default="strong"' in src
