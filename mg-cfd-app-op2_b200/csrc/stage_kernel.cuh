@@ -63,21 +63,9 @@ __device__ __forceinline__ void derive_nr(const double u[5], double &p, double &
     s = sqrt_nr(q2) + sqrt_nr(GAMMA * p * rinv);
 }
 
-// boundary entries of one owned node (boundary chunks only): out of line, so that the common path keeps its registers
-__device__ __noinline__ void stage2_bnd(const double *u5, double *acc, int b0, int b1, const int *b_group, const double *b_wt,
-                                        const DevConsts *c)
-{
-    double u[5], a[5];
-#pragma unroll
-    for (int v = 0; v < 5; v++) { u[v] = u5[v]; a[v] = acc[v]; }
-    bnd_apply(u, a, b0, b1, b_group, b_wt, *c);
-#pragma unroll
-    for (int v = 0; v < 5; v++) acc[v] = a[v];
-}
-
 template <int MAXE, int MAXL, bool TILES, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__restrict__ chunk_list,
+rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__restrict__ chunk_list, int pf_chunk,
                  const unsigned char *__restrict__ blob, const double *__restrict__ var, RkStageArgs rk)
 {
     using L = Stage2Layout<MAXE, MAXL, TILES>;
@@ -109,6 +97,14 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     const int n_edges = q1.x, e_pad = q1.y;
     const long long blob_off = (long long)(unsigned)q2.x | ((long long)q2.y << 32);
     const int has_bnd = q2.z, bnd_off = q2.w;
+    // experiment (MGCFD_STAGE2_PF=distance): thread 64 fetches the descriptor of the chunk `distance` launches ahead and
+    // later prefetches that chunk's contiguous inputs into L2, so that its CTA finds them there
+    int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
+    const bool pf = pf_chunk > 0 && tid == 64 && (int)blockIdx.x + pf_chunk < (int)gridDim.x && !chunk_list;
+    if (pf) {
+        const int4 *r2 = reinterpret_cast<const int4 *>(xtab + (size_t)(chunk + pf_chunk) * xs);
+        p0 = __ldg(r2); p1 = __ldg(r2 + 1); p2 = __ldg(r2 + 2);
+    }
     const uint32_t pb = (uint32_t)e_pad * 8u;               // bytes of one weight plane in the blob
     const uint32_t own_b = ((uint32_t)n_own * 40u) & ~15u, sf_b = ((uint32_t)n_own * 8u) & ~15u;
 
@@ -158,6 +154,16 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     }
     __syncthreads();
 
+    if (pf) {
+        const long long boff = (long long)(unsigned)p2.x | ((long long)p2.y << 32);
+        const uint32_t ob = ((uint32_t)p0.y * 40u) & ~15u;
+        bulk_prefetch_l2(blob + boff, (uint32_t)p2.w);                              // weights | lab | rowptr | csr
+        bulk_prefetch_l2(xtab + (size_t)(chunk + pf_chunk) * xs, (uint32_t)(48 + ((p0.z * 4 + 15) & ~15)));
+        if (ob) {
+            bulk_prefetch_l2(var + (size_t)p0.x * 5, ob);
+            bulk_prefetch_l2(rk.old + (size_t)p0.x * 5, ob);
+        }
+    }
     // ---- 5. one thread per edge: the edge's weights are replaced in place by its flux vector
     const uint32_t *lab = reinterpret_cast<const uint32_t *>(sm + L::TAIL);
     {
@@ -183,6 +189,18 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     const int n = tid >> 1, part = tid & 1;
     const bool active = n < n_own;
     const size_t g0 = (size_t)node0 * 5;
+    // boundary chunks: the node's boundary entries (straight from the level's arrays, sorted by owned node) start the
+    // sum of the node's first thread -- here, where nothing else is live, the divisions of bnd_apply cost no spills
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (has_bnd && active && part == 0) {
+        const int b0 = __ldg(rk.bnd_ptr + node0 + n), b1 = __ldg(rk.bnd_ptr + node0 + n + 1);
+        if (b1 > b0) {
+            double u[5];
+#pragma unroll
+            for (int v = 0; v < 5; v++) u[v] = raw[n * 5 + v];
+            bnd_apply(u, acc, b0, b1, rk.b_group, rk.b_wt, rk.c);
+        }
+    }
     // this thread finishes components part, part+2, part+4 of its node
     double o[3] = {0.0, 0.0, 0.0}, sfn = 0.0;
     if (active) {
@@ -200,7 +218,6 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
                 if (part + 2 * k < 5) o[k] = __ldg(rk.old + g0 + n * 5 + part + 2 * k);
         }
     }
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     {
         const int j1 = active ? rowptr[n + 1] : 0;
         const unsigned char *pl = sm + L::W0;
@@ -217,11 +234,6 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     double sq = 0.0;
     int bad = 0;
     if (active) {
-        if (has_bnd) {
-            // boundary chunks only: the node's entries straight from the level's arrays (sorted by owned node)
-            const int b0 = __ldg(rk.bnd_ptr + node0 + n), b1 = __ldg(rk.bnd_ptr + node0 + n + 1);
-            if (b1 > b0) stage2_bnd(raw + n * 5, acc, b0, b1, rk.b_group, rk.b_wt, &rk.c);
-        }
         const double factor = sfn * rk.inv_denom;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -255,7 +267,8 @@ template <int MAXE, int MAXL, bool TILES, int MINB>
 inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const OwnerPlanDev &p, const FluxArgs &a, const RkStageArgs &ra)
 {
     const size_t smem = Stage2Layout<MAXE, MAXL, TILES>::TAIL + tail;     // dynamic shared memory opt-in: configure()
-    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list, p.blob, a.var, ra);
+    const char *pf = getenv("MGCFD_STAGE2_PF");
+    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list, pf ? atoi(pf) : 0, p.blob, a.var, ra);
 }
 
 // returns 1 when the launch was made, 0 when the plan does not fit a compiled configuration (caller falls back)
