@@ -41,7 +41,8 @@ enum {
     MGCFD_ERR_NODEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
     MGCFD_ERR_MIN_DT = -4,     /* min_dt < 0 (euler3d.cpp:480-484) */
     MGCFD_ERR_BAD_VALS = -5,   /* NaN/Inf in variables (euler3d.cpp:544-548) */
-    MGCFD_ERR_PLAN = -6        /* planner limit exceeded */
+    MGCFD_ERR_PLAN = -6,       /* planner limit exceeded */
+    MGCFD_ERR_COMM = -7        /* a peer rank did not answer a halo / min_dt exchange in time (bounded device-side wait ran out) */
 };
 
 /* flux-edge implementations (north_star: colouring scheme vs atomics, choice by measurement) */

@@ -20,7 +20,7 @@ FLUX_VARIANTS = {"atomic": FLUX_ATOMIC, "colour": FLUX_COLOUR, "owner": FLUX_OWN
                  "emit": FLUX_EMIT}
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NODEVICE", -4: "ERR_MIN_DT",
-             -5: "ERR_BAD_VALS", -6: "ERR_PLAN"}
+             -5: "ERR_BAD_VALS", -6: "ERR_PLAN", -7: "ERR_COMM"}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -194,7 +194,7 @@ int mgcfd_create(mgcfd_ctx **out, int device, int n_levels, const mgcfd_options 
     k_reset_min_slots(ctx->stream, 2 * n_levels, ctx->d_min_enc);
     if ((e = cudaMalloc((void **)&ctx->d_flags, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMemset(ctx->d_flags, 0, sizeof(int) * 4)) != cudaSuccess) return fail("cudaMemset", e);
-    if ((e = cudaMallocHost((void **)&ctx->h_pinned, sizeof(double) * 8)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void **)&ctx->h_pinned, sizeof(double) * 16)) != cudaSuccess) return fail("cudaMallocHost", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -243,6 +243,9 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
         if (h.d_export_idx) cudaFree(h.d_export_idx);
         if (h.sendbuf) cudaFree(h.sendbuf);
         if (h.d_chunk_list) cudaFree(h.d_chunk_list);
+        if (h.d_xp_base) cudaFree(h.d_xp_base);
+        if (h.d_xp_ptr) cudaFree(h.d_xp_ptr);
+        if (h.d_xp_ent) cudaFree(h.d_xp_ent);
     }
     if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
     if (ctx->d_rms) cudaFree(ctx->d_rms);
@@ -254,6 +257,8 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
         if (ctx->p2p.ipc && ctx->p2p.peer_base[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->p2p.peer_base[r]);
     if (ctx->p2p.arena_owner && ctx->p2p.arena) cudaFree(ctx->p2p.arena);
     if (ctx->p2p.d_counters) cudaFree(ctx->p2p.d_counters);
+    if (ctx->p2p.d_push) cudaFree(ctx->p2p.d_push);
+    if (ctx->p2p.d_done) cudaFree(ctx->p2p.d_done);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -377,6 +382,7 @@ static int upload_bnd(mgcfd_ctx *ctx, int level)
     L.bnd_group_sorted = group;
     L.bnd_wt_sorted = wt;
     D.owner.valid = D.emit.valid = false;              // chunk descriptors carry a has-boundary flag
+    cycle_drop_graphs(ctx);                            // captured graphs hold the pointers that are reallocated below
     int rc;
     if ((rc = dev_upload(ctx, &D.bu_node, bu_node))) return rc;
     if ((rc = dev_upload(ctx, &D.bu_ptr, bu_ptr))) return rc;
@@ -477,7 +483,7 @@ int mgcfd_plan(mgcfd_ctx *ctx)
                 if (cnt > 0) { P.me.import_off[l][ctx->H[l].nbr_rank[k]] = ctx->H[l].import_ptr[k]; P.me.import_cnt[l][ctx->H[l].nbr_rank[k]] = cnt; }
             }
         }
-        P.me.off_flags = (long long)take(sizeof(unsigned long long) * P2P_MAX_RANKS * 4);
+        P.me.off_flags = (long long)take(sizeof(unsigned long long) * P2P_MAX_RANKS * (3 + 2 * P2P_MAX_LEVELS));
         P.arena_bytes = off;
         CK(cudaMalloc((void **)&P.arena, P.arena_bytes));
         CK(cudaMemsetAsync(P.arena, 0, P.arena_bytes, ctx->stream));
@@ -843,9 +849,36 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         }
         Hd.n_boundary_chunks = (int)first.size();
         Hd.n_chunks = O.n_chunks;
+        // fused push: per chunk with exported nodes the row pointers of its owned nodes into the (destination slot, row)
+        // entries; destination slots number the neighbours that receive rows from this rank, in neighbour order, and a
+        // row is the node's position in the export list for that neighbour (= its row in the neighbour's import range)
+        std::vector<std::vector<int2>> ent_of(L.n_owned);
+        {
+            int slot = 0;
+            for (size_t k = 0; k < L.nbr_rank.size(); k++) {
+                if (L.export_ptr[k + 1] == L.export_ptr[k]) continue;
+                for (int j = L.export_ptr[k]; j < L.export_ptr[k + 1]; j++)
+                    ent_of[L.new_of_old[L.export_idx[j]]].push_back(make_int2(slot, j - L.export_ptr[k]));
+                slot++;
+            }
+        }
+        Hd.xp_base.assign(O.n_chunks, -1);
+        std::vector<int> xp_ptr;
+        std::vector<int2> xp_ent;
+        for (int k : first) {
+            Hd.xp_base[k] = (int)xp_ptr.size();
+            for (int v = O.node0[k]; v < O.node0[k + 1]; v++) {
+                xp_ptr.push_back((int)xp_ent.size());
+                xp_ent.insert(xp_ent.end(), ent_of[v].begin(), ent_of[v].end());
+            }
+            xp_ptr.push_back((int)xp_ent.size());
+        }
         first.insert(first.end(), rest.begin(), rest.end());
         int rcl = dev_upload(ctx, &Hd.d_chunk_list, first);
         if (rcl) return rcl;
+        if ((rcl = dev_upload(ctx, &Hd.d_xp_base, Hd.xp_base))) return rcl;
+        if ((rcl = dev_upload(ctx, &Hd.d_xp_ptr, xp_ptr))) return rcl;
+        if ((rcl = dev_upload(ctx, &Hd.d_xp_ent, xp_ent))) return rcl;
     }
     // edge slots inside a chunk are chosen against shared-memory bank conflicts (MGCFD_OWNER_SLOTTING=0: plan order);
     // the fused stage's node phase uses two threads per owned node in the fast build (CTAs have 128 threads for up to
@@ -915,6 +948,8 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         static_assert(sizeof(OwnerChunkDesc) == 48, "record head = descriptor");
         for (int k = 0; k < O.n_chunks; k++) {
             memcpy(&xtab[(size_t)k * xs], &desc[k], sizeof(OwnerChunkDesc));
+            // word 3 (halo_off in the descriptor; the record carries the ids itself) = base of the chunk's export row pointers
+            xtab[(size_t)k * xs + 3] = ctx->n_ranks > 1 && !ctx->halo[level].xp_base.empty() ? ctx->halo[level].xp_base[k] : -1;
             std::copy(O.halo_gid.begin() + O.halo_off[k], O.halo_gid.begin() + O.halo_off[k + 1], xtab.begin() + (size_t)k * xs + 12);
         }
         if (D.owner.xtab) { cudaFree(D.owner.xtab); D.owner.xtab = nullptr; }

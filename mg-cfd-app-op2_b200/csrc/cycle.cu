@@ -87,9 +87,11 @@ int finish_run(mgcfd_ctx *ctx)
 {
     int rc = api_check_launch(ctx, "mgcfd_run_cycles");
     if (rc) return rc;
-    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[6]);
-    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    int *hp = reinterpret_cast<int *>(&ctx->h_pinned[8]);
+    CK(cudaMemcpyAsync(hp, ctx->d_flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
+    if (hp[3]) { ctx->err = "a peer rank did not answer a halo / min_dt exchange in time"; return MGCFD_ERR_COMM; }
     if (hp[1]) { ctx->err = "Fatal error during 'step factor' calculation, min_dt < 0"; return MGCFD_ERR_MIN_DT; }
     if (hp[0] > 0) { ctx->err = "Bad variable values detected"; return MGCFD_ERR_BAD_VALS; }
     return MGCFD_OK;
@@ -144,7 +146,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                     }
                     continue;
                 }
-                RkStageArgs ra;
+                RkStageArgs ra{};
                 ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
                 ra.d_rms = level == 0 ? ctx->d_rms : nullptr;
                 ra.d_bad = &ctx->d_flags[0];
@@ -345,6 +347,7 @@ int exchange_p2p(mgcfd_ctx *ctx, int level, int which)
     if (!H.nbr_rank.empty()) {
         PushTable t;
         memset(&t, 0, sizeof(t));
+        t.err_flag = &ctx->d_flags[3];
         const int me = ctx->rank;
         // which of the two variables buffers is "var" right now (identical on every rank: they swap in lock step)
         const int buf = ctx->D[level].var == reinterpret_cast<double *>(P.arena + P.me.off_var[0][level]) ? 0 : 1;
@@ -394,19 +397,109 @@ int min_exchange_p2p(mgcfd_ctx *ctx, int level, const unsigned long long *slot, 
         if (q == ctx->rank) continue;
         int d = t.n_peers++;
         unsigned long long *qflags = reinterpret_cast<unsigned long long *>(P.peer_base[q] + P.peer[q].off_flags);
-        t.dst_box[d] = qflags + 2 * P2P_MAX_RANKS + 2 * ctx->rank + parity;
+        t.dst_box[d] = qflags + 2 * P2P_MAX_RANKS + 2 * (ctx->rank * P2P_MAX_LEVELS + level) + parity;   // one box per level and parity
         t.dst_flag[d] = qflags + P2P_MAX_RANKS + ctx->rank;
         t.sent[d] = cnt + 2 * P2P_MAX_RANKS + q;
         t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
         t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
     }
+    t.err_flag = &ctx->d_flags[3];
     CK(cudaEventRecord(ctx->ev_prod, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
     ctx->launches += k_min_exchange(ctx->comm_stream, slot, t);
     CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready, 0));
-    (void)level;
     return api_check_launch(ctx, "p2p min exchange");
+}
+
+// device-resident StagePush tables of a p2p context: [level][output buffer][without / with residuals] (built once, after
+// the flux plans -- they hold the export row pointers)
+int build_push_tables(mgcfd_ctx *ctx)
+{
+    P2PState &P = ctx->p2p;
+    if (P.d_push) return MGCFD_OK;
+    const int nl = ctx->n_levels, me = ctx->rank;
+    std::vector<StagePush> tab((size_t)nl * 4);
+    CK(cudaMalloc((void **)&P.d_done, sizeof(unsigned int)));
+    CK(cudaMemset(P.d_done, 0, sizeof(unsigned int)));
+    unsigned long long *cnt = P.d_counters;
+    for (int l = 0; l < nl; l++) {
+        HaloLevel &H = ctx->halo[l];
+        for (int ob = 0; ob < 2; ob++)
+            for (int wr = 0; wr < 2; wr++) {
+                StagePush &t = tab[(size_t)(l * 2 + ob) * 2 + wr];
+                memset(&t, 0, sizeof(t));
+                t.xp_base = H.d_xp_base; t.xp_ptr = H.d_xp_ptr; t.xp_ent = H.d_xp_ent;
+                t.n_boundary = H.n_boundary_chunks;
+                t.done = P.d_done;
+                t.err_flag = &ctx->d_flags[3];
+                for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+                    const int q = H.nbr_rank[k];
+                    const int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
+                    const P2PInfo &Q = P.peer[q];
+                    if (ns) {
+                        if (Q.import_cnt[l][me] != ns) { ctx->err = "halo lists of the ranks do not match"; return MGCFD_ERR_ARG; }
+                        const int d = t.n_dst++;
+                        const size_t row0 = (size_t)(Q.n_owned[l] + Q.import_off[l][me]) * 5;
+                        t.var_dst[d] = reinterpret_cast<double *>(P.peer_base[q] + Q.off_var[ob][l]) + row0;
+                        t.res_dst[d] = wr ? reinterpret_cast<double *>(P.peer_base[q] + Q.off_res[l]) + row0 : nullptr;
+                        t.dst_flag[d] = reinterpret_cast<unsigned long long *>(P.peer_base[q] + Q.off_flags) + me;
+                        t.sent[d] = cnt + q;
+                    }
+                    if (nr) {
+                        const int sidx = t.n_src++;
+                        t.src_flag[sidx] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + q;
+                        t.expected[sidx] = cnt + P2P_MAX_RANKS + q;
+                    }
+                }
+            }
+    }
+    CK(cudaMalloc((void **)&P.d_push, tab.size() * sizeof(StagePush)));
+    CK(cudaMemcpy(P.d_push, tab.data(), tab.size() * sizeof(StagePush), cudaMemcpyHostToDevice));
+    return MGCFD_OK;
+}
+
+// the sources of a level as a stand-alone wait (flag >= expected, no increment)
+WaitTable wait_table(mgcfd_ctx *ctx, int level)
+{
+    WaitTable t;
+    memset(&t, 0, sizeof(t));
+    HaloLevel &H = ctx->halo[level];
+    P2PState &P = ctx->p2p;
+    for (size_t k = 0; k < H.nbr_rank.size(); k++)
+        if (H.imp_ptr[k + 1] > H.imp_ptr[k]) {
+            const int q = H.nbr_rank[k], sidx = t.n_src++;
+            t.src_flag[sidx] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + q;
+            t.expected[sidx] = P.d_counters + P2P_MAX_RANKS + q;
+        }
+    t.err_flag = &ctx->d_flags[3];
+    return t;
+}
+
+// end of a multi-rank run, one process per GPU, p2p: every rank's deferred error flags (bad values, min_dt < 0, a wait
+// that ran out) reach every rank through the status mailboxes, so that all ranks return the same code
+int status_exchange_p2p(mgcfd_ctx *ctx)
+{
+    P2PState &P = ctx->p2p;
+    MinTable t;
+    memset(&t, 0, sizeof(t));
+    t.me = ctx->rank;
+    unsigned long long *cnt = P.d_counters;
+    const size_t status0 = 2 * P2P_MAX_RANKS + 2 * (size_t)P2P_MAX_RANKS * P2P_MAX_LEVELS;
+    for (int q = 0; q < ctx->n_ranks; q++) {
+        if (q == ctx->rank) continue;
+        int d = t.n_peers++;
+        unsigned long long *qflags = reinterpret_cast<unsigned long long *>(P.peer_base[q] + P.peer[q].off_flags);
+        t.dst_box[d] = qflags + status0 + ctx->rank;
+        t.dst_flag[d] = qflags + P2P_MAX_RANKS + ctx->rank;
+        t.sent[d] = cnt + 2 * P2P_MAX_RANKS + q;
+        t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
+        t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
+    }
+    t.err_flag = &ctx->d_flags[3];
+    const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + status0;
+    ctx->launches += k_status_exchange(ctx->stream, ctx->d_flags, boxes, ctx->n_ranks, t);
+    return api_check_launch(ctx, "p2p status exchange");
 }
 
 // mark "the producers of this exchange are queued" on every rank's main stream
@@ -481,11 +574,37 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
     // halos of the start state (a caller may have set variables on the owned nodes only)
     for (int l = 0; l < nl; l++)
         if ((rc = exchange(R, n, l, DAT_VAR))) return rc;
+    // fused push: the stage kernels store their exported rows into the neighbours and hand-shake themselves
+    for (int r = 0; r < n; r++) {
+        mgcfd_ctx *c = R[r];
+        if (!c->p2p.enabled || !c->p2p.fused_push) continue;
+        cudaSetDevice(c->device);
+        if ((rc = build_push_tables(c))) { ctx->err = c->err; return rc; }
+    }
     // one process per GPU: the whole multi-stream schedule, NCCL calls included, replays as a CUDA graph
     if (remote) rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_ranks(R, n, k); });
     else rc = enqueue_ranks(R, n, n_cycles);
     if (rc) return rc;
-    return MGCFD_OK;
+    // deferred host checks (euler3d.cpp:480, :544) and exchange time-outs: every rank returns the same code
+    if (remote && ctx->p2p.enabled && ctx->n_ranks > 1) {
+        if ((rc = status_exchange_p2p(ctx))) return rc;
+    } else if (remote && nccl && ctx->n_ranks > 1) {
+        CK(cudaEventRecord(ctx->ev_prod, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
+        NCK(g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclInt, ncclMax, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->comm_stream));
+        CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready, 0));
+    }
+    int worst = MGCFD_OK;
+    std::string worst_msg;
+    for (int r = 0; r < n; r++) {
+        mgcfd_ctx *c = R[r];
+        cudaSetDevice(c->device);
+        int rcr = finish_run(c);
+        if (rcr && !worst) { worst = rcr; worst_msg = c->err; }
+    }
+    if (worst) { ctx->err = worst_msg; for (int r = 0; r < n; r++) R[r]->err = worst_msg; }
+    return worst;
 }
 
 int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
@@ -520,7 +639,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 MinSlots ms;
                 ms.n = 0;
                 const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(c->p2p.arena + c->p2p.me.off_flags) + 2 * P2P_MAX_RANKS;
-                for (int q = 0; q < c->n_ranks; q++) ms.p[ms.n++] = q == c->rank ? slot : boxes + 2 * q + D.visit_parity;
+                for (int q = 0; q < c->n_ranks; q++) ms.p[ms.n++] = q == c->rank ? slot : boxes + 2 * (q * P2P_MAX_LEVELS + level) + D.visit_parity;
                 c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags);
             } else if (nccl) {
                 ctx = c;
@@ -545,7 +664,56 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
         for (int r = 0; r < n; r++) R[r]->D[level].visit_parity ^= 1;
         // ---- three fused Runge-Kutta stages (euler3d.cpp:492-531).  Per stage: chunks owning exported nodes first,
         //      then the halo exchange of the new variables starts and the interior chunks run underneath it
-        for (int rk = 0; rk < MGCFD_RK; rk++) {
+        const bool fp = ctx->p2p.enabled && ctx->p2p.fused_push;
+        for (int rk = 0; fp && rk < MGCFD_RK; rk++) {
+            // fused push: ONE launch per stage over all chunks (those that own exported nodes first); the kernel waits
+            // for its sources, pushes var_new (+ residuals after the last stage of a level >= 1) and publishes the epoch
+            const bool last = rk == MGCFD_RK - 1;
+            for (int r = 0; r < n; r++) {
+                mgcfd_ctx *c = R[r];
+                cudaSetDevice(c->device);
+                LevelHost &L = c->H[level];
+                LevelDev &D = c->D[level];
+                HaloLevel &Hd = c->halo[level];
+                RkStageArgs ra{};
+                ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
+                ra.d_rms = level == 0 ? c->d_rms : nullptr;
+                ra.d_bad = &c->d_flags[0];
+                ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
+                ra.rk = rk; ra.last = last; ra.c = api_dev_consts(c);
+                const int ob = D.var_alt == reinterpret_cast<double *>(c->p2p.arena + c->p2p.me.off_var[0][level]) ? 0 : 1;
+                const int wr = (last && level >= 1) ? 1 : 0;
+                ra.push = Hd.n_boundary_chunks > 0 ? c->p2p.d_push + ((size_t)(level * 2 + ob) * 2 + wr) : nullptr;
+                FluxArgs a;
+                a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
+                a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
+                a.chunk_list = Hd.d_chunk_list; a.n_list = Hd.n_chunks;
+                {
+                    LoopScope t(c, "rk_stage", level, L.n_edges);
+                    c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
+                }
+                c->halo_bytes += (long long)Hd.n_export * 40 * (1 + wr);
+                if (Hd.n_boundary_chunks == 0) {
+                    // nothing to export on this level, yet rows may arrive (restrict / prolong halos): keep the epoch book
+                    PushTable t;
+                    memset(&t, 0, sizeof(t));
+                    t.err_flag = &c->d_flags[3];
+                    WaitTable w = wait_table(c, level);
+                    for (int q = 0; q < w.n_src; q++) { t.src_flag[q] = w.src_flag[q]; t.expected[q] = const_cast<unsigned long long *>(w.expected[q]); }
+                    t.n_src = w.n_src;
+                    c->launches += k_signal_wait(c->stream, t);
+                }
+                if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
+            }
+            for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
+            if (last)      // the next kernel that reads halo rows (restrict, prolong, a visit prologue) is not a stage kernel
+                for (int r = 0; r < n; r++) {
+                    mgcfd_ctx *c = R[r];
+                    cudaSetDevice(c->device);
+                    if (c->halo[level].n_boundary_chunks > 0) c->launches += k_halo_wait(c->stream, wait_table(c, level));
+                }
+        }
+        for (int rk = 0; !fp && rk < MGCFD_RK; rk++) {
             const bool last = rk == MGCFD_RK - 1;
             for (int part = 0; part < 2; part++) {
                 for (int r = 0; r < n; r++) {
@@ -554,7 +722,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                     LevelHost &L = c->H[level];
                     LevelDev &D = c->D[level];
                     HaloLevel &Hd = c->halo[level];
-                    RkStageArgs ra;
+                    RkStageArgs ra{};
                     ra.old = D.old; ra.sf = D.sf; ra.var_out = D.var_alt; ra.res = D.res;
                     ra.d_rms = level == 0 ? c->d_rms : nullptr;
                     ra.d_bad = &c->d_flags[0];
@@ -615,6 +783,14 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
 
 }  // namespace
 
+// the stage kernels push and hand-shake themselves unless MGCFD_FUSED_PUSH=0 (the exchange then runs as separate pack /
+// signal kernels on the communication stream, overlapped with the interior chunks); owner variant only
+static bool fused_push_wanted(const mgcfd_ctx *ctx)
+{
+    const char *e = getenv("MGCFD_FUSED_PUSH");
+    return !(e && atoi(e) == 0) && ctx->opt.flux_variant == MGCFD_FLUX_OWNER;
+}
+
 void mgcfd::cycle_drop_graphs(mgcfd_ctx *ctx)
 {
     for (auto &kv : ctx->graphs)
@@ -631,7 +807,7 @@ int mgcfd_run_cycles(mgcfd_ctx *ctx, int n_cycles)
     if (ctx->device < 0) { ctx->err = "planning-only context (device -1): compute entry points need a CUDA device"; return MGCFD_ERR_NODEVICE; }
     REQUIRE(n_cycles >= 0, "negative cycle count");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->nccl_comm || ctx->p2p.ipc) return run_ranks(&ctx, 1, n_cycles);
+    if (ctx->n_ranks > 1 && (ctx->nccl_comm || ctx->p2p.ipc)) return run_ranks(&ctx, 1, n_cycles);
     REQUIRE(ctx->n_ranks == 1, "a partitioned context needs mgcfd_comm_init_nccl(), mgcfd_comm_init_ipc() or mgcfd_group_run_cycles()");
     return cycle_run_single(ctx, n_cycles);
 }
@@ -708,6 +884,7 @@ int mgcfd_group_enable_p2p(mgcfd_ctx **ranks, int n_ranks)
             }
         }
         ranks[a]->p2p.enabled = true;
+        ranks[a]->p2p.fused_push = fused_push_wanted(ranks[a]);
         cycle_drop_graphs(ranks[a]);
     }
     return MGCFD_OK;
@@ -743,6 +920,7 @@ int mgcfd_comm_init_ipc(mgcfd_ctx *ctx, const void *blobs)
         ctx->p2p.peer_base[r] = static_cast<unsigned char *>(p);
     }
     ctx->p2p.enabled = ctx->p2p.ipc = true;
+    ctx->p2p.fused_push = fused_push_wanted(ctx);
     cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }

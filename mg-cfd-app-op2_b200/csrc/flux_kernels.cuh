@@ -375,6 +375,64 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- multi-GPU (p2p transport): system-scope flags and the fused halo push of the stage kernels (StagePush, internal.h)
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// wait until *flag >= e, at most ~2 s: a peer that never arrives raises *err (MGCFD_ERR_COMM) instead of hanging the GPU
+__device__ __forceinline__ void bounded_wait(const unsigned long long *flag, unsigned long long e, int *err)
+{
+    for (int it = 0; it < (1 << 22); it++) {
+        if (ld_acquire_sys(flag) >= e) return;
+        __nanosleep(it < 64 ? 32 : 512);
+    }
+    atomicExch(err, 1);
+}
+// consumer side of a chunk that owns exported nodes: all sources' rows of the previous exchange have landed (and the
+// neighbours are done reading what this stage overwrites).  Call with all threads of the CTA.
+__device__ __forceinline__ void push_wait_sources(const StagePush *P, int tid)
+{
+    if (tid < P->n_src) bounded_wait(P->src_flag[tid], *P->expected[tid], P->err_flag);
+    __syncthreads();
+}
+// producer side, per owned node `n` of the chunk (row pointers at xb): store component v of var_new (and of the residual)
+// into every destination that holds the node in its halo
+__device__ __forceinline__ void push_component(const StagePush *P, int xb, int n, int v, double vn, double r, bool with_res)
+{
+    const int j1 = __ldg(P->xp_ptr + xb + n + 1);
+    for (int j = __ldg(P->xp_ptr + xb + n); j < j1; j++) {
+        const int2 t = __ldg(P->xp_ent + j);
+        P->var_dst[t.x][(size_t)t.y * 5 + v] = vn;
+        if (with_res && P->res_dst[t.x]) P->res_dst[t.x][(size_t)t.y * 5 + v] = r;
+    }
+}
+// after the chunk's pushes: count the chunk; the last one of the launch publishes the epoch and arms the next consumer
+__device__ __forceinline__ void push_publish(const StagePush *P, int tid)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(P->done, 1u);
+        if (prev + 1u == (unsigned int)P->n_boundary) {
+            atomicExch(P->done, 0u);
+            __threadfence_system();
+            for (int d = 0; d < P->n_dst; d++) {
+                const unsigned long long e = *P->sent[d] + 1;
+                *P->sent[d] = e;
+                st_release_sys(P->dst_flag[d], e);
+            }
+            for (int q = 0; q < P->n_src; q++) *P->expected[q] += 1;
+        }
+    }
+}
+
 // state of local node i for the edge body: conserved variables from the AoS tile, derived quantities from 3 planes
 template <int NREC>
 __device__ __forceinline__ void load_state(const double *raw, const double *der, int stride, int i, double r[NREC])
@@ -473,7 +531,7 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
                                            const double *raw, const double *w0, const double *w1, const double *w2,
                                            const double *gg, const double *Fx, const uint16_t *rowptr, const uint16_t *csr,
                                            int max_edges, const double *told, const double *tsf, double *__restrict__ flux,
-                                           const RkStageArgs &rk)
+                                           const RkStageArgs &rk, int xb = -1)
 {
     constexpr int lg_split = LG_SPLIT, step = 1 << LG_SPLIT;      // threads per owned node (fast build: 1, 2 or 4)
     const int n = tid >> lg_split, part = tid & (step - 1);
@@ -591,12 +649,13 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
                         const double o = (!TAIL || f < old_n) ? told[f] : rk.old[g0 + f];
                         const double vn = __dadd_rn(o, __dmul_rn(factor, mine[k]));
                         rk.var_out[g0 + f] = vn;
+                        const double r = vn - o;
                         if (rk.last) {
-                            const double r = vn - o;
                             rk.res[g0 + f] = r;
                             sq += r * r;
                             bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
                         }
+                        if (xb >= 0) push_component(rk.push, xb, n, v, vn, r, rk.last != 0);
                     }
                 }
             };
@@ -648,6 +707,12 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     const OwnerChunkDesc d = descs[chunk_list ? chunk_list[blockIdx.x] : blockIdx.x];
     const int tid = threadIdx.x, nloc = d.n_own + d.n_halo;
     const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
+    // multi-GPU, fused push: a chunk that owns exported nodes waits for its sources before it reads halo rows
+    int xb = -1;
+    if (FUSE && REGEPI && rk.push) {
+        xb = __ldg(rk.push->xp_base + (chunk_list ? chunk_list[blockIdx.x] : blockIdx.x));
+        if (xb >= 0) push_wait_sources(rk.push, tid);
+    }
 
     // 1. bulk async copies (TMA 1-D) of the chunk's blob and of the owned nodes' conserved variables; 2. halo nodes
     //    by 8-byte async copies straight into the tile
@@ -714,13 +779,14 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     // 5. (REGEPI) node sums, boundary entries and the update straight from registers: see node_phase
     if constexpr (REGEPI) {
 #ifdef MGCFD_EXACT
-        node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+        node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk, xb);
 #else
         if (2 * rk.max_own <= (int)blockDim.x)
-            node_phase<OVERWRITE, FUSE, 1>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+            node_phase<OVERWRITE, FUSE, 1>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk, xb);
         else
-            node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk);
+            node_phase<OVERWRITE, FUSE, 0>(tid, d, sblob, raw, w0, w1, w2, gg, Fx, rowptr, csr, max_edges, told, tsf, flux, rk, xb);
 #endif
+        if (xb >= 0) push_publish(rk.push, tid);
         return;
     }
     // 5. one thread per owned node (chunks never own more than blockDim nodes) sums its incident edges in ascending
@@ -1540,7 +1606,7 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
     // chunk prefetched into L2; 2 = persistent CTAs, two shared-memory stages
     const char *pipe_s = getenv("MGCFD_OWNER_PIPE");
     const int pipe = pipe_s ? atoi(pipe_s) : MGCFD_OWNER_PIPE_DEFAULT;
-    if (pipe > 0 && !a.stream_kernel && threads >= 128) {
+    if (pipe > 0 && !a.stream_kernel && threads >= 128 && !(a.rk && a.rk->push)) {      // (the pipelined variants have no fused push)
         int rc = launch_owner_pipe(s, a, p, h, threads, pipe >= 2 ? 2 : 1);
         if (rc >= 0) return rc;
     }
@@ -1557,7 +1623,7 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
         if (threads == 128 && launch_stage2(s, a, p, h, grid)) return 1;
         // MGCFD_OWNER_LEAN=1: the lean kernel (needs the fixed-stride descriptor + halo-id table of ensure_owner)
         const char *lean_s = getenv("MGCFD_OWNER_LEAN");
-        if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64) {
+        if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64 && !ra.push) {
             flux_owner_lean_kernel<<<grid, 128, fsmem, s>>>(h.max_loc, h.max_edges, h.dev_max_blob, p.xtab, p.xs, p.hs, a.chunk_list,
                                                             p.blob, a.var, ra);
             return 1;
@@ -1565,7 +1631,7 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
 #endif
         // MGCFD_OWNER_EPILOGUE=0: node sums staged through shared memory and a separate coalesced update pass
         const char *epi_s = getenv("MGCFD_OWNER_EPILOGUE");
-        if (epi_s && atoi(epi_s) == 0)
+        if (epi_s && atoi(epi_s) == 0 && !ra.push)
             flux_owner_kernel<false, true, true, false><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
         else
             flux_owner_kernel<false, true, true, true><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);

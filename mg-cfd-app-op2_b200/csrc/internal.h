@@ -203,6 +203,11 @@ struct HaloLevel {
     int n_export = 0;
     int *d_chunk_list = nullptr;     // owner chunks that own exported nodes first (n_boundary_chunks), then the rest
     int n_boundary_chunks = 0, n_chunks = 0;
+    // fused push (the stage kernel stores exported rows straight into the neighbours' halo ranges): per chunk the base
+    // of its (n_own + 1) row pointers in d_xp_ptr or -1, and per exported node its (destination slot, row) entries
+    std::vector<int> xp_base;
+    int *d_xp_base = nullptr, *d_xp_ptr = nullptr;
+    int2 *d_xp_ent = nullptr;
 };
 
 struct GraphEntry {
@@ -216,11 +221,40 @@ struct GraphEntry {
 // all levels, its flag words and the min_dt mailboxes in ONE arena that its peers map (CUDA IPC between processes,
 // plain pointers inside one process) and write into.
 constexpr int P2P_MAX_RANKS = 16, P2P_MAX_LEVELS = 16;
+// Everything a stage kernel needs to push its exported rows and to hand-shake with the neighbours (device-resident, one
+// per level x output buffer x with/without residuals; RkStageArgs::push points at the one a launch uses).
+//   consumer side: a chunk that owns exported nodes (the only chunks that read rank-halo nodes) first waits until every
+//                  source's flag has reached expected[s] -- the neighbours' rows of the previous exchange have landed and
+//                  the neighbours have finished reading the halo ranges this stage is about to overwrite;
+//   producer side: after its node phase the chunk stores var_new (and the residuals after the last stage) of its exported
+//                  nodes into the destinations' halo ranges, fences, and counts itself in `done`; the last such chunk of the
+//                  launch publishes the next epoch to every destination and advances `expected` for the next consumer.
+struct StagePush {
+    int n_dst, n_src, n_boundary, pad_;
+    const int *xp_base, *xp_ptr;
+    const int2 *xp_ent;
+    double *var_dst[P2P_MAX_RANKS];                  // where my rows start in destination d's halo range (output buffer)
+    double *res_dst[P2P_MAX_RANKS];                  // the same in its residual array, or null
+    unsigned long long *dst_flag[P2P_MAX_RANKS];     // the destination's halo_flag[my rank]
+    unsigned long long *sent[P2P_MAX_RANKS];         // my epoch counter towards that destination
+    const unsigned long long *src_flag[P2P_MAX_RANKS];   // my halo_flag[source rank]
+    unsigned long long *expected[P2P_MAX_RANKS];     // epoch the next consumer needs from that source
+    unsigned int *done;                              // chunks with exports finished in this launch
+    int *err_flag;                                   // d_flags[3]: a bounded wait ran out
+};
+struct WaitTable {                       // kernel parameter of a stand-alone halo wait
+    int n_src;
+    const unsigned long long *src_flag[P2P_MAX_RANKS];
+    const unsigned long long *expected[P2P_MAX_RANKS];
+    int *err_flag;
+};
+
 struct P2PInfo {                         // what a peer must know about a rank's arena (exchanged as an opaque blob)
     unsigned char ipc_handle[64];
     int n_levels, rank;
     long long off_var[2][P2P_MAX_LEVELS], off_res[P2P_MAX_LEVELS];
-    long long off_flags;                 // u64 halo_flag[P2P_MAX_RANKS] | u64 min_flag[P2P_MAX_RANKS] | u64 min_box[P2P_MAX_RANKS][2]
+    long long off_flags;                 // u64 halo_flag[P2P_MAX_RANKS] | u64 min_flag[P2P_MAX_RANKS] |
+                                         // u64 min_box[P2P_MAX_RANKS][P2P_MAX_LEVELS][2] | u64 status_box[P2P_MAX_RANKS]
     int n_owned[P2P_MAX_LEVELS];
     int import_off[P2P_MAX_LEVELS][P2P_MAX_RANKS];   // where rows from rank r land in the halo range (nodes), -1: none
     int import_cnt[P2P_MAX_LEVELS][P2P_MAX_RANKS];
@@ -233,6 +267,9 @@ struct P2PState {
     P2PInfo peer[P2P_MAX_RANKS];
     unsigned char *peer_base[P2P_MAX_RANKS] = {};
     unsigned long long *d_counters = nullptr;   // sent_halo[16] | expected_halo[16] | sent_min[16] | expected_min[16]
+    StagePush *d_push = nullptr;                // [n_levels][2 output buffers][without / with residuals]
+    unsigned int *d_done = nullptr;
+    bool fused_push = false;                    // the stage kernels push and hand-shake themselves (default with p2p)
 };
 
 struct PushTable {                       // kernel parameter of one halo push
@@ -243,6 +280,7 @@ struct PushTable {                       // kernel parameter of one halo push
     unsigned long long *sent[P2P_MAX_RANKS];         // my epoch counter towards that destination
     const unsigned long long *src_flag[P2P_MAX_RANKS];   // my halo_flag[source rank]
     unsigned long long *expected[P2P_MAX_RANKS];     // my epoch counter for that source
+    int *err_flag;
 };
 struct MinTable {
     int n_peers, me, parity;
@@ -251,6 +289,7 @@ struct MinTable {
     unsigned long long *sent[P2P_MAX_RANKS];
     const unsigned long long *src_flag[P2P_MAX_RANKS];
     unsigned long long *expected[P2P_MAX_RANKS];
+    int *err_flag;
 };
 
 struct LoopTimer {
@@ -276,7 +315,7 @@ struct mgcfd_ctx {
     unsigned long long *d_min_enc = nullptr;   // [n_levels][2] order-encoded min_dt slots of the fused path
     double *d_rms = nullptr;
     int *d_flags = nullptr;          // [0]=bad value count, [1]=min_dt<0 flag, [2]=validate count
-    double *h_pinned = nullptr;      // pinned host scratch (8 doubles)
+    double *h_pinned = nullptr;      // pinned host scratch (16 doubles)
     void *d_stage = nullptr, *h_stage = nullptr;   // device / pinned-host staging for file-order transfers
     size_t d_stage_bytes = 0, h_stage_bytes = 0;
     long long launches = 0;
@@ -379,7 +418,9 @@ int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double
 // p2p transport: rows straight into the peers' halo ranges, then epoch flags; returns kernels launched
 int k_push_rows(cudaStream_t s, int n_rows, const int *idx, const double *src, const PushTable &t);
 int k_signal_wait(cudaStream_t s, const PushTable &t);
+int k_halo_wait(cudaStream_t s, const WaitTable &t);
 int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t);
+int k_status_exchange(cudaStream_t s, int *flags, const unsigned long long *boxes, int n_ranks, const MinTable &t);
 
 // extra arguments of the fused Runge-Kutta stage (flux + boundary flux + time_step [+ residual, rms, bad values])
 struct RkStageArgs {
@@ -391,6 +432,7 @@ struct RkStageArgs {
     const int *b_group;
     const double *b_wt;
     int rk, last;
+    const StagePush *push;       // multi-GPU: push exported rows from the node phase (null: no fused push)
     int max_own, pad_;           // filled by the launcher: tile sizes of the prefetched update operands
     double inv_denom;            // filled by the launcher: 1 / (RK + 1 - rk) (stage2 kernel)
     DevConsts c;

@@ -196,16 +196,9 @@ __global__ void pack_rows_kernel(int n5, const int *__restrict__ idx, const doub
 }
 
 // ---- p2p transport ---------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+using exact::st_release_sys;
+using exact::ld_acquire_sys;
+using exact::bounded_wait;
 
 // gather the exported rows and store them straight into each destination rank's halo range (peer-mapped pointers)
 __global__ void push_rows_kernel(int n5, const int *__restrict__ idx, const double *__restrict__ src, PushTable t)
@@ -232,8 +225,15 @@ __global__ void signal_wait_kernel(PushTable t)
     if (lane < t.n_src) {
         unsigned long long e = *t.expected[lane] + 1;
         *t.expected[lane] = e;
-        while (ld_acquire_sys(t.src_flag[lane]) < e) { }
+        bounded_wait(t.src_flag[lane], e, t.err_flag);
     }
+}
+
+// stand-alone consumer wait (after the last fused-push stage of a visit): every source's flag has reached `expected`
+__global__ void halo_wait_kernel(WaitTable t)
+{
+    const int lane = threadIdx.x;
+    if (lane < t.n_src) bounded_wait(t.src_flag[lane], *t.expected[lane], t.err_flag);
 }
 
 // all-reduce(MIN) of min_dt by mailboxes: my encoded minimum goes into every peer's box, then the same flag handshake
@@ -251,8 +251,38 @@ __global__ void min_exchange_kernel(const unsigned long long *my_slot, MinTable 
     if (lane < t.n_peers) {
         unsigned long long e = *t.expected[lane] + 1;
         *t.expected[lane] = e;
-        while (ld_acquire_sys(t.src_flag[lane]) < e) { }
+        bounded_wait(t.src_flag[lane], e, t.err_flag);
     }
+}
+
+// end of a multi-rank run: my deferred error flags go into every peer's status box (same mailbox handshake as the min_dt
+// exchange), theirs are folded into mine
+__global__ void status_exchange_kernel(int *flags, const unsigned long long *boxes, int n_ranks, MinTable t)
+{
+    const int lane = threadIdx.x;
+    const unsigned long long mine = (flags[0] > 0 ? 1ull : 0ull) | (flags[1] ? 2ull : 0ull) | (flags[3] ? 4ull : 0ull);
+    if (lane < t.n_peers) {
+        *t.dst_box[lane] = mine;
+        unsigned long long e = *t.sent[lane] + 1;
+        *t.sent[lane] = e;
+        __threadfence_system();
+        st_release_sys(t.dst_flag[lane], e);
+    }
+    __syncwarp();
+    if (lane < t.n_peers) {
+        unsigned long long e = *t.expected[lane] + 1;
+        *t.expected[lane] = e;
+        bounded_wait(t.src_flag[lane], e, t.err_flag);
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int q = 0; q < n_ranks; q++) {
+            if (q == t.me) continue;
+            const unsigned long long u = *reinterpret_cast<const volatile unsigned long long *>(boxes + q);
+            if ((u & 1ull) && flags[0] == 0) flags[0] = 1;
+            if (u & 2ull) flags[1] = 1;
+            if (u & 4ull) flags[3] = 1;
+        }
 }
 
 __global__ void reset_min_slots_kernel(int n, unsigned long long *slots)
@@ -508,9 +538,20 @@ int k_signal_wait(cudaStream_t s, const PushTable &t)
     signal_wait_kernel<<<1, 32, 0, s>>>(t);
     return 1;
 }
+int k_halo_wait(cudaStream_t s, const WaitTable &t)
+{
+    if (t.n_src == 0) return 0;
+    halo_wait_kernel<<<1, 32, 0, s>>>(t);
+    return 1;
+}
 int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t)
 {
     min_exchange_kernel<<<1, 32, 0, s>>>(my_slot, t);
+    return 1;
+}
+int k_status_exchange(cudaStream_t s, int *flags, const unsigned long long *boxes, int n_ranks, const MinTable &t)
+{
+    status_exchange_kernel<<<1, 32, 0, s>>>(flags, boxes, n_ranks, t);
     return 1;
 }
 int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots)

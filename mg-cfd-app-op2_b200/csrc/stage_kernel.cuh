@@ -97,6 +97,10 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     const int n_edges = q1.x, e_pad = q1.y;
     const long long blob_off = (long long)(unsigned)q2.x | ((long long)q2.y << 32);
     const int has_bnd = q2.z, bnd_off = q2.w;
+    // multi-GPU, fused push: word 3 of the record is the chunk's base into the export row pointers (-1: no exported node);
+    // such a chunk -- the only kind that reads rank-halo rows -- first waits for its sources
+    const int xb = rk.push ? q0.w : -1;
+    if (xb >= 0) push_wait_sources(rk.push, tid);
     // experiment (MGCFD_STAGE2_PF=distance): thread 64 fetches the descriptor of the chunk `distance` launches ahead and
     // later prefetches that chunk's contiguous inputs into L2, so that its CTA finds them there
     int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
@@ -242,15 +246,17 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
                 const double f = (k == 0) ? (part ? acc[1] : acc[0]) : (k == 1) ? (part ? acc[3] : acc[2]) : acc[4];
                 const double vn = fma(factor, f, o[k]);
                 rk.var_out[g0 + n * 5 + v] = vn;
+                const double r = vn - o[k];
                 if (rk.last) {
-                    const double r = vn - o[k];
                     rk.res[g0 + n * 5 + v] = r;
                     sq = fma(r, r, sq);
                     bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
                 }
+                if (xb >= 0) push_component(rk.push, xb, n, v, vn, r, rk.last != 0);
             }
         }
     }
+    if (xb >= 0) push_publish(rk.push, tid);
     if (rk.last && rk.d_rms) {
         for (int off = 16; off > 0; off >>= 1) {
             sq += __shfl_xor_sync(0xffffffffu, sq, off);

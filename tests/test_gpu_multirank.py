@@ -81,3 +81,61 @@ def test_partitioned_context_refuses_plain_run(pkg, meshgen):
     with pkg.MGCFD(local_mesh=lm) as g:
         with pytest.raises(pkg.MgcfdError):
             g.run_cycles(1)          # no communicator: a partition cannot advance alone
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4])
+def test_p2p_unfused_exchange_still_bit_identical(pkg, meshgen, golden, n_ranks, monkeypatch):
+    """MGCFD_FUSED_PUSH=0: the round-1 schedule (pack + signal kernels on the communication stream, stages split into
+    export chunks and interior chunks) stays available and exact"""
+    monkeypatch.setenv("MGCFD_FUSED_PUSH", "0")
+    mesh = meshgen.make_multigrid("small")
+    got, _ = run_decomposed(pkg, mesh, n_ranks, 10, exact_arith=True, p2p=True)
+    g = golden("small_cycles10.npz")
+    for l in range(len(mesh["levels"])):
+        assert np.array_equal(got[l], g[f"var_L{l}"])
+
+
+def test_fused_push_needs_fewer_launches(pkg, meshgen, monkeypatch):
+    """the stage kernels push their exported rows and hand-shake themselves: no pack / signal launches per stage and no
+    split into export and interior launches"""
+    mesh = meshgen.make_multigrid("small")
+    counts = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MGCFD_FUSED_PUSH", fused)
+        parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 2)
+        lms = [pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, 2) for r in range(2)]
+        ranks = [pkg.MGCFD(local_mesh=lm, device=0) for lm in lms]
+        try:
+            pkg.group_enable_p2p(ranks)
+            pkg.group_run_cycles(ranks, 1)
+            before = ranks[0].kernel_launches()
+            pkg.group_run_cycles(ranks, 2)
+            counts[fused] = (ranks[0].kernel_launches() - before) / 2
+        finally:
+            for g in ranks:
+                g.close()
+    n_levels = len(mesh["levels"])
+    visits = 2 * n_levels - 2
+    assert counts["1"] <= counts["0"] - 3 * 3 * visits + visits, counts      # 3 launches fewer per stage, one wait per visit
+
+
+@pytest.mark.parametrize("p2p", [False, True], ids=["events", "p2p"])
+def test_bad_values_on_one_rank_fail_the_group_run(pkg, meshgen, p2p):
+    """euler3d.cpp:544-548 on a decomposed run: NaNs that appear on one rank make the run return MGCFD_ERR_BAD_VALS
+    (round 1 returned OK from multi-rank runs without looking at the flags)"""
+    mesh = meshgen.make_multigrid("small")
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 2)
+    lms = [pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, 2) for r in range(2)]
+    ranks = [pkg.MGCFD(local_mesh=lm, device=0) for lm in lms]
+    try:
+        if p2p:
+            pkg.group_enable_p2p(ranks)
+        v = ranks[1].fetch(0, "variables")
+        v[ranks[1].n_owned[0] // 2, 0] = np.nan
+        ranks[1].set(0, "variables", v)
+        with pytest.raises(pkg.MgcfdError) as ei:
+            pkg.group_run_cycles(ranks, 1)
+        assert ei.value.code in (-4, -5)
+    finally:
+        for g in ranks:
+            g.close()
