@@ -525,15 +525,16 @@ def main():
     cpu, ref_first = None, None
     want_parity = not args.no_parity and levels0 is not None
     if rank == 0 and (want_parity or (world == 1 and not args.no_cpu)):
-        if world == 1:
-            perms = [gpu.plan_query(l, "node_perm") for l in range(len(sizes))]
-            orders = [gpu.plan_query(l, "edge_order") for l in range(len(sizes))]
-            deck = reorder_for_cpu(levels0, perms, orders)
-        else:
-            perms, deck = None, levels0                      # file order: slower on the CPU, only one cycle is needed
+        # the CPU runs the deck in the GPU planner's locality order (at N>1 from a planning-only context over the whole deck)
+        pl = gpu if world == 1 else pkg.MGCFD(mesh["levels"], base_array_index=mesh["base_array_index"], device=-1, init=False)
+        perms = [pl.plan_query(l, "node_perm") for l in range(len(sizes))]
+        orders = [pl.plan_query(l, "edge_order") for l in range(len(sizes))]
+        if world > 1:
+            pl.close()
+        deck = reorder_for_cpu(levels0, perms, orders)
         n_cpu = 0 if (world > 1 or args.no_cpu) else args.cpu_cycles
         r = cpu_run(deck, n_cpu, 1, nthreads, keep_first_cycle=True)
-        ref_first = r["first_cycle"] if perms is None else [r["first_cycle"][l][perms[l].astype(np.int64)] for l in range(len(sizes))]
+        ref_first = [r["first_cycle"][l][perms[l].astype(np.int64)] for l in range(len(sizes))]      # back to file order
         if n_cpu:
             cpu = dict({"value": r["edges_per_s"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
                         "sample": f"{n_cpu} full V-cycles (+1 warm-up) of the same deck with the GPU run's node/edge ordering, "
@@ -545,6 +546,7 @@ def main():
     parity = {"checked": False, "why": "disabled (--no-parity)" if args.no_parity else "deck generated per rank: no single-host oracle run"}
     failed = False
     if want_parity:
+        barrier()                        # rank 0 may have spent a while on the CPU oracle: start the cycle together
         gpu.reinit_variables()
         gpu.run_cycles(1)
         max_rel, n_bad, vcount, bitwise = 0.0, 0, 0, True

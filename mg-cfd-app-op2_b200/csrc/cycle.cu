@@ -257,6 +257,14 @@ struct NcclApi {
 
 enum { DAT_VAR = 0, DAT_RES = 1 };
 
+// bound on every device-side wait for a peer (MGCFD_COMM_TIMEOUT_MS, default 60 s)
+long long comm_timeout_ns()
+{
+    const char *e = getenv("MGCFD_COMM_TIMEOUT_MS");
+    const long long ms = e && atoll(e) > 0 ? atoll(e) : 60000;
+    return ms * 1000000ll;
+}
+
 inline double *dat_ptr(mgcfd_ctx *c, int level, int which) { return which == DAT_VAR ? c->D[level].var : c->D[level].res; }
 
 // ---- halo exchange.  Every transfer runs on the rank's communication stream:
@@ -347,7 +355,7 @@ int exchange_p2p(mgcfd_ctx *ctx, int level, int which)
     if (!H.nbr_rank.empty()) {
         PushTable t;
         memset(&t, 0, sizeof(t));
-        t.err_flag = &ctx->d_flags[3];
+        t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
         const int me = ctx->rank;
         // which of the two variables buffers is "var" right now (identical on every rank: they swap in lock step)
         const int buf = ctx->D[level].var == reinterpret_cast<double *>(P.arena + P.me.off_var[0][level]) ? 0 : 1;
@@ -403,7 +411,7 @@ int min_exchange_p2p(mgcfd_ctx *ctx, int level, const unsigned long long *slot, 
         t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
         t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
     }
-    t.err_flag = &ctx->d_flags[3];
+    t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
     CK(cudaEventRecord(ctx->ev_prod, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
     ctx->launches += k_min_exchange(ctx->comm_stream, slot, t);
@@ -432,7 +440,7 @@ int build_push_tables(mgcfd_ctx *ctx)
                 t.xp_base = H.d_xp_base; t.xp_ptr = H.d_xp_ptr; t.xp_ent = H.d_xp_ent;
                 t.n_boundary = H.n_boundary_chunks;
                 t.done = P.d_done;
-                t.err_flag = &ctx->d_flags[3];
+                t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
                 for (size_t k = 0; k < H.nbr_rank.size(); k++) {
                     const int q = H.nbr_rank[k];
                     const int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
@@ -472,7 +480,7 @@ WaitTable wait_table(mgcfd_ctx *ctx, int level)
             t.src_flag[sidx] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + q;
             t.expected[sidx] = P.d_counters + P2P_MAX_RANKS + q;
         }
-    t.err_flag = &ctx->d_flags[3];
+    t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
     return t;
 }
 
@@ -496,7 +504,7 @@ int status_exchange_p2p(mgcfd_ctx *ctx)
         t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
         t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
     }
-    t.err_flag = &ctx->d_flags[3];
+    t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
     const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + status0;
     ctx->launches += k_status_exchange(ctx->stream, ctx->d_flags, boxes, ctx->n_ranks, t);
     return api_check_launch(ctx, "p2p status exchange");
@@ -697,7 +705,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                     // nothing to export on this level, yet rows may arrive (restrict / prolong halos): keep the epoch book
                     PushTable t;
                     memset(&t, 0, sizeof(t));
-                    t.err_flag = &c->d_flags[3];
+                    t.err_flag = &c->d_flags[3]; t.timeout_ns = comm_timeout_ns();
                     WaitTable w = wait_table(c, level);
                     for (int q = 0; q < w.n_src; q++) { t.src_flag[q] = w.src_flag[q]; t.expected[q] = const_cast<unsigned long long *>(w.expected[q]); }
                     t.n_src = w.n_src;

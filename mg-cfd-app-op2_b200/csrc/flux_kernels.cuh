@@ -386,12 +386,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// wait until *flag >= e, at most ~2 s: a peer that never arrives raises *err (MGCFD_ERR_COMM) instead of hanging the GPU
-__device__ __forceinline__ void bounded_wait(const unsigned long long *flag, unsigned long long e, int *err)
+// wait until *flag >= e, at most timeout_ns of wall clock (%globaltimer): a peer that never arrives raises *err
+// (MGCFD_ERR_COMM) instead of hanging the GPU for ever.  MGCFD_COMM_TIMEOUT_MS sets the bound (default 60 s).
+__device__ __forceinline__ unsigned long long global_ns()
 {
-    for (int it = 0; it < (1 << 22); it++) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void bounded_wait(const unsigned long long *flag, unsigned long long e, int *err, long long timeout_ns)
+{
+    if (ld_acquire_sys(flag) >= e) return;
+    const unsigned long long t0 = global_ns();
+    for (unsigned it = 0;; it++) {
         if (ld_acquire_sys(flag) >= e) return;
         __nanosleep(it < 64 ? 32 : 512);
+        if ((it & 1023u) == 1023u && (long long)(global_ns() - t0) > timeout_ns) break;
     }
     atomicExch(err, 1);
 }
@@ -399,7 +409,7 @@ __device__ __forceinline__ void bounded_wait(const unsigned long long *flag, uns
 // neighbours are done reading what this stage overwrites).  Call with all threads of the CTA.
 __device__ __forceinline__ void push_wait_sources(const StagePush *P, int tid)
 {
-    if (tid < P->n_src) bounded_wait(P->src_flag[tid], *P->expected[tid], P->err_flag);
+    if (tid < P->n_src) bounded_wait(P->src_flag[tid], *P->expected[tid], P->err_flag, P->timeout_ns);
     __syncthreads();
 }
 // producer side, per owned node `n` of the chunk (row pointers at xb): store component v of var_new (and of the residual)

@@ -241,12 +241,14 @@ struct StagePush {
     unsigned long long *expected[P2P_MAX_RANKS];     // epoch the next consumer needs from that source
     unsigned int *done;                              // chunks with exports finished in this launch
     int *err_flag;                                   // d_flags[3]: a bounded wait ran out
+    long long timeout_ns;
 };
 struct WaitTable {                       // kernel parameter of a stand-alone halo wait
     int n_src;
     const unsigned long long *src_flag[P2P_MAX_RANKS];
     const unsigned long long *expected[P2P_MAX_RANKS];
     int *err_flag;
+    long long timeout_ns;
 };
 
 struct P2PInfo {                         // what a peer must know about a rank's arena (exchanged as an opaque blob)
@@ -281,6 +283,7 @@ struct PushTable {                       // kernel parameter of one halo push
     const unsigned long long *src_flag[P2P_MAX_RANKS];   // my halo_flag[source rank]
     unsigned long long *expected[P2P_MAX_RANKS];     // my epoch counter for that source
     int *err_flag;
+    long long timeout_ns;
 };
 struct MinTable {
     int n_peers, me, parity;
@@ -290,6 +293,7 @@ struct MinTable {
     const unsigned long long *src_flag[P2P_MAX_RANKS];
     unsigned long long *expected[P2P_MAX_RANKS];
     int *err_flag;
+    long long timeout_ns;
 };
 
 struct LoopTimer {

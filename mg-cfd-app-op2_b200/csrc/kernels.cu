@@ -225,7 +225,7 @@ __global__ void signal_wait_kernel(PushTable t)
     if (lane < t.n_src) {
         unsigned long long e = *t.expected[lane] + 1;
         *t.expected[lane] = e;
-        bounded_wait(t.src_flag[lane], e, t.err_flag);
+        bounded_wait(t.src_flag[lane], e, t.err_flag, t.timeout_ns);
     }
 }
 
@@ -233,7 +233,7 @@ __global__ void signal_wait_kernel(PushTable t)
 __global__ void halo_wait_kernel(WaitTable t)
 {
     const int lane = threadIdx.x;
-    if (lane < t.n_src) bounded_wait(t.src_flag[lane], *t.expected[lane], t.err_flag);
+    if (lane < t.n_src) bounded_wait(t.src_flag[lane], *t.expected[lane], t.err_flag, t.timeout_ns);
 }
 
 // all-reduce(MIN) of min_dt by mailboxes: my encoded minimum goes into every peer's box, then the same flag handshake
@@ -251,7 +251,7 @@ __global__ void min_exchange_kernel(const unsigned long long *my_slot, MinTable 
     if (lane < t.n_peers) {
         unsigned long long e = *t.expected[lane] + 1;
         *t.expected[lane] = e;
-        bounded_wait(t.src_flag[lane], e, t.err_flag);
+        bounded_wait(t.src_flag[lane], e, t.err_flag, t.timeout_ns);
     }
 }
 
@@ -272,7 +272,7 @@ __global__ void status_exchange_kernel(int *flags, const unsigned long long *box
     if (lane < t.n_peers) {
         unsigned long long e = *t.expected[lane] + 1;
         *t.expected[lane] = e;
-        bounded_wait(t.src_flag[lane], e, t.err_flag);
+        bounded_wait(t.src_flag[lane], e, t.err_flag, t.timeout_ns);
     }
     __syncwarp();
     if (lane == 0)
