@@ -238,11 +238,20 @@ def time_cycles(gpu, stream, steps, barrier, max_over_ranks):
     return max_over_ranks(e0.elapsed_time(e1))
 
 
-def stage_timing(gpu, stream, steps, n_levels, fused, barrier, max_over_ranks):
-    """the same K cycles with every flux-edge / fused-stage launch bracketed by CUDA events (library timers, mode 2)"""
+LOOPS = ("visit_begin", "compute_step_factor", "min_exchange", "rk_stage", "compute_flux_edge", "compute_bnd_node_flux", "time_step",
+         "copy_double", "calculate_dt", "get_min_dt", "residual", "calc_rms", "count_bad_vals", "halo_wait", "halo_exchange",
+         "restrict", "up_pre", "up", "up_post", "down")
+
+
+def stage_timing(gpu, stream, steps, n_levels, fused, barrier, max_over_ranks, mode=2):
+    """the same K cycles with the library's device timers on.  mode 2: every flux-edge / fused-stage launch bracketed by
+    CUDA events, launch by launch (no graph).  mode 3: every call site timed INSIDE CUDA-graph replay (event-record nodes
+    in the captured graph), which also gives the per-loop breakdown of a cycle as it actually runs."""
     import torch
     name = "rk_stage" if fused else "compute_flux_edge"
-    gpu.timers_enable(2)
+    gpu.timers_enable(mode)
+    if mode == 3:
+        gpu.run_cycles(2)          # capture the two timed graphs outside the measurement
     gpu.timers_reset()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,9 +266,14 @@ def stage_timing(gpu, stream, steps, n_levels, fused, barrier, max_over_ranks):
         ms_l, calls_l, _ = gpu.timer(name, l)
         per_level.append(round(1e3 * ms_l / max(calls_l, 1), 2))
         per_level_ms.append(ms_l)
+    loops = {}
+    for ln in LOOPS:
+        ms_l, calls_l, _ = gpu.timer(ln)
+        if calls_l:
+            loops[ln] = {"ms_per_step": ms_l / steps, "launch_sites_per_step": calls_l / steps}
     gpu.timers_enable(0)
     return {"ms_timed": ms_timed, "flux_ms": flux_ms, "calls": flux_calls, "elems": flux_elems, "per_level_us": per_level,
-            "per_level_ms": per_level_ms}
+            "per_level_ms": per_level_ms, "loops": loops}
 
 
 def m6_subrecord(pkg, device, steps, warmup, peak):
@@ -272,7 +286,7 @@ def m6_subrecord(pkg, device, steps, warmup, peak):
     sync = torch.cuda.synchronize
     gpu.run_cycles(warmup + warmup % 2)
     ms = time_cycles(gpu, stream, steps, sync, lambda x: x)
-    st = stage_timing(gpu, stream, steps, len(sizes), True, sync, lambda x: x)
+    st = stage_timing(gpu, stream, steps, len(sizes), True, sync, lambda x: x, mode=3)
     launches0 = gpu.kernel_launches()
     gpu.run_cycles(1)
     launches = gpu.kernel_launches() - launches0
@@ -281,8 +295,9 @@ def m6_subrecord(pkg, device, steps, warmup, peak):
     return {"workload": describe("m6", sizes, 1, "strong", False, "geom"), "steps": steps, "ms_per_step": ms / steps,
             "mg_cycles_per_s": steps / (ms * 1e-3), "edges_per_s": flux_edges_per_cycle(sizes) * steps / (ms * 1e-3),
             "launches_per_cycle": launches,
-            "stage_frac_launch_timed": nbytes / (st["flux_ms"] * 1e-3) / 1e9 / peak,
+            "stage_frac_in_graph": nbytes / (st["flux_ms"] * 1e-3) / 1e9 / peak,
             "stage_per_level_us": st["per_level_us"],
+            "cycle_breakdown_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in st["loops"].items()},
             "note": "levels are L2-sized (300K..81K nodes): the roofline fraction of the line is quoted on the 8M-node deck"}
 
 
@@ -445,7 +460,11 @@ def main():
     launches = gpu.kernel_launches() - launches0
     # ---- timed region 2: the same K cycles launch by launch, every flux-edge / fused-stage launch event-timed
     fused = run_info["fused_schedule"]
-    st = stage_timing(gpu, stream, args.steps, len(sizes), fused, barrier, max_over_ranks)
+    st2 = stage_timing(gpu, stream, args.steps, len(sizes), fused, barrier, max_over_ranks, mode=2)
+    # ---- timed region 3: the same K cycles as CUDA-graph replays with event-record nodes around every call site
+    st = stage_timing(gpu, stream, args.steps, len(sizes), fused, barrier, max_over_ranks, mode=3) if not args.no_graphs else st2
+    if not st["calls"]:
+        st = st2
     clocks = sampler.stop() if sampler else None
     flux_ms, flux_calls, flux_elems, ms_timed = st["flux_ms"], st["calls"], st["elems"], st["ms_timed"]
 
@@ -481,11 +500,17 @@ def main():
                 "frac_fused_L0": frac_fused_l0, "frac_flux_only_L0": frac_flux_only_l0, "avg_launch_us_L0": l0_us,
                 "avg_launch_us": 1e3 * flux_ms / max(flux_calls, 1), "launches": flux_calls,
                 "kernel_edges_per_s": flux_elems / (flux_ms * 1e-3), "share_of_step": flux_ms / ms_timed,
-                "ms_per_step_with_launch_timers": ms_timed / args.steps,
+                "timing": "CUDA events recorded by event-record nodes INSIDE the replayed one-cycle graphs (timers mode 3)" if st is not st2
+                          else "CUDA events around every launch, launch by launch (timers mode 2)",
+                "ms_per_step_with_timers": ms_timed / args.steps,
                 "other_kernels_ms_per_step": (ms_timed - flux_ms) / args.steps,
                 "per_level_avg_launch_us": st["per_level_us"],
+                "cycle_breakdown_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in st["loops"].items()},
+                "launch_timed": {"frac": flux_bytes / (st2["flux_ms"] * 1e-3) / 1e9 / peak, "per_level_avg_launch_us": st2["per_level_us"],
+                                 "ms_per_step": st2["ms_timed"] / args.steps},
                 "note": "achieved = algorithmic bytes of all timed stage launches / their summed CUDA-event time (every level of the "
-                        "deck exceeds the 126 MB L2); frac_*_L0 = the level-0 launches alone under both accountings"}
+                        "deck exceeds the 126 MB L2); frac_*_L0 = the level-0 launches alone under both accountings; "
+                        "cycle_breakdown = device time per call site and cycle inside graph replay (its sum + gaps = ms_per_step_with_timers)"}
     if rank == 0:
         log(f"timed regions done after {time.time() - t_start:.1f} s: {ms / args.steps:.3f} ms/cycle, stage frac {achieved / peak:.3f}")
 

@@ -236,7 +236,9 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
 
 /* ---- measurement hooks ---- */
 /* per-call-site device timers (CUDA events on the context's stream): 0 off (default), 1 every call site,
- * 2 compute_flux_edge launches only */
+ * 2 compute_flux_edge launches only (both: mgcfd_run_cycles then enqueues launch by launch instead of replaying graphs),
+ * 3 every call site of mgcfd_run_cycles INSIDE CUDA-graph replay: the one-cycle graphs are captured with event-record
+ *   nodes around each call site and read back after every replay */
 int  mgcfd_timers_enable(mgcfd_ctx *ctx, int on);
 int  mgcfd_timers_reset(mgcfd_ctx *ctx);
 /* accumulated milliseconds / launch count / element count of a call site ("compute_flux_edge", ...) */

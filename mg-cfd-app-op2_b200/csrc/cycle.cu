@@ -45,15 +45,17 @@ unsigned parity_state(mgcfd_ctx *ctx)
 template <typename Enqueue>
 int run_with_graph(mgcfd_ctx *ctx, int n_cycles, Enqueue enqueue)
 {
-    bool usable = !ctx->opt.no_graphs && !ctx->timers_on && n_cycles >= 1 && ctx->n_levels <= 15;
+    const bool timed = ctx->timers_on == 3;
+    bool usable = !ctx->opt.no_graphs && (!ctx->timers_on || timed) && n_cycles >= 1 && ctx->n_levels <= 15;
     for (int l = 0; l < ctx->n_levels && usable; l++) usable = ctx->D[l].flux_is_zero;
     if (!usable) return enqueue(n_cycles);
     for (int i = 0; i < n_cycles; i++) {
-        const unsigned key = parity_state(ctx);
+        const unsigned key = parity_state(ctx) | (timed ? 0x80000000u : 0u);      // timed graphs carry event-record nodes
         auto it = ctx->graphs.find(key);
         if (it == ctx->graphs.end()) {
             GraphEntry g;
             long long l0 = ctx->launches, h0 = ctx->halo_bytes;
+            ctx->capture_spans.clear();
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             int rc = enqueue(1);
             cudaGraph_t graph = nullptr;
@@ -65,6 +67,7 @@ int run_with_graph(mgcfd_ctx *ctx, int n_cycles, Enqueue enqueue)
             if (e != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return MGCFD_ERR_CUDA; }
             g.launches = ctx->launches - l0;
             g.halo_bytes = ctx->halo_bytes - h0;
+            g.spans.swap(ctx->capture_spans);
             ctx->launches = l0;              // capturing enqueues nothing; the replay below does
             ctx->halo_bytes = h0;
             for (int l = 0; l < ctx->n_levels; l++)
@@ -72,6 +75,16 @@ int run_with_graph(mgcfd_ctx *ctx, int n_cycles, Enqueue enqueue)
             it = ctx->graphs.emplace(key, g).first;
         }
         CK(cudaGraphLaunch(it->second.exec, ctx->stream));
+        if (timed && !it->second.spans.empty()) {
+            // one replay at a time: read the spans of this cycle before the next replay re-records the events
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (const GraphEntry::TimedSpan &sp : it->second.spans) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+                LoopTimer &t = ctx->timers[sp.key];
+                t.ms += ms; t.calls++; t.elements += sp.elems;
+            }
+        }
         ctx->launches += it->second.launches;
         ctx->halo_bytes += it->second.halo_bytes;
         for (int l = 0; l < ctx->n_levels; l++) {
@@ -382,6 +395,7 @@ int exchange_p2p(mgcfd_ctx *ctx, int level, int which)
         }
         // export lists are grouped by neighbour in ascending order, and neighbours without exports have empty ranges:
         // the destinations' row ranges are contiguous in the export list
+        LoopScope ts(ctx, "halo_exchange", level, H.n_export, ctx->comm_stream);
         ctx->launches += k_push_rows(ctx->comm_stream, H.n_export, H.d_export_idx, dat_ptr(ctx, level, which), t);
         ctx->launches += k_signal_wait(ctx->comm_stream, t);
         ctx->halo_bytes += (long long)H.n_export * 40;
@@ -414,7 +428,10 @@ int min_exchange_p2p(mgcfd_ctx *ctx, int level, const unsigned long long *slot, 
     t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
     CK(cudaEventRecord(ctx->ev_prod, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prod, 0));
-    ctx->launches += k_min_exchange(ctx->comm_stream, slot, t);
+    {
+        LoopScope ts(ctx, "min_exchange", level, 1, ctx->comm_stream);
+        ctx->launches += k_min_exchange(ctx->comm_stream, slot, t);
+    }
     CK(cudaEventRecord(ctx->ev_ready, ctx->comm_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready, 0));
     return api_check_launch(ctx, "p2p min exchange");
@@ -718,7 +735,10 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 for (int r = 0; r < n; r++) {
                     mgcfd_ctx *c = R[r];
                     cudaSetDevice(c->device);
-                    if (c->halo[level].n_boundary_chunks > 0) c->launches += k_halo_wait(c->stream, wait_table(c, level));
+                    if (c->halo[level].n_boundary_chunks > 0) {
+                        LoopScope ts(c, "halo_wait", level, 1);
+                        c->launches += k_halo_wait(c->stream, wait_table(c, level));
+                    }
                 }
         }
         for (int rk = 0; !fp && rk < MGCFD_RK; rk++) {
@@ -801,8 +821,10 @@ static bool fused_push_wanted(const mgcfd_ctx *ctx)
 
 void mgcfd::cycle_drop_graphs(mgcfd_ctx *ctx)
 {
-    for (auto &kv : ctx->graphs)
+    for (auto &kv : ctx->graphs) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        for (auto &sp : kv.second.spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    }
     ctx->graphs.clear();
 }
 

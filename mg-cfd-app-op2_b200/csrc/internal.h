@@ -215,6 +215,9 @@ struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long launches = 0, halo_bytes = 0;   // per replay (one cycle)
     std::vector<LevelState> after;            // host bookkeeping the cycle leaves behind
+    // timers mode 3: event-record nodes captured around every call site (name#level, start, end, elements)
+    struct TimedSpan { std::string key; cudaEvent_t e0, e1; long long elems; };
+    std::vector<TimedSpan> spans;
 };
 
 // ---- direct peer-store halo exchange ("p2p" transport): every rank keeps variables (both buffers) and residuals of
@@ -323,7 +326,9 @@ struct mgcfd_ctx {
     void *d_stage = nullptr, *h_stage = nullptr;   // device / pinned-host staging for file-order transfers
     size_t d_stage_bytes = 0, h_stage_bytes = 0;
     long long launches = 0;
-    int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only
+    int timers_on = 0;                // 0 off, 1 every call site, 2 compute_flux_edge only (both: launch by launch, no graphs),
+                                      // 3 every call site INSIDE CUDA-graph replay (event-record nodes in the captured graph)
+    std::vector<mgcfd::GraphEntry::TimedSpan> capture_spans;   // spans recorded by the capture in progress (mode 3)
     std::map<std::string, mgcfd::LoopTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     std::map<unsigned, mgcfd::GraphEntry> graphs;   // captured one-cycle graphs by parity state
@@ -365,20 +370,41 @@ struct LoopScope {
         cudaEventCreate(&e);
         return e;
     }
-    LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements) : ctx(c), elems(elements)
+    cudaStream_t stream = nullptr;
+    std::string key;
+    bool in_graph = false;
+    LoopScope(mgcfd_ctx *c, const char *name, int level, long long elements, cudaStream_t on = nullptr) : ctx(c), elems(elements)
     {
         if (!ctx->timers_on) return;
         if (ctx->timers_on == 2 && strcmp(name, "compute_flux_edge") != 0 && strcmp(name, "rk_stage") != 0)
             return;   // flux-edge launches (stand-alone or as the fused Runge-Kutta stage) only
-        t = &ctx->timers[std::string(name) + "#" + std::to_string(level)];
-        e0 = get_event(ctx);
-        e1 = get_event(ctx);
-        cudaEventRecord(e0, ctx->stream);
+        stream = on ? on : ctx->stream;
+        key = std::string(name) + "#" + std::to_string(level);
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        in_graph = cs == cudaStreamCaptureStatusActive;
+        if (ctx->timers_on == 3 && !in_graph) return;       // mode 3 times graph replays only
+        t = &ctx->timers[key];
+        if (in_graph) {
+            // event-record NODES in the captured graph: the events are re-recorded by every replay
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecordWithFlags(e0, stream, cudaEventRecordExternal);
+        } else {
+            e0 = get_event(ctx);
+            e1 = get_event(ctx);
+            cudaEventRecord(e0, stream);
+        }
     }
     ~LoopScope()
     {
         if (!t) return;
-        cudaEventRecord(e1, ctx->stream);
+        if (in_graph) {
+            cudaEventRecordWithFlags(e1, stream, cudaEventRecordExternal);
+            ctx->capture_spans.push_back({key, e0, e1, elems});
+            return;
+        }
+        cudaEventRecord(e1, stream);
         t->pending.push_back({e0, e1});
         t->pending_elems.push_back(elems);
     }
