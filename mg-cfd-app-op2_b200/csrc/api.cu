@@ -246,6 +246,8 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
         if (h.d_xp_base) cudaFree(h.d_xp_base);
         if (h.d_xp_ptr) cudaFree(h.d_xp_ptr);
         if (h.d_xp_ent) cudaFree(h.d_xp_ent);
+        if (h.d_xn_ptr) cudaFree(h.d_xn_ptr);
+        if (h.d_xn_ent) cudaFree(h.d_xn_ent);
     }
     if (ctx->d_min_dt) cudaFree(ctx->d_min_dt);
     if (ctx->d_rms) cudaFree(ctx->d_rms);
@@ -257,7 +259,6 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
         if (ctx->p2p.ipc && ctx->p2p.peer_base[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->p2p.peer_base[r]);
     if (ctx->p2p.arena_owner && ctx->p2p.arena) cudaFree(ctx->p2p.arena);
     if (ctx->p2p.d_counters) cudaFree(ctx->p2p.d_counters);
-    if (ctx->p2p.d_push) cudaFree(ctx->p2p.d_push);
     if (ctx->p2p.d_done) cudaFree(ctx->p2p.d_done);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -572,6 +573,28 @@ int mgcfd_plan(mgcfd_ctx *ctx)
             if ((rc = dev_upload(ctx, &Hd.d_export_idx, idx))) return rc;
             if ((rc = dev_alloc(ctx, &Hd.sendbuf, (size_t)Hd.n_export * 5))) return rc;
         }
+        if (ctx->n_ranks > 1 && ctx->device >= 0) {
+            // the export lists per owned node (internal numbering): (destination slot, row in that destination's import
+            // range); destination slots number the neighbours that receive rows, in neighbour order
+            std::vector<std::vector<int2>> ent_of(L.n_owned);
+            int slot = 0;
+            for (size_t k = 0; k < L.nbr_rank.size(); k++) {
+                if (L.export_ptr[k + 1] == L.export_ptr[k]) continue;
+                for (int j = L.export_ptr[k]; j < L.export_ptr[k + 1]; j++)
+                    ent_of[L.new_of_old[L.export_idx[j]]].push_back(make_int2(slot, j - L.export_ptr[k]));
+                slot++;
+            }
+            std::vector<int> xn_ptr(L.n_owned + 1, 0);
+            std::vector<int2> xn_ent;
+            for (int v = 0; v < L.n_owned; v++) {
+                xn_ptr[v] = (int)xn_ent.size();
+                xn_ent.insert(xn_ent.end(), ent_of[v].begin(), ent_of[v].end());
+            }
+            xn_ptr[L.n_owned] = (int)xn_ent.size();
+            int rc;
+            if ((rc = dev_upload(ctx, &Hd.d_xn_ptr, xn_ptr))) return rc;
+            if ((rc = dev_upload(ctx, &Hd.d_xn_ent, xn_ent))) return rc;
+        }
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->planned = true;
@@ -874,6 +897,7 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
             xp_ptr.push_back((int)xp_ent.size());
         }
         first.insert(first.end(), rest.begin(), rest.end());
+        Hd.launch_order = first;
         int rcl = dev_upload(ctx, &Hd.d_chunk_list, first);
         if (rcl) return rcl;
         if ((rcl = dev_upload(ctx, &Hd.d_xp_base, Hd.xp_base))) return rcl;
@@ -946,11 +970,15 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         const int xs = 12 + hs;
         std::vector<int> xtab((size_t)O.n_chunks * xs, -1);
         static_assert(sizeof(OwnerChunkDesc) == 48, "record head = descriptor");
-        for (int k = 0; k < O.n_chunks; k++) {
-            memcpy(&xtab[(size_t)k * xs], &desc[k], sizeof(OwnerChunkDesc));
+        // records are stored in LAUNCH order (multi-GPU: chunks that own exported nodes first), so that a CTA finds its
+        // record at blockIdx.x without an indirection
+        const std::vector<int> &order = ctx->halo[level].launch_order;
+        for (int i = 0; i < O.n_chunks; i++) {
+            const int k = order.empty() ? i : order[i];
+            memcpy(&xtab[(size_t)i * xs], &desc[k], sizeof(OwnerChunkDesc));
             // word 3 (halo_off in the descriptor; the record carries the ids itself) = base of the chunk's export row pointers
-            xtab[(size_t)k * xs + 3] = ctx->n_ranks > 1 && !ctx->halo[level].xp_base.empty() ? ctx->halo[level].xp_base[k] : -1;
-            std::copy(O.halo_gid.begin() + O.halo_off[k], O.halo_gid.begin() + O.halo_off[k + 1], xtab.begin() + (size_t)k * xs + 12);
+            xtab[(size_t)i * xs + 3] = ctx->n_ranks > 1 && !ctx->halo[level].xp_base.empty() ? ctx->halo[level].xp_base[k] : -1;
+            std::copy(O.halo_gid.begin() + O.halo_off[k], O.halo_gid.begin() + O.halo_off[k + 1], xtab.begin() + (size_t)i * xs + 12);
         }
         if (D.owner.xtab) { cudaFree(D.owner.xtab); D.owner.xtab = nullptr; }
         if ((rc = dev_upload(ctx, &D.owner.xtab, xtab))) return rc;

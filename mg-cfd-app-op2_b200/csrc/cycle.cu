@@ -442,7 +442,7 @@ int min_exchange_p2p(mgcfd_ctx *ctx, int level, const unsigned long long *slot, 
 int build_push_tables(mgcfd_ctx *ctx)
 {
     P2PState &P = ctx->p2p;
-    if (P.d_push) return MGCFD_OK;
+    if (!P.h_push.empty()) return MGCFD_OK;
     const int nl = ctx->n_levels, me = ctx->rank;
     std::vector<StagePush> tab((size_t)nl * 4);
     CK(cudaMalloc((void **)&P.d_done, sizeof(unsigned int)));
@@ -479,8 +479,7 @@ int build_push_tables(mgcfd_ctx *ctx)
                 }
             }
     }
-    CK(cudaMalloc((void **)&P.d_push, tab.size() * sizeof(StagePush)));
-    CK(cudaMemcpy(P.d_push, tab.data(), tab.size() * sizeof(StagePush), cudaMemcpyHostToDevice));
+    P.h_push.swap(tab);
     return MGCFD_OK;
 }
 
@@ -499,6 +498,65 @@ WaitTable wait_table(mgcfd_ctx *ctx, int level)
         }
     t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
     return t;
+}
+
+// node kernels of a fused-push cycle: push the `which` dat of `push_level` (current buffer), wait for the sources of
+// `wait_level` (the level whose halo rows the kernel reads; -1: none)
+int node_push_table(mgcfd_ctx *ctx, int push_level, int which, int wait_level, NodePush &t)
+{
+    memset(&t, 0, sizeof(t));
+    P2PState &P = ctx->p2p;
+    HaloLevel &H = ctx->halo[push_level];
+    const int me = ctx->rank;
+    unsigned long long *cnt = P.d_counters;
+    t.on = 1;
+    t.xn_ptr = H.d_xn_ptr; t.xn_ent = H.d_xn_ent;
+    t.done = P.d_done; t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
+    const int buf = ctx->D[push_level].var == reinterpret_cast<double *>(P.arena + P.me.off_var[0][push_level]) ? 0 : 1;
+    for (size_t k = 0; k < H.nbr_rank.size(); k++) {
+        const int q = H.nbr_rank[k];
+        const int ns = H.exp_ptr[k + 1] - H.exp_ptr[k], nr = H.imp_ptr[k + 1] - H.imp_ptr[k];
+        const P2PInfo &Q = P.peer[q];
+        if (ns) {
+            if (Q.import_cnt[push_level][me] != ns) { ctx->err = "halo lists of the ranks do not match"; return MGCFD_ERR_ARG; }
+            const int d = t.n_dst++;
+            const long long off = which == DAT_VAR ? Q.off_var[buf][push_level] : Q.off_res[push_level];
+            t.dst[d] = reinterpret_cast<double *>(P.peer_base[q] + off) + (size_t)(Q.n_owned[push_level] + Q.import_off[push_level][me]) * 5;
+            t.dst_flag[d] = reinterpret_cast<unsigned long long *>(P.peer_base[q] + Q.off_flags) + me;
+            t.sent[d] = cnt + q;
+        }
+        if (nr) {
+            const int sidx = t.n_src++;
+            t.src_flag[sidx] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + q;
+            t.expected[sidx] = cnt + P2P_MAX_RANKS + q;
+        }
+    }
+    if (wait_level >= 0) {
+        const WaitTable w = wait_table(ctx, wait_level);
+        t.n_wait = w.n_src;
+        for (int i = 0; i < w.n_src; i++) { t.wait_flag[i] = w.src_flag[i]; t.wait_expected[i] = w.expected[i]; }
+    }
+    return MGCFD_OK;
+}
+
+// min_dt all-reduce folded into the visit prologue / step-factor kernels (mailboxes per level and visit parity)
+void min_push_table(mgcfd_ctx *ctx, int level, int parity, MinPush &t)
+{
+    memset(&t, 0, sizeof(t));
+    P2PState &P = ctx->p2p;
+    unsigned long long *cnt = P.d_counters;
+    t.on = 1;
+    for (int q = 0; q < ctx->n_ranks; q++) {
+        if (q == ctx->rank) continue;
+        const int d = t.n_peers++;
+        unsigned long long *qflags = reinterpret_cast<unsigned long long *>(P.peer_base[q] + P.peer[q].off_flags);
+        t.dst_box[d] = qflags + 2 * P2P_MAX_RANKS + 2 * (ctx->rank * P2P_MAX_LEVELS + level) + parity;
+        t.dst_flag[d] = qflags + P2P_MAX_RANKS + ctx->rank;
+        t.sent[d] = cnt + 2 * P2P_MAX_RANKS + q;
+        t.src_flag[d] = reinterpret_cast<const unsigned long long *>(P.arena + P.me.off_flags) + P2P_MAX_RANKS + q;
+        t.expected[d] = cnt + 3 * P2P_MAX_RANKS + q;
+    }
+    t.done = P.d_done; t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
 }
 
 // end of a multi-rank run, one process per GPU, p2p: every rank's deferred error flags (bad values, min_dt < 0, a wait
@@ -646,7 +704,13 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             LevelDev &D = c->D[level];
             unsigned long long *slot = &c->d_min_enc[2 * level + D.visit_parity];
             LoopScope t(c, "visit_begin", level, c->H[level].n_owned);
-            c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot);
+            if (c->p2p.enabled && c->p2p.fused_push) {
+                MinPush mp;                       // the last block sends the rank's minimum to every peer's mailbox
+                min_push_table(c, level, D.visit_parity, mp);
+                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot, &mp);
+            } else {
+                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot);
+            }
             if (n > 1 && !c->p2p.enabled) cudaEventRecord(c->ev_k1, c->stream);
         }
         // ---- global minimum + step factor (euler3d.cpp:477-489)
@@ -660,12 +724,15 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             LoopScope t(c, "compute_step_factor", level, no);
             if (c->p2p.enabled) {
                 // mailboxes: my minimum goes to every peer, theirs arrive in my arena; K2 reads my slot + the boxes
-                if ((rc = min_exchange_p2p(c, level, slot, D.visit_parity))) { ctx->err = c->err; return rc; }
+                const bool folded = c->p2p.fused_push;
+                if (!folded && (rc = min_exchange_p2p(c, level, slot, D.visit_parity))) { ctx->err = c->err; return rc; }
+                MinPush mp;
+                min_push_table(c, level, D.visit_parity, mp);
                 MinSlots ms;
                 ms.n = 0;
                 const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(c->p2p.arena + c->p2p.me.off_flags) + 2 * P2P_MAX_RANKS;
                 for (int q = 0; q < c->n_ranks; q++) ms.p[ms.n++] = q == c->rank ? slot : boxes + 2 * (q * P2P_MAX_LEVELS + level) + D.visit_parity;
-                c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags);
+                c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags, folded ? &mp : nullptr);
             } else if (nccl) {
                 ctx = c;
                 // every NCCL call of this rank goes through the communication stream, in one program order
@@ -708,11 +775,12 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 ra.rk = rk; ra.last = last; ra.c = api_dev_consts(c);
                 const int ob = D.var_alt == reinterpret_cast<double *>(c->p2p.arena + c->p2p.me.off_var[0][level]) ? 0 : 1;
                 const int wr = (last && level >= 1) ? 1 : 0;
-                ra.push = Hd.n_boundary_chunks > 0 ? c->p2p.d_push + ((size_t)(level * 2 + ob) * 2 + wr) : nullptr;
+                ra.push_on = Hd.n_boundary_chunks > 0 ? 1 : 0;
+                if (ra.push_on) ra.push = c->p2p.h_push[(size_t)(level * 2 + ob) * 2 + wr];
                 FluxArgs a;
                 a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
                 a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
-                a.chunk_list = Hd.d_chunk_list; a.n_list = Hd.n_chunks;
+                a.chunk_list = Hd.d_chunk_list; a.n_list = Hd.n_chunks; a.list_offset = 0;
                 {
                     LoopScope t(c, "rk_stage", level, L.n_edges);
                     c->launches += flux_owner(c->stream, a, D.owner, L.owner, c->opt.exact_arith != 0);
@@ -731,15 +799,8 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
             }
             for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
-            if (last)      // the next kernel that reads halo rows (restrict, prolong, a visit prologue) is not a stage kernel
-                for (int r = 0; r < n; r++) {
-                    mgcfd_ctx *c = R[r];
-                    cudaSetDevice(c->device);
-                    if (c->halo[level].n_boundary_chunks > 0) {
-                        LoopScope ts(c, "halo_wait", level, 1);
-                        c->launches += k_halo_wait(c->stream, wait_table(c, level));
-                    }
-                }
+            // (no stand-alone wait after the last stage: the next kernel that reads halo rows -- restrict, prolong or the
+            //  next stage -- waits for its sources itself)
         }
         for (int rk = 0; !fp && rk < MGCFD_RK; rk++) {
             const bool last = rk == MGCFD_RK - 1;
@@ -760,6 +821,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                     a.n_edges = L.n_edges; a.n_owned = L.n_owned; a.n_nodes = L.n_nodes;
                     a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
                     a.chunk_list = Hd.d_chunk_list + (part == 0 ? 0 : Hd.n_boundary_chunks);
+                    a.list_offset = part == 0 ? 0 : Hd.n_boundary_chunks;
                     a.n_list = part == 0 ? Hd.n_boundary_chunks : Hd.n_chunks - Hd.n_boundary_chunks;
                     {
                         LoopScope t(c, "rk_stage", level, part == 0 ? 0 : L.n_edges);
@@ -789,9 +851,16 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 cudaSetDevice(c->device);
                 LevelDev &A = c->D[level], &F = c->D[level - 1];
                 LoopScope t(c, "restrict", level, c->H[level - 1].n_owned);
-                c->launches += k_restrict_fused(c->stream, c->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
+                if (fp) {
+                    NodePush np;                  // reads the fine level's halo children, pushes the coarse level's variables
+                    if ((rc = node_push_table(c, level, DAT_VAR, level - 1, np))) { ctx->err = c->err; return rc; }
+                    c->launches += k_restrict_fused(c->stream, c->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count, &np);
+                    c->halo_bytes += (long long)c->halo[level].n_export * 40;
+                } else {
+                    c->launches += k_restrict_fused(c->stream, c->H[level].n_nodes, A.child_ptr, A.child_idx, F.var, A.var, A.up_count);
+                }
             }
-            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+            if (!fp && (rc = exchange(R, n, level, DAT_VAR))) return rc;
             if (level == nl - 1) dir = 1;
         } else {
             level--;
@@ -800,9 +869,16 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 cudaSetDevice(c->device);
                 LevelDev &F = c->D[level], &A = c->D[level + 1];
                 LoopScope t(c, "down", level, c->H[level].n_owned);
-                c->launches += k_down(c->stream, c->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords);
+                if (fp) {
+                    NodePush np;                  // reads the coarse level's halo residuals, pushes this level's variables
+                    if ((rc = node_push_table(c, level, DAT_VAR, level + 1, np))) { ctx->err = c->err; return rc; }
+                    c->launches += k_down(c->stream, c->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords, &np);
+                    c->halo_bytes += (long long)c->halo[level].n_export * 40;
+                } else {
+                    c->launches += k_down(c->stream, c->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords);
+                }
             }
-            if ((rc = exchange(R, n, level, DAT_VAR))) return rc;
+            if (!fp && (rc = exchange(R, n, level, DAT_VAR))) return rc;
             if (level == 0) { dir = 0; i++; }
         }
     }

@@ -407,38 +407,39 @@ __device__ __forceinline__ void bounded_wait(const unsigned long long *flag, uns
 }
 // consumer side of a chunk that owns exported nodes: all sources' rows of the previous exchange have landed (and the
 // neighbours are done reading what this stage overwrites).  Call with all threads of the CTA.
-__device__ __forceinline__ void push_wait_sources(const StagePush *P, int tid)
+__device__ __forceinline__ void push_wait_sources(const StagePush &P, int tid)
 {
-    if (tid < P->n_src) bounded_wait(P->src_flag[tid], *P->expected[tid], P->err_flag, P->timeout_ns);
+    if (tid < P.n_src) bounded_wait(P.src_flag[tid], *P.expected[tid], P.err_flag, P.timeout_ns);
     __syncthreads();
 }
-// producer side, per owned node `n` of the chunk (row pointers at xb): store component v of var_new (and of the residual)
-// into every destination that holds the node in its halo
-__device__ __forceinline__ void push_component(const StagePush *P, int xb, int n, int v, double vn, double r, bool with_res)
+// producer side, per owned node: store component v of var_new (and of the residual) into every destination that holds
+// the node in its halo; [j0, j1) = the node's entries
+__device__ __forceinline__ void push_component(const StagePush &P, int j0, int j1, int v, double vn, double r, bool with_res)
 {
-    const int j1 = __ldg(P->xp_ptr + xb + n + 1);
-    for (int j = __ldg(P->xp_ptr + xb + n); j < j1; j++) {
-        const int2 t = __ldg(P->xp_ent + j);
-        P->var_dst[t.x][(size_t)t.y * 5 + v] = vn;
-        if (with_res && P->res_dst[t.x]) P->res_dst[t.x][(size_t)t.y * 5 + v] = r;
+    for (int j = j0; j < j1; j++) {
+        const int2 t = __ldg(P.xp_ent + j);
+        P.var_dst[t.x][(size_t)t.y * 5 + v] = vn;
+        if (with_res && P.res_dst[t.x]) P.res_dst[t.x][(size_t)t.y * 5 + v] = r;
     }
 }
-// after the chunk's pushes: count the chunk; the last one of the launch publishes the epoch and arms the next consumer
-__device__ __forceinline__ void push_publish(const StagePush *P, int tid)
+// after the chunk's pushes: count the chunk; the last one of the launch publishes the epoch and arms the next consumer.
+// One system-scope fence by thread 0 after the CTA barrier orders every thread's peer stores before the count (the
+// pattern of a cooperative grid barrier).
+__device__ __forceinline__ void push_publish(const StagePush &P, int tid)
 {
-    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int prev = atomicAdd(P->done, 1u);
-        if (prev + 1u == (unsigned int)P->n_boundary) {
-            atomicExch(P->done, 0u);
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(P.done, 1u);
+        if (prev + 1u == (unsigned int)P.n_boundary) {
+            atomicExch(P.done, 0u);
             __threadfence_system();
-            for (int d = 0; d < P->n_dst; d++) {
-                const unsigned long long e = *P->sent[d] + 1;
-                *P->sent[d] = e;
-                st_release_sys(P->dst_flag[d], e);
+            for (int d = 0; d < P.n_dst; d++) {
+                const unsigned long long e = *P.sent[d] + 1;
+                *P.sent[d] = e;
+                st_release_sys(P.dst_flag[d], e);
             }
-            for (int q = 0; q < P->n_src; q++) *P->expected[q] += 1;
+            for (int q = 0; q < P.n_src; q++) *P.expected[q] += 1;
         }
     }
 }
@@ -647,6 +648,8 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
         } else {
             // An odd owned run (the last chunk of a level only) has one old_variables element and one step factor
             // outside the bulk-copied tiles; the test is uniform, so that every other chunk runs without it.
+            int xj0 = 0, xj1 = 0;
+            if (xb >= 0) { xj0 = __ldg(rk.push.xp_ptr + xb + n); xj1 = __ldg(rk.push.xp_ptr + xb + n + 1); }
             auto finish = [&](auto tail_c) {
                 constexpr bool TAIL = decltype(tail_c)::value;
                 const int old_n = (int)(owned_bulk_bytes(d.n_own) >> 3), sf_n = (int)((((uint32_t)d.n_own * 8u) & ~15u) >> 3);
@@ -665,7 +668,7 @@ __device__ __forceinline__ void node_phase(int tid, const OwnerChunkDesc &d, con
                             sq += r * r;
                             bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
                         }
-                        if (xb >= 0) push_component(rk.push, xb, n, v, vn, r, rk.last != 0);
+                        if (xb >= 0) push_component(rk.push, xj0, xj1, v, vn, r, rk.last != 0);
                     }
                 }
             };
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(256, MGCFD_OWNER_MINB)
 flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc *__restrict__ descs,
                   const int *__restrict__ chunk_list, const int *__restrict__ halo_gid,
                   const unsigned char *__restrict__ blob, const double *__restrict__ var, double *__restrict__ flux,
-                  RkStageArgs rk)
+                  const __grid_constant__ RkStageArgs rk)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int NREC = STREAM ? 5 : NF;
@@ -719,8 +722,8 @@ flux_owner_kernel(int max_loc, int max_edges, int max_blob, const OwnerChunkDesc
     const uint32_t old_bulk = FUSE ? owned_bulk_bytes(d.n_own) : 0u, sf_bulk = FUSE ? (((uint32_t)d.n_own * 8u) & ~15u) : 0u;
     // multi-GPU, fused push: a chunk that owns exported nodes waits for its sources before it reads halo rows
     int xb = -1;
-    if (FUSE && REGEPI && rk.push) {
-        xb = __ldg(rk.push->xp_base + (chunk_list ? chunk_list[blockIdx.x] : blockIdx.x));
+    if (FUSE && REGEPI && rk.push_on) {
+        xb = __ldg(rk.push.xp_base + (chunk_list ? chunk_list[blockIdx.x] : blockIdx.x));
         if (xb >= 0) push_wait_sources(rk.push, tid);
     }
 
@@ -862,7 +865,7 @@ constexpr int LEAN_ROWS = 8;            // halo rows per 8-lane group requested 
                                         // halo nodes; longer lists finish in a loop once the descriptor is known
 __global__ void __launch_bounds__(128, 6)
 flux_owner_lean_kernel(int max_loc, int max_edges, int max_blob, const int *__restrict__ xtab, int xs, int hs,
-                       const int *__restrict__ chunk_list, const unsigned char *__restrict__ blob,
+                       int rec0, const unsigned char *__restrict__ blob,
                        const double *__restrict__ var, RkStageArgs rk)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -874,7 +877,7 @@ flux_owner_lean_kernel(int max_loc, int max_edges, int max_blob, const int *__re
     double *told = raw + (((size_t)NF * max_loc + 1) & ~(size_t)1);
     double *tsf = told + (((size_t)rk.max_own * 5 + 1) & ~(size_t)1);
     const int tid = threadIdx.x, grp = tid >> 3, comp = tid & 7;
-    const int chunk = chunk_list ? chunk_list[blockIdx.x] : blockIdx.x;
+    const int chunk = rec0 + (int)blockIdx.x;                // the records are stored in launch order
     const int *rec = xtab + (size_t)chunk * xs;
     // halo ids of this thread's rows and the descriptor: independent loads, one round trip
     int hgv[LEAN_ROWS];
@@ -1616,7 +1619,7 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
     // chunk prefetched into L2; 2 = persistent CTAs, two shared-memory stages
     const char *pipe_s = getenv("MGCFD_OWNER_PIPE");
     const int pipe = pipe_s ? atoi(pipe_s) : MGCFD_OWNER_PIPE_DEFAULT;
-    if (pipe > 0 && !a.stream_kernel && threads >= 128 && !(a.rk && a.rk->push)) {      // (the pipelined variants have no fused push)
+    if (pipe > 0 && !a.stream_kernel && threads >= 128 && !(a.rk && a.rk->push_on)) {      // (the pipelined variants have no fused push)
         int rc = launch_owner_pipe(s, a, p, h, threads, pipe >= 2 ? 2 : 1);
         if (rc >= 0) return rc;
     }
@@ -1633,15 +1636,15 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
         if (threads == 128 && launch_stage2(s, a, p, h, grid)) return 1;
         // MGCFD_OWNER_LEAN=1: the lean kernel (needs the fixed-stride descriptor + halo-id table of ensure_owner)
         const char *lean_s = getenv("MGCFD_OWNER_LEAN");
-        if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64 && !ra.push) {
-            flux_owner_lean_kernel<<<grid, 128, fsmem, s>>>(h.max_loc, h.max_edges, h.dev_max_blob, p.xtab, p.xs, p.hs, a.chunk_list,
+        if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64 && !ra.push_on) {
+            flux_owner_lean_kernel<<<grid, 128, fsmem, s>>>(h.max_loc, h.max_edges, h.dev_max_blob, p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0,
                                                             p.blob, a.var, ra);
             return 1;
         }
 #endif
         // MGCFD_OWNER_EPILOGUE=0: node sums staged through shared memory and a separate coalesced update pass
         const char *epi_s = getenv("MGCFD_OWNER_EPILOGUE");
-        if (epi_s && atoi(epi_s) == 0 && !ra.push)
+        if (epi_s && atoi(epi_s) == 0 && !ra.push_on)
             flux_owner_kernel<false, true, true, false><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);
         else
             flux_owner_kernel<false, true, true, true><<<grid, threads, fsmem, s>>>(OWNER_ARGS, ra);

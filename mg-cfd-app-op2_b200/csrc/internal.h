@@ -206,8 +206,11 @@ struct HaloLevel {
     // fused push (the stage kernel stores exported rows straight into the neighbours' halo ranges): per chunk the base
     // of its (n_own + 1) row pointers in d_xp_ptr or -1, and per exported node its (destination slot, row) entries
     std::vector<int> xp_base;
+    std::vector<int> launch_order;   // host copy of d_chunk_list
     int *d_xp_base = nullptr, *d_xp_ptr = nullptr;
     int2 *d_xp_ent = nullptr;
+    int *d_xn_ptr = nullptr;         // the same entries per owned node of the level (node kernels: restrict, prolong)
+    int2 *d_xn_ent = nullptr;
 };
 
 struct GraphEntry {
@@ -246,6 +249,35 @@ struct StagePush {
     int *err_flag;                                   // d_flags[3]: a bounded wait ran out
     long long timeout_ns;
 };
+// The same hand-shake for the node kernels of a multi-rank cycle (visit prologue, step factor, restrict, prolong), passed by
+// value: wait for the sources of the level whose halo rows the kernel READS, push the rows of the exported nodes the kernel
+// WRITES, and let the last block publish the epoch (and arm the next consumer of the pushed level).
+struct NodePush {
+    int on, n_dst, n_src, n_wait;
+    const int *xn_ptr;                               // [n_owned + 1] of the pushed level: entries per owned node
+    const int2 *xn_ent;                              // (destination slot, row)
+    double *dst[P2P_MAX_RANKS];                      // where my rows start in destination d's halo range of the pushed dat
+    unsigned long long *dst_flag[P2P_MAX_RANKS], *sent[P2P_MAX_RANKS];
+    const unsigned long long *src_flag[P2P_MAX_RANKS];
+    unsigned long long *expected[P2P_MAX_RANKS];
+    const unsigned long long *wait_flag[P2P_MAX_RANKS];
+    const unsigned long long *wait_expected[P2P_MAX_RANKS];
+    unsigned int *done;
+    int *err_flag;
+    long long timeout_ns;
+};
+// min_dt all-reduce folded into the visit prologue (the last block stores the rank's minimum into every peer's mailbox and
+// publishes) and the step-factor kernel (every block waits for the peers' flags, then reads the mailboxes)
+struct MinPush {
+    int on, n_peers;
+    unsigned long long *dst_box[P2P_MAX_RANKS], *dst_flag[P2P_MAX_RANKS], *sent[P2P_MAX_RANKS];
+    const unsigned long long *src_flag[P2P_MAX_RANKS];
+    unsigned long long *expected[P2P_MAX_RANKS];
+    unsigned int *done;
+    int *err_flag;
+    long long timeout_ns;
+};
+
 struct WaitTable {                       // kernel parameter of a stand-alone halo wait
     int n_src;
     const unsigned long long *src_flag[P2P_MAX_RANKS];
@@ -272,7 +304,7 @@ struct P2PState {
     P2PInfo peer[P2P_MAX_RANKS];
     unsigned char *peer_base[P2P_MAX_RANKS] = {};
     unsigned long long *d_counters = nullptr;   // sent_halo[16] | expected_halo[16] | sent_min[16] | expected_min[16]
-    StagePush *d_push = nullptr;                // [n_levels][2 output buffers][without / with residuals]
+    std::vector<StagePush> h_push;              // [n_levels][2 output buffers][without / with residuals]
     unsigned int *d_done = nullptr;
     bool fused_push = false;                    // the stage kernels push and hand-shake themselves (default with p2p)
 };
@@ -425,7 +457,7 @@ int k_up(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_id
          double *var_above, int *count_above);
 int k_up_post(cudaStream_t s, int n_coarse, double *var, const int *count);
 int k_down(cudaStream_t s, int n_fine, const int *mg, double *var, const double *res, const double *coords,
-           const double *res_above, const double *coords_above);
+           const double *res_above, const double *coords_above, const NodePush *np = nullptr);
 int k_bnd_flux(cudaStream_t s, int n_unique, const int *bu_node, const int *bu_ptr, const int *b_group,
                const double *b_wt, const double *var, double *flux, const DevConsts &c, bool exact);
 int k_validate(cudaStream_t s, int n, const double *test, const double *master, int *d_count);
@@ -435,15 +467,15 @@ int k_permute_rows(cudaStream_t s, int n, int dim, const double *src, const int 
 int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c);
 // fused node kernels of mgcfd_run_cycles
 int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
-                  unsigned long long *min_slot);
+                  unsigned long long *min_slot, const MinPush *mp = nullptr);
 int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
                         double *sf, double *d_min_out, int *d_flags);
 int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
-                     double *var_above, int *count_above);
+                     double *var_above, int *count_above, const NodePush *np = nullptr);
 int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots);
 struct MinSlots { const unsigned long long *p[16]; int n; };
 int k_step_factor_group(cudaStream_t s, int n, const double *vol, MinSlots slots, unsigned long long *next_slot, double *sf,
-                        double *d_min_out, int *d_flags);
+                        double *d_min_out, int *d_flags, const MinPush *mp = nullptr);
 int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double *dst);
 // p2p transport: rows straight into the peers' halo ranges, then epoch flags; returns kernels launched
 int k_push_rows(cudaStream_t s, int n_rows, const int *idx, const double *src, const PushTable &t);
@@ -462,7 +494,8 @@ struct RkStageArgs {
     const int *b_group;
     const double *b_wt;
     int rk, last;
-    const StagePush *push;       // multi-GPU: push exported rows from the node phase (null: no fused push)
+    int push_on, pad2_;          // multi-GPU: push exported rows from the node phase and hand-shake (fused push)
+    StagePush push;
     int max_own, pad_;           // filled by the launcher: tile sizes of the prefetched update operands
     double inv_denom;            // filled by the launcher: 1 / (RK + 1 - rk) (stage2 kernel)
     DevConsts c;
@@ -477,6 +510,7 @@ struct FluxArgs {
     const RkStageArgs *rk = nullptr; // owner variant: fuse the rest of the Runge-Kutta stage into the kernel
     const int *chunk_list = nullptr; // owner variant: launch only these chunks (device array of n_list chunk ids)
     int n_list = 0;
+    int list_offset = 0;             // position of chunk_list[0] in the level's launch order (the xtab records are stored in that order)
 };
 int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
 int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);

@@ -5,6 +5,7 @@
 // streaming kernels; contraction would not make them faster.
 #define MGCFD_EXACT 1
 #include <cfloat>
+#include <cstring>
 
 #include "flux_kernels.cuh"
 
@@ -119,11 +120,54 @@ __global__ void encode_min_kernel(unsigned long long *d_min)
     *d_min = enc_min(*reinterpret_cast<double *>(d_min));
 }
 
+using exact::st_release_sys;
+using exact::ld_acquire_sys;
+using exact::bounded_wait;
+
+// multi-rank node kernels (NodePush): every block first waits for the sources of the halo rows it reads ...
+__device__ __forceinline__ void node_wait(const NodePush &P)
+{
+    if ((int)threadIdx.x < P.n_wait) bounded_wait(P.wait_flag[threadIdx.x], *P.wait_expected[threadIdx.x], P.err_flag, P.timeout_ns);
+    __syncthreads();
+}
+// ... stores the 5-vector of an exported node into the destinations' halo ranges ...
+__device__ __forceinline__ void node_push(const NodePush &P, int node, const double v[5])
+{
+    const int j1 = __ldg(P.xn_ptr + node + 1);
+    for (int j = __ldg(P.xn_ptr + node); j < j1; j++) {
+        const int2 t = __ldg(P.xn_ent + j);
+        double *d = P.dst[t.x] + (size_t)t.y * 5;
+#pragma unroll
+        for (int k = 0; k < 5; k++) d[k] = v[k];
+    }
+}
+// ... and the last block of the grid publishes the epoch to every destination and arms the next consumer
+__device__ __forceinline__ void node_publish(const NodePush &P)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(P.done, 1u);
+        if (prev + 1u == gridDim.x) {
+            atomicExch(P.done, 0u);
+            __threadfence_system();
+            for (int d = 0; d < P.n_dst; d++) {
+                const unsigned long long e = *P.sent[d] + 1;
+                *P.sent[d] = e;
+                st_release_sys(P.dst_flag[d], e);
+            }
+            for (int q = 0; q < P.n_src; q++) *P.expected[q] += 1;
+        }
+    }
+}
+
 // fused start of a level visit: copy_double_kernel + calculate_dt_kernel + get_min_dt_kernel (euler3d.cpp:467-479)
 __global__ void visit_begin_kernel(int n, const double *__restrict__ var, const double *__restrict__ cbrt_vol,
-                                   double *__restrict__ old, double *__restrict__ dt, unsigned long long *__restrict__ min_slot)
+                                   double *__restrict__ old, double *__restrict__ dt, unsigned long long *__restrict__ min_slot,
+                                   const __grid_constant__ MinPush mp)
 {
     __shared__ unsigned long long smin[TPB / 32];
+    __shared__ int s_last;
     unsigned long long m = ~0ull;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -149,6 +193,26 @@ __global__ void visit_begin_kernel(int n, const double *__restrict__ var, const 
         for (int w = 1; w < TPB / 32; w++)
             if (smin[w] < m) m = smin[w];
         atomicMin(min_slot, m);
+        s_last = 0;
+        if (mp.on) {
+            // multi-rank: the last block of the grid holds the rank's minimum and sends it to every peer's mailbox
+            __threadfence();
+            const unsigned int prev = atomicAdd(mp.done, 1u);
+            if (prev + 1u == gridDim.x) { atomicExch(mp.done, 0u); s_last = 1; }
+        }
+    }
+    if (!mp.on) return;
+    __syncthreads();
+    if (!s_last) return;
+    const int lane = threadIdx.x;
+    if (lane < mp.n_peers) {
+        const unsigned long long mine = atomicMin(min_slot, ~0ull);       // the finished reduction (atomic read)
+        *mp.dst_box[lane] = mine;
+        const unsigned long long e = *mp.sent[lane] + 1;
+        *mp.sent[lane] = e;
+        __threadfence_system();
+        st_release_sys(mp.dst_flag[lane], e);
+        *mp.expected[lane] += 1;                                           // what the step-factor kernel waits for
     }
 }
 
@@ -168,11 +232,16 @@ __global__ void step_factor_fused_kernel(int n, const double *__restrict__ vol, 
     if (i < n) sf[i] = m / vol[i];
 }
 
-// the same with the minimum taken over the slots of all ranks of a single-process group (peer-mapped pointers)
+// the same with the minimum taken over the slots of all ranks (peer-mapped pointers / mailboxes); mp.on: every block
+// first waits until all peers' minima of this visit have arrived (flags published by their visit prologues)
 __global__ void step_factor_group_kernel(int n, const double *__restrict__ vol, MinSlots slots,
                                          unsigned long long *__restrict__ next_slot, double *__restrict__ sf,
-                                         double *__restrict__ d_min_out, int *__restrict__ d_flags)
+                                         double *__restrict__ d_min_out, int *__restrict__ d_flags, const __grid_constant__ MinPush mp)
 {
+    if (mp.on) {
+        if ((int)threadIdx.x < mp.n_peers) bounded_wait(mp.src_flag[threadIdx.x], *mp.expected[threadIdx.x], mp.err_flag, mp.timeout_ns);
+        __syncthreads();
+    }
     unsigned long long u = ~0ull;
     for (int r = 0; r < slots.n; r++) {
         unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(slots.p[r]);
@@ -196,10 +265,6 @@ __global__ void pack_rows_kernel(int n5, const int *__restrict__ idx, const doub
 }
 
 // ---- p2p transport ---------------------------------------------------------------------------------
-using exact::st_release_sys;
-using exact::ld_acquire_sys;
-using exact::bounded_wait;
-
 // gather the exported rows and store them straight into each destination rank's halo range (peer-mapped pointers)
 __global__ void push_rows_kernel(int n5, const int *__restrict__ idx, const double *__restrict__ src, PushTable t)
 {
@@ -295,22 +360,29 @@ __global__ void reset_min_slots_kernel(int n, unsigned long long *slots)
 // 0.0 in ascending file order exactly as the three loops do; a childless coarse node is left untouched (x * 1.0 == x)
 __global__ void restrict_fused_kernel(int n_coarse, const int *__restrict__ child_ptr, const int *__restrict__ child_idx,
                                       const double *__restrict__ var, double *__restrict__ var_above,
-                                      int *__restrict__ count_above)
+                                      int *__restrict__ count_above, const __grid_constant__ NodePush np)
 {
+    if (np.on) node_wait(np);                       // the children's rows on other ranks (pushed by their last stage) are in
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_coarse) return;
-    int j0 = child_ptr[p], j1 = child_ptr[p + 1];
-    if (j0 == j1) return;
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int j = j0; j < j1; j++) {
-        const double *u = var + (size_t)child_idx[j] * 5;
+    if (p < n_coarse) {
+        int j0 = child_ptr[p], j1 = child_ptr[p + 1];
+        if (j0 != j1) {
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int j = j0; j < j1; j++) {
+                const double *u = var + (size_t)child_idx[j] * 5;
 #pragma unroll
-        for (int v = 0; v < 5; v++) acc[v] += u[v];
+                for (int v = 0; v < 5; v++) acc[v] += u[v];
+            }
+            double avg = 1.0 / (double)(j1 - j0);
+#pragma unroll
+            for (int v = 0; v < 5; v++) { acc[v] = acc[v] * avg; var_above[(size_t)p * 5 + v] = acc[v]; }
+            count_above[p] = j1 - j0;
+            if (np.on) node_push(np, p, acc);       // only owned coarse nodes have children here
+        }
+        // (a childless owned coarse node keeps its value, Q8: the neighbours already hold it -- pushed by the last stage
+        // of the level's previous visit into this same buffer)
     }
-    double avg = 1.0 / (double)(j1 - j0);
-#pragma unroll
-    for (int v = 0; v < 5; v++) var_above[(size_t)p * 5 + v] = acc[v] * avg;
-    count_above[p] = j1 - j0;
+    if (np.on) node_publish(np);
 }
 
 // time_stepping_kernels.h:43-64 (only line :63 has an effect)
@@ -434,22 +506,30 @@ __global__ void up_post_kernel(int n_coarse, double *__restrict__ var, const int
 // mg.h:66-88
 __global__ void down_kernel(int n_fine, const int *__restrict__ mg, double *__restrict__ var,
                             const double *__restrict__ res, const double *__restrict__ xyz,
-                            const double *__restrict__ res_above, const double *__restrict__ xyz_above)
+                            const double *__restrict__ res_above, const double *__restrict__ xyz_above,
+                            const __grid_constant__ NodePush np)
 {
+    if (np.on) node_wait(np);                       // the parents' residuals on other ranks (pushed by their last stage) are in
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_fine) return;
-    int p = mg[i];
-    double dx = fabs(xyz[(size_t)i * 3] - xyz_above[(size_t)p * 3]);
-    double dy = fabs(xyz[(size_t)i * 3 + 1] - xyz_above[(size_t)p * 3 + 1]);
-    double dz = fabs(xyz[(size_t)i * 3 + 2] - xyz_above[(size_t)p * 3 + 2]);
-    double dm = sqrt(dx * dx + dy * dy + dz * dz);
-    double *u = var + (size_t)i * 5;
-    const double *r = res + (size_t)i * 5, *ra = res_above + (size_t)p * 5;
-    u[0] -= dm * (ra[0] - r[0]);
-    u[1] -= dx * (ra[1] - r[1]);
-    u[2] -= dy * (ra[2] - r[2]);
-    u[3] -= dz * (ra[3] - r[3]);
-    u[4] -= dm * (ra[4] - r[4]);
+    if (i < n_fine) {
+        int p = mg[i];
+        double dx = fabs(xyz[(size_t)i * 3] - xyz_above[(size_t)p * 3]);
+        double dy = fabs(xyz[(size_t)i * 3 + 1] - xyz_above[(size_t)p * 3 + 1]);
+        double dz = fabs(xyz[(size_t)i * 3 + 2] - xyz_above[(size_t)p * 3 + 2]);
+        double dm = sqrt(dx * dx + dy * dy + dz * dz);
+        double *u = var + (size_t)i * 5;
+        const double *r = res + (size_t)i * 5, *ra = res_above + (size_t)p * 5;
+        double w[5];
+        w[0] = u[0] - dm * (ra[0] - r[0]);
+        w[1] = u[1] - dx * (ra[1] - r[1]);
+        w[2] = u[2] - dy * (ra[2] - r[2]);
+        w[3] = u[3] - dz * (ra[3] - r[3]);
+        w[4] = u[4] - dm * (ra[4] - r[4]);
+#pragma unroll
+        for (int v = 0; v < 5; v++) u[v] = w[v];
+        if (np.on) node_push(np, i, w);
+    }
+    if (np.on) node_publish(np);
 }
 
 }  // namespace
@@ -502,10 +582,12 @@ int k_min_dt(cudaStream_t s, int n, const double *sf, double *d_min, int *d_flag
     return launches;
 }
 int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
-                  unsigned long long *min_slot)
+                  unsigned long long *min_slot, const MinPush *mp)
 {
-    if (n == 0) return 0;
-    visit_begin_kernel<<<blocks_for(n), TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot);
+    MinPush none;
+    memset(&none, 0, sizeof(none));
+    if (n == 0 && !(mp && mp->on)) return 0;
+    visit_begin_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot, mp ? *mp : none);
     return 1;
 }
 int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
@@ -515,9 +597,11 @@ int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long 
     return 1;
 }
 int k_step_factor_group(cudaStream_t s, int n, const double *vol, MinSlots slots, unsigned long long *next_slot, double *sf,
-                        double *d_min_out, int *d_flags)
+                        double *d_min_out, int *d_flags, const MinPush *mp)
 {
-    step_factor_group_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, vol, slots, next_slot, sf, d_min_out, d_flags);
+    MinPush none;
+    memset(&none, 0, sizeof(none));
+    step_factor_group_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, vol, slots, next_slot, sf, d_min_out, d_flags, mp ? *mp : none);
     return 1;
 }
 int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double *dst)
@@ -560,10 +644,13 @@ int k_reset_min_slots(cudaStream_t s, int n, unsigned long long *slots)
     return 1;
 }
 int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
-                     double *var_above, int *count_above)
+                     double *var_above, int *count_above, const NodePush *np)
 {
-    if (n_coarse == 0) return 0;
-    restrict_fused_kernel<<<blocks_for(n_coarse), TPB, 0, s>>>(n_coarse, child_ptr, child_idx, var, var_above, count_above);
+    NodePush none;
+    memset(&none, 0, sizeof(none));
+    if (n_coarse == 0 && !(np && np->on)) return 0;
+    restrict_fused_kernel<<<n_coarse > 0 ? blocks_for(n_coarse) : 1, TPB, 0, s>>>(n_coarse, child_ptr, child_idx, var, var_above, count_above,
+                                                                                np ? *np : none);
     return 1;
 }
 int k_step_factor(cudaStream_t s, int n, const double *vol, const double *d_min, double *sf)
@@ -631,10 +718,12 @@ int k_up_post(cudaStream_t s, int n_coarse, double *var, const int *count)
     return 1;
 }
 int k_down(cudaStream_t s, int n_fine, const int *mg, double *var, const double *res, const double *coords,
-           const double *res_above, const double *coords_above)
+           const double *res_above, const double *coords_above, const NodePush *np)
 {
-    if (n_fine == 0) return 0;
-    down_kernel<<<blocks_for(n_fine), TPB, 0, s>>>(n_fine, mg, var, res, coords, res_above, coords_above);
+    NodePush none;
+    memset(&none, 0, sizeof(none));
+    if (n_fine == 0 && !(np && np->on)) return 0;
+    down_kernel<<<n_fine > 0 ? blocks_for(n_fine) : 1, TPB, 0, s>>>(n_fine, mg, var, res, coords, res_above, coords_above, np ? *np : none);
     return 1;
 }
 

@@ -65,8 +65,8 @@ __device__ __forceinline__ void derive_nr(const double u[5], double &p, double &
 
 template <int MAXE, int MAXL, bool TILES, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__restrict__ chunk_list, int pf_chunk,
-                 const unsigned char *__restrict__ blob, const double *__restrict__ var, RkStageArgs rk)
+rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_chunk,
+                 const unsigned char *__restrict__ blob, const double *__restrict__ var, const __grid_constant__ RkStageArgs rk)
 {
     using L = Stage2Layout<MAXE, MAXL, TILES>;
     extern __shared__ __align__(128) unsigned char sm2[];
@@ -75,7 +75,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     double *raw = reinterpret_cast<double *>(sm + L::RAW);
     double *der = reinterpret_cast<double *>(sm + L::DER);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunk = chunk_list ? __ldg(chunk_list + blockIdx.x) : (int)blockIdx.x;
+    const int chunk = rec0 + (int)blockIdx.x;               // the records are stored in launch order
     const int *rec = xtab + (size_t)chunk * xs;
 
     // ---- 1. the chunk's record: halo ids of this thread's rows and the descriptor, independent loads (one round trip)
@@ -99,12 +99,12 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     const int has_bnd = q2.z, bnd_off = q2.w;
     // multi-GPU, fused push: word 3 of the record is the chunk's base into the export row pointers (-1: no exported node);
     // such a chunk -- the only kind that reads rank-halo rows -- first waits for its sources
-    const int xb = rk.push ? q0.w : -1;
+    const int xb = rk.push_on ? q0.w : -1;
     if (xb >= 0) push_wait_sources(rk.push, tid);
     // experiment (MGCFD_STAGE2_PF=distance): thread 64 fetches the descriptor of the chunk `distance` launches ahead and
     // later prefetches that chunk's contiguous inputs into L2, so that its CTA finds them there
     int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
-    const bool pf = pf_chunk > 0 && tid == 64 && (int)blockIdx.x + pf_chunk < (int)gridDim.x && !chunk_list;
+    const bool pf = pf_chunk > 0 && tid == 64 && (int)blockIdx.x + pf_chunk < (int)gridDim.x;
     if (pf) {
         const int4 *r2 = reinterpret_cast<const int4 *>(xtab + (size_t)(chunk + pf_chunk) * xs);
         p0 = __ldg(r2); p1 = __ldg(r2 + 1); p2 = __ldg(r2 + 2);
@@ -207,6 +207,8 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
     }
     // this thread finishes components part, part+2, part+4 of its node
     double o[3] = {0.0, 0.0, 0.0}, sfn = 0.0;
+    int xj0 = 0, xj1 = 0;                                   // the node's export entries (requested now, used after the sums)
+    if (xb >= 0 && active) { xj0 = __ldg(rk.push.xp_ptr + xb + n); xj1 = __ldg(rk.push.xp_ptr + xb + n + 1); }
     if (active) {
         if (TILES) {
             const double *told = reinterpret_cast<const double *>(sm + L::OLD), *tsf = reinterpret_cast<const double *>(sm + L::SF);
@@ -252,7 +254,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, const int *__rest
                     sq = fma(r, r, sq);
                     bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
                 }
-                if (xb >= 0) push_component(rk.push, xb, n, v, vn, r, rk.last != 0);
+                if (xb >= 0) push_component(rk.push, xj0, xj1, v, vn, r, rk.last != 0);
             }
         }
     }
@@ -274,7 +276,8 @@ inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const Owner
 {
     const size_t smem = Stage2Layout<MAXE, MAXL, TILES>::TAIL + tail;     // dynamic shared memory opt-in: configure()
     const char *pf = getenv("MGCFD_STAGE2_PF");
-    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list, pf ? atoi(pf) : 0, p.blob, a.var, ra);
+    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0, pf ? atoi(pf) : 0,
+                                                                      p.blob, a.var, ra);
 }
 
 // returns 1 when the launch was made, 0 when the plan does not fit a compiled configuration (caller falls back)
