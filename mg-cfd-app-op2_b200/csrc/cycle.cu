@@ -143,9 +143,13 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
             unsigned long long *slot = &ctx->d_min_enc[2 * level + D.visit_parity];
             unsigned long long *next = &ctx->d_min_enc[2 * level + (D.visit_parity ^ 1)];
             D.visit_parity ^= 1;
-            { LoopScope t(ctx, "visit_begin", level, no); ctx->launches += k_visit_begin(s, no, D.var, D.cbrt_vol, D.old, D.sf, slot); }
-            { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor_fused(s, no, D.vol, slot, next, D.sf, &ctx->d_min_dt[level], ctx->d_flags); }
-            if (level == 0) ctx->launches += k_fill(s, 1, ctx->d_rms, 0.0);
+            // compute_step_factor rides in the first stage when that stage runs the stage2 kernel (fast build)
+            const bool fold = ctx->opt.flux_variant == MGCFD_FLUX_OWNER && D.flux_is_zero && flux_owner_uses_stage2(D.owner, L.owner, exact);
+            {
+                LoopScope t(ctx, "visit_begin", level, no);
+                ctx->launches += k_visit_begin(s, no, D.var, D.cbrt_vol, D.old, D.sf, slot, nullptr, level == 0 ? ctx->d_rms : nullptr);
+            }
+            if (!fold) { LoopScope t(ctx, "compute_step_factor", level, no); ctx->launches += k_step_factor_fused(s, no, D.vol, slot, next, D.sf, &ctx->d_min_dt[level], ctx->d_flags); }
             for (int rk = 0; rk < MGCFD_RK; rk++) {
                 if (!D.flux_is_zero) {      // only after a caller poked the fluxes: unfused stage keeps OP_INC semantics
                     int rc = api_run_flux(ctx, level, false);
@@ -165,6 +169,11 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                 ra.d_bad = &ctx->d_flags[0];
                 ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
                 ra.rk = rk; ra.last = rk == MGCFD_RK - 1; ra.c = dc;
+                if (fold && rk == 0) {
+                    ra.fold.on = 1; ra.fold.n_slots = 1; ra.fold.slot[0] = slot; ra.fold.n_wait = 0;
+                    ra.fold.next_slot = next; ra.fold.d_min_out = &ctx->d_min_dt[level]; ra.fold.d_flags = ctx->d_flags;
+                    ra.fold.vol = D.vol; ra.fold.sf_out = D.sf;
+                }
                 FluxArgs a;
                 a.n_edges = L.n_edges; a.n_owned = no; a.n_nodes = L.n_nodes;
                 a.var = D.var; a.flux = D.flux; a.overwrite = true; a.rk = &ra;
@@ -707,9 +716,9 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             if (c->p2p.enabled && c->p2p.fused_push) {
                 MinPush mp;                       // the last block sends the rank's minimum to every peer's mailbox
                 min_push_table(c, level, D.visit_parity, mp);
-                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot, &mp);
+                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot, &mp, level == 0 ? c->d_rms : nullptr);
             } else {
-                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot);
+                c->launches += k_visit_begin(c->stream, c->H[level].n_owned, D.var, D.cbrt_vol, D.old, D.sf, slot, nullptr, level == 0 ? c->d_rms : nullptr);
             }
             if (n > 1 && !c->p2p.enabled) cudaEventRecord(c->ev_k1, c->stream);
         }
@@ -721,6 +730,10 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             unsigned long long *slot = &c->d_min_enc[2 * level + D.visit_parity];
             unsigned long long *next = &c->d_min_enc[2 * level + (D.visit_parity ^ 1)];
             const int no = c->H[level].n_owned;
+            // fused push + stage2: the step factor (and the wait for the peers' minima) rides in the first stage
+            if (c->p2p.enabled && c->p2p.fused_push && c->H[level].n_owned > 0 &&
+                flux_owner_uses_stage2(D.owner, c->H[level].owner, c->opt.exact_arith != 0))
+                continue;
             LoopScope t(c, "compute_step_factor", level, no);
             if (c->p2p.enabled) {
                 // mailboxes: my minimum goes to every peer, theirs arrive in my arena; K2 reads my slot + the boxes
@@ -751,7 +764,6 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 }
                 c->launches += k_step_factor_group(c->stream, no, D.vol, ms, next, D.sf, &c->d_min_dt[level], c->d_flags);
             }
-            if (level == 0) c->launches += k_fill(c->stream, 1, c->d_rms, 0.0);
         }
         for (int r = 0; r < n; r++) R[r]->D[level].visit_parity ^= 1;
         // ---- three fused Runge-Kutta stages (euler3d.cpp:492-531).  Per stage: chunks owning exported nodes first,
@@ -773,6 +785,22 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 ra.d_bad = &c->d_flags[0];
                 ra.bnd_ptr = D.bnd_ptr; ra.b_group = D.b_group; ra.b_wt = D.b_wt;
                 ra.rk = rk; ra.last = last; ra.c = api_dev_consts(c);
+                if (rk == 0 && L.n_owned > 0 && flux_owner_uses_stage2(D.owner, L.owner, c->opt.exact_arith != 0)) {
+                    // (visit_parity was flipped after the prologue: the slot of this visit is the other one)
+                    const int par = D.visit_parity ^ 1;
+                    MinPush mp;
+                    min_push_table(c, level, par, mp);
+                    StepFold &f = ra.fold;
+                    f.on = 1;
+                    const unsigned long long *boxes = reinterpret_cast<const unsigned long long *>(c->p2p.arena + c->p2p.me.off_flags) + 2 * P2P_MAX_RANKS;
+                    for (int q = 0; q < c->n_ranks; q++)
+                        f.slot[f.n_slots++] = q == c->rank ? &c->d_min_enc[2 * level + par] : boxes + 2 * (q * P2P_MAX_LEVELS + level) + par;
+                    f.n_wait = mp.n_peers;
+                    for (int q = 0; q < mp.n_peers; q++) { f.wait_flag[q] = mp.src_flag[q]; f.wait_expected[q] = mp.expected[q]; }
+                    f.next_slot = &c->d_min_enc[2 * level + (par ^ 1)];
+                    f.d_min_out = &c->d_min_dt[level]; f.d_flags = c->d_flags;
+                    f.vol = D.vol; f.sf_out = D.sf; f.timeout_ns = comm_timeout_ns();
+                }
                 const int ob = D.var_alt == reinterpret_cast<double *>(c->p2p.arena + c->p2p.me.off_var[0][level]) ? 0 : 1;
                 const int wr = (last && level >= 1) ? 1 : 0;
                 ra.push_on = Hd.n_boundary_chunks > 0 ? 1 : 0;

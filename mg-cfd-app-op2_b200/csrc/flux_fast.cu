@@ -24,6 +24,7 @@ size_t fast_gather_smem(int max_loc) { return fast::gather_smem(max_loc, false);
 int flux_emit(cudaStream_t s, const FluxArgs &a, const EmitPlanDev &p) { return fast::launch_emit(s, a, p); }
 size_t flux_emit_smem_bytes(int max_loc, int max_ent, int max_blob, int max_own) { return fast::emit_smem(max_loc, max_ent, max_blob, max_own); }
 std::string fast_configure() { return fast::configure(); }
+bool fast_owner_uses_stage2(const OwnerPlanDev &p, const OwnerPlanHost &h) { return fast::stage2_applies(p, h) && h.max_own <= 64; }
 size_t fast_owner_smem(int max_loc, int max_edges, int max_blob) { return fast::owner_smem(max_loc, max_edges, max_blob, false); }
 size_t fast_colour_smem(int max_nodes) { return fast::colour_smem(max_nodes, false); }
 }  // namespace mgcfd

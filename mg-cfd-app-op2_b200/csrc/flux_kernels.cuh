@@ -375,6 +375,18 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// order-preserving map double -> uint64 so that atomicMin implements OP_MIN on doubles
+__device__ __forceinline__ unsigned long long enc_min(double d)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_min(unsigned long long u)
+{
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
 // ---- multi-GPU (p2p transport): system-scope flags and the fused halo push of the stage kernels (StagePush, internal.h)
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
@@ -428,18 +440,24 @@ __device__ __forceinline__ void push_component(const StagePush &P, int j0, int j
 __device__ __forceinline__ void push_publish(const StagePush &P, int tid)
 {
     __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();
-        const unsigned int prev = atomicAdd(P.done, 1u);
-        if (prev + 1u == (unsigned int)P.n_boundary) {
-            atomicExch(P.done, 0u);
+    if (tid < 32) {
+        int last = 0;
+        if (tid == 0) {
             __threadfence_system();
-            for (int d = 0; d < P.n_dst; d++) {
-                const unsigned long long e = *P.sent[d] + 1;
-                *P.sent[d] = e;
-                st_release_sys(P.dst_flag[d], e);
+            const unsigned int prev = atomicAdd(P.done, 1u);
+            last = prev + 1u == (unsigned int)P.n_boundary;
+            if (last) atomicExch(P.done, 0u);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            // one lane per destination: the release stores travel in parallel, not one NVLink round trip after the other
+            if (tid < P.n_dst) {
+                const unsigned long long e = *P.sent[tid] + 1;
+                *P.sent[tid] = e;
+                __threadfence_system();
+                st_release_sys(P.dst_flag[tid], e);
             }
-            for (int q = 0; q < P.n_src; q++) *P.expected[q] += 1;
+            if (tid < P.n_src) *P.expected[tid] += 1;
         }
     }
 }

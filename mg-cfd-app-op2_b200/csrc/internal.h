@@ -467,7 +467,7 @@ int k_permute_rows(cudaStream_t s, int n, int dim, const double *src, const int 
 int k_init_vars(cudaStream_t s, int n, double *var, const DevConsts &c);
 // fused node kernels of mgcfd_run_cycles
 int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
-                  unsigned long long *min_slot, const MinPush *mp = nullptr);
+                  unsigned long long *min_slot, const MinPush *mp = nullptr, double *zero_me = nullptr);
 int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
                         double *sf, double *d_min_out, int *d_flags);
 int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const int *child_idx, const double *var,
@@ -484,6 +484,22 @@ int k_halo_wait(cudaStream_t s, const WaitTable &t);
 int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t);
 int k_status_exchange(cudaStream_t s, int *flags, const unsigned long long *boxes, int n_ranks, const MinTable &t);
 
+// compute_step_factor_kernel folded into the first Runge-Kutta stage of a visit (stage2 kernel): every chunk takes the minimum
+// over the reduced slots (its own and, multi-rank, the peers' mailboxes -- after their flags have arrived), divides by its
+// nodes' volumes, uses the result and stores it as `step_factors` for the later stages
+struct StepFold {
+    int on, n_slots, n_wait, pad_;
+    const unsigned long long *slot[P2P_MAX_RANKS];
+    const unsigned long long *wait_flag[P2P_MAX_RANKS];
+    const unsigned long long *wait_expected[P2P_MAX_RANKS];
+    unsigned long long *next_slot;
+    double *d_min_out;
+    int *d_flags;
+    const double *vol;
+    double *sf_out;
+    long long timeout_ns;
+};
+
 // extra arguments of the fused Runge-Kutta stage (flux + boundary flux + time_step [+ residual, rms, bad values])
 struct RkStageArgs {
     const double *old, *sf;
@@ -496,6 +512,7 @@ struct RkStageArgs {
     int rk, last;
     int push_on, pad2_;          // multi-GPU: push exported rows from the node phase and hand-shake (fused push)
     StagePush push;
+    StepFold fold;               // first stage of a visit: step factors computed in the kernel (stage2 only)
     int max_own, pad_;           // filled by the launcher: tile sizes of the prefetched update operands
     double inv_denom;            // filled by the launcher: 1 / (RK + 1 - rk) (stage2 kernel)
     DevConsts c;
@@ -515,6 +532,8 @@ struct FluxArgs {
 int flux_atomic(cudaStream_t s, const FluxArgs &a, const AtomicPlanDev &p, bool exact);
 int flux_colour(cudaStream_t s, const FluxArgs &a, const ColourPlanDev &p, const ColourPlanHost &h, bool exact);
 int flux_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact);
+// whether a fused stage on this plan runs the stage2 kernel (which can compute the step factors itself)
+bool flux_owner_uses_stage2(const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact);
 int flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc, bool exact);
 int fast_flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n_chunks, int max_loc);
 size_t flux_gather_smem_bytes(int max_loc, bool exact);

@@ -12,6 +12,7 @@
 namespace mgcfd {
 
 size_t fast_owner_smem(int max_loc, int max_edges, int max_blob);
+bool fast_owner_uses_stage2(const OwnerPlanDev &p, const OwnerPlanHost &h);
 size_t fast_colour_smem(int max_nodes);
 size_t fast_gather_smem(int max_loc);
 
@@ -20,17 +21,8 @@ namespace {
 constexpr int TPB = 256;
 inline int blocks_for(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
 
-// order-preserving map double -> uint64 so that atomicMin implements OP_MIN on doubles
-__device__ __forceinline__ unsigned long long enc_min(double d)
-{
-    unsigned long long b = (unsigned long long)__double_as_longlong(d);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dec_min(unsigned long long u)
-{
-    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
-    return __longlong_as_double((long long)b);
-}
+using exact::enc_min;
+using exact::dec_min;
 
 // copy_double_kernel.h:6-13 over the flattened [n*5] array
 __global__ void copy_kernel(long long n, const double *__restrict__ src, double *__restrict__ dst)
@@ -131,32 +123,39 @@ __device__ __forceinline__ void node_wait(const NodePush &P)
     __syncthreads();
 }
 // ... stores the 5-vector of an exported node into the destinations' halo ranges ...
-__device__ __forceinline__ void node_push(const NodePush &P, int node, const double v[5])
+__device__ __forceinline__ int node_push(const NodePush &P, int node, const double v[5])
 {
-    const int j1 = __ldg(P.xn_ptr + node + 1);
-    for (int j = __ldg(P.xn_ptr + node); j < j1; j++) {
+    const int j0 = __ldg(P.xn_ptr + node), j1 = __ldg(P.xn_ptr + node + 1);
+    for (int j = j0; j < j1; j++) {
         const int2 t = __ldg(P.xn_ent + j);
         double *d = P.dst[t.x] + (size_t)t.y * 5;
 #pragma unroll
         for (int k = 0; k < 5; k++) d[k] = v[k];
     }
+    return j1 > j0;
 }
-// ... and the last block of the grid publishes the epoch to every destination and arms the next consumer
-__device__ __forceinline__ void node_publish(const NodePush &P)
+// ... and the last block of the grid publishes the epoch to every destination and arms the next consumer (a block pays for
+// the system-scope fence only when one of its threads stored into a peer)
+__device__ __forceinline__ void node_publish(const NodePush &P, int pushed)
 {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned int prev = atomicAdd(P.done, 1u);
-        if (prev + 1u == gridDim.x) {
-            atomicExch(P.done, 0u);
-            __threadfence_system();
-            for (int d = 0; d < P.n_dst; d++) {
-                const unsigned long long e = *P.sent[d] + 1;
-                *P.sent[d] = e;
-                st_release_sys(P.dst_flag[d], e);
+    const int any = __syncthreads_or(pushed);
+    if (threadIdx.x < 32) {
+        int last = 0;
+        if (threadIdx.x == 0) {
+            if (any) __threadfence_system();
+            const unsigned int prev = atomicAdd(P.done, 1u);
+            last = prev + 1u == gridDim.x;
+            if (last) atomicExch(P.done, 0u);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if ((int)threadIdx.x < P.n_dst) {        // one lane per destination: the release stores travel in parallel
+                const unsigned long long e = *P.sent[threadIdx.x] + 1;
+                *P.sent[threadIdx.x] = e;
+                __threadfence_system();
+                st_release_sys(P.dst_flag[threadIdx.x], e);
             }
-            for (int q = 0; q < P.n_src; q++) *P.expected[q] += 1;
+            if ((int)threadIdx.x < P.n_src) *P.expected[threadIdx.x] += 1;
         }
     }
 }
@@ -164,12 +163,13 @@ __device__ __forceinline__ void node_publish(const NodePush &P)
 // fused start of a level visit: copy_double_kernel + calculate_dt_kernel + get_min_dt_kernel (euler3d.cpp:467-479)
 __global__ void visit_begin_kernel(int n, const double *__restrict__ var, const double *__restrict__ cbrt_vol,
                                    double *__restrict__ old, double *__restrict__ dt, unsigned long long *__restrict__ min_slot,
-                                   const __grid_constant__ MinPush mp)
+                                   const __grid_constant__ MinPush mp, double *__restrict__ zero_me)
 {
     __shared__ unsigned long long smin[TPB / 32];
     __shared__ int s_last;
     unsigned long long m = ~0ull;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && zero_me) *zero_me = 0.0;          // level 0: the rms accumulator of this visit (euler3d.cpp:534)
     if (i < n) {
         double u[5];
 #pragma unroll
@@ -363,6 +363,7 @@ __global__ void restrict_fused_kernel(int n_coarse, const int *__restrict__ chil
                                       int *__restrict__ count_above, const __grid_constant__ NodePush np)
 {
     if (np.on) node_wait(np);                       // the children's rows on other ranks (pushed by their last stage) are in
+    int pushed = 0;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_coarse) {
         int j0 = child_ptr[p], j1 = child_ptr[p + 1];
@@ -377,12 +378,12 @@ __global__ void restrict_fused_kernel(int n_coarse, const int *__restrict__ chil
 #pragma unroll
             for (int v = 0; v < 5; v++) { acc[v] = acc[v] * avg; var_above[(size_t)p * 5 + v] = acc[v]; }
             count_above[p] = j1 - j0;
-            if (np.on) node_push(np, p, acc);       // only owned coarse nodes have children here
+            if (np.on) pushed = node_push(np, p, acc);       // only owned coarse nodes have children here
         }
         // (a childless owned coarse node keeps its value, Q8: the neighbours already hold it -- pushed by the last stage
         // of the level's previous visit into this same buffer)
     }
-    if (np.on) node_publish(np);
+    if (np.on) node_publish(np, pushed);
 }
 
 // time_stepping_kernels.h:43-64 (only line :63 has an effect)
@@ -510,6 +511,7 @@ __global__ void down_kernel(int n_fine, const int *__restrict__ mg, double *__re
                             const __grid_constant__ NodePush np)
 {
     if (np.on) node_wait(np);                       // the parents' residuals on other ranks (pushed by their last stage) are in
+    int pushed = 0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_fine) {
         int p = mg[i];
@@ -527,9 +529,9 @@ __global__ void down_kernel(int n_fine, const int *__restrict__ mg, double *__re
         w[4] = u[4] - dm * (ra[4] - r[4]);
 #pragma unroll
         for (int v = 0; v < 5; v++) u[v] = w[v];
-        if (np.on) node_push(np, i, w);
+        if (np.on) pushed = node_push(np, i, w);
     }
-    if (np.on) node_publish(np);
+    if (np.on) node_publish(np, pushed);
 }
 
 }  // namespace
@@ -582,12 +584,12 @@ int k_min_dt(cudaStream_t s, int n, const double *sf, double *d_min, int *d_flag
     return launches;
 }
 int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_vol, double *old, double *dt,
-                  unsigned long long *min_slot, const MinPush *mp)
+                  unsigned long long *min_slot, const MinPush *mp, double *zero_me)
 {
     MinPush none;
     memset(&none, 0, sizeof(none));
     if (n == 0 && !(mp && mp->on)) return 0;
-    visit_begin_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot, mp ? *mp : none);
+    visit_begin_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot, mp ? *mp : none, zero_me);
     return 1;
 }
 int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
@@ -753,6 +755,10 @@ int flux_gather(cudaStream_t s, const FluxArgs &a, const GatherPlanDev &p, int n
 size_t flux_gather_smem_bytes(int max_loc, bool exact_mode)
 {
     return exact_mode ? exact::gather_smem(max_loc, false) : fast_gather_smem(max_loc);
+}
+bool flux_owner_uses_stage2(const OwnerPlanDev &p, const OwnerPlanHost &h, bool exact_mode)
+{
+    return !exact_mode && fast_owner_uses_stage2(p, h);
 }
 std::string flux_configure()
 {

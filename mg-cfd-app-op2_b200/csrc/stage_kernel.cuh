@@ -185,6 +185,28 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
             for (int v = 0; v < 5; v++) w0[v * MAXE + e] = F[v];      // slot e is private to this thread
         }
     }
+    // first stage of a visit with the step factor folded in (compute_step_factor_kernel, time_stepping_kernels.h:43-64):
+    // warp 0 takes the minimum over the reduced slots -- multi-rank: once the peers' minima have arrived, which the
+    // chunk's staging and edge phase have given them time for -- and leaves it in shared memory for the node phase
+    if (!TILES && rk.fold.on && warp == 0) {
+        if (lane < rk.fold.n_wait) bounded_wait(rk.fold.wait_flag[lane], *rk.fold.wait_expected[lane], rk.d_bad + 3, rk.fold.timeout_ns);
+        __syncwarp();
+        unsigned long long u = ~0ull;
+        if (lane < rk.fold.n_slots) u = *reinterpret_cast<const volatile unsigned long long *>(rk.fold.slot[lane]);
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, u, off);
+            if (t < u) u = t;
+        }
+        if (lane == 0) {
+            const double m = dec_min(u);
+            *reinterpret_cast<double *>(sm + L::BAR + 8) = m;
+            if (blockIdx.x == 0) {
+                *rk.fold.next_slot = enc_min(1.7976931348623157e308);       // re-arm the level's other slot (DBL_MAX)
+                *rk.fold.d_min_out = m;
+                if (m < 0.0f) rk.fold.d_flags[1] = 1;                       // euler3d.cpp:480, checked at the end of the run
+            }
+        }
+    }
     __syncthreads();
 
     // ---- 6. node phase: two threads per owned node (even / odd incidences), boundary entries, update, stores
@@ -218,7 +240,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
             for (int k = 0; k < 3; k++)
                 if (part + 2 * k < 5) o[k] = (tail && n * 5 + part + 2 * k >= (int)(own_b >> 3)) ? rk.old[g0 + n * 5 + part + 2 * k] : told[n * 5 + part + 2 * k];
         } else {
-            sfn = __ldg(rk.sf + node0 + n);
+            sfn = rk.fold.on ? __ldg(rk.fold.vol + node0 + n) : __ldg(rk.sf + node0 + n);      // fold: the volume for now
 #pragma unroll
             for (int k = 0; k < 3; k++)
                 if (part + 2 * k < 5) o[k] = __ldg(rk.old + g0 + n * 5 + part + 2 * k);
@@ -240,6 +262,10 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     double sq = 0.0;
     int bad = 0;
     if (active) {
+        if (!TILES && rk.fold.on) {
+            sfn = *reinterpret_cast<const double *>(sm + L::BAR + 8) / sfn;          // min_dt / volume
+            if (part == 0) rk.fold.sf_out[node0 + n] = sfn;
+        }
         const double factor = sfn * rk.inv_denom;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -280,17 +306,23 @@ inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const Owner
                                                                       p.blob, a.var, ra);
 }
 
+// whether the plan fits a compiled stage2 configuration (and the kernel is not switched off by MGCFD_STAGE2=0)
+inline bool stage2_applies(const OwnerPlanDev &p, const OwnerPlanHost &h)
+{
+    if (!p.xtab || h.max_own > 64 || h.max_loc > 240 || h.max_edges > 384) return false;
+    const char *off = getenv("MGCFD_STAGE2");
+    return !(off && atoi(off) == 0);
+}
+
 // returns 1 when the launch was made, 0 when the plan does not fit a compiled configuration (caller falls back)
 inline int launch_stage2(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p, const OwnerPlanHost &h, int grid)
 {
-    if (!a.rk || !p.xtab || h.max_own > 64 || h.max_loc > 240 || h.max_edges > 384) return 0;
-    const char *off = getenv("MGCFD_STAGE2");
-    if (off && atoi(off) == 0) return 0;
+    if (!a.rk || !stage2_applies(p, h)) return 0;
     RkStageArgs ra = *a.rk;
     ra.max_own = h.max_own;
     ra.inv_denom = 1.0 / (double)(MGCFD_RK + 1 - ra.rk);
     const char *tl = getenv("MGCFD_STAGE2_TILES"), *mb = getenv("MGCFD_STAGE2_MINB");
-    const int tiles = tl ? atoi(tl) : 0;
+    const int tiles = (tl && !ra.fold.on) ? atoi(tl) : 0;        // the folded step factor lives in the tile-less instances
     const int minb = mb ? atoi(mb) : 7;
     const size_t tail = (size_t)h.dev_max_tail;
     if (h.max_edges <= 336) {
