@@ -989,6 +989,10 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     if ((rc = dev_upload(ctx, &D.owner.blob, blob))) return rc;
     D.owner.blob_bytes = (long long)blob.size();
     D.owner.valid = true;
+    if (getenv("MGCFD_DEBUG"))
+        fprintf(stderr, "[mgcfd] level %d owner plan: %d chunks, max_own %d max_loc %d max_edges %d max_inc %d tail %d blob %d, stage2 %s\n", level,
+                O.n_chunks, O.max_own, O.max_loc, O.max_edges, O.max_inc, O.dev_max_tail, O.dev_max_blob,
+                flux_owner_uses_stage2(D.owner, O, ctx->opt.exact_arith != 0) ? "yes" : "no");
     cycle_drop_graphs(ctx);
     return MGCFD_OK;
 }

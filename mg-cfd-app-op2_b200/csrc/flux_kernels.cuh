@@ -1637,6 +1637,10 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
     // chunk prefetched into L2; 2 = persistent CTAs, two shared-memory stages
     const char *pipe_s = getenv("MGCFD_OWNER_PIPE");
     const int pipe = pipe_s ? atoi(pipe_s) : MGCFD_OWNER_PIPE_DEFAULT;
+#ifndef MGCFD_EXACT
+    // default: the second-generation stage kernel (stage_kernel.cuh) whenever the plan fits it
+    if (a.rk && !a.stream_kernel && stage2_applies(p, h) && launch_stage2(s, a, p, h, grid)) return 1;
+#endif
     if (pipe > 0 && !a.stream_kernel && threads >= 128 && !(a.rk && a.rk->push_on)) {      // (the pipelined variants have no fused push)
         int rc = launch_owner_pipe(s, a, p, h, threads, pipe >= 2 ? 2 : 1);
         if (rc >= 0) return rc;
@@ -1649,9 +1653,6 @@ inline int launch_owner(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &p
         ra.max_own = h.max_own;
         size_t fsmem = owner_smem(h.max_loc, h.max_edges, h.dev_max_blob, false, h.max_own);
 #ifndef MGCFD_EXACT
-        // default: the second-generation stage kernel (stage_kernel.cuh); MGCFD_STAGE2=0 or a plan outside its
-        // compiled limits falls through to flux_owner_kernel<FUSE>
-        if (threads == 128 && launch_stage2(s, a, p, h, grid)) return 1;
         // MGCFD_OWNER_LEAN=1: the lean kernel (needs the fixed-stride descriptor + halo-id table of ensure_owner)
         const char *lean_s = getenv("MGCFD_OWNER_LEAN");
         if (lean_s && atoi(lean_s) == 1 && p.xtab && threads == 128 && h.max_own <= 64 && !ra.push_on) {
@@ -1694,9 +1695,8 @@ inline std::string configure()
     OPT_IN((rk_stage2_kernel<336, 240, true, 6>));
     OPT_IN((rk_stage2_kernel<336, 240, false, 6>));
     OPT_IN((rk_stage2_kernel<336, 240, false, 7>));
-    OPT_IN((rk_stage2_kernel<384, 240, true, 6>));
-    OPT_IN((rk_stage2_kernel<384, 240, false, 6>));
-    OPT_IN((rk_stage2_kernel<384, 240, false, 7>));
+    OPT_IN((rk_stage2_kernel<400, 240, true, 6>));
+    OPT_IN((rk_stage2_kernel<400, 240, false, 6>));
 #endif
 #define OPT_IN_PIPE(T, B, S)                                    \
     OPT_IN((flux_owner_pipe_kernel<T, B, S, true, true>));     \

@@ -306,12 +306,16 @@ inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const Owner
                                                                       p.blob, a.var, ra);
 }
 
-// whether the plan fits a compiled stage2 configuration (and the kernel is not switched off by MGCFD_STAGE2=0)
+// whether a fused stage on this plan runs the stage2 kernel: the plan fits a compiled configuration and no experiment knob
+// selects another kernel (MGCFD_STAGE2=0, MGCFD_OWNER_PIPE>0, MGCFD_OWNER_THREADS=256)
 inline bool stage2_applies(const OwnerPlanDev &p, const OwnerPlanHost &h)
 {
-    if (!p.xtab || h.max_own > 64 || h.max_loc > 240 || h.max_edges > 384) return false;
-    const char *off = getenv("MGCFD_STAGE2");
-    return !(off && atoi(off) == 0);
+    if (!p.xtab || h.max_own > 64 || h.max_loc > 240 || h.max_edges > 400) return false;
+    const char *off = getenv("MGCFD_STAGE2"), *pipe = getenv("MGCFD_OWNER_PIPE"), *thr = getenv("MGCFD_OWNER_THREADS");
+    if (off && atoi(off) == 0) return false;
+    if ((pipe ? atoi(pipe) : MGCFD_OWNER_PIPE_DEFAULT) > 0) return false;
+    if (thr && atoi(thr) == 256) return false;
+    return true;
 }
 
 // returns 1 when the launch was made, 0 when the plan does not fit a compiled configuration (caller falls back)
@@ -330,9 +334,9 @@ inline int launch_stage2(cudaStream_t s, const FluxArgs &a, const OwnerPlanDev &
         else if (minb >= 7) stage2_launch_one<336, 240, false, 7>(s, grid, tail, p, a, ra);
         else stage2_launch_one<336, 240, false, 6>(s, grid, tail, p, a, ra);
     } else {
-        if (tiles) stage2_launch_one<384, 240, true, 6>(s, grid, tail, p, a, ra);
-        else if (minb >= 7) stage2_launch_one<384, 240, false, 7>(s, grid, tail, p, a, ra);
-        else stage2_launch_one<384, 240, false, 6>(s, grid, tail, p, a, ra);
+        // chunks of dense levels (4-5 edges per node fill the 6C edge cap, which is soft by one node): 6 CTAs per SM
+        if (tiles) stage2_launch_one<400, 240, true, 6>(s, grid, tail, p, a, ra);
+        else stage2_launch_one<400, 240, false, 6>(s, grid, tail, p, a, ra);
     }
     return 1;
 }
