@@ -177,3 +177,41 @@ def test_rotor37_1m_full_size(pkg, meshgen, orc_mod):
         gpu.run_cycles(1)
         ff = np.array(list(gpu.consts.ff_variable))
         check_levels(gpu, [a["var"] for a in run.levels], ff)
+
+
+def test_m6_full_size_ten_cycles_validate(pkg, meshgen, orc_mod):
+    """BASELINE.json configs[0] at its stated length: the M6-shaped 4-level deck at full size, 10 cycles, -v validation
+    (validation.h:46-100) of every level against the CPU reference plus the 1e-10 normwise bound."""
+    mesh = meshgen.make_multigrid("m6")
+    lev0 = [meshgen.zero_based(l) for l in mesh["levels"]]
+    o = orc_mod.Oracle("ref" if orc_mod.available("ref") else "port")
+    o.set_threads(1)                      # OP2-seq order: the exact build must reproduce it bit for bit
+    run = o.make_state(lev0)
+    run.init()
+    assert run.run(10)[0] == 0
+    with pkg.MGCFD(mesh["levels"]) as gpu:
+        gpu.run_cycles(10)
+        ff = np.array(list(gpu.consts.ff_variable))
+        check_levels(gpu, [a["var"] for a in run.levels], ff)
+        for l in range(len(lev0)):
+            assert gpu.validate(l, run.levels[l]["var"]) == 0
+    with pkg.MGCFD(mesh["levels"], exact_arith=True) as gpu:      # reference operation order: bit for bit after 10 cycles
+        gpu.run_cycles(10)
+        for l in range(len(lev0)):
+            assert np.array_equal(gpu.fetch(l, "variables"), run.levels[l]["var"])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MGCFD_TEST_LARGE") != "1", reason="8M-node deck: ~2 min (bench.py checks it on every run)")
+def test_rotor37_8m_one_cycle(pkg, meshgen, orc_mod):
+    """BASELINE.json configs[3] at full size, one cycle against the CPU oracle (bench.py's `parity` block does the same
+    on the benchmarked context at every GPU count)."""
+    mesh = meshgen.make_multigrid("rotor37_8m")
+    lev0 = [meshgen.zero_based(l) for l in mesh["levels"]]
+    o = orc_mod.Oracle("port_fast" if orc_mod.available("port_fast") else "port")
+    run = o.make_state(lev0)
+    run.init()
+    assert run.run(1)[0] == 0
+    with pkg.MGCFD(mesh["levels"]) as gpu:
+        gpu.run_cycles(1)
+        ff = np.array(list(gpu.consts.ff_variable))
+        check_levels(gpu, [a["var"] for a in run.levels], ff)
