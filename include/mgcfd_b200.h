@@ -114,7 +114,9 @@ typedef struct {
     int rank, n_ranks;     /* position of this context in a multi-GPU run (default 0 of 1) */
     int no_graphs;         /* 1: mgcfd_run_cycles enqueues every launch; 0 (default): each cycle replays as a
                               captured CUDA graph (also with NCCL: halo exchanges and the all-reduce are captured) */
-    int reserved[7];
+    int measure_mem_bound; /* 1: mgcfd_run_cycles also runs unstructured_stream_kernel after every Runge-Kutta stage, as the
+                              reference does with -b (euler3d.cpp:518-525); it writes p_dummy_fluxes only */
+    int reserved[6];
 } mgcfd_options;
 
 /* ---- lifetime (op_init / op_exit, euler3d.cpp:126, :824) ---- */

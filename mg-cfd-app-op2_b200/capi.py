@@ -52,7 +52,8 @@ class LevelHost(C.Structure):
 class Options(C.Structure):
     _fields_ = [("flux_variant", C.c_int), ("renumber", C.c_int), ("owner_chunk_nodes", C.c_int),
                 ("colour_block_edges", C.c_int), ("exact_arith", C.c_int), ("no_fusion", C.c_int),
-                ("rank", C.c_int), ("n_ranks", C.c_int), ("no_graphs", C.c_int), ("reserved", C.c_int * 7)]
+                ("rank", C.c_int), ("n_ranks", C.c_int), ("no_graphs", C.c_int), ("measure_mem_bound", C.c_int),
+                ("reserved", C.c_int * 6)]
 
 
 _lib = None
@@ -321,7 +322,7 @@ class MGCFD:
 
     def __init__(self, levels=None, base_array_index=1, device=0, flux_variant="owner", renumber=True,
                  exact_arith=False, owner_chunk_nodes=64, colour_block_edges=256, consts=None,
-                 init=True, fuse=True, local_mesh=None, graphs=True):
+                 init=True, fuse=True, local_mesh=None, graphs=True, measure_mem_bound=False):
         """levels: list of dicts keyed by the reference's dataset names (meshgen.make_multigrid()["levels"]), or
         local_mesh: a LocalMesh (this rank's share of a partitioned deck)."""
         self.lib = load_library()
@@ -335,6 +336,7 @@ class MGCFD:
         opt.colour_block_edges = int(colour_block_edges)
         opt.no_fusion = int(not fuse)
         opt.no_graphs = int(not graphs)
+        opt.measure_mem_bound = int(bool(measure_mem_bound))
         opt.rank = local_mesh.rank if local_mesh is not None else 0
         opt.n_ranks = local_mesh.n_ranks if local_mesh is not None else 1
         self.rank, self.n_ranks = opt.rank, opt.n_ranks

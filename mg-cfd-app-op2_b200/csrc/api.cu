@@ -1391,6 +1391,16 @@ extern "C++" int mgcfd::api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kern
     return api_check_launch(ctx, "compute_flux_edge_kernel");
 }
 
+extern "C++" int mgcfd::api_ensure_dummy_flux(mgcfd_ctx *ctx)
+{
+    for (int l = 0; l < ctx->n_levels; l++)
+        if (!ctx->D[l].dummy_flux) {
+            int rc = dev_alloc(ctx, &ctx->D[l].dummy_flux, (size_t)ctx->H[l].n_nodes * 5);
+            if (rc) return rc;
+        }
+    return MGCFD_OK;
+}
+
 int mgcfd_loop_compute_flux_edge(mgcfd_ctx *ctx, int level)
 {
     CHECK_LEVEL(level); CHECK_PLANNED();

@@ -120,6 +120,10 @@ int mgcfd::cycle_run_single(mgcfd_ctx *ctx, int n_cycles)
         if (rc) return rc;
     }
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, ctx->stream));
+    if (ctx->opt.measure_mem_bound) {
+        int rcm = api_ensure_dummy_flux(ctx);       // p_dummy_fluxes (euler3d.cpp:397-400): allocated outside graph capture
+        if (rcm) return rcm;
+    }
     int rc = run_with_graph(ctx, n_cycles, [&](int k) { return enqueue_single(ctx, k); });
     if (rc) return rc;
     return finish_run(ctx);
@@ -186,6 +190,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                                        cudaMemcpyDeviceToDevice, s));
                 std::swap(D.var, D.var_alt);
                 D.var_flip ^= 1;
+                if (ctx->opt.measure_mem_bound) { int rcm = api_run_flux(ctx, level, true); if (rcm) return rcm; }      // -b, euler3d.cpp:518-525
             }
         } else {
             { LoopScope t(ctx, "copy_double", level, no); ctx->launches += k_copy(s, no, D.var, D.old); }
@@ -205,6 +210,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                 }
                 { LoopScope t(ctx, "time_step", level, no); ctx->launches += k_time_step(s, no, rk, D.sf, D.flux, D.old, D.var); }
                 D.flux_is_zero = true;
+                if (ctx->opt.measure_mem_bound) { int rcm = api_run_flux(ctx, level, true); if (rcm) return rcm; }      // -b, euler3d.cpp:518-525
             }
             { LoopScope t(ctx, "residual", level, no); ctx->launches += k_residual(s, no, D.old, D.var, D.res); }
             if (level == 0) {
@@ -664,6 +670,7 @@ int run_ranks(mgcfd_ctx **R, int n, int n_cycles)
         for (int l = 0; l < nl; l++) {
             int rc = api_ensure_flux_plan(c, l);
             if (rc) { ctx->err = c->err; return rc; }
+            if (c->opt.measure_mem_bound && (rc = api_ensure_dummy_flux(c))) { ctx->err = c->err; return rc; }
             if (!c->D[l].flux_is_zero) { ctx->err = "fluxes must be zero before a multi-GPU run"; return MGCFD_ERR_ARG; }
         }
         if (cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 4, c->stream) != cudaSuccess) return MGCFD_ERR_CUDA;
@@ -833,6 +840,11 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
                 if ((rc = api_check_launch(c, "rk_stage"))) { ctx->err = c->err; return rc; }
             }
             for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
+            for (int r = 0; r < n; r++)
+                if (R[r]->opt.measure_mem_bound) {      // -b, euler3d.cpp:518-525 (owned + recomputed cut edges of the rank)
+                    cudaSetDevice(R[r]->device);
+                    if ((rc = api_run_flux(R[r], level, true))) { ctx->err = R[r]->err; return rc; }
+                }
             // (no stand-alone wait after the last stage: the next kernel that reads halo rows -- restrict, prolong or the
             //  next stage -- waits for its sources itself)
         }
@@ -875,6 +887,11 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
             }
             for (int r = 0; r < n; r++) { std::swap(R[r]->D[level].var, R[r]->D[level].var_alt); R[r]->D[level].var_flip ^= 1; }
             exchange_wait(R, n);
+            for (int r = 0; r < n; r++)
+                if (R[r]->opt.measure_mem_bound) {      // -b, euler3d.cpp:518-525
+                    cudaSetDevice(R[r]->device);
+                    if ((rc = api_run_flux(R[r], level, true))) { ctx->err = R[r]->err; return rc; }
+                }
         }
         if (nl <= 1) {
             i++;

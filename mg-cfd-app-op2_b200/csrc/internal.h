@@ -390,6 +390,7 @@ int api_check_launch(mgcfd_ctx *ctx, const char *what);
 DevConsts api_dev_consts(const mgcfd_ctx *ctx);
 int api_ensure_flux_plan(mgcfd_ctx *ctx, int level);
 int api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel);
+int api_ensure_dummy_flux(mgcfd_ctx *ctx);
 void timers_collect(mgcfd_ctx *ctx);
 int cycle_run_single(mgcfd_ctx *ctx, int n_cycles);
 void cycle_drop_graphs(mgcfd_ctx *ctx);

@@ -381,6 +381,7 @@ int main(int argc, char **argv)
     mgcfd_default_options(&o);
     o.renumber = conf.renumber;
     o.exact_arith = conf.exact;
+    o.measure_mem_bound = conf.mem_bound ? 1 : 0;                  // -b: unstructured_stream_kernel after every RK stage (:518-525)
     o.flux_variant = conf.variant == "atomic" ? MGCFD_FLUX_ATOMIC : conf.variant == "colour" ? MGCFD_FLUX_COLOUR
                    : conf.variant == "gather" ? MGCFD_FLUX_GATHER : MGCFD_FLUX_OWNER;
     std::vector<mgcfd_ctx *> R(P, nullptr);
@@ -440,12 +441,36 @@ int main(int argc, char **argv)
     int n_file_io_writes = 0;
     if (P > 1 || !conf.loopwise) {
         // device-driven schedule (host checks of :480 and :544 deferred to the end of the run)
-        if (conf.flow_interval > 0 || conf.mem_bound) printf("note: -I / -b need --loopwise on one GPU; ignored\n");
-        for (int i = 0; i < conf.cycles; i++) printf("Performing MG cycle %d / %d\n", i + 1, conf.cycles);
-        int rc = P > 1 ? mgcfd_group_run_cycles(R.data(), P, conf.cycles) : mgcfd_run_cycles(ctx, conf.cycles);
-        if (rc == MGCFD_ERR_MIN_DT) { printf("Fatal error during 'step factor' calculation\n"); return 1; }
-        if (rc == MGCFD_ERR_BAD_VALS) { printf("Bad variable values detected, aborting\n"); return 1; }
-        if (rc) { fprintf(stderr, "run failed (%d): %s\n", rc, mgcfd_last_error(ctx)); return 1; }
+        // -I <n> (euler3d.cpp:552-571): the run is cut into pieces of n cycles and the level-0 flow is written after each
+        const int piece = conf.flow_interval > 0 ? conf.flow_interval : conf.cycles;
+        for (int done = 0; done < conf.cycles;) {
+            const int k = std::min(piece, conf.cycles - done);
+            for (int i = 0; i < k; i++) printf("Performing MG cycle %d / %d\n", done + i + 1, conf.cycles);
+            int rc = P > 1 ? mgcfd_group_run_cycles(R.data(), P, k) : mgcfd_run_cycles(ctx, k);
+            if (rc == MGCFD_ERR_MIN_DT) { printf("Fatal error during 'step factor' calculation\n"); return 1; }
+            if (rc == MGCFD_ERR_BAD_VALS) { printf("Bad variable values detected, aborting\n"); return 1; }
+            if (rc) { fprintf(stderr, "run failed (%d): %s\n", rc, mgcfd_last_error(ctx)); return 1; }
+            done += k;
+            if (conf.flow_interval > 0 && done % conf.flow_interval == 0) {
+                std::vector<double> v((size_t)lv[0].n_nodes * 5, 0.0);
+                if (P == 1) {
+                    CHECK(mgcfd_fetch_dat(ctx, 0, "variables", v.data()));
+                } else {
+                    for (int r = 0; r < P; r++) {
+                        const mgcfd_level_host *h = mgcfd_local_mesh_level(LM[r], 0);
+                        std::vector<double> loc((size_t)h->n_nodes * 5);
+                        CHECK(mgcfd_fetch_dat(R[r], 0, "variables", loc.data()));
+                        for (int i = 0; i < h->n_owned_nodes; i++)
+                            for (int d = 0; d < 5; d++) v[(size_t)h->global_node_id[i] * 5 + d] = loc[(size_t)i * 5 + d];
+                    }
+                }
+                const double w0 = wall();
+                write_container(conf.prefix + "variables.L0.cycle=" + std::to_string(done) + ".mgb", "p_variables", v.data(),
+                                lv[0].n_nodes, 5);
+                file_io_seconds += wall() - w0;
+                n_file_io_writes++;
+            }
+        }
     } else {
         // euler3d.cpp:458-641, call site by call site
         int level = 0, mg_dir = 0, i = 0, bad_val_count = 0;

@@ -22,6 +22,7 @@ def make_deck(tmp_path, meshgen, golden):
 
 
 @pytest.mark.parametrize("extra", [[], ["--loopwise"], ["--loopwise", "-b", "--variant", "colour"], ["--exact"],
+                                   ["-b"], ["-b", "--gpus", "2", "--same-device", "--exact"],
                                    ["--gpus", "2", "--same-device"], ["--gpus", "4", "--same-device", "--exact"]])
 def test_driver_validates(tmp_path, meshgen, golden, extra):
     mesh, g = make_deck(tmp_path, meshgen, golden)
@@ -69,3 +70,20 @@ def test_driver_hdf5_deck_end_to_end(tmp_path, meshgen, golden):
     for l in range(len(mesh["levels"])):
         got = meshgen.read_h5(f"{out}variables.L{l}.cycles=10.h5")[f"p_variables_result_L{l}"]
         assert np.array_equal(got, g[f"var_L{l}"])
+
+
+@pytest.mark.parametrize("extra", [[], ["--gpus", "2", "--same-device"]])
+def test_driver_periodic_flow_dumps_on_the_default_path(tmp_path, meshgen, golden, extra):
+    """-I <n> (euler3d.cpp:552-571) on the device-driven schedule: the level-0 flow is written every n cycles and the run
+    still ends on the 10-cycle reference solution (round 1 honoured -I only with --loopwise)"""
+    mesh, g = make_deck(tmp_path, meshgen, golden)
+    out = os.path.join(str(tmp_path), "out.")
+    cmd = [EXE, "-i", "input.dat", "-d", str(tmp_path), "-g", "10", "-v", "-I", "4", "--exact", "-o", out] + extra
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Validation passed" in p.stdout
+    dumps = sorted(f for f in os.listdir(str(tmp_path)) if f.startswith("out.variables.L0.cycle="))
+    assert dumps == ["out.variables.L0.cycle=4.mgb", "out.variables.L0.cycle=8.mgb"]
+    v4 = meshgen.read_container(os.path.join(str(tmp_path), dumps[0]))["p_variables"]
+    v8 = meshgen.read_container(os.path.join(str(tmp_path), dumps[1]))["p_variables"]
+    assert v4.shape == g["var_L0"].shape and np.isfinite(v4).all() and not np.array_equal(v4, v8)
