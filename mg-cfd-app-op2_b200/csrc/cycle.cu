@@ -472,10 +472,6 @@ int build_push_tables(mgcfd_ctx *ctx)
                 t.xp_base = H.d_xp_base; t.xp_ptr = H.d_xp_ptr; t.xp_ent = H.d_xp_ent;
                 t.n_boundary = H.n_boundary_chunks;
                 t.done = P.d_done;
-                t.done2 = P.d_done + 1;
-                t.export_idx = H.d_export_idx;
-                t.n_rows = H.n_export;
-                t.n_pushers = H.n_export > 0 ? std::max(1, std::min(16, (H.n_export * 5 + 2047) / 2048)) : 0;
                 t.err_flag = &ctx->d_flags[3]; t.timeout_ns = comm_timeout_ns();
                 for (size_t k = 0; k < H.nbr_rank.size(); k++) {
                     const int q = H.nbr_rank[k];
@@ -484,8 +480,6 @@ int build_push_tables(mgcfd_ctx *ctx)
                     if (ns) {
                         if (Q.import_cnt[l][me] != ns) { ctx->err = "halo lists of the ranks do not match"; return MGCFD_ERR_ARG; }
                         const int d = t.n_dst++;
-                        t.exp_ptr[d] = H.exp_ptr[k];
-                        t.exp_ptr[d + 1] = H.exp_ptr[k + 1];         // export lists are grouped by neighbour: contiguous row ranges
                         const size_t row0 = (size_t)(Q.n_owned[l] + Q.import_off[l][me]) * 5;
                         t.var_dst[d] = reinterpret_cast<double *>(P.peer_base[q] + Q.off_var[ob][l]) + row0;
                         t.res_dst[d] = wr ? reinterpret_cast<double *>(P.peer_base[q] + Q.off_res[l]) + row0 : nullptr;

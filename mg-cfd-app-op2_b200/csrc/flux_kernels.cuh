@@ -435,18 +435,19 @@ __device__ __forceinline__ void push_component(const StagePush &P, int j0, int j
     }
 }
 // after the chunk's pushes: count the chunk; the last one of the launch publishes the epoch and arms the next consumer.
-// One system-scope fence by thread 0 after the CTA barrier orders every thread's peer stores before the count (the
-// pattern of a cooperative grid barrier).
+// Every chunk orders its threads' peer stores before its count with a CTA barrier and ONE device-scope fence; the last
+// chunk -- which has observed all counts -- issues the only system-scope fence of the launch before the flags go out
+// (causality is cumulative across the two scopes; a system-scope fence in every chunk measured 15-20 us per launch).
 __device__ __forceinline__ void push_publish(const StagePush &P, int tid)
 {
     __syncthreads();
     if (tid < 32) {
         int last = 0;
         if (tid == 0) {
-            __threadfence_system();
+            __threadfence();
             const unsigned int prev = atomicAdd(P.done, 1u);
             last = prev + 1u == (unsigned int)P.n_boundary;
-            if (last) atomicExch(P.done, 0u);
+            if (last) { atomicExch(P.done, 0u); __threadfence_system(); }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {

@@ -248,15 +248,6 @@ struct StagePush {
     unsigned int *done;                              // chunks with exports finished in this launch
     int *err_flag;                                   // d_flags[3]: a bounded wait ran out
     long long timeout_ns;
-    // stage2 kernel: the rows are not pushed by the chunks themselves but by `n_pushers` extra CTAs of the same launch
-    // (placed right behind the chunks that own exported nodes), which wait until those chunks are done, copy the
-    // exported rows out of the freshly written buffers into the destinations' halo ranges -- coalesced, full sectors --
-    // and publish; the compute chunks then pay one device-scope fence + one atomic instead of peer stores and a
-    // system-scope fence each
-    int n_pushers, n_rows;
-    const int *export_idx;                           // internal ids of the exported nodes, concatenated per destination slot
-    int exp_ptr[P2P_MAX_RANKS + 1];                  // row ranges of the destination slots
-    unsigned int *done2;                             // pusher CTAs finished
 };
 // The same hand-shake for the node kernels of a multi-rank cycle (visit prologue, step factor, restrict, prolong), passed by
 // value: wait for the sources of the level whose halo rows the kernel READS, push the rows of the exported nodes the kernel

@@ -134,18 +134,19 @@ __device__ __forceinline__ int node_push(const NodePush &P, int node, const doub
     }
     return j1 > j0;
 }
-// ... and the last block of the grid publishes the epoch to every destination and arms the next consumer (a block pays for
-// the system-scope fence only when one of its threads stored into a peer)
+// ... and the last block of the grid publishes the epoch to every destination and arms the next consumer (a block that
+// stored into a peer orders those stores before its count with a device-scope fence; the last block issues the only
+// system-scope fence before the flags go out)
 __device__ __forceinline__ void node_publish(const NodePush &P, int pushed)
 {
     const int any = __syncthreads_or(pushed);
     if (threadIdx.x < 32) {
         int last = 0;
         if (threadIdx.x == 0) {
-            if (any) __threadfence_system();
+            if (any) __threadfence();
             const unsigned int prev = atomicAdd(P.done, 1u);
             last = prev + 1u == gridDim.x;
-            if (last) atomicExch(P.done, 0u);
+            if (last) { atomicExch(P.done, 0u); __threadfence_system(); }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {

@@ -63,55 +63,6 @@ __device__ __forceinline__ void derive_nr(const double u[5], double &p, double &
     s = sqrt_nr(q2) + sqrt_nr(GAMMA * p * rinv);
 }
 
-// A pusher CTA of a fused-push launch (see StagePush): waits until every chunk that owns exported nodes has finished, copies
-// its share of the exported rows from the buffers this stage wrote into the destinations' halo ranges (consecutive threads
-// store consecutive 8-byte elements: full sectors over NVLink), and the last pusher publishes the epoch.
-__device__ __noinline__ void stage2_pusher(const RkStageArgs &rk, int p, int tid)
-{
-    const StagePush &P = rk.push;
-    if (tid == 0) {
-        const unsigned long long t0 = global_ns();
-        for (unsigned it = 0;; it++) {
-            unsigned int v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.done) : "memory");
-            if (v >= (unsigned int)P.n_boundary) break;
-            __nanosleep(256);
-            if ((it & 1023u) == 1023u && (long long)(global_ns() - t0) > P.timeout_ns) { atomicExch(P.err_flag, 1); break; }
-        }
-    }
-    __syncthreads();
-    const bool with_res = rk.last != 0;
-    const int total = P.n_rows * 5;
-    for (int e = p * 128 + tid; e < total; e += P.n_pushers * 128) {
-        const int row = e / 5, c = e - row * 5;
-        int d = 0;
-        while (d + 1 < P.n_dst && row >= P.exp_ptr[d + 1]) d++;
-        const size_t src = (size_t)__ldg(P.export_idx + row) * 5 + c, dst = (size_t)(row - P.exp_ptr[d]) * 5 + c;
-        P.var_dst[d][dst] = __ldcg(rk.var_out + src);
-        if (with_res && P.res_dst[d]) P.res_dst[d][dst] = __ldcg(rk.res + src);
-    }
-    __syncthreads();
-    if (tid < 32) {
-        int last = 0;
-        if (tid == 0) {
-            __threadfence_system();
-            const unsigned int prev = atomicAdd(P.done2, 1u);
-            last = prev + 1u == (unsigned int)P.n_pushers;
-            if (last) { atomicExch(P.done2, 0u); atomicExch(P.done, 0u); }
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            if (tid < P.n_dst) {
-                const unsigned long long e = *P.sent[tid] + 1;
-                *P.sent[tid] = e;
-                __threadfence_system();
-                st_release_sys(P.dst_flag[tid], e);
-            }
-            if (tid < P.n_src) *P.expected[tid] += 1;
-        }
-    }
-}
-
 template <int MAXE, int MAXL, bool TILES, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_chunk,
@@ -124,13 +75,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     double *raw = reinterpret_cast<double *>(sm + L::RAW);
     double *der = reinterpret_cast<double *>(sm + L::DER);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // multi-GPU, fused push: the launch is [chunks that own exported nodes | pusher CTAs | interior chunks]
-    const int n_first = rk.push_on ? rk.push.n_boundary : 0, n_push = rk.push_on ? rk.push.n_pushers : 0;
-    if (n_push && (int)blockIdx.x >= n_first && (int)blockIdx.x < n_first + n_push) {
-        stage2_pusher(rk, (int)blockIdx.x - n_first, tid);
-        return;
-    }
-    const int chunk = rec0 + (int)blockIdx.x - ((int)blockIdx.x >= n_first ? n_push : 0);      // records are stored in launch order
+    const int chunk = rec0 + (int)blockIdx.x;               // the records are stored in launch order
     const int *rec = xtab + (size_t)chunk * xs;
 
     // ---- 1. the chunk's record: halo ids of this thread's rows and the descriptor, independent loads (one round trip)
@@ -159,7 +104,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     // experiment (MGCFD_STAGE2_PF=distance): thread 64 fetches the descriptor of the chunk `distance` launches ahead and
     // later prefetches that chunk's contiguous inputs into L2, so that its CTA finds them there
     int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
-    const bool pf = pf_chunk > 0 && tid == 64 && chunk + pf_chunk < (int)gridDim.x - n_push;
+    const bool pf = pf_chunk > 0 && tid == 64 && chunk + pf_chunk < (int)gridDim.x;
     if (pf) {
         const int4 *r2 = reinterpret_cast<const int4 *>(xtab + (size_t)(chunk + pf_chunk) * xs);
         p0 = __ldg(r2); p1 = __ldg(r2 + 1); p2 = __ldg(r2 + 2);
@@ -284,6 +229,8 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     }
     // this thread finishes components part, part+2, part+4 of its node
     double o[3] = {0.0, 0.0, 0.0}, sfn = 0.0;
+    int xj0 = 0, xj1 = 0;                                   // the node's export entries (requested now, used after the sums)
+    if (xb >= 0 && active) { xj0 = __ldg(rk.push.xp_ptr + xb + n); xj1 = __ldg(rk.push.xp_ptr + xb + n + 1); }
     if (active) {
         if (TILES) {
             const double *told = reinterpret_cast<const double *>(sm + L::OLD), *tsf = reinterpret_cast<const double *>(sm + L::SF);
@@ -333,17 +280,11 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
                     sq = fma(r, r, sq);
                     bad += (isnan(vn) || isinf(vn)) ? 1 : 0;
                 }
+                if (xb >= 0) push_component(rk.push, xj0, xj1, v, vn, r, rk.last != 0);
             }
         }
     }
-    if (xb >= 0) {
-        // this chunk's exported rows are in var_out / res: tell the pusher CTAs (device-scope fence, one atomic)
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(rk.push.done, 1u);
-        }
-    }
+    if (xb >= 0) push_publish(rk.push, tid);
     if (rk.last && rk.d_rms) {
         for (int off = 16; off > 0; off >>= 1) {
             sq += __shfl_xor_sync(0xffffffffu, sq, off);
@@ -361,9 +302,8 @@ inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const Owner
 {
     const size_t smem = Stage2Layout<MAXE, MAXL, TILES>::TAIL + tail;     // dynamic shared memory opt-in: configure()
     const char *pf = getenv("MGCFD_STAGE2_PF");
-    const int pushers = ra.push_on ? ra.push.n_pushers : 0;
-    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid + pushers, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0,
-                                                                                pf ? atoi(pf) : 0, p.blob, a.var, ra);
+    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0, pf ? atoi(pf) : 0,
+                                                                      p.blob, a.var, ra);
 }
 
 // whether a fused stage on this plan runs the stage2 kernel: the plan fits a compiled configuration and no experiment knob
