@@ -709,9 +709,23 @@ static int build_owner_host(mgcfd_ctx *ctx, int level)
 // read incidences 2*it, 2*it+1).  On the M6-shaped deck this takes the state gathers from 1.98 to 1.08 wavefronts per
 // half-warp and the flux-vector gathers from 2.08 to 1.24 (ideal 1).  slot[i] = new position of plan edge i.
 // ---------------------------------------------------------------------------------------
+// node order of a chunk's node phase: owned nodes by descending degree (stable), so that the 16 nodes a warp handles (two
+// threads per node) have about the same number of incidences and the warp's trip count is not set by one outlier
+static void degree_order(int n_own, const uint16_t *rowptr, unsigned char *order)
+{
+    std::vector<int> idx(n_own);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y]; });
+    for (int i = 0; i < n_own; i++) order[i] = (unsigned char)idx[i];
+}
+
 static void bank_aware_slots(int ne, const uint32_t *lab, int n_own, const uint16_t *rowptr, const uint16_t *csr, int split,
                              std::vector<int> &slot)
 {
+    // thread slot -> node of the node phase (split 2 = the fast build's stage2 kernel: degree order; else identity)
+    std::vector<unsigned char> norder(std::max(n_own, 1));
+    if (split == 2 && n_own <= 64) degree_order(n_own, rowptr, norder.data());      // (chunks of up to 64 nodes run the stage2 kernel)
+    else for (int i = 0; i < n_own; i++) norder[i] = (unsigned char)i;
     slot.assign(ne, 0);
     std::vector<int> order;
     order.reserve(ne);
@@ -744,13 +758,17 @@ static void bank_aware_slots(int ne, const uint32_t *lab, int n_own, const uint1
     const int nodes_per_hw = 16 / split;
     for (int n0 = 0; n0 < n_own; n0 += nodes_per_hw) {
         int max_it = 0;
-        for (int n = n0; n < std::min(n_own, n0 + nodes_per_hw); n++)
+        for (int q = n0; q < std::min(n_own, n0 + nodes_per_hw); q++) {
+            const int n = n_own <= 256 ? norder[q] : q;
             max_it = std::max(max_it, (rowptr[n + 1] - rowptr[n] + split - 1) / split);
-        for (int n = n0; n < std::min(n_own, n0 + nodes_per_hw); n++)
+        }
+        for (int q = n0; q < std::min(n_own, n0 + nodes_per_hw); q++) {
+            const int n = n_own <= 256 ? norder[q] : q;
             for (int j = rowptr[n]; j < rowptr[n + 1]; j++) {
                 const int e = csr[j] & 0x7fff, sid = n_sets + (j - rowptr[n]) / split;
                 (set_of[0][e] == -1 ? set_of[0][e] : set_of[1][e]) = sid;
             }
+        }
         n_sets += max_it;
     }
     std::vector<unsigned char> set_bank((size_t)std::max(n_sets, 1) * 16, 0);     // edges already placed per (set, bank)
@@ -850,10 +868,11 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
     for (int k = 0; k < O.n_chunks; k++) {
         long long nb = L.bnd_node_ptr[O.node0[k + 1]] - L.bnd_node_ptr[O.node0[k]];
         const long long n_own = O.node0[k + 1] - O.node0[k];
-        long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + (nb ? pad16(nb * (24 + 2) + ((n_own + 2) & ~1ll) * 2) : 0);
+        // plan blob | node order of the node phase (u8 per owned node) | boundary entries
+        long long bytes = (O.blob_off[k + 1] - O.blob_off[k]) + pad16(n_own) + (nb ? pad16(nb * (24 + 2) + ((n_own + 2) & ~1ll) * 2) : 0);
         O.dev_blob_off[k + 1] = O.dev_blob_off[k] + bytes;
         O.dev_max_blob = std::max(O.dev_max_blob, (int)bytes);
-        O.dev_max_tail = std::max(O.dev_max_tail, (int)(O.blob_off[k + 1] - O.blob_off[k]) - 32 * ((O.n_edges[k] + 3) & ~3));
+        O.dev_max_tail = std::max(O.dev_max_tail, (int)(O.blob_off[k + 1] - O.blob_off[k] + pad16(n_own)) - 32 * ((O.n_edges[k] + 3) & ~3));
     }
     if (flux_owner_smem_bytes(O.max_loc, O.max_edges, O.dev_max_blob, ctx->opt.exact_arith != 0) > 227 * 1024) {
         ctx->err = "owner chunk does not fit in shared memory; lower owner_chunk_nodes";
@@ -928,8 +947,11 @@ static int ensure_owner(mgcfd_ctx *ctx, int level)
         d.blob_bytes = (int)(O.dev_blob_off[k + 1] - O.dev_blob_off[k]);
         const int b_first = L.bnd_node_ptr[O.node0[k]];
         d.has_bnd = L.bnd_node_ptr[O.node0[k + 1]] - b_first;
-        d.bnd_off = (int)(O.blob_off[k + 1] - O.blob_off[k]);
+        const int order_off = (int)(O.blob_off[k + 1] - O.blob_off[k]);
+        d.bnd_off = order_off + (int)pad16(d.n_own);
         unsigned char *base = blob.data() + d.blob_off;
+        if (O.max_own <= 64 && node_split == 2) degree_order(d.n_own, &O.rowptr[O.rowptr_off[k]], base + order_off);
+        else for (int i = 0; i < d.n_own && i < 256; i++) base[order_off + i] = (unsigned char)i;
         if (d.has_bnd) {
             double *bw = reinterpret_cast<double *>(base + d.bnd_off);
             uint16_t *bptr = reinterpret_cast<uint16_t *>(bw + (size_t)d.has_bnd * 3);       // [n_own+1] entry ranges

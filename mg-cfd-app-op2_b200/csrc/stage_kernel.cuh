@@ -94,7 +94,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     const int4 q1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
     const int4 q2 = __ldg(reinterpret_cast<const int4 *>(rec) + 2);
     const int node0 = q0.x, n_own = q0.y, n_halo = q0.z;
-    const int n_edges = q1.x, e_pad = q1.y;
+    const int n_edges = q1.x, e_pad = q1.y, n_inc = q1.z;
     const long long blob_off = (long long)(unsigned)q2.x | ((long long)q2.y << 32);
     const int has_bnd = q2.z, bnd_off = q2.w;
     // multi-GPU, fused push: word 3 of the record is the chunk's base into the export row pointers (-1: no exported node);
@@ -212,8 +212,12 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     // ---- 6. node phase: two threads per owned node (even / odd incidences), boundary entries, update, stores
     const uint16_t *rowptr = reinterpret_cast<const uint16_t *>(lab + e_pad);
     const uint16_t *csr = rowptr + (((n_own + 1) + 7) & ~7);
-    const int n = tid >> 1, part = tid & 1;
-    const bool active = n < n_own;
+    // thread slot -> node: the chunk's owned nodes by descending degree (u8 table behind the csr), so that the 16 nodes of a
+    // warp have about the same number of incidences and no outlier sets the warp's trip count
+    const unsigned char *order = reinterpret_cast<const unsigned char *>(csr) + (((uint32_t)n_inc * 2u + 15u) & ~15u);
+    const int part = tid & 1;
+    const bool active = (tid >> 1) < n_own;
+    const int n = active ? order[tid >> 1] : 0;
     const size_t g0 = (size_t)node0 * 5;
     // boundary chunks: the node's boundary entries (straight from the level's arrays, sorted by owned node) start the
     // sum of the node's first thread -- here, where nothing else is live, the divisions of bnd_apply cost no spills
