@@ -21,8 +21,10 @@ def main():
                 g.run_cycles_loopwise(1)
                 g.unstructured_stream(0)
                 g.sync()
-    with pkg.MGCFD(mesh["levels"]) as g:          # graph replay
+    with pkg.MGCFD(mesh["levels"]) as g:          # graph replay (stage2 kernel with the folded step factor)
         g.run_cycles(3)
+    with pkg.MGCFD(mesh["levels"], measure_mem_bound=True) as g:      # -b: stream kernel after every stage
+        g.run_cycles(2)
     parts = pkg.partition_levels(mesh["levels"], 1, 3)
     lms = [pkg.LocalMesh(mesh["levels"], 1, parts, r, 3) for r in range(3)]
     ranks = [pkg.MGCFD(local_mesh=lm) for lm in lms]
