@@ -525,11 +525,8 @@ def main():
             if it == 2:
                 barrier()
                 t0 = time.perf_counter()
-            for l in range(len(sizes)):
-                gpu.set(l, "variables", pinned[l].array)
-            gpu.run_cycles(1)
-            for l in range(len(sizes)):
-                gpu.fetch_into(l, "variables", pinned[l].array)
+            arrs = [p_.array for p_ in pinned]
+            gpu.run_cycles_host(1, arrs, arrs)       # upload every level, one cycle, fetch every level: one C-ABI call
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         for p_ in pinned:
@@ -541,8 +538,9 @@ def main():
             nbytes = int(t.item())
         e2e = {"value": edges_step * n_e2e / dt, "unit": "edges/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
-               "what": "per step: mgcfd_set_dat(variables) for every level from page-locked host arrays, mgcfd_run_cycles(1), "
-                       "mgcfd_fetch_dat(variables) for every level back into them; wall clock around the loop"}
+               "what": "per step one mgcfd_run_cycles_host(1, in, out): the flow state of every level goes up from page-locked host "
+                       "arrays, one V-cycle runs, every level comes back into them (one GPU: coarse-level copies overlap the "
+                       "level visits on a copy stream; N>1: set_dat / run_cycles / fetch_dat in sequence); wall clock around the loop"}
         if rank == 0:
             log(f"e2e done after {time.time() - t_start:.1f} s: {1e3 * dt / n_e2e:.2f} ms/step")
 

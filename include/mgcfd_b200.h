@@ -236,6 +236,17 @@ int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master_variabl
  * elements written, or a negative error; out may be NULL to query the count. */
 long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out, long long capacity);
 
+/* ---- end-to-end call with HOST buffers ----
+ * variables_in[l] / variables_out[l]: the flow state of level l in FILE order ([n_nodes][5], as op_decl_dat_hdf5 /
+ * op_fetch_data_hdf5_file hold it, euler3d.cpp:379, :740-770); either array or single entries may be NULL (level not
+ * uploaded / not fetched).  One call = mgcfd_set_dat("variables") for the given levels + mgcfd_run_cycles(n_cycles) +
+ * mgcfd_fetch_dat("variables"), pipelined on one GPU when the buffers are page-locked (mgcfd_host_alloc): level 0 is
+ * uploaded first and the first level visit starts as soon as it has landed, the coarser levels arrive underneath it on a
+ * copy stream (each is first touched by the restrict into it); on the way down every coarse level is fetched as soon as
+ * its last visit of the run has finished, underneath the remaining visits.  Same results and error codes as the three
+ * separate calls. */
+int  mgcfd_run_cycles_host(mgcfd_ctx *ctx, int n_cycles, const double *const *variables_in, double *const *variables_out);
+
 /* ---- measurement hooks ---- */
 /* per-call-site device timers (CUDA events on the context's stream): 0 off (default), 1 every call site,
  * 2 compute_flux_edge launches only (both: mgcfd_run_cycles then enqueues launch by launch instead of replaying graphs),

@@ -74,6 +74,7 @@ def load_library():
     lib.mgcfd_destroy.argtypes = [C.c_void_p]
     lib.mgcfd_plan_query.restype = C.c_longlong
     lib.mgcfd_plan_query.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _ip, C.c_longlong]
+    lib.mgcfd_run_cycles_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.mgcfd_kernel_launches.restype = C.c_longlong
     lib.mgcfd_kernel_launches.argtypes = [C.c_void_p]
     lib.mgcfd_stream.restype = C.c_void_p
@@ -103,7 +104,7 @@ ABI_SYMBOLS = [
     "mgcfd_loop_compute_step_factor", "mgcfd_loop_compute_flux_edge", "mgcfd_loop_compute_bnd_node_flux",
     "mgcfd_loop_time_step", "mgcfd_loop_unstructured_stream", "mgcfd_loop_residual", "mgcfd_loop_calc_rms",
     "mgcfd_loop_count_bad_vals", "mgcfd_loop_up_pre", "mgcfd_loop_up", "mgcfd_loop_up_post", "mgcfd_loop_down",
-    "mgcfd_run_cycles", "mgcfd_fetch_dat", "mgcfd_set_dat", "mgcfd_sync", "mgcfd_validate_level",
+    "mgcfd_run_cycles", "mgcfd_run_cycles_host", "mgcfd_fetch_dat", "mgcfd_set_dat", "mgcfd_sync", "mgcfd_validate_level",
     "mgcfd_plan_query", "mgcfd_timers_enable", "mgcfd_timers_reset", "mgcfd_timers_get",
     "mgcfd_kernel_launches", "mgcfd_set_flux_variant", "mgcfd_stream", "mgcfd_device_ptr",
     "mgcfd_host_alloc", "mgcfd_host_free", "mgcfd_partition_graph",
@@ -462,6 +463,23 @@ class MGCFD:
     def run_cycles(self, n):
         """Device-driven V-cycles (host checks deferred to one flag read)."""
         self._ck(self.lib.mgcfd_run_cycles(self.ctx, int(n)))
+
+    def run_cycles_host(self, n, variables_in=None, variables_out=None):
+        """mgcfd_run_cycles_host: upload the flow state of the given levels (file order), run n cycles, fetch it back -- one
+        call, pipelined on one GPU when the arrays are page-locked (PinnedArray.array).  Lists with one entry per level;
+        None entries are skipped."""
+        def table(arrs, const):
+            if arrs is None:
+                return None
+            t = (C.c_void_p * self.n_levels)()
+            for l in range(self.n_levels):
+                a = arrs[l] if l < len(arrs) else None
+                if a is not None:
+                    assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64 and a.size == self.sizes[l][0] * 5
+                    t[l] = a.ctypes.data
+            return t
+        tin, tout = table(variables_in, True), table(variables_out, False)
+        self._ck(self.lib.mgcfd_run_cycles_host(self.ctx, int(n), tin, tout))
 
     def run_cycles_loopwise(self, n_cycles):
         """euler3d.cpp:458-641 call site by call site, host checks included.  Returns (rms, min_dt)."""

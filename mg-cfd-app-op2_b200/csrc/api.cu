@@ -261,6 +261,8 @@ void mgcfd_destroy(mgcfd_ctx *ctx)
     if (ctx->p2p.d_counters) cudaFree(ctx->p2p.d_counters);
     if (ctx->p2p.d_done) cudaFree(ctx->p2p.d_done);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    for (double *p : ctx->io_stage)
+        if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -407,6 +409,8 @@ static int ensure_staging(mgcfd_ctx *ctx, size_t bytes, bool need_pinned)
 {
     if (ctx->d_stage_bytes < bytes) {
         if (ctx->d_stage) cudaFree(ctx->d_stage);
+    for (double *p : ctx->io_stage)
+        if (p) cudaFree(p);
         ctx->d_stage = nullptr; ctx->d_stage_bytes = 0;
         CK(cudaMalloc(&ctx->d_stage, bytes));
         ctx->d_stage_bytes = bytes;
@@ -1622,6 +1626,80 @@ int mgcfd_set_dat(mgcfd_ctx *ctx, int level, const char *name, const void *host_
     REQUIRE(find_node_dat(ctx, level, name, r), std::string("unknown dat '") + name + "'");
     if (s == "fluxes") D.flux_is_zero = false;
     return upload_node_dat(ctx, level, r.ptr, static_cast<const double *>(host_in), r.dim);
+}
+
+int mgcfd_run_cycles_host(mgcfd_ctx *ctx, int n_cycles, const double *const *vin, double *const *vout)
+{
+    if (!ctx) return MGCFD_ERR_ARG;
+    CHECK_PLANNED();
+    REQUIRE(n_cycles >= 0, "negative cycle count");
+    const int nl = ctx->n_levels;
+    bool pinned = true;
+    for (int l = 0; l < nl; l++) {
+        if (vin && vin[l] && !is_pinned(vin[l])) pinned = false;
+        if (vout && vout[l] && !is_pinned(vout[l])) pinned = false;
+    }
+    const bool fused_single = ctx->n_ranks == 1 && !ctx->nccl_comm && !ctx->p2p.ipc && n_cycles >= 1 && pinned;
+    if (!fused_single) {
+        // decomposed contexts, pageable buffers: the three calls one after the other
+        int rc;
+        for (int l = 0; l < nl; l++)
+            if (vin && vin[l] && (rc = mgcfd_set_dat(ctx, l, "variables", vin[l]))) return rc;
+        if ((rc = mgcfd_run_cycles(ctx, n_cycles))) return rc;
+        for (int l = 0; l < nl; l++)
+            if (vout && vout[l] && (rc = mgcfd_fetch_dat(ctx, l, "variables", vout[l]))) return rc;
+        return MGCFD_OK;
+    }
+    CK(cudaSetDevice(ctx->device));
+    // per-level device staging (file order <-> internal order is a device-side permutation)
+    if (ctx->io_stage.size() != (size_t)nl) ctx->io_stage.assign(nl, nullptr);
+    for (int l = 0; l < nl; l++)
+        if (!ctx->io_stage[l] && ((vin && vin[l]) || (vout && vout[l])))
+            CK(cudaMalloc((void **)&ctx->io_stage[l], (size_t)std::max(ctx->H[l].n_nodes, 1) * 5 * sizeof(double)));
+    mgcfd_ctx::IoHooks io;
+    io.uploaded.resize(nl); io.final_.resize(nl);
+    io.wait_upload.assign(nl, 0); io.want_final.assign(nl, 0);
+    io.last_cycle = n_cycles - 1;
+    for (int l = 0; l < nl; l++) {
+        CK(cudaEventCreateWithFlags(&io.uploaded[l], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&io.final_[l], cudaEventDisableTiming));
+    }
+    cudaStream_t cs = ctx->comm_stream;
+    auto cleanup = [&]() {
+        for (int l = 0; l < nl; l++) { cudaEventDestroy(io.uploaded[l]); cudaEventDestroy(io.final_[l]); }
+        ctx->io = nullptr;
+    };
+    // uploads: level 0 on the compute stream (the cycle starts with it), the coarser levels on the copy stream
+    for (int l = 0; l < nl; l++) {
+        if (!(vin && vin[l])) continue;
+        cudaStream_t st = l == 0 ? ctx->stream : cs;
+        const size_t bytes = (size_t)ctx->H[l].n_nodes * 5 * sizeof(double);
+        if (cudaMemcpyAsync(ctx->io_stage[l], vin[l], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { cleanup(); ctx->err = "upload failed"; return MGCFD_ERR_CUDA; }
+        ctx->launches += k_permute_rows(st, ctx->H[l].n_nodes, 5, ctx->io_stage[l], ctx->D[l].perm, ctx->D[l].var, true);
+        if (l > 0) { cudaEventRecord(io.uploaded[l], cs); io.wait_upload[l] = 1; }
+    }
+    for (int l = 0; l < nl; l++) io.want_final[l] = (vout && vout[l] && l > 0) ? 1 : 0;
+    ctx->io = &io;
+    int rc = cycle_enqueue_single_nograph(ctx, n_cycles);
+    ctx->io = nullptr;
+    if (rc) { cleanup(); return rc; }
+    // a level the cycle never restricted into (single-level decks have none) still orders its upload before the end
+    for (int l = 1; l < nl; l++)
+        if (io.wait_upload[l]) cudaStreamWaitEvent(ctx->stream, io.uploaded[l], 0);
+    // downloads: coarse levels on the copy stream as soon as they are final, level 0 behind the cycle
+    for (int l = nl - 1; l >= 0; l--) {
+        if (!(vout && vout[l])) continue;
+        cudaStream_t st = l == 0 ? ctx->stream : cs;
+        if (l > 0) cudaStreamWaitEvent(cs, io.final_[l], 0);
+        const size_t bytes = (size_t)ctx->H[l].n_nodes * 5 * sizeof(double);
+        ctx->launches += k_permute_rows(st, ctx->H[l].n_nodes, 5, ctx->D[l].var, ctx->D[l].perm, ctx->io_stage[l], false);
+        if (cudaMemcpyAsync(vout[l], ctx->io_stage[l], bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) { cleanup(); ctx->err = "download failed"; return MGCFD_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(cs);
+    rc = cycle_finish_run(ctx);                      // synchronises the compute stream, reads the deferred error flags
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("copy stream: ") + cudaGetErrorString(e); return MGCFD_ERR_CUDA; }
+    return rc;
 }
 
 int mgcfd_validate_level(mgcfd_ctx *ctx, int level, const double *master, int *n_diff)

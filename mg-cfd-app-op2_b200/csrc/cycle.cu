@@ -218,10 +218,21 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
                 { LoopScope t(ctx, "count_bad_vals", level, no); ctx->launches += k_bad_vals(s, no, D.var, &ctx->d_flags[0]); }
             }
         }
+        // mgcfd_run_cycles_host: in the run's last cycle the level just visited is final when no further visit of it follows
+        // (the coarsest level, every level on the way down, level 0 once the prolongation into it has run)
+        auto mark_final = [&](int l) {
+            if (ctx->io && i == ctx->io->last_cycle && ctx->io->want_final[l]) cudaEventRecord(ctx->io->final_[l], s);
+        };
         if (nl <= 1) {
+            mark_final(0);
             i++;
         } else if (dir == 0) {
             level++;
+            if (ctx->io && ctx->io->wait_upload[level]) {
+                // the level's uploaded variables must have landed before the restrict writes into them
+                cudaStreamWaitEvent(s, ctx->io->uploaded[level], 0);
+                ctx->io->wait_upload[level] = 0;
+            }
             LevelDev &A = ctx->D[level], &F = ctx->D[level - 1];
             const int nf = ctx->H[level - 1].n_owned;
             if (fused) {
@@ -234,14 +245,32 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
             }
             if (level == nl - 1) dir = 1;
         } else {
+            // the level just visited (on the way down, or the coarsest) gets no further visit in this cycle
+            mark_final(level);
             level--;
             LevelDev &F = ctx->D[level], &A = ctx->D[level + 1];
             { LoopScope t(ctx, "down", level, ctx->H[level].n_owned); ctx->launches += k_down(s, ctx->H[level].n_owned, F.mg, F.var, F.res, F.coords, A.res, A.coords); }
-            if (level == 0) { dir = 0; i++; }
+            if (level == 0) { mark_final(0); dir = 0; i++; }
         }
     }
     return MGCFD_OK;
 }
+
+int mgcfd::cycle_enqueue_single_nograph(mgcfd_ctx *ctx, int n_cycles)
+{
+    for (int l = 0; l < ctx->n_levels; l++) {
+        int rc = api_ensure_flux_plan(ctx, l);
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 4, ctx->stream));
+    if (ctx->opt.measure_mem_bound) {
+        int rcm = api_ensure_dummy_flux(ctx);
+        if (rcm) return rcm;
+    }
+    return enqueue_single(ctx, n_cycles);
+}
+
+int mgcfd::cycle_finish_run(mgcfd_ctx *ctx) { return finish_run(ctx); }
 
 // ------------------------------------------------------------------------------------------
 // NCCL, loaded lazily from whatever libnccl.so.2 the process already has (torch's when launched by torchrun)

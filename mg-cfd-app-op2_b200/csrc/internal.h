@@ -364,6 +364,11 @@ struct mgcfd_ctx {
     std::map<std::string, mgcfd::LoopTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     std::map<unsigned, mgcfd::GraphEntry> graphs;   // captured one-cycle graphs by parity state
+    // mgcfd_run_cycles_host in flight: per level the event its upload records (waited for before the level's first use)
+    // and, in the run's last cycle, the event recorded when the level's variables are final (its download waits for it)
+    struct IoHooks { std::vector<cudaEvent_t> uploaded, final_; std::vector<char> wait_upload, want_final; int last_cycle = 0; };
+    IoHooks *io = nullptr;
+    std::vector<double *> io_stage;   // per-level device staging of mgcfd_run_cycles_host
     // multi-GPU
     std::vector<mgcfd::HaloLevel> halo;
     int rank = 0, n_ranks = 1;
@@ -382,6 +387,8 @@ DevConsts api_dev_consts(const mgcfd_ctx *ctx);
 int api_ensure_flux_plan(mgcfd_ctx *ctx, int level);
 int api_run_flux(mgcfd_ctx *ctx, int level, bool stream_kernel);
 int api_ensure_dummy_flux(mgcfd_ctx *ctx);
+int cycle_enqueue_single_nograph(mgcfd_ctx *ctx, int n_cycles);
+int cycle_finish_run(mgcfd_ctx *ctx);
 void timers_collect(mgcfd_ctx *ctx);
 int cycle_run_single(mgcfd_ctx *ctx, int n_cycles);
 void cycle_drop_graphs(mgcfd_ctx *ctx);

@@ -215,3 +215,35 @@ def test_rotor37_8m_one_cycle(pkg, meshgen, orc_mod):
         gpu.run_cycles(1)
         ff = np.array(list(gpu.consts.ff_variable))
         check_levels(gpu, [a["var"] for a in run.levels], ff)
+
+
+@pytest.mark.parametrize("name,cycles", [("small", 3), ("tiny", 1)])
+def test_run_cycles_host_equals_set_run_fetch(pkg, meshgen, name, cycles):
+    """mgcfd_run_cycles_host (upload / cycles / download pipelined across a copy stream) returns exactly what
+    set_dat + run_cycles + fetch_dat return; also with pageable buffers and with levels left out"""
+    mesh = meshgen.make_multigrid(name)
+    nl = len(mesh["levels"])
+    with pkg.MGCFD(mesh["levels"], exact_arith=True) as a, pkg.MGCFD(mesh["levels"], exact_arith=True) as b:
+        a.run_cycles(2)
+        b.run_cycles(2)
+        start = [a.fetch(l, "variables") * (1.0 + 1e-3 * (l + 1)) for l in range(nl)]      # a state neither context holds
+        for l in range(nl):
+            a.set(l, "variables", start[l])
+        a.run_cycles(cycles)
+        ref = [a.fetch(l, "variables") for l in range(nl)]
+        pin_in = [pkg.PinnedArray((s[0], 5)) for s in b.sizes]
+        pin_out = [pkg.PinnedArray((s[0], 5)) for s in b.sizes]
+        for l in range(nl):
+            pin_in[l].array[:] = start[l]
+        b.run_cycles_host(cycles, [p.array for p in pin_in], [p.array for p in pin_out])
+        for l in range(nl):
+            assert np.array_equal(pin_out[l].array, ref[l]), l
+            assert np.array_equal(b.fetch(l, "variables"), ref[l]), l
+        # pageable buffers, only level 0 fetched: the sequential path, same numbers
+        for l in range(nl):
+            b.set(l, "variables", start[l])
+        out0 = np.empty_like(start[0])
+        b.run_cycles_host(cycles, None, [out0] + [None] * (nl - 1))
+        assert np.array_equal(out0, ref[0])
+        for p in pin_in + pin_out:
+            p.free()
