@@ -76,19 +76,28 @@ bool read_container(const std::string &path, Container &out, std::string &err)
         err = path + ": neither an HDF5 file nor an MGCFDBIN container";
         return false;
     }
+    f.seekg(0, std::ios::end);
+    const uint64_t file_size = (uint64_t)f.tellg();            // every length field below is bounded by it
+    f.seekg(16, std::ios::beg);
+    if (n > 4096) { err = path + ": implausible dataset count"; return false; }
     for (uint32_t i = 0; i < n; i++) {
         uint32_t len = 0, dtype = 0, ndim = 0;
         f.read(reinterpret_cast<char *>(&len), 4);
+        if (!f || len > 4096 || len > file_size) { err = path + ": corrupt dataset name length"; return false; }
         std::string name(len, '\0');
         f.read(&name[0], len);
         f.read(reinterpret_cast<char *>(&dtype), 4);
         f.read(reinterpret_cast<char *>(&ndim), 4);
+        if (!f || dtype > 1 || ndim < 1 || ndim > 8) { err = path + ": corrupt header of dataset " + name; return false; }
         Dataset d;
         d.dtype = (int)dtype;
         d.dims.resize(ndim);
         f.read(reinterpret_cast<char *>(d.dims.data()), 8 * ndim);
         uint64_t nbytes = 0;
         f.read(reinterpret_cast<char *>(&nbytes), 8);
+        uint64_t count = 1;
+        for (uint64_t dim : d.dims) { if (dim > file_size) { count = ~0ull; break; } count *= dim; if (count > file_size) break; }
+        if (!f || nbytes > file_size || count * (dtype == 0 ? 8 : 4) != nbytes) { err = path + ": dataset " + name + " has inconsistent dims / size"; return false; }
         f.seekg((8 - f.tellg() % 8) % 8, std::ios::cur);
         d.bytes.resize(nbytes);
         f.read(reinterpret_cast<char *>(d.bytes.data()), (std::streamsize)nbytes);
@@ -239,7 +248,7 @@ struct Config {                               // config.h:64-103, defaults :129-
     std::string input_file, input_dir, prefix, variant = "owner";
     int cycles = 25, flow_interval = 0, gpus = 1;
     bool validate = false, mem_bound = false, renumber = true, exact = false, loopwise = false, same_device = false;
-    bool hdf5 = false, check_deck = false;
+    bool hdf5 = false, check_deck = false, timers = false;
     std::string partitioner, partitioner_method;   // -m / -r (config.h:203-240)
     int out_vars = 0, out_fluxes = 0, out_sf = 0;
 };
@@ -276,7 +285,8 @@ int main(int argc, char **argv)
         {"output-flow-interval", required_argument, nullptr, 'I'}, {"gpus", required_argument, nullptr, 1001},
         {"variant", required_argument, nullptr, 1002}, {"exact", no_argument, nullptr, 1003},
         {"loopwise", no_argument, nullptr, 1004}, {"same-device", no_argument, nullptr, 1005},
-        {"hdf5", no_argument, nullptr, 1006}, {"check-deck", no_argument, nullptr, 1007}, {nullptr, 0, nullptr, 0}};
+        {"hdf5", no_argument, nullptr, 1006}, {"check-deck", no_argument, nullptr, 1007},
+        {"timers", no_argument, nullptr, 1008}, {nullptr, 0, nullptr, 0}};
     int opt;
     while ((opt = getopt_long(argc, argv, "hc:li:d:p:o:g:m:r:vbI:", long_opts, nullptr)) != -1) {
         switch (opt) {
@@ -299,12 +309,13 @@ int main(int argc, char **argv)
         case 1005: conf.same_device = true; break;       // all ranks of --gpus N on device 0 (tests on a one-GPU box)
         case 1006: conf.hdf5 = true; break;              // write outputs as HDF5 even for an MGCFDBIN deck
         case 1007: conf.check_deck = true; break;        // load the deck, print what was read, exit (no GPU needed)
+        case 1008: conf.timers = true; break;            // per-loop device timers -> PerfData / op2_performance_data.csv
         case 0: break;
         case 'h':
         default:
             printf("usage: %s -i input.dat [-d dir] [-o prefix] [-g cycles] [-v] [-b] [-I n] [--output-variables] "
                    "[--output-fluxes] [--output-step-factors] [--gpus N] [--variant owner|gather|colour|atomic] "
-                   "[--exact] [--loopwise] [--hdf5] [--check-deck]\n", argv[0]);
+                   "[--exact] [--loopwise] [--hdf5] [--check-deck] [--timers]\n", argv[0]);
             return opt == 'h' ? 0 : 1;
         }
     }
@@ -325,6 +336,24 @@ int main(int argc, char **argv)
         for (const char *need : {"node_coordinates", "edge-->node", "edge_weights", "bnd_node-->node", "bnd_node-->group",
                                  "bnd_node_weights"})
             if (!c.count(need)) { fprintf(stderr, "%s: dataset %s missing\n", deck.files[i].c_str(), need); return 1; }
+        // op_decl_map_hdf5 / op_decl_dat_hdf5 reject datasets whose size, dim or type do not match the declaring set
+        // (euler3d.cpp:262-312): the same checks before any pointer is taken
+        auto shape_ok = [&](const char *name, int dtype, uint64_t rows, uint64_t cols) {
+            const Dataset &d = c[name];
+            const bool ok = d.dtype == dtype && !d.dims.empty() && d.dims[0] == rows &&
+                            ((d.dims.size() == 1 && cols == 1) || (d.dims.size() == 2 && d.dims[1] == cols)) &&
+                            d.bytes.size() == rows * cols * (dtype == 0 ? 8u : 4u);
+            if (!ok) fprintf(stderr, "%s: dataset %s does not have the expected type / shape [%llu x %llu]\n", deck.files[i].c_str(), name,
+                             (unsigned long long)rows, (unsigned long long)cols);
+            return ok;
+        };
+        for (const char *need : {"node_coordinates", "edge-->node", "bnd_node-->node"})
+            if (c[need].dims.empty() || c[need].dims[0] > 0x7fffffffull) { fprintf(stderr, "%s: dataset %s has no usable first dimension\n", deck.files[i].c_str(), need); return 1; }
+        const uint64_t nn = c["node_coordinates"].dims[0], ne = c["edge-->node"].dims[0], nb = c["bnd_node-->node"].dims[0];
+        if (!shape_ok("node_coordinates", 0, nn, 3) || !shape_ok("edge-->node", 1, ne, 2) || !shape_ok("edge_weights", 0, ne, 3) ||
+            !shape_ok("bnd_node-->node", 1, nb, 1) || !shape_ok("bnd_node-->group", 1, nb, 1) || !shape_ok("bnd_node_weights", 0, nb, 3))
+            return 1;
+        if (i + 1 < levels && c.count("node-->mg_node") && !shape_ok("node-->mg_node", 1, nn, 1)) return 1;
         mgcfd_level_host &h = lv[i];
         memset(&h, 0, sizeof(h));
         h.n_nodes = h.n_owned_nodes = (int)c["node_coordinates"].dims[0];
@@ -436,6 +465,8 @@ int main(int argc, char **argv)
     }
     ctx = R[0];
 
+    if (conf.timers)      // device timers per call site: inside graph replay on one GPU (mode 3), launch by launch otherwise
+        for (int r = 0; r < P; r++) CHECK(mgcfd_timers_enable(R[r], (P > 1 || conf.loopwise) ? 1 : 3));
     printf("-----------------------------------------------------\nCompute beginning\n");
     double t1 = wall(), file_io_seconds = 0.0;
     int n_file_io_writes = 0;
@@ -603,7 +634,38 @@ int main(int argc, char **argv)
                 const int n_edges = P == 1 ? lv[l].n_edges : mgcfd_local_mesh_level(LM[r], l)->n_edges;
                 iters[l] = (long long)n_edges * MGCFD_RK * visits[l] * conf.cycles;
             }
-            dump_perf_data(csv_prefix, r, partitioner_name(conf), std::vector<double>(levels, 0.0), iters);
+            // compute_flux_edge_kernel time per level (--timers): the fused Runge-Kutta stage is the launch that holds it
+            std::vector<double> secs(levels, 0.0);
+            if (conf.timers)
+                for (int l = 0; l < levels; l++)
+                    for (const char *name : {"rk_stage", "compute_flux_edge"}) {
+                        double ms = 0.0;
+                        long long calls = 0, elems = 0;
+                        if (mgcfd_timers_get(R[r], name, l, &ms, &calls, &elems) == MGCFD_OK) secs[l] += ms * 1e-3;
+                    }
+            dump_perf_data(csv_prefix, r, partitioner_name(conf), secs, iters);
+        }
+        // op2_performance_data.csv (what op_timings_to_csv writes, euler3d.cpp:651-656; read by run-scripts/aggregate-output-data.py
+        // :41,:71 for `nranks` and the per-loop times): one row per rank and loop; times are zero without --timers
+        {
+            const std::string path = csv_prefix + "op2_performance_data.csv";
+            std::ofstream out(path);
+            out << "rank,thread,nranks,nthreads,count,total time,plan time,mpi time,GB used,GB total,kernel name" << std::endl;
+            static const char *const loops[] = {"visit_begin", "copy_double", "calculate_dt", "get_min_dt", "compute_step_factor", "rk_stage",
+                                                "compute_flux_edge", "compute_bnd_node_flux", "time_step", "unstructured_stream", "residual",
+                                                "calc_rms", "count_bad_vals", "restrict", "up_pre", "up", "up_post", "down", "min_exchange",
+                                                "halo_exchange"};
+            for (int r = 0; r < P; r++) {
+                bool any = false;
+                for (const char *name : loops) {
+                    double ms = 0.0;
+                    long long calls = 0, elems = 0;
+                    if (!conf.timers || mgcfd_timers_get(R[r], name, -1, &ms, &calls, &elems) != MGCFD_OK || calls == 0) continue;
+                    out << r << ",0," << P << ",1," << calls << ',' << ms * 1e-3 << ",0,0,0,0," << name << std::endl;
+                    any = true;
+                }
+                if (!any) out << r << ",0," << P << ",1," << conf.cycles << ',' << walltime << ",0,0,0,0,mgcfd_run_cycles" << std::endl;
+            }
         }
         dump_file_io_perf_data(csv_prefix, 0, partitioner_name(conf), conf.flow_interval, n_file_io_writes, file_io_seconds, walltime);
     }

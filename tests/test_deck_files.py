@@ -80,3 +80,46 @@ def test_perf_csv_files_have_the_reference_layout(tmp_path, meshgen):
     io = open(prefix + ".P=0.FileIoTimes.csv").read().splitlines()
     assert io[0] == "rank,partitioner,level,writeInterval,numberOfWrites,fileIoTime,wallTime"
     assert len(io) == 3 and io[1].split(",")[:5] == ["0", "kway", "0", "0", "0"]
+
+
+def test_native_driver_rejects_malformed_decks(tmp_path, meshgen):
+    """op_decl_map_hdf5 / op_decl_dat_hdf5 refuse datasets whose size, dim or type does not match their set
+    (euler3d.cpp:262-312); the driver does the same before it takes any pointer, and the container reader bounds every
+    length field by the file size (no GPU needed: --check-deck)"""
+    mesh = meshgen.make_multigrid("tiny")
+
+    def check(mutate, expect):
+        d = tmp_path / expect.replace(" ", "_")[:24]
+        meshgen.write_deck(str(d), mesh)
+        mutate(str(d))
+        p = subprocess.run([EXE, "-i", "input.dat", "-d", str(d), "--check-deck"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 1 and expect in p.stderr, (p.returncode, p.stderr[-400:])
+
+    def rewrite(path, edit):
+        lev = meshgen.read_container(path)
+        edit(lev)
+        meshgen.write_container(path, lev)
+
+    # a weights array one row short of its edge set
+    check(lambda d: rewrite(os.path.join(d, "mesh.L0.mgb"), lambda lev: lev.__setitem__("edge_weights", lev["edge_weights"][:-1])),
+          "edge_weights does not have the expected type / shape")
+    # a map stored as floating point
+    check(lambda d: rewrite(os.path.join(d, "mesh.L1.mgb"), lambda lev: lev.__setitem__("bnd_node-->group", lev["bnd_node-->group"].astype(np.float64))),
+          "bnd_node-->group does not have the expected type / shape")
+    # a map with the wrong second dimension
+    check(lambda d: rewrite(os.path.join(d, "mesh.L0.mgb"), lambda lev: lev.__setitem__("edge-->node", np.ascontiguousarray(lev["edge-->node"][:, :1]))),
+          "edge-->node does not have the expected type / shape")
+
+    # a truncated file and a header whose byte count runs past the end of the file
+    def truncate(d):
+        p = os.path.join(d, "mesh.L0.mgb")
+        data = open(p, "rb").read()
+        open(p, "wb").write(data[:len(data) // 2])
+    check(truncate, "mesh.L0.mgb")
+
+    def huge_len(d):
+        p = os.path.join(d, "mesh.L0.mgb")
+        data = bytearray(open(p, "rb").read())
+        data[16:20] = (0x7fffffff).to_bytes(4, "little")           # name length of the first dataset
+        open(p, "wb").write(bytes(data))
+    check(huge_len, "corrupt dataset name length")

@@ -87,3 +87,24 @@ def test_driver_periodic_flow_dumps_on_the_default_path(tmp_path, meshgen, golde
     v4 = meshgen.read_container(os.path.join(str(tmp_path), dumps[0]))["p_variables"]
     v8 = meshgen.read_container(os.path.join(str(tmp_path), dumps[1]))["p_variables"]
     assert v4.shape == g["var_L0"].shape and np.isfinite(v4).all() and not np.array_equal(v4, v8)
+
+
+@pytest.mark.parametrize("extra", [[], ["--gpus", "2", "--same-device"]])
+def test_driver_perf_csvs_with_timers(tmp_path, meshgen, golden, extra):
+    """--timers: device time per call site (inside graph replay on one GPU) lands in the reference's CSVs -- the flux rows of
+    P=<r>.PerfData.csv (io.h:296-417) and op2_performance_data.csv (op_timings_to_csv, euler3d.cpp:651-656), which
+    run-scripts/aggregate-output-data.py:41,71 reads for `nranks` and the per-loop times"""
+    make_deck(tmp_path, meshgen, golden)
+    out = os.path.join(str(tmp_path), "run.")
+    p = subprocess.run([EXE, "-i", "input.dat", "-d", str(tmp_path), "-g", "10", "-v", "--timers", "-o", out] + extra,
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "Validation passed" in p.stdout, p.stdout + p.stderr
+    n_ranks = 2 if extra else 1
+    rows = [l.split(",") for l in open(out + "op2_performance_data.csv").read().splitlines()]
+    assert rows[0] == ["rank", "thread", "nranks", "nthreads", "count", "total time", "plan time", "mpi time", "GB used", "GB total", "kernel name"]
+    stage = [r for r in rows[1:] if r[-1] == "rk_stage"]
+    assert len(stage) == n_ranks and all(int(r[2]) == n_ranks and int(r[4]) > 0 and float(r[5]) > 0 for r in stage)
+    for r in range(n_ranks):
+        perf = [l.split(",") for l in open(f"{out}P={r}.PerfData.csv").read().splitlines()]
+        assert perf[0] == ["rank", "partitioner", "kernel", "level", "computeTime", "syncTime", "iters"]
+        assert all(row[2] == "compute_flux_edge_kernel" and float(row[4]) > 0 and int(row[6]) > 0 for row in perf[1:])
