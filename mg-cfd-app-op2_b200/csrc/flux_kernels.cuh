@@ -406,12 +406,25 @@ __device__ __forceinline__ unsigned long long global_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// ACQUIRE = true: ld.acquire.sys -- on this hardware a strong load followed by an invalidation of the SM's whole L1.  The
+// stage kernels need it: their halo gathers allocate in L1, and the line that holds the first rank-halo rows also holds
+// the last owned rows, which a chunk without exports may have pulled in before the neighbours' rows landed.
+// ACQUIRE = false: a strong (relaxed, system-scope) load only -- for kernels in which EVERY block waits before it reads
+// anything a peer writes (node kernels, min_dt mailboxes): L1 starts empty at kernel launch, so nothing stale can be
+// cached, and the 4-16 K blocks of such a grid do not flush each other's L1 4-16 K times.
+template <bool ACQUIRE = true>
 __device__ __forceinline__ void bounded_wait(const unsigned long long *flag, unsigned long long e, int *err, long long timeout_ns)
 {
-    if (ld_acquire_sys(flag) >= e) return;
+    if ((ACQUIRE ? ld_acquire_sys(flag) : ld_relaxed_sys(flag)) >= e) return;
     const unsigned long long t0 = global_ns();
     for (unsigned it = 0;; it++) {
-        if (ld_acquire_sys(flag) >= e) return;
+        if ((ACQUIRE ? ld_acquire_sys(flag) : ld_relaxed_sys(flag)) >= e) return;
         __nanosleep(it < 64 ? 32 : 512);
         if ((it & 1023u) == 1023u && (long long)(global_ns() - t0) > timeout_ns) break;
     }

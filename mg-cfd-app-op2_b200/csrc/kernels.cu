@@ -115,11 +115,12 @@ __global__ void encode_min_kernel(unsigned long long *d_min)
 using exact::st_release_sys;
 using exact::ld_acquire_sys;
 using exact::bounded_wait;
+using exact::ld_relaxed_sys;
 
 // multi-rank node kernels (NodePush): every block first waits for the sources of the halo rows it reads ...
 __device__ __forceinline__ void node_wait(const NodePush &P)
 {
-    if ((int)threadIdx.x < P.n_wait) bounded_wait(P.wait_flag[threadIdx.x], *P.wait_expected[threadIdx.x], P.err_flag, P.timeout_ns);
+    if ((int)threadIdx.x < P.n_wait) bounded_wait<false>(P.wait_flag[threadIdx.x], *P.wait_expected[threadIdx.x], P.err_flag, P.timeout_ns);
     __syncthreads();
 }
 // ... stores the 5-vector of an exported node into the destinations' halo ranges ...
@@ -240,7 +241,7 @@ __global__ void step_factor_group_kernel(int n, const double *__restrict__ vol, 
                                          double *__restrict__ d_min_out, int *__restrict__ d_flags, const __grid_constant__ MinPush mp)
 {
     if (mp.on) {
-        if ((int)threadIdx.x < mp.n_peers) bounded_wait(mp.src_flag[threadIdx.x], *mp.expected[threadIdx.x], mp.err_flag, mp.timeout_ns);
+        if ((int)threadIdx.x < mp.n_peers) bounded_wait<false>(mp.src_flag[threadIdx.x], *mp.expected[threadIdx.x], mp.err_flag, mp.timeout_ns);
         __syncthreads();
     }
     unsigned long long u = ~0ull;

@@ -189,7 +189,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     // warp 0 takes the minimum over the reduced slots -- multi-rank: once the peers' minima have arrived, which the
     // chunk's staging and edge phase have given them time for -- and leaves it in shared memory for the node phase
     if (!TILES && rk.fold.on && warp == 0) {
-        if (lane < rk.fold.n_wait) bounded_wait(rk.fold.wait_flag[lane], *rk.fold.wait_expected[lane], rk.d_bad + 3, rk.fold.timeout_ns);
+        if (lane < rk.fold.n_wait) bounded_wait<false>(rk.fold.wait_flag[lane], *rk.fold.wait_expected[lane], rk.d_bad + 3, rk.fold.timeout_ns);
         __syncwarp();
         unsigned long long u = ~0ull;
         if (lane < rk.fold.n_slots) u = *reinterpret_cast<const volatile unsigned long long *>(rk.fold.slot[lane]);
