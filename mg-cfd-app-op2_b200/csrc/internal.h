@@ -278,7 +278,7 @@ struct MinPush {
     long long timeout_ns;
 };
 
-struct WaitTable {                       // kernel parameter of a stand-alone halo wait
+struct WaitTable {                       // the sources of a level: (flag, expected epoch) pairs
     int n_src;
     const unsigned long long *src_flag[P2P_MAX_RANKS];
     const unsigned long long *expected[P2P_MAX_RANKS];
@@ -488,7 +488,6 @@ int k_pack_rows(cudaStream_t s, int n, const int *idx, const double *src, double
 // p2p transport: rows straight into the peers' halo ranges, then epoch flags; returns kernels launched
 int k_push_rows(cudaStream_t s, int n_rows, const int *idx, const double *src, const PushTable &t);
 int k_signal_wait(cudaStream_t s, const PushTable &t);
-int k_halo_wait(cudaStream_t s, const WaitTable &t);
 int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t);
 int k_status_exchange(cudaStream_t s, int *flags, const unsigned long long *boxes, int n_ranks, const MinTable &t);
 

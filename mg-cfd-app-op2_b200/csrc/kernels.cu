@@ -296,13 +296,6 @@ __global__ void signal_wait_kernel(PushTable t)
     }
 }
 
-// stand-alone consumer wait (after the last fused-push stage of a visit): every source's flag has reached `expected`
-__global__ void halo_wait_kernel(WaitTable t)
-{
-    const int lane = threadIdx.x;
-    if (lane < t.n_src) bounded_wait(t.src_flag[lane], *t.expected[lane], t.err_flag, t.timeout_ns);
-}
-
 // all-reduce(MIN) of min_dt by mailboxes: my encoded minimum goes into every peer's box, then the same flag handshake
 __global__ void min_exchange_kernel(const unsigned long long *my_slot, MinTable t)
 {
@@ -624,12 +617,6 @@ int k_signal_wait(cudaStream_t s, const PushTable &t)
 {
     if (t.n_dst == 0 && t.n_src == 0) return 0;
     signal_wait_kernel<<<1, 32, 0, s>>>(t);
-    return 1;
-}
-int k_halo_wait(cudaStream_t s, const WaitTable &t)
-{
-    if (t.n_src == 0) return 0;
-    halo_wait_kernel<<<1, 32, 0, s>>>(t);
     return 1;
 }
 int k_min_exchange(cudaStream_t s, const unsigned long long *my_slot, const MinTable &t)
