@@ -464,6 +464,32 @@ int mgcfd_plan(mgcfd_ctx *ctx)
         if (l + 1 < ctx->n_levels) REQUIRE((int)L.mg.size() == L.n_nodes, "node-->mg_node missing on a non-coarsest level");
         plan_renumber(L, ctx->opt.renumber != 0);
     }
+    if (ctx->n_ranks > 1)
+        for (int l = 0; l < ctx->n_levels; l++) {
+            // the export lists per owned node (internal numbering): (destination slot, row in that destination's import
+            // range); destination slots number the neighbours that receive rows, in neighbour order.  The stage and node
+            // kernels push exported rows with these; plan_query exposes them for the CPU tests.
+            LevelHost &L = ctx->H[l];
+            HaloLevel &Hd = ctx->halo[l];
+            std::vector<std::vector<int>> ent_of(L.n_owned);
+            int slot = 0;
+            for (size_t k = 0; k < L.nbr_rank.size(); k++) {
+                if (L.export_ptr[k + 1] == L.export_ptr[k]) continue;
+                for (int j = L.export_ptr[k]; j < L.export_ptr[k + 1]; j++) {
+                    std::vector<int> &e = ent_of[L.new_of_old[L.export_idx[j]]];
+                    e.push_back(slot);
+                    e.push_back(j - L.export_ptr[k]);
+                }
+                slot++;
+            }
+            Hd.xn_ptr.assign(L.n_owned + 1, 0);
+            Hd.xn_ent.clear();
+            for (int v = 0; v < L.n_owned; v++) {
+                Hd.xn_ptr[v] = (int)Hd.xn_ent.size() / 2;
+                Hd.xn_ent.insert(Hd.xn_ent.end(), ent_of[v].begin(), ent_of[v].end());
+            }
+            Hd.xn_ptr[L.n_owned] = (int)Hd.xn_ent.size() / 2;
+        }
     if (ctx->device < 0) { ctx->planned = true; return MGCFD_OK; }
     CK(cudaSetDevice(ctx->device));
     if (ctx->n_ranks > 1) {
@@ -577,27 +603,13 @@ int mgcfd_plan(mgcfd_ctx *ctx)
             if ((rc = dev_upload(ctx, &Hd.d_export_idx, idx))) return rc;
             if ((rc = dev_alloc(ctx, &Hd.sendbuf, (size_t)Hd.n_export * 5))) return rc;
         }
-        if (ctx->n_ranks > 1 && ctx->device >= 0) {
-            // the export lists per owned node (internal numbering): (destination slot, row in that destination's import
-            // range); destination slots number the neighbours that receive rows, in neighbour order
-            std::vector<std::vector<int2>> ent_of(L.n_owned);
-            int slot = 0;
-            for (size_t k = 0; k < L.nbr_rank.size(); k++) {
-                if (L.export_ptr[k + 1] == L.export_ptr[k]) continue;
-                for (int j = L.export_ptr[k]; j < L.export_ptr[k + 1]; j++)
-                    ent_of[L.new_of_old[L.export_idx[j]]].push_back(make_int2(slot, j - L.export_ptr[k]));
-                slot++;
-            }
-            std::vector<int> xn_ptr(L.n_owned + 1, 0);
-            std::vector<int2> xn_ent;
-            for (int v = 0; v < L.n_owned; v++) {
-                xn_ptr[v] = (int)xn_ent.size();
-                xn_ent.insert(xn_ent.end(), ent_of[v].begin(), ent_of[v].end());
-            }
-            xn_ptr[L.n_owned] = (int)xn_ent.size();
+        if (ctx->n_ranks > 1) {
+            // per-owned-node export entries (built on the host before the device part of the plan): (slot, row) pairs
+            std::vector<int2> ent(Hd.xn_ent.size() / 2);
+            for (size_t j = 0; j < ent.size(); j++) ent[j] = make_int2(Hd.xn_ent[2 * j], Hd.xn_ent[2 * j + 1]);
             int rc;
-            if ((rc = dev_upload(ctx, &Hd.d_xn_ptr, xn_ptr))) return rc;
-            if ((rc = dev_upload(ctx, &Hd.d_xn_ent, xn_ent))) return rc;
+            if ((rc = dev_upload(ctx, &Hd.d_xn_ptr, Hd.xn_ptr))) return rc;
+            if ((rc = dev_upload(ctx, &Hd.d_xn_ent, ent))) return rc;
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1750,6 +1762,8 @@ long long mgcfd_plan_query(mgcfd_ctx *ctx, int level, const char *what, int *out
             v[L.sorted.order[i]] = (s == "edge_thread_colour") ? C.thread_colour[i] : C.block_colour[i / C.block_edges];
         return emit(v, out, cap);
     }
+    if (s == "export_node_ptr") return emit(ctx->halo[level].xn_ptr, out, cap);
+    if (s == "export_node_ent") return emit(ctx->halo[level].xn_ent, out, cap);
     if (s.rfind("owner_", 0) == 0) {
         if (build_owner_host(ctx, level)) return MGCFD_ERR_PLAN;
         OwnerPlanHost &O = L.owner;

@@ -209,6 +209,7 @@ struct HaloLevel {
     std::vector<int> launch_order;   // host copy of d_chunk_list
     int *d_xp_base = nullptr, *d_xp_ptr = nullptr;
     int2 *d_xp_ent = nullptr;
+    std::vector<int> xn_ptr, xn_ent; // host copies (plan_query "export_node_ptr" / "export_node_ent": slot, row pairs)
     int *d_xn_ptr = nullptr;         // the same entries per owned node of the level (node kernels: restrict, prolong)
     int2 *d_xn_ent = nullptr;
 };

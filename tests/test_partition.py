@@ -126,3 +126,44 @@ def test_partition_unknown_method_is_an_error(pkg, meshgen):
     mesh = meshgen.make_multigrid("tiny")
     with pytest.raises(pkg.capi.MgcfdError):
         pkg.partition_levels(mesh["levels"], mesh["base_array_index"], 2, method="metis5")
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_export_tables_of_the_fused_push(pkg, meshgen, n_ranks):
+    """the kernels of a multi-rank cycle push exported rows themselves: per owned node (internal
+    numbering) the (destination slot, row) entries.  They must be exactly the export lists seen from the node's side --
+    slot = position of the neighbour among those that receive rows, row = position in the export list for it, which
+    is the row of the node in that neighbour's import range -- and both ends of every pair must agree on the counts.
+    CPU only (planning-only contexts)."""
+    mesh = meshgen.make_multigrid("small")
+    parts = pkg.partition_levels(mesh["levels"], mesh["base_array_index"], n_ranks)
+    lms = [pkg.LocalMesh(mesh["levels"], mesh["base_array_index"], parts, r, n_ranks) for r in range(n_ranks)]
+    ctxs = [pkg.MGCFD(local_mesh=lm, device=-1, init=False) for lm in lms]
+    try:
+        for l in range(len(mesh["levels"])):
+            for r, (lm, g) in enumerate(zip(lms, ctxs)):
+                perm = g.plan_query(l, "node_perm").astype(np.int64)           # internal index of local file node i
+                nbr, ep, ei = lm.query(l, "neighbour_rank"), lm.query(l, "export_ptr"), lm.query(l, "export_idx")
+                ptr = g.plan_query(l, "export_node_ptr")
+                ent = g.plan_query(l, "export_node_ent").reshape(-1, 2)
+                n_owned = g.n_owned[l]
+                assert ptr.size == n_owned + 1 and ptr[0] == 0 and ptr[-1] == ent.shape[0] == ei.size
+                expect = [[] for _ in range(n_owned)]
+                slot = 0
+                for k in range(nbr.size):
+                    if ep[k + 1] == ep[k]:
+                        continue
+                    for j in range(ep[k], ep[k + 1]):
+                        expect[perm[ei[j]]].append((slot, j - ep[k]))
+                    slot += 1
+                for v in range(n_owned):
+                    assert [tuple(x) for x in ent[ptr[v]:ptr[v + 1]]] == expect[v], (l, r, v)
+                # the receiving side expects as many rows from this rank as this rank sends
+                for k in range(nbr.size):
+                    q = int(nbr[k])
+                    nbr_q, ip_q = lms[q].query(l, "neighbour_rank"), lms[q].query(l, "import_ptr")
+                    kq = int(np.where(nbr_q == r)[0][0])
+                    assert ip_q[kq + 1] - ip_q[kq] == ep[k + 1] - ep[k]
+    finally:
+        for g in ctxs:
+            g.close()
