@@ -74,6 +74,17 @@ def rk_stage_bytes_per_cycle(sizes):
                for l in visits_per_cycle(len(sizes)))
 
 
+def node_kernel_bytes_per_cycle(sizes):
+    """algorithmic bytes per cycle of the fused node kernels (SURVEY.md 8d per-argument figures):
+    visit_begin = copy_double (80 N) + calculate_dt (56 N) + get_min_dt (8 N) per visit; restrict = up_pre + up + up_post
+    (48 N_fine + 216 N_coarse) per step up; down (148 N_fine + 64 N_coarse) per step down"""
+    nl = len(sizes)
+    n = [s[0] for s in sizes]
+    return {"visit_begin": sum(144 * n[l] for l in visits_per_cycle(nl)),
+            "restrict": sum(48 * n[l] + 216 * n[l + 1] for l in range(nl - 1)),
+            "down": sum(148 * n[l] + 64 * n[l + 1] for l in range(nl - 1))}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -513,6 +524,14 @@ def main():
                 "note": "achieved = algorithmic bytes of all timed stage launches / their summed CUDA-event time (every level of the "
                         "deck exceeds the 126 MB L2); frac_*_L0 = the level-0 launches alone under both accountings; "
                         "cycle_breakdown = device time per call site and cycle inside graph replay (its sum + gaps = ms_per_step_with_timers)"}
+    # the other kernels of the cycle against the same roofline (timers mode 3 only: they are not timed launch by launch)
+    nk = node_kernel_bytes_per_cycle(local_sizes)
+    roofline["node_kernels"] = {k: {"ms_per_step": round(st["loops"][k]["ms_per_step"], 5), "algorithmic_mb_per_step": round(b / 1e6, 1),
+                                    "frac": round(b / (st["loops"][k]["ms_per_step"] * 1e-3) / 1e9 / peak, 4)}
+                                for k, b in nk.items() if k in st["loops"] and st["loops"][k]["ms_per_step"] > 0 and b > 0}
+    roofline["node_kernels_note"] = ("algorithmic bytes of the reference's separate loops (visit_begin = copy_double + calculate_dt + get_min_dt; "
+                                     "restrict = up_pre + up + up_post; down) over the fused kernel's in-graph time; a fraction above 1 means "
+                                     "the fusion moves fewer bytes than the separate loops stream")
     if rank == 0:
         log(f"timed regions done after {time.time() - t_start:.1f} s: {ms / args.steps:.3f} ms/cycle, stage frac {achieved / peak:.3f}")
 

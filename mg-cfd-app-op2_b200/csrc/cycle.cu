@@ -28,6 +28,22 @@ using namespace mgcfd;
         }                                                                                                \
     } while (0)
 
+// programmatic dependent launch of the cycle's kernels (internal.h): on for the enqueues of the device-driven schedule
+// unless the per-call-site timers are recording (event nodes between the kernels would serialise them anyway)
+thread_local int mgcfd::tl_pdl = 0;
+bool mgcfd::pdl_wanted()
+{
+    const char *e = getenv("MGCFD_PDL");
+    return e ? atoi(e) != 0 : MGCFD_PDL_DEFAULT != 0;
+}
+namespace {
+struct PdlScope {
+    int saved;
+    explicit PdlScope(const mgcfd_ctx *ctx, bool allowed = true) : saved(tl_pdl) { tl_pdl = allowed && pdl_wanted() && !ctx->timers_on; }
+    ~PdlScope() { tl_pdl = saved; }
+};
+}  // namespace
+
 // ------------------------------------------------------------------------------------------
 // one context, no communication
 // ------------------------------------------------------------------------------------------
@@ -136,6 +152,7 @@ static int enqueue_single(mgcfd_ctx *ctx, int n_cycles)
     cudaStream_t s = ctx->stream;
     const bool exact = ctx->opt.exact_arith != 0;
     const DevConsts dc = api_dev_consts(ctx);
+    PdlScope pdl(ctx);
     // the owner variant runs the fused schedule: one kernel per Runge-Kutta stage, fused visit prologue and restrict
     const bool fused = (ctx->opt.flux_variant == MGCFD_FLUX_OWNER || ctx->opt.flux_variant == MGCFD_FLUX_EMIT) && !ctx->opt.no_fusion;
     int level = 0, dir = 0, i = 0;
@@ -740,6 +757,7 @@ int enqueue_ranks(mgcfd_ctx **R, int n, int n_cycles)
     mgcfd_ctx *ctx = R[0];
     const int nl = ctx->n_levels;
     const bool nccl = n == 1 && ctx->nccl_comm;
+    PdlScope pdl(ctx, ctx->p2p.enabled && ctx->p2p.fused_push);      // the exchange schedules with pack kernels / NCCL stay as they are
     int level = 0, dir = 0, i = 0, rc;
     while (i < n_cycles) {
         // ---- visit prologue: copy, dt, local min (euler3d.cpp:467-479)

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -20,6 +21,39 @@ namespace mgcfd {
 
 constexpr int NVAR = MGCFD_NVAR;
 constexpr int NDIM = MGCFD_NDIM;
+
+// ------------------------------------------------------------------ programmatic dependent launch (MGCFD_PDL)
+// The four kernels of the device-driven cycle (visit_begin, rk_stage2, restrict_fused, down) can be launched with the
+// programmatic-stream-serialization attribute: a kernel's CTAs then become resident while the previous kernel's last
+// wave drains, do everything that touches only static plan data (chunk record, mbarrier set-up, the bulk copies of the
+// chunk's weight blob, index loads) and block in griddepcontrol.wait until the previous grid has completed and its
+// memory is visible.  Every such kernel executes the wait in every CTA before its first access to mutable data, so
+// completion stays transitive along the stream.  Without the launch attribute both instructions are no-ops.
+// tl_pdl is set by the cycle drivers (cycle.cu: PdlScope) for the enqueue they are doing; the per-call-site API never sets it.
+extern thread_local int tl_pdl;
+#ifndef MGCFD_PDL_DEFAULT
+#define MGCFD_PDL_DEFAULT 0
+#endif
+bool pdl_wanted();                       // MGCFD_PDL=0|1 (default MGCFD_PDL_DEFAULT)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KA, typename... A>
+inline cudaError_t launch_k(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = tl_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------ host-side plans
 // Sorted edge list shared by the atomic and colour variants: edges ordered by

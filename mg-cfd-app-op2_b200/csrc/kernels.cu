@@ -171,6 +171,9 @@ __global__ void visit_begin_kernel(int n, const double *__restrict__ var, const 
     __shared__ int s_last;
     unsigned long long m = ~0ull;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    const double cv = i < n ? __ldg(cbrt_vol + i) : 0.0;      // static: requested before the previous kernel has finished
+    pdl_wait();                                     // programmatic dependent launch (internal.h): nothing mutable is touched above
     if (i == 0 && zero_me) *zero_me = 0.0;          // level 0: the rms accumulator of this visit (euler3d.cpp:534)
     if (i < n) {
         double u[5];
@@ -181,7 +184,7 @@ __global__ void visit_begin_kernel(int n, const double *__restrict__ var, const 
         double q2 = vx * vx + vy * vy + vz * vz;
         double p = (1.4 - 1.0) * (u[4] - 0.5 * rho * q2);
         double c = sqrt(1.4 * p / rho);
-        double d = 0.5 * (cbrt_vol[i] / (sqrt(q2) + c));
+        double d = 0.5 * (cv / (sqrt(q2) + c));
         dt[i] = d;
         if (d == d) m = enc_min(d);
     }
@@ -357,11 +360,14 @@ __global__ void restrict_fused_kernel(int n_coarse, const int *__restrict__ chil
                                       const double *__restrict__ var, double *__restrict__ var_above,
                                       int *__restrict__ count_above, const __grid_constant__ NodePush np)
 {
-    if (np.on) node_wait(np);                       // the children's rows on other ranks (pushed by their last stage) are in
+    pdl_launch_dependents();
     int pushed = 0;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int j0 = 0, j1 = 0;
+    if (p < n_coarse) { j0 = __ldg(child_ptr + p); j1 = __ldg(child_ptr + p + 1); }      // static index data
+    pdl_wait();                                     // programmatic dependent launch (internal.h): nothing mutable is touched above
+    if (np.on) node_wait(np);                       // the children's rows on other ranks (pushed by their last stage) are in
     if (p < n_coarse) {
-        int j0 = child_ptr[p], j1 = child_ptr[p + 1];
         if (j0 != j1) {
             double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             for (int j = j0; j < j1; j++) {
@@ -505,14 +511,20 @@ __global__ void down_kernel(int n_fine, const int *__restrict__ mg, double *__re
                             const double *__restrict__ res_above, const double *__restrict__ xyz_above,
                             const __grid_constant__ NodePush np)
 {
-    if (np.on) node_wait(np);                       // the parents' residuals on other ranks (pushed by their last stage) are in
+    pdl_launch_dependents();
     int pushed = 0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = 0;
+    double dx = 0.0, dy = 0.0, dz = 0.0;
+    if (i < n_fine) {                               // static: the map and the coordinates
+        p = mg[i];
+        dx = fabs(xyz[(size_t)i * 3] - xyz_above[(size_t)p * 3]);
+        dy = fabs(xyz[(size_t)i * 3 + 1] - xyz_above[(size_t)p * 3 + 1]);
+        dz = fabs(xyz[(size_t)i * 3 + 2] - xyz_above[(size_t)p * 3 + 2]);
+    }
+    pdl_wait();                                     // programmatic dependent launch (internal.h): nothing mutable is touched above
+    if (np.on) node_wait(np);                       // the parents' residuals on other ranks (pushed by their last stage) are in
     if (i < n_fine) {
-        int p = mg[i];
-        double dx = fabs(xyz[(size_t)i * 3] - xyz_above[(size_t)p * 3]);
-        double dy = fabs(xyz[(size_t)i * 3 + 1] - xyz_above[(size_t)p * 3 + 1]);
-        double dz = fabs(xyz[(size_t)i * 3 + 2] - xyz_above[(size_t)p * 3 + 2]);
         double dm = sqrt(dx * dx + dy * dy + dz * dz);
         double *u = var + (size_t)i * 5;
         const double *r = res + (size_t)i * 5, *ra = res_above + (size_t)p * 5;
@@ -584,7 +596,7 @@ int k_visit_begin(cudaStream_t s, int n, const double *var, const double *cbrt_v
     MinPush none;
     memset(&none, 0, sizeof(none));
     if (n == 0 && !(mp && mp->on)) return 0;
-    visit_begin_kernel<<<n > 0 ? blocks_for(n) : 1, TPB, 0, s>>>(n, var, cbrt_vol, old, dt, min_slot, mp ? *mp : none, zero_me);
+    launch_k(visit_begin_kernel, dim3(n > 0 ? blocks_for(n) : 1), dim3(TPB), 0, s, n, var, cbrt_vol, old, dt, min_slot, mp ? *mp : none, zero_me);
     return 1;
 }
 int k_step_factor_fused(cudaStream_t s, int n, const double *vol, unsigned long long *min_slot, unsigned long long *next_slot,
@@ -640,8 +652,8 @@ int k_restrict_fused(cudaStream_t s, int n_coarse, const int *child_ptr, const i
     NodePush none;
     memset(&none, 0, sizeof(none));
     if (n_coarse == 0 && !(np && np->on)) return 0;
-    restrict_fused_kernel<<<n_coarse > 0 ? blocks_for(n_coarse) : 1, TPB, 0, s>>>(n_coarse, child_ptr, child_idx, var, var_above, count_above,
-                                                                                np ? *np : none);
+    launch_k(restrict_fused_kernel, dim3(n_coarse > 0 ? blocks_for(n_coarse) : 1), dim3(TPB), 0, s, n_coarse, child_ptr, child_idx, var, var_above,
+             count_above, np ? *np : none);
     return 1;
 }
 int k_step_factor(cudaStream_t s, int n, const double *vol, const double *d_min, double *sf)
@@ -714,7 +726,7 @@ int k_down(cudaStream_t s, int n_fine, const int *mg, double *var, const double 
     NodePush none;
     memset(&none, 0, sizeof(none));
     if (n_fine == 0 && !(np && np->on)) return 0;
-    down_kernel<<<n_fine > 0 ? blocks_for(n_fine) : 1, TPB, 0, s>>>(n_fine, mg, var, res, coords, res_above, coords_above, np ? *np : none);
+    launch_k(down_kernel, dim3(n_fine > 0 ? blocks_for(n_fine) : 1), dim3(TPB), 0, s, n_fine, mg, var, res, coords, res_above, coords_above, np ? *np : none);
     return 1;
 }
 

@@ -76,6 +76,7 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     double *der = reinterpret_cast<double *>(sm + L::DER);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = rec0 + (int)blockIdx.x;               // the records are stored in launch order
+    pdl_launch_dependents();                                // programmatic dependent launch (internal.h); a no-op otherwise
     const int *rec = xtab + (size_t)chunk * xs;
 
     // ---- 1. the chunk's record: halo ids of this thread's rows and the descriptor, independent loads (one round trip)
@@ -100,7 +101,6 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     // multi-GPU, fused push: word 3 of the record is the chunk's base into the export row pointers (-1: no exported node);
     // such a chunk -- the only kind that reads rank-halo rows -- first waits for its sources
     const int xb = rk.push_on ? q0.w : -1;
-    if (xb >= 0) push_wait_sources(rk.push, tid);
     // experiment (MGCFD_STAGE2_PF=distance): thread 64 fetches the descriptor of the chunk `distance` launches ahead and
     // later prefetches that chunk's contiguous inputs into L2, so that its CTA finds them there
     int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
@@ -113,7 +113,9 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
     const uint32_t own_b = ((uint32_t)n_own * 40u) & ~15u, sf_b = ((uint32_t)n_own * 8u) & ~15u;
 
     // ---- 2. bulk async copies (TMA 1-D): four weight planes, the blob's tail, the owned nodes' variables
-    //         (+ old_variables and step factors: they land while the fluxes are computed)
+    //         (+ old_variables and step factors: they land while the fluxes are computed).  The blob is static plan data:
+    //         under a programmatic dependent launch it is requested while the previous kernel is still draining; everything
+    //         the previous kernels (or the peers) write is touched only behind pdl_wait()
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (uint32_t)bnd_off + own_b + (TILES ? own_b + sf_b : 0u));
@@ -125,6 +127,10 @@ rk_stage2_kernel(const int *__restrict__ xtab, int xs, int hs, int rec0, int pf_
             bulk_g2s(sm + L::G, src + 3 * pb, pb, bar);
         }
         bulk_g2s(sm + L::TAIL, src + 4 * pb, (uint32_t)bnd_off - 4 * pb, bar);      // lab | rowptr | csr (not the boundary entries)
+    }
+    pdl_wait();
+    if (xb >= 0) push_wait_sources(rk.push, tid);
+    if (tid == 0) {
         if (own_b) bulk_g2s(raw, var + (size_t)node0 * 5, own_b, bar);
         if (TILES) {
             if (own_b) bulk_g2s(sm + L::OLD, rk.old + (size_t)node0 * 5, own_b, bar);
@@ -306,8 +312,8 @@ inline void stage2_launch_one(cudaStream_t s, int grid, size_t tail, const Owner
 {
     const size_t smem = Stage2Layout<MAXE, MAXL, TILES>::TAIL + tail;     // dynamic shared memory opt-in: configure()
     const char *pf = getenv("MGCFD_STAGE2_PF");
-    rk_stage2_kernel<MAXE, MAXL, TILES, MINB><<<grid, 128, smem, s>>>(p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0, pf ? atoi(pf) : 0,
-                                                                      p.blob, a.var, ra);
+    launch_k(rk_stage2_kernel<MAXE, MAXL, TILES, MINB>, dim3(grid), dim3(128), smem, s, p.xtab, p.xs, p.hs, a.chunk_list ? a.list_offset : 0,
+             pf ? atoi(pf) : 0, p.blob, a.var, ra);
 }
 
 // whether a fused stage on this plan runs the stage2 kernel: the plan fits a compiled configuration and no experiment knob

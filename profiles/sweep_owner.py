@@ -22,7 +22,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 KNOBS = {"pipe": "MGCFD_OWNER_PIPE", "thr": "MGCFD_OWNER_THREADS", "ctas": "MGCFD_OWNER_PIPE_CTAS", "minb": "MGCFD_OWNER_PIPE_MINB", "slot": "MGCFD_OWNER_SLOTTING", "lean": "MGCFD_OWNER_LEAN", "epi": "MGCFD_OWNER_EPILOGUE", "split": "MGCFD_OWNER_SLOT_SPLIT",
          "maxloc": "MGCFD_OWNER_MAX_LOC", "maxedges": "MGCFD_OWNER_MAX_EDGES",
-         "s2": "MGCFD_STAGE2", "tiles": "MGCFD_STAGE2_TILES", "s2minb": "MGCFD_STAGE2_MINB", "pf": "MGCFD_STAGE2_PF"}
+         "pdl": "MGCFD_PDL", "s2": "MGCFD_STAGE2", "tiles": "MGCFD_STAGE2_TILES", "s2minb": "MGCFD_STAGE2_MINB", "pf": "MGCFD_STAGE2_PF"}
 
 
 def main():

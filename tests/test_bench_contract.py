@@ -56,6 +56,7 @@ def test_b200_arm_line():
     assert d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["value"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["scaling"] == "strong" and {"frac_fused_L0", "frac_flux_only_L0"} <= set(r)
+    assert {"visit_begin", "restrict", "down"} <= set(r["node_kernels"]) and all(v["frac"] > 0 for v in r["node_kernels"].values())
     # the line checks itself against the CPU oracle (one cycle from the initial state) and carries the M6 cycle
     p = d["parity"]
     assert p["checked"] and p["ok"] and p["max_rel_err"] <= 1e-10 and p["validate_count"] == 0
