@@ -13,9 +13,11 @@
 //          default settings for such a file.
 // Not supported (reported as errors, never silently misread): dense link storage (fractal heaps), v4 layouts with the
 // new chunk indices, variable-length / compound / reference types as dataset element types, external storage, szip.
-// Parity note: there is no libhdf5 / h5py / sample .h5 file in the build image, so interoperability with real HDF5 is
-// unpinned; the implementation is cross-checked against an independent pure-Python restatement of the same
-// specification (oracle/h5_oracle.py, tests/test_h5lite.py) in both directions.
+// Parity note: there is no libhdf5 / h5py in the build image.  The one genuine libhdf5-written file it holds (a MATLAB 7.3
+// MAT-file, tests/golden/libhdf5_matlab73_testdouble.mat: user block, superblock 0, old-style group, v1 object header,
+// contiguous doubles, string attribute) is read correctly; beyond that interoperability with real HDF5 is unpinned and
+// the implementation is cross-checked against an independent pure-Python restatement of the same specification
+// (oracle/h5_oracle.py, tests/test_h5lite.py) in both directions.
 #pragma once
 #include <fcntl.h>
 #include <sys/stat.h>

@@ -3,7 +3,9 @@
 (mg-cfd-app-op2_b200/host/h5lite.hpp) in both directions: files written here are read by the C++ reader, files written
 by the C++ writer are read here.  The reference reads its level files through OP2's op_decl_*_hdf5 (euler3d.cpp:248-327)
 and writes solutions through op_fetch_data_hdf5_file (euler3d.cpp:564,740-770); libhdf5 / h5py do not exist in this
-image, so parity with the real library is unpinned (stated in DESIGN.md).
+image.  Pinning: the one genuine libhdf5-written file the image holds (tests/golden/libhdf5_matlab73_testdouble.mat, a
+MATLAB 7.3 MAT-file from scipy's test data) is read here and by the C++ reader with identical, known results; the
+chunked / filtered / version-2 structures have no genuine sample: parity unpinned for those (stated in DESIGN.md).
 
 write_h5(path, datasets, ...) can produce every structural variant the C++ reader claims to handle:
   superblock 0 (symbol-table root group: B-tree "TREE" + "SNOD" + local heap) or 2 ("OHDR" v2 root with Link messages),
@@ -360,19 +362,40 @@ class _Reader:
         for mtype, m in msgs:
             if mtype != 0x08:
                 continue
-            assert m[0] == 3
             n = int(np.prod(shape)) if shape else 1
-            if m[1] == 1:
-                addr, size = struct.unpack_from("<QQ", m, 2)
+            if m[0] in (1, 2):
+                # versions 1 and 2 (HDF5 1.6 and older writers): dimensionality, class, 5 reserved bytes, the address (not
+                # for compact storage), `dimensionality` 4-byte sizes (chunked: the chunk shape followed by the element size)
+                ndim, cls, q = m[1], m[2], 8
+                addr = UNDEF
+                if cls != 0:
+                    addr = struct.unpack_from("<Q", m, q)[0]
+                    q += 8
+                dims = struct.unpack_from(f"<{ndim}I", m, q)
+                q += 4 * ndim
+                if cls == 0:
+                    size = struct.unpack_from("<I", m, q)[0]
+                    compact = m[q + 4:q + 4 + size]
+                else:
+                    rank, bt, chunk = ndim - 1, addr, dims[:-1]
+            else:
+                assert m[0] == 3
+                cls = m[1]
+                if cls == 1:
+                    addr = struct.unpack_from("<Q", m, 2)[0]
+                elif cls == 0:
+                    size = struct.unpack_from("<H", m, 2)[0]
+                    compact = m[4:4 + size]
+                else:
+                    rank = m[2] - 1
+                    bt = struct.unpack_from("<Q", m, 3)[0]
+                    chunk = struct.unpack_from(f"<{rank}I", m, 11)
+            if cls == 1:
                 raw = self.at(addr, n * dt.itemsize) if addr != UNDEF else b"\0" * (n * dt.itemsize)
                 data = np.frombuffer(raw, dtype=dt).reshape(shape)
-            elif m[1] == 0:
-                size = struct.unpack_from("<H", m, 2)[0]
-                data = np.frombuffer(m[4:4 + size], dtype=dt).reshape(shape)
+            elif cls == 0:
+                data = np.frombuffer(compact, dtype=dt).reshape(shape)
             else:
-                rank = m[2] - 1
-                bt = struct.unpack_from("<Q", m, 3)[0]
-                chunk = struct.unpack_from(f"<{rank}I", m, 11)
                 data = np.zeros(shape, dtype=dt)
 
                 def walk(node):

@@ -2,7 +2,9 @@
 pure-Python restatement of the file-format specification (oracle/h5_oracle.py), in both directions, over every
 structural variant the reader claims: superblock 0 / 2, object headers v1 / v2, old-style and link-message groups,
 contiguous / compact / chunked storage with shuffle + deflate + fletcher32, either byte order, user blocks, nested
-groups, attributes.  No libhdf5 exists in the image: parity with the real library is unpinned."""
+groups, attributes.  No libhdf5 exists in the image; the one genuine libhdf5-written file it holds (a MATLAB 7.3 MAT-file
+among scipy's test data, tests/golden/libhdf5_matlab73_testdouble.mat) pins the structures OP2's level files use; the
+chunked / filtered / version-2 variants stay unpinned against the real library."""
 import ctypes as C
 import os
 import re
@@ -328,3 +330,72 @@ def test_corrupted_files_never_crash_the_reader(h5, tmp_path):
                 out = np.empty(max(n, 1), dtype=np.float64)
                 h5.mgcfd_h5_read_f64(r, name, out.ctypes.data, err, 512)
             h5.mgcfd_h5_close(r)
+
+
+GENUINE = os.path.join(ROOT, "tests", "golden", "libhdf5_matlab73_testdouble.mat")
+
+
+def test_reads_a_file_written_by_the_real_hdf5_library(h5):
+    """The one genuine libhdf5 product in the image: scipy's test file `testhdf5_7.4_GLNX86.mat` (scipy/io/matlab/tests/data,
+    BSD-3-Clause, committed unchanged as tests/golden/libhdf5_matlab73_testdouble.mat).  MATLAB 7.4 wrote it in 2008 with its
+    bundled HDF5 1.6-era library ("MAT-file version 7.3"): a 512-byte user block, superblock 0, an old-style root group
+    (B-tree + local heap + symbol node), a version-1 object header, a version-1 dataspace, an IEEE double datatype, a
+    version-1/2 data-layout message (contiguous) and a string attribute.  Known content (scipy's `testdouble` case):
+    0 : pi/4 : 2*pi as a 9 x 1 dataset.  Both the C++ reader and the Python restatement must return it bit for bit."""
+    assert h5.mgcfd_h5_is_hdf5(GENUINE.encode()) == 1
+    raw = open(GENUINE, "rb").read()
+    assert raw.startswith(b"MATLAB 7.0 MAT-file") and raw[512:520] == h5_oracle.SIG and raw[:8] != h5_oracle.SIG
+    got = c_read(h5, GENUINE)
+    assert got.pop("__superblock__") == 0
+    assert list(got) == ["testdouble"]
+    a, info = got["testdouble"]
+    assert a.shape == (9, 1) and info == {"class": 1, "bytes": 8, "layout": 1}
+    ref = h5_oracle.read_h5(GENUINE)
+    assert list(ref) == ["testdouble"] and ref["testdouble"]["data"].dtype == np.dtype("<f8")
+    assert np.array_equal(a, ref["testdouble"]["data"])                          # the two readers agree bit for bit ...
+    # ... and the bytes are MATLAB's 0:pi/4:2*pi stored in the file, read here without any HDF5 code at all: the
+    # dataset is contiguous, so its 72 bytes sit somewhere in the file exactly as IEEE little-endian doubles
+    expect = np.pi / 4 * np.arange(9)
+    assert np.allclose(a.ravel(), expect, rtol=0, atol=1e-15)
+    assert a.tobytes() in raw
+    assert ref["testdouble"]["attrs"] == {"MATLAB_class": "double"}
+    buf = C.create_string_buffer(64)
+    err = C.create_string_buffer(256)
+    r = h5.mgcfd_h5_open(GENUINE.encode(), err, 256)
+    try:
+        assert h5.mgcfd_h5_attr_str(r, b"testdouble", b"MATLAB_class", buf, 64) == 0 and buf.value == b"double"
+    finally:
+        h5.mgcfd_h5_close(r)
+
+
+def test_writer_uses_the_encodings_the_real_library_wrote(h5, tmp_path):
+    """the same 9 x 1 dataset written by the C++ writer: the fixed part of the superblock (format versions, sizes of
+    offsets / lengths, group leaf / internal node K) and the root symbol-table entry (cached B-tree + heap addresses,
+    cache type 1) are encoded exactly as the genuine libhdf5 file encodes them; the dataset's object header holds the
+    same kinds of messages (dataspace, datatype, layout, attribute) and the same data bytes"""
+    lib_raw = open(GENUINE, "rb").read()[512:]
+    a = (np.pi / 4 * np.arange(9)).reshape(9, 1)
+    path = str(tmp_path / "ours.h5")
+    w = h5.mgcfd_h5_create(path.encode())
+    dims = (C.c_ulonglong * 2)(9, 1)
+    assert h5.mgcfd_h5_add(w, b"testdouble", 3, 2, dims, a.ctypes.data) == 0
+    err = C.create_string_buffer(256)
+    assert h5.mgcfd_h5_finish(w, err, 256) == 0, err.value
+    ours = open(path, "rb").read()
+    assert ours[:20] == lib_raw[:20]                      # signature, versions 0/0/0/0, 8-byte offsets and lengths, K = 4 / 16
+    # root symbol-table entry at byte 56: name offset 0, header address, cache type 1, reserved, scratch = B-tree + heap
+    for f in (ours, lib_raw):
+        name_off, hdr, cache, _res, btree, heap = np.frombuffer(f[56:56 + 40], dtype="<u8, <u8, <u4, <u4, <u8, <u8")[0]
+        assert name_off == 0 and cache == 1 and hdr > 0 and btree > 0 and heap > 0
+    # the dataset headers, message types in both files (ours adds OP2's attributes and a fill-value message at most)
+    class R(h5_oracle._Reader):
+        def __init__(self, b):
+            self.b, self.base = b, 0
+    def dataset_message_types(b, root_hdr):
+        r = R(b)
+        (_, addr), = r.children(r.messages(root_hdr))
+        return {t for t, _ in r.messages(addr)}
+    t_ours = dataset_message_types(ours, int(np.frombuffer(ours[64:72], dtype="<u8")[0]))
+    t_lib = dataset_message_types(lib_raw, int(np.frombuffer(lib_raw[64:72], dtype="<u8")[0]))
+    assert {0x01, 0x03, 0x08, 0x0C} <= t_ours and {0x01, 0x03, 0x08, 0x0C} <= t_lib
+    assert a.tobytes() in ours and a.tobytes() in lib_raw[:]
