@@ -23,10 +23,17 @@ static std::string g_create_error;
         }                                                                                                \
     } while (0)
 
+// (a null context has no error slot: the text goes where mgcfd_last_error(NULL) reads it)
+static inline void set_error(mgcfd_ctx *ctx, std::string msg)
+{
+    if (ctx) ctx->err = std::move(msg);
+    else g_create_error = std::move(msg);
+}
+
 #define REQUIRE(cond, msg)                                                                               \
     do {                                                                                                 \
         if (!(cond)) {                                                                                   \
-            ctx->err = (msg);                                                                            \
+            set_error(ctx, (msg));                                                                       \
             return MGCFD_ERR_ARG;                                                                        \
         }                                                                                                \
     } while (0)
@@ -314,6 +321,9 @@ int mgcfd_decl_level(mgcfd_ctx *ctx, int level, const mgcfd_level_host *lv, int 
     L = LevelHost();
     L.n_nodes = lv->n_nodes; L.n_edges = lv->n_edges; L.n_bnd = lv->n_bnd_nodes; L.n_owned = lv->n_owned_nodes;
     const size_t n = L.n_nodes, E = L.n_edges, B = L.n_bnd;
+    REQUIRE(n == 0 || lv->node_coordinates, "null node_coordinates");
+    REQUIRE(E == 0 || (lv->edge_to_node && lv->edge_weights), "null edge-->node / edge_weights");
+    REQUIRE(B == 0 || (lv->bnd_node_to_node && lv->bnd_node_to_group && lv->bnd_node_weights), "null boundary dataset");
     L.coords.assign(lv->node_coordinates, lv->node_coordinates + n * 3);
     L.ewt.assign(lv->edge_weights, lv->edge_weights + E * 3);
     L.bwt.assign(lv->bnd_node_weights, lv->bnd_node_weights + B * 3);
@@ -463,6 +473,16 @@ int mgcfd_plan(mgcfd_ctx *ctx)
         LevelHost &L = ctx->H[l];
         if (l + 1 < ctx->n_levels) REQUIRE((int)L.mg.size() == L.n_nodes, "node-->mg_node missing on a non-coarsest level");
         plan_renumber(L, ctx->opt.renumber != 0);
+    }
+    // node-->mg_node points into the next level (declared by now): range check in file order, also on planning-only contexts
+    for (int l = 0; l + 1 < ctx->n_levels; l++) {
+        const LevelHost &L = ctx->H[l];
+        const int nc = ctx->H[l + 1].n_nodes;
+        for (int f = 0; f < L.n_nodes; f++) {
+            const int p = L.mg[f];
+            if (p == -1 && f >= L.n_owned) continue;                       // halo node whose parent lives on another rank
+            REQUIRE(p >= 0 && p < nc, "node-->mg_node entry out of range (check base_array_index)");
+        }
     }
     if (ctx->n_ranks > 1)
         for (int l = 0; l < ctx->n_levels; l++) {
