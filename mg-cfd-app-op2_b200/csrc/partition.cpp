@@ -277,6 +277,24 @@ int mgcfd_local_mesh_build(int n_levels, const mgcfd_level_host *global_levels, 
                            int rank, int n_ranks, mgcfd_local_mesh **out)
 {
     if (!global_levels || !part || !out || n_levels < 1 || rank < 0 || rank >= n_ranks) return MGCFD_ERR_ARG;
+    // the deck and the partition vectors are indexed below without further checks: refuse anything that does not fit
+    for (int l = 0; l < n_levels; l++) {
+        const mgcfd_level_host &G = global_levels[l];
+        if (G.n_nodes < 0 || G.n_edges < 0 || G.n_bnd_nodes < 0 || !part[l]) return MGCFD_ERR_ARG;
+        if ((G.n_nodes > 0 && !G.node_coordinates) || (G.n_edges > 0 && (!G.edge_to_node || !G.edge_weights)) ||
+            (G.n_bnd_nodes > 0 && (!G.bnd_node_to_node || !G.bnd_node_to_group || !G.bnd_node_weights)) ||
+            (l + 1 < n_levels && G.n_nodes > 0 && !G.node_to_mg_node))
+            return MGCFD_ERR_ARG;
+        for (int n = 0; n < G.n_nodes; n++)
+            if (part[l][n] < 0 || part[l][n] >= n_ranks) return MGCFD_ERR_ARG;
+        for (size_t i = 0; i < 2 * (size_t)G.n_edges; i++)
+            if (G.edge_to_node[i] - base < 0 || G.edge_to_node[i] - base >= G.n_nodes) return MGCFD_ERR_ARG;
+        for (int i = 0; i < G.n_bnd_nodes; i++)
+            if (G.bnd_node_to_node[i] - base < 0 || G.bnd_node_to_node[i] - base >= G.n_nodes) return MGCFD_ERR_ARG;
+        if (l + 1 < n_levels)
+            for (int f = 0; f < G.n_nodes; f++)
+                if (G.node_to_mg_node[f] - base < 0 || G.node_to_mg_node[f] - base >= global_levels[l + 1].n_nodes) return MGCFD_ERR_ARG;
+    }
     mgcfd_local_mesh *M = new mgcfd_local_mesh();
     M->n_levels = n_levels; M->rank = rank; M->n_ranks = n_ranks;
     M->levels.resize(n_levels);

@@ -169,3 +169,58 @@ print(json.dumps(out))
             assert res[n] <= 0, (n, res[n])
         elif "*" in ret and n != "mgcfd_last_error":
             assert not res[n], (n, res[n])
+
+
+def test_local_mesh_build_refuses_what_does_not_fit(pkg, tiny):
+    """mgcfd_local_mesh_build indexes the deck by the partition vectors and the maps: every one of them is checked first"""
+    levels, base = tiny["levels"], tiny["base_array_index"]
+    parts = pkg.partition_levels(levels, base, 2)
+    pkg.LocalMesh(levels, base, parts, 1, 2).free()                        # the well-formed case
+    n0 = levels[0]["node_coordinates"].shape[0]
+
+    def bad_build(lv, pt, rank=0, n_ranks=2):
+        with pytest.raises(pkg.MgcfdError) as ei:
+            pkg.LocalMesh(lv, base, pt, rank, n_ranks)
+        assert ei.value.code == -1
+
+    p = [q.copy() for q in parts]; p[0][5] = 2                             # owner rank outside the world
+    bad_build(levels, p)
+    p = [q.copy() for q in parts]; p[1][0] = -1
+    bad_build(levels, p)
+    bad_build(levels, parts, rank=2)                                       # this rank outside the world
+    lv = [dict(l) for l in levels]; e = lv[0]["edge-->node"].copy(); e[0, 0] = n0 + base; lv[0]["edge-->node"] = e
+    bad_build(lv, parts)
+    lv = [dict(l) for l in levels]; b = lv[0]["bnd_node-->node"].copy(); b[0] = base - 1; lv[0]["bnd_node-->node"] = b
+    bad_build(lv, parts)
+    lv = [dict(l) for l in levels]; m = lv[0]["node-->mg_node"].copy()
+    m[3] = levels[1]["node_coordinates"].shape[0] + base; lv[0]["node-->mg_node"] = m
+    bad_build(lv, parts)
+    lv = [dict(l) for l in levels]; del lv[0]["node-->mg_node"]           # a finer level without its map
+    bad_build(lv, parts)
+
+
+def test_partitioners_check_their_arguments(pkg, tiny):
+    import ctypes as C
+    lib = pkg.load_library()
+    lev = tiny["levels"][0]
+    xyz = np.ascontiguousarray(lev["node_coordinates"], dtype=np.float64)
+    e2n = np.ascontiguousarray(lev["edge-->node"], dtype=np.int32)
+    n, E = xyz.shape[0], e2n.shape[0]
+    out = np.empty(n, dtype=np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    X, Eptr, O = xyz.ctypes.data_as(dp), e2n.ctypes.data_as(ip), out.ctypes.data_as(ip)
+    assert lib.mgcfd_partition_rcb(n, X, 0, O) == -1                        # no parts
+    assert lib.mgcfd_partition_rcb(n, None, 2, O) == -1
+    assert lib.mgcfd_partition_rcb(n, X, 2, None) == -1
+    assert lib.mgcfd_partition_rcb(0, None, 2, O) == 0                      # an empty set is a valid set
+    assert lib.mgcfd_partition_graph(n, X, E, Eptr, tiny["base_array_index"], 2, b"kway", O) == 0
+    assert set(out.tolist()) == {0, 1}
+    assert lib.mgcfd_partition_graph(n, X, E, Eptr, tiny["base_array_index"] + 1, 2, b"kway", O) == -1      # an entry becomes -1
+    assert lib.mgcfd_partition_graph(n, X, E, None, tiny["base_array_index"], 2, b"kway", O) == -1
+    assert lib.mgcfd_partition_graph(n, X, E, Eptr, tiny["base_array_index"], 2, None, O) == -1
+    assert lib.mgcfd_partition_graph(n, X, E, Eptr, tiny["base_array_index"], 2, b"metis5", O) == -1        # unknown method
+    # more parts than nodes: every node still gets a valid owner
+    few = np.ascontiguousarray(xyz[:3])
+    o3 = np.empty(3, dtype=np.int32)
+    assert lib.mgcfd_partition_rcb(3, few.ctypes.data_as(dp), 8, o3.ctypes.data_as(ip)) == 0
+    assert ((o3 >= 0) & (o3 < 8)).all()
