@@ -167,3 +167,64 @@ def test_export_tables_of_the_fused_push(pkg, meshgen, n_ranks):
     finally:
         for g in ctxs:
             g.close()
+
+
+@pytest.mark.parametrize("seed,n_ranks,method", [(11, 2, "geom"), (12, 3, "geom"), (13, 5, "kway"), (14, 8, "geom"), (15, 4, "random")])
+def test_partition_of_irregular_two_level_decks_bit_exact(pkg, plan_oracle, seed, n_ranks, method):
+    """decks that are not perturbed grids: random graphs with hubs, duplicated edges and isolated nodes, a random
+    fine -> coarse map that leaves some coarse nodes childless (Q8) -- partition vectors, local meshes and halo lists of
+    the C++ library against the restatement, plus the cross-rank invariants"""
+    from test_plan_oracle import random_level
+    rng = np.random.default_rng(seed)
+    fine = random_level(rng, 400, 1800, hubs=2, dup=30, isolated=10)
+    coarse = random_level(rng, 90, 300, hubs=0, dup=0, isolated=5)
+    fine["node-->mg_node"] = rng.integers(1, 70 + 1, size=(400, 1)).astype(np.int32)       # coarse nodes 70..89 stay childless
+    levels = [fine, coarse]
+    lev0 = []
+    for lv in levels:
+        z = dict(lv)
+        for k in ("edge-->node", "bnd_node-->node", "node-->mg_node"):
+            if k in z:
+                z[k] = z[k] - 1
+        z["bnd_node-->node"] = z["bnd_node-->node"].reshape(-1)
+        z["bnd_node-->group"] = z["bnd_node-->group"].reshape(-1)
+        if "node-->mg_node" in z:
+            z["node-->mg_node"] = z["node-->mg_node"].reshape(-1)
+        lev0.append(z)
+    parts = pkg.partition_levels(levels, 1, n_ranks, method=method)
+    if method in ("geom", "kway"):
+        ref_parts = plan_oracle.partition_levels(lev0, n_ranks, method=method)
+    else:
+        # the trivial partitioners are not restated: take their level-0 vector, restate the coarse rule and the halos on it
+        ref_parts = [parts[0], plan_oracle.coarse_part(parts[0], lev0[0]["node-->mg_node"], 90, lev0[1]["edge-->node"],
+                                                       np.asarray(lev0[1]["node_coordinates"]))]
+    for a, b in zip(parts, ref_parts):
+        assert np.array_equal(a, b)
+        assert a.min() >= 0 and a.max() < n_ranks
+    owned_total = [0, 0]
+    for r in range(n_ranks):
+        lm = pkg.LocalMesh(levels, 1, parts, r, n_ranks)
+        ref = plan_oracle.local_mesh(lev0, ref_parts, r)
+        for l in range(2):
+            n_nodes, n_edges, n_bnd, n_owned = lm.sizes(l)
+            gn = lm.query(l, "global_node")
+            assert np.array_equal(gn, ref[l]["global_node"]) and n_owned == ref[l]["n_owned"]
+            assert np.array_equal(lm.query(l, "global_edge"), ref[l]["global_edge"])
+            assert np.array_equal(lm.query(l, "global_bnd"), ref[l]["global_bnd"])
+            assert np.array_equal(lm.query(l, "edge_to_node").reshape(-1, 2), ref[l]["e2n"])
+            if l == 0:
+                assert np.array_equal(lm.query(l, "node_to_mg_node"), ref[l]["mg"])
+            nbr = lm.query(l, "neighbour_rank")
+            assert list(nbr) == ref[l]["neighbour_rank"]
+            ep, ei, ip = lm.query(l, "export_ptr"), lm.query(l, "export_idx"), lm.query(l, "import_ptr")
+            for k, q in enumerate(nbr):
+                assert list(gn[ei[ep[k]:ep[k + 1]]]) == ref[l]["exports"][q]
+                assert list(gn[n_owned + ip[k]:n_owned + ip[k + 1]]) == ref[l]["imports"][q]
+            owned_total[l] += n_owned
+            # the rank's context plans on it (chunks, export tables) without a GPU
+        ctx = pkg.MGCFD(local_mesh=lm, device=-1, init=False)
+        for l in range(2):
+            assert int(ctx.plan_query(l, "owner_stats")[3]) <= 64
+        ctx.close()
+        lm.free()
+    assert owned_total == [400, 90]

@@ -77,3 +77,70 @@ def test_owner_chunks_bit_exact(pkg, meshgen, plan_oracle, name, chunk):
             counts = np.bincount(efile, minlength=lev["edge-->node"].shape[0])
             chunk_of = np.searchsorted(starts, perm[lev["edge-->node"]], side="right") - 1
             assert np.array_equal(counts, 1 + (chunk_of[:, 0] != chunk_of[:, 1]))
+
+
+def random_level(rng, n, e, hubs=0, dup=0, isolated=0):
+    """a level whose graph is NOT a perturbed grid: random endpoints (self edges excluded), optional hub nodes that a large
+    share of the edges touch, duplicated edges, nodes without any edge; 1-based maps like a level file"""
+    a = rng.integers(0, n - isolated, size=e)
+    b = rng.integers(0, n - isolated, size=e)
+    if hubs:
+        pick = rng.random(e) < 0.3
+        a[pick] = rng.integers(0, hubs, size=int(pick.sum()))
+    clash = a == b
+    b[clash] = (a[clash] + 1) % (n - isolated)
+    e2n = np.stack([a, b], axis=1).astype(np.int32)
+    if dup:
+        e2n = np.concatenate([e2n, e2n[:dup], e2n[:dup, ::-1]])
+    nb = max(1, n // 10)
+    return {"node_coordinates": rng.random((n, 3)), "edge-->node": e2n + 1,
+            "edge_weights": rng.standard_normal((e2n.shape[0], 3)),
+            "bnd_node-->node": rng.integers(1, n + 1, size=(nb, 1)).astype(np.int32),
+            "bnd_node-->group": rng.integers(0, 10, size=(nb, 1)).astype(np.int32),
+            "bnd_node_weights": rng.standard_normal((nb, 3))}
+
+
+@pytest.mark.parametrize("seed,n,e,hubs,dup,isolated,chunk,bs", [
+    (1, 200, 700, 0, 0, 0, 64, 64),
+    (2, 333, 1500, 3, 0, 0, 64, 256),         # three hubs with hundreds of edges each
+    (3, 97, 400, 0, 40, 0, 32, 32),           # duplicated and reversed edges
+    (4, 150, 300, 0, 0, 25, 64, 64),          # nodes without edges
+    (5, 1000, 6000, 2, 100, 50, 128, 256),    # everything at once, dense
+    (6, 2, 1, 0, 0, 0, 64, 64),               # the smallest graph there is
+])
+def test_planner_on_irregular_graphs_bit_exact(pkg, plan_oracle, seed, n, e, hubs, dup, isolated, chunk, bs):
+    """the decks of the other tests are perturbed structured grids (degree <= 8); the planner's rules are stated for any
+    graph, so the C++ planner and the restatement must also agree on hubs, multi-edges and isolated nodes"""
+    rng = np.random.default_rng(seed)
+    lev = random_level(rng, n, e, hubs, dup, isolated)
+    e0 = lev["edge-->node"] - 1
+    with pkg.MGCFD([lev], init=False, device=-1, owner_chunk_nodes=chunk, colour_block_edges=bs) as gpu:
+        perm = gpu.plan_query(0, "node_perm")
+        assert np.array_equal(perm, plan_oracle.hilbert_renumber(lev["node_coordinates"]))
+        order = gpu.plan_query(0, "edge_order")
+        assert np.array_equal(order, plan_oracle.sort_edges(e0, perm))
+        tc, bc = gpu.plan_query(0, "edge_thread_colour"), gpu.plan_query(0, "edge_block_colour")
+        rt, rb, nbc = plan_oracle.colour_edges(e0, perm, order, bs)
+        if rt.max() < 63 and nbc <= 63:
+            assert np.array_equal(tc, rt) and np.array_equal(bc, rb) and gpu.plan_query(0, "n_block_colours")[0] == nbc
+            assert plan_oracle.check_colouring(e0, order, bs, tc, bc)
+        else:
+            # a node with more than 63 edges inside one block (the sorted order puts a hub's edges next to each other):
+            # the colour masks are 64 bits wide, the plan saturates at colour 63 and the colour variant refuses to run on
+            # it (MGCFD_ERR_PLAN in ensure_colour); the default owner variant below has no such limit
+            assert hubs and tc.max() == 63
+            ok = rt < 63
+            assert np.array_equal(tc[ok & (tc < 63)], rt[ok & (tc < 63)])
+        starts = gpu.plan_query(0, "owner_chunk_start")
+        hoff, hgid = gpu.plan_query(0, "owner_halo_off"), gpu.plan_query(0, "owner_halo_gid")
+        eoff, efile = gpu.plan_query(0, "owner_edge_off"), gpu.plan_query(0, "owner_edge_file")
+        rs, rh, re = plan_oracle.owner_chunks(e0, perm, perm.size, chunk, chunk + (chunk * 3) // 2 + 64, chunk * 6)
+        assert list(starts) == rs
+        for k in range(len(rs) - 1):
+            assert list(hgid[hoff[k]:hoff[k + 1]]) == rh[k]
+            assert list(efile[eoff[k]:eoff[k + 1]]) == re[k]
+        assert starts[0] == 0 and starts[-1] == n and (np.diff(starts) > 0).all()
+        chunk_of = np.searchsorted(starts, perm[e0], side="right") - 1
+        assert np.array_equal(np.bincount(efile, minlength=e0.shape[0]), 1 + (chunk_of[:, 0] != chunk_of[:, 1]))
+        # every chunk starts on an even node (16-byte aligned bulk-copy source of its owned rows)
+        assert (np.asarray(starts[:-1]) % 2 == 0).all()
