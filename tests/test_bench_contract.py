@@ -70,3 +70,32 @@ def test_defaults_are_baseline_configs3():
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert 'ap.add_argument("--mesh", default="rotor37_8m"' in src
     assert 'ap.add_argument("--scaling", default="strong"' in src
+
+
+def test_algorithmic_byte_accounting_matches_the_survey():
+    """SURVEY.md 8(d): flux-edge loop 32 E + 120 N per invocation; M6-shaped deck: flux-edge share ~0.68 GB per V-cycle;
+    fused stage = flux-edge + time_step (168 N), + residual (120 N) after the last stage; restrict 48 N_f + 216 N_c;
+    prolong 148 N_f + 64 N_c; visit prologue copy 80 N + dt 56 N + min 8 N"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    # bench.py redirects fd 1 at import (library banners must not reach stdout): keep this process's stdout
+    saved = os.dup(1)
+    try:
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    m6 = [(300000, 930000, 0), (165000, 643000, 0), (111000, 488000, 0), (81000, 377117, 0)]
+    assert bench.visits_per_cycle(4) == [0, 1, 2, 3, 2, 1] and bench.visits_per_cycle(1) == [0]
+    assert bench.flux_edges_per_cycle(m6) == 3 * (930000 + 2 * 643000 + 2 * 488000 + 377117)
+    fb = bench.flux_bytes_per_cycle(m6)
+    assert fb == 3 * sum(32 * m6[l][1] + 120 * m6[l][0] for l in [0, 1, 2, 3, 2, 1]) and 0.67e9 < fb < 0.69e9
+    sb = bench.rk_stage_bytes_per_cycle(m6)
+    assert sb == fb + sum((3 * 168 + 120) * m6[l][0] for l in [0, 1, 2, 3, 2, 1])
+    nk = bench.node_kernel_bytes_per_cycle(m6)
+    assert nk["visit_begin"] == 144 * (300000 + 2 * 165000 + 2 * 111000 + 81000)
+    assert nk["restrict"] == 48 * (300000 + 165000 + 111000) + 216 * (165000 + 111000 + 81000)
+    assert nk["down"] == 148 * (300000 + 165000 + 111000) + 64 * (165000 + 111000 + 81000)
+    one = [(1000, 3000, 0)]
+    assert bench.node_kernel_bytes_per_cycle(one) == {"visit_begin": 144000, "restrict": 0, "down": 0}
