@@ -15,8 +15,8 @@ it fits one GPU, so N=1 is the same job undecomposed).  The N=1 line also carrie
                the CUDA-event time of the flux launches inside the timed region, against the measured HBM peak
   cpu_baseline the reference's own elemental kernels (oracle/_ref, OpenMP block-coloured, all host threads)
                on a bounded sample of the same deck
-  parity       after the timed regions the variables are re-initialised (euler3d.cpp:414-417), ONE cycle runs on the
-               GPU(s) and every level's owned-node state is compared with the CPU oracle's after one cycle
+  parity       after the timed regions the variables are re-initialised (euler3d.cpp:414-417), TWO cycles run on the
+               GPU(s) and every level's owned-node state is compared with the CPU oracle's after the same cycles
                (<= 1e-10 relative to the variable's largest magnitude, north_star's tolerance; -v criterion of
                validation.h:46-100 counted beside it).  A mismatch makes the run fail (exit code 3).
 
